@@ -1,0 +1,398 @@
+"""Generate tests/golden/*.npz|json by running the REFERENCE's own code.
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.gen_golden
+
+Everything written here comes out of the reference's unmodified modules
+(imported through oracle/ref_shim.py).  Where a fixture involves physics
+(`rollout_*`), the reference's QuadrupedGymEnv drives the CPU oracle world via
+the fake BulletClient, so what is pinned is the reference's control flow,
+task/sensor/interface arithmetic and bookkeeping -- not Bullet itself
+("parity unpinned" for the physics layer, see oracle/qso.h).
+"""
+import json
+import os
+import sys
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+
+ref_shim.install()
+
+from quadruped_spring.env.quadruped_gym_env import QuadrupedGymEnv  # noqa: E402
+from quadruped_spring.utils import action_filter  # noqa: E402
+
+
+def make_env(**kw):
+    cfg = dict(
+        enable_springs=True, task_env="JUMPING_IN_PLACE", motor_control_mode="PD", action_space_mode="SYMMETRIC",
+        observation_space_mode="ARS_BASIC", env_randomizer_mode="GROUND_RANDOMIZER",
+    )
+    cfg.update(kw)
+    return QuadrupedGymEnv(**cfg)
+
+
+def flat(d):
+    return np.concatenate([np.asarray(v, dtype=np.float64).reshape(-1) for v in d.values()])
+
+
+# ----------------------------------------------------------------------------- urdf
+def gen_urdf():
+    path = os.path.join(ref_shim.REFERENCE_ROOT, "quadruped_spring/go1/go1_description/urdf/go1.urdf")
+    r = ET.parse(path).getroot()
+    links, joints = {}, []
+    f3 = lambda s: [float(x) for x in s.split()]
+    for l in r.findall("link"):
+        i = l.find("inertial")
+        o = i.find("origin")
+        ent = {"mass": float(i.find("mass").get("value")), "com": f3(o.get("xyz")) if o is not None else [0, 0, 0],
+               "collision": []}
+        for c in l.findall("collision"):
+            g = c.find("geometry")[0]
+            oo = c.find("origin")
+            ent["collision"].append({"type": g.tag, **{k: f3(v) for k, v in g.attrib.items()},
+                                     "xyz": f3(oo.get("xyz")), "rpy": f3(oo.get("rpy"))})
+        links[l.get("name")] = ent
+    for j in r.findall("joint"):
+        o = j.find("origin")
+        a = j.find("axis")
+        lim = j.find("limit")
+        joints.append({"name": j.get("name"), "type": j.get("type"), "parent": j.find("parent").get("link"),
+                       "child": j.find("child").get("link"), "xyz": f3(o.get("xyz")), "rpy": f3(o.get("rpy")),
+                       "axis": f3(a.get("xyz")) if a is not None else None,
+                       "lower": float(lim.get("lower")) if lim is not None else None,
+                       "upper": float(lim.get("upper")) if lim is not None else None})
+    with open(os.path.join(OUT, "go1_urdf.json"), "w") as f:
+        json.dump({"links": links, "joints": joints}, f, indent=1)
+
+
+# ----------------------------------------------------------------------------- analytic paths
+def gen_analytic():
+    rng = np.random.default_rng(12345)
+    out = {}
+    n = 64
+    for springs in (True, False):
+        tag = "s1" if springs else "s0"
+        env = make_env(enable_springs=springs)
+        env.reset()
+        rob = env.robot
+        cfg = env._robot_config
+        q = rng.uniform(cfg.REAL_LOWER_ANGLE_JOINT, cfg.REAL_UPPER_ANGLE_JOINT, size=(n, 12))
+        q[0] = cfg.INIT_MOTOR_ANGLES
+        q[1] = cfg.INIT_MOTOR_ANGLES + 0.1
+        qd = rng.normal(size=(n, 12)) * 8
+        qd[1] = 0.5
+        cmd = rng.uniform(cfg.REAL_LOWER_ANGLE_JOINT, cfg.REAL_UPPER_ANGLE_JOINT, size=(n, 12))
+        cmd[0] = cmd[1] = cfg.INIT_MOTOR_ANGLES
+        out[f"{tag}_q"], out[f"{tag}_qd"], out[f"{tag}_cmd"] = q, qd, cmd
+        # a11: quadruped_motor.py:45-99 (PD and TORQUE branches)
+        out[f"{tag}_tau_pd"] = np.stack([rob._motor_model.convert_to_torque(cmd[i], q[i], qd[i])[0] for i in range(n)])
+        tcmd = rng.normal(size=(n, 12)) * 25
+        out[f"{tag}_tcmd"] = tcmd
+        out[f"{tag}_tau_torque"] = np.stack(
+            [rob._motor_model.convert_to_torque(tcmd[i], q[i], qd[i], motor_control_mode="TORQUE")[0] for i in range(n)])
+        if springs:  # a12: springs.py:28-74
+            out[f"{tag}_tau_spring"] = np.stack([rob._motor_model.compute_spring_torques(q[i], qd[i]) for i in range(n)])
+        # a16 / a9
+        J = np.zeros((n, 4, 3, 3)); P = np.zeros((n, 4, 3)); IK = np.zeros((n, 4, 3)); V = np.zeros((n, 4, 3))
+        for i in range(n):
+            for leg in range(4):
+                J[i, leg], P[i, leg] = rob._compute_jacobian_and_position(q[i], leg)
+                IK[i, leg] = rob.ComputeInverseKinematics(leg, P[i, leg])
+                V[i, leg] = J[i, leg] @ qd[i, 3 * leg:3 * leg + 3]
+        out[f"{tag}_fk_J"], out[f"{tag}_fk_pos"], out[f"{tag}_ik_of_fk"], out[f"{tag}_foot_vel"] = J, P, IK, V
+        xyz = rng.uniform(-0.5, 0.5, size=(n, 4, 3))  # includes unreachable targets (D clip, sqrt clamp)
+        out[f"{tag}_ik_xyz"] = xyz
+        out[f"{tag}_ik_q"] = np.stack([[rob.ComputeInverseKinematics(leg, xyz[i, leg]) for leg in range(4)] for i in range(n)])
+        # a5-a8 for every control x action-space combination
+        for ctrl in ("PD", "CARTESIAN_PD"):
+            for am, dim in (("DEFAULT", 12), ("SYMMETRIC", 6), ("SYMMETRIC_NO_HIP", 4)):
+                e2 = make_env(enable_springs=springs, motor_control_mode=ctrl, action_space_mode=am)
+                e2.reset()
+                a = rng.uniform(-1.6, 1.6, size=(n, dim))
+                a[0] = 0
+                if dim == 6:
+                    a[1] = [0.5, -0.25, 0.75, -1.5, 0.1, -0.9]
+                key = f"{tag}_{ctrl}_{am}"
+                out[key + "_a"] = a
+                out[key + "_cmd"] = np.stack([e2._ac_interface._transform_action_to_motor_command(a[i]) for i in range(n)])
+                out[key + "_init_action"] = np.asarray(e2._last_action, dtype=np.float64)
+        # constants
+        for name in ("INIT_MOTOR_ANGLES", "RL_UPPER_ANGLE_JOINT", "RL_LOWER_ANGLE_JOINT", "RL_UPPER_CARTESIAN_POS",
+                     "RL_LOWER_CARTESIAN_POS", "RL_TORQUE_LIMITS", "MOTOR_KP", "MOTOR_KD", "NOMINAL_FOOT_POS_LEG_FRAME",
+                     "IS_FALLEN_HEIGHT", "JOINT_ANGLES_NOISE", "JOINT_VELOCITIES_NOISE", "HEIGHT_NOISE", "PITCH_NOISE",
+                     "VEL_LIN_NOISE", "VEL_ANG_NOISE", "PITCH_RATE_NOISE", "FEET_POS_NOISE", "FEET_VEL_NOISE"):
+            out[f"{tag}_cfg_{name}"] = np.asarray(getattr(cfg, name), dtype=np.float64)
+        if springs:
+            for name in ("SPRINGS_STIFFNESS", "SPRINGS_DAMPING", "SPRINGS_REST_ANGLE"):
+                out[f"{tag}_cfg_{name}"] = np.asarray(getattr(cfg, name), dtype=np.float64)
+    # BACKFLIP limit mutation (motor_interface.py:20-22); do it LAST: it mutates module state
+    e3 = make_env(enable_springs=True, task_env="BACKFLIP", observation_space_mode="ARS_BACKFLIP")
+    e3.reset()
+    a = rng.uniform(-1.2, 1.2, size=(n, 6))
+    out["backflip_PD_SYMMETRIC_a"] = a
+    out["backflip_PD_SYMMETRIC_cmd"] = np.stack([e3._ac_interface._transform_action_to_motor_command(a[i]) for i in range(n)])
+    # orientation quantities (a14, App. A.5)
+    quat = rng.normal(size=(n, 4))
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    quat[0] = [0, 0, 0, 1]
+    quat[1] = [0, np.sin(np.pi / 4), 0, np.cos(np.pi / 4)]  # gimbal branch
+    quat[2] = [0, -np.sin(np.pi / 4), 0, np.cos(np.pi / 4)]
+    omega = rng.normal(size=(n, 3)) * 3
+    rpy = np.zeros((n, 3)); rate = np.zeros((n, 3)); R = np.zeros((n, 9)); bf0 = np.zeros(n); bf1 = np.zeros(n)
+    w = e3._pybullet_client.world
+    from quadruped_spring.env.sensors.robot_sensors import PitchBackFlip
+    for i in range(n):
+        s = w.get_state()
+        s[3:7] = quat[i]; s[10:13] = omega[i]
+        w.set_state(s)
+        rpy[i] = e3.robot.GetBaseOrientationRollPitchYaw()
+        rate[i] = e3.robot.GetTrueBaseRollPitchYawRate()
+        R[i] = e3.robot.GetBaseOrientationMatrix().reshape(9)
+        e3.task._switched_controller = False
+        bf0[i] = PitchBackFlip._get_pitch(e3)
+        e3.task._switched_controller = True
+        bf1[i] = PitchBackFlip._get_pitch(e3)
+    out.update(orient_quat=quat, orient_omega=omega, orient_rpy=rpy, orient_rate=rate, orient_R=R,
+               orient_bf_pitch0=bf0, orient_bf_pitch1=bf1)
+    # a4: Butterworth action filter
+    f = action_filter.ActionFilterButter(sampling_rate=100.0, num_joints=6)
+    out["filter_b"], out["filter_a"] = f.b[0], f.a[0]
+    f.reset()
+    x0 = rng.uniform(-1, 1, 6)
+    f.init_history(x0)
+    xs = rng.uniform(-1, 1, size=(40, 6))
+    out["filter_x0"], out["filter_x"] = x0, xs
+    out["filter_y"] = np.stack([f.filter(x) for x in xs])
+    np.savez_compressed(os.path.join(OUT, "analytic.npz"), **out)
+
+
+# ----------------------------------------------------------------------------- observation spaces
+def gen_obs_spaces():
+    out = {}
+    modes = ["ENCODER", "ENCODER_2", "CARTESIAN_NO_IMU", "ARS_BASIC", "ARS_SENSOR", "LANDING_SENSOR", "PPO_BASIC",
+             "PPO_BASIC_X", "PPO_BASIC_CONTACT", "ARS_BACKFLIP", "PPO_BACKFLIP"]
+    rng = np.random.default_rng(777)
+    for springs in (True, False):
+        for m in modes:
+            env = make_env(enable_springs=springs, observation_space_mode=m)
+            env.reset()
+            tag = f"{'s1' if springs else 's0'}_{m}"
+            out[tag + "_low"] = np.asarray(env.observation_space.low, dtype=np.float64)
+            out[tag + "_high"] = np.asarray(env.observation_space.high, dtype=np.float64)
+            out[tag + "_noise_std"] = np.concatenate(
+                [np.asarray(s._noise_std, dtype=np.float64).reshape(-1) for s in env._robot_sensors._sensor_list])
+            # clean reads at random states
+            w = env._pybullet_client.world
+            S = np.zeros((8, 37)); O = []
+            for i in range(8):
+                s = w.get_state()
+                s[0:3] = rng.normal(size=3) * 0.3 + [0, 0, 0.4]
+                qq = rng.normal(size=4); s[3:7] = qq / np.linalg.norm(qq)
+                s[7:13] = rng.normal(size=6)
+                s[13:25] = rng.uniform(env._robot_config.REAL_LOWER_ANGLE_JOINT, env._robot_config.REAL_UPPER_ANGLE_JOINT)
+                s[25:37] = rng.normal(size=12) * 5
+                w.set_state(s)
+                env.task._switched_controller = bool(i % 2)
+                env._robot_sensors._on_step()
+                S[i] = s
+                O.append(flat(env._robot_sensors.get_obs()))
+            out[tag + "_state"], out[tag + "_obs"] = S, np.stack(O)
+    np.savez_compressed(os.path.join(OUT, "obs_spaces.npz"), **out)
+
+
+# ----------------------------------------------------------------------------- rollouts
+def jump_actions(dim, n, rng, amp=1.0, crouch=25, push=12, period=70):
+    """Open-loop crouch/extend pattern that produces take-off, flight and landing."""
+    acts = np.zeros((n, dim))
+    for t in range(n):
+        ph = t % period
+        if ph < crouch:
+            th, ca = 0.9, -0.9          # thigh forward, calf folded
+        elif ph < crouch + push:
+            th, ca = -0.6 * amp, 1.0 * amp  # extend
+        else:
+            th, ca = 0.0, 0.0
+        noise = rng.normal(size=dim) * 0.03
+        if dim == 6:
+            a = np.array([0, th, ca, 0, th, ca])
+        elif dim == 12:
+            a = np.array([0, th, ca] * 4)
+        else:
+            a = np.array([th, ca, th, ca])
+        acts[t] = a + noise
+    return acts
+
+
+def cart_jump_actions(n, rng, period=70):
+    acts = np.zeros((n, 6))
+    for t in range(n):
+        ph = t % period
+        if ph < 25:
+            z = 1.0    # foot high (body low)
+            x = 0.3
+        elif ph < 37:
+            z = -1.0   # push down
+            x = -0.5
+        else:
+            z, x = -0.1, 0.0
+        acts[t] = np.array([x, 0, z, x, 0, z]) + rng.normal(size=6) * 0.03
+    return acts
+
+
+def rollout(name, cfg, actions, seed, world_params=None):
+    ref_shim.FakeBulletClient.world_params = dict(world_params or {})
+    np.random.seed(seed)
+    env = make_env(**cfg)
+    env.reset()
+    mu = env._pybullet_client._mu_ground
+    w = env._pybullet_client.world
+    rec = {k: [] for k in ("state", "obs", "reward", "done", "truncated", "tau", "n_invalid", "foot_force",
+                           "foot_contact", "task", "pre_state")}
+    init_state = w.get_state()
+    init_obs = flat(env._robot_sensors.get_obs())
+    init_last_action = np.asarray(env._last_action, dtype=np.float64)
+    T = env.task
+
+    def task_vec():
+        g = lambda n, d=0.0: float(getattr(T, n, d))
+        return np.array([g("_switched_controller"), g("_all_feet_in_the_air"), g("_time_take_off"), g("_init_height"),
+                         g("_max_flight_time"), g("_max_forward_distance"), g("_max_pitch"), g("_relative_max_height"),
+                         g("_max_delta_x"), g("_max_height"), g("max_pitch"), g("old_fwd"), g("actual_fwd")])
+
+    init_task = task_vec()
+    n_done = 0
+    for a in actions:
+        rec["pre_state"].append(w.get_state())
+        obs, r, d, info = env.step(np.asarray(a, dtype=np.float64))
+        _, ninv, ff, fc = env.robot.GetContactInfo()
+        rec["state"].append(w.get_state())
+        rec["obs"].append(flat(env._robot_sensors.get_obs()))
+        rec["reward"].append(r)
+        rec["done"].append(d)
+        rec["truncated"].append(bool(info.get("TimeLimit.truncated", False)))
+        rec["tau"].append(np.asarray(env.robot.GetMotorTorques(), dtype=np.float64))
+        rec["n_invalid"].append(ninv)
+        rec["foot_force"].append(np.asarray(ff, dtype=np.float64))
+        rec["foot_contact"].append(np.asarray(fc, dtype=np.float64))
+        rec["task"].append(task_vec())
+        if d:
+            n_done += 1
+            break
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    out.update(actions=np.asarray(actions)[: len(out["reward"])], mu=mu, init_state=init_state, init_obs=init_obs,
+               init_last_action=init_last_action, init_task=init_task,
+               cfg=json.dumps(cfg), world_params=json.dumps(world_params or {}))
+    np.savez_compressed(os.path.join(OUT, f"rollout_{name}.npz"), **out)
+    ref_shim.FakeBulletClient.world_params = {}
+    fl = out["foot_contact"].sum(axis=1) == 0
+    print(f"rollout_{name}: {len(out['reward'])} steps, done={bool(out['done'][-1])} trunc={bool(out['truncated'][-1])} "
+          f"flight_steps={int(fl.sum())} ret={out['reward'].sum():.4f} max_h={out['state'][:, 2].max():.3f}")
+
+
+def gen_rollouts():
+    rng = np.random.default_rng(2024)
+    base = dict(enable_springs=True, task_env="JUMPING_IN_PLACE", motor_control_mode="PD",
+                action_space_mode="SYMMETRIC", observation_space_mode="ARS_BASIC")
+    # BASELINE config 1: random actions, PEA on, jumping in place
+    rollout("jip_random", base, np.random.default_rng(0).uniform(-1, 1, size=(120, 6)), seed=0)
+    rollout("jip_jump", base, jump_actions(6, 160, rng), seed=1)
+    rollout("jip_nosprings_random", dict(base, enable_springs=False),
+            np.random.default_rng(1).uniform(-1, 1, size=(120, 6)), seed=2)
+    rollout("jip_nosprings_jump", dict(base, enable_springs=False, observation_space_mode="PPO_BASIC_CONTACT"),
+            jump_actions(6, 160, rng), seed=3)
+    rollout("jf_cartesian_jump", dict(base, task_env="JUMPING_FORWARD", motor_control_mode="CARTESIAN_PD"),
+            cart_jump_actions(160, rng), seed=4)
+    rollout("jf_cartesian_random", dict(base, task_env="JUMPING_FORWARD", motor_control_mode="CARTESIAN_PD"),
+            np.random.default_rng(3).uniform(-1, 1, size=(100, 6)), seed=5)
+    rollout("jip_ppo_jump", dict(base, task_env="JUMPING_IN_PLACE_PPO", observation_space_mode="PPO_BASIC"),
+            jump_actions(6, 160, rng), seed=6)
+    rollout("jf_ppo_jump", dict(base, task_env="JUMPING_FORWARD_PPO", observation_space_mode="PPO_BASIC_X",
+                                action_space_mode="DEFAULT"), jump_actions(12, 160, rng), seed=7)
+    rollout("jf_ppo_hp_nohip", dict(base, task_env="JUMPING_FORWARD_PPO_HP", observation_space_mode="LANDING_SENSOR",
+                                    action_space_mode="SYMMETRIC_NO_HIP"), jump_actions(4, 160, rng), seed=8)
+    rollout("jip_ppo_hp_filter", dict(base, task_env="JUMPING_IN_PLACE_PPO_HP", observation_space_mode="ARS_SENSOR",
+                                      enable_action_filter=True), jump_actions(6, 160, rng), seed=9)
+    rollout("backflip_ppo", dict(base, task_env="BACKFLIP_PPO", observation_space_mode="PPO_BACKFLIP"),
+            jump_actions(6, 160, rng, amp=1.0), seed=10)
+    rollout("encoder2_notask", dict(base, task_env="NO_TASK", observation_space_mode="ENCODER_2"),
+            np.random.default_rng(5).uniform(-0.5, 0.5, size=(60, 6)), seed=11)
+    rollout("cartesian_noimu", dict(base, task_env="JUMPING_FORWARD", observation_space_mode="CARTESIAN_NO_IMU",
+                                    motor_control_mode="CARTESIAN_PD", action_space_mode="DEFAULT"),
+            np.random.default_rng(6).uniform(-0.4, 0.4, size=(60, 12)), seed=12)
+    # BACKFLIP mutates RL_UPPER_ANGLE_JOINT for the rest of the process (App. D.7): keep it last
+    rollout("backflip", dict(base, task_env="BACKFLIP", observation_space_mode="ARS_BACKFLIP"),
+            jump_actions(6, 160, rng, amp=1.0), seed=13)
+
+
+# ----------------------------------------------------------------------------- CPG
+def gen_hopf():
+    from quadruped_spring.hopf_network import HopfNetwork
+    import contextlib
+    import io
+
+    out = {}
+    for gait, osw, ost in (("TROT", 16 * np.pi, 4 * np.pi), ("BOUND", 10 * np.pi, 40 * np.pi),
+                           ("WALK", 24 * np.pi, 25 * np.pi), ("PACE", 20 * np.pi, 20 * np.pi)):
+        np.random.seed(5)
+        with contextlib.redirect_stdout(io.StringIO()):
+            cpg = HopfNetwork(gait=gait, omega_swing=osw, omega_stance=ost, time_step=0.001)
+        X0 = cpg.X.copy()
+        Xs, xs, zs = [], [], []
+        for _ in range(600):
+            x, z = cpg.update()
+            Xs.append(cpg.X.copy()); xs.append(x); zs.append(z)
+        out[f"{gait}_PHI"] = cpg.PHI
+        out[f"{gait}_X0"], out[f"{gait}_X"] = X0, np.stack(Xs)
+        out[f"{gait}_xs"], out[f"{gait}_zs"] = np.stack(xs), np.stack(zs)
+        out[f"{gait}_params"] = np.array([cpg._mu, osw, ost, cpg._coupling_strength, cpg._dt, cpg._des_step_len,
+                                          cpg._robot_height, cpg._ground_clearance, cpg._ground_penetration])
+    # torque law of hopf_network.py:241-289 evaluated with the reference's IK / Jacobian
+    env = make_env(enable_springs=True)
+    env.reset()
+    rob = env.robot
+    rng = np.random.default_rng(99)
+    n = 32
+    q = rng.uniform(env._robot_config.RL_LOWER_ANGLE_JOINT, env._robot_config.RL_UPPER_ANGLE_JOINT, size=(n, 12))
+    dq = rng.normal(size=(n, 12)) * 3
+    xs = rng.uniform(-0.05, 0.05, size=(n, 4)); zs = rng.uniform(-0.3, -0.2, size=(n, 4))
+    kp = np.array([150, 70, 70]); kd = np.array([2, 0.5, 0.5])
+    kpC = np.diag([2500] * 3); kdC = np.diag([40] * 3)
+    side = np.array([-1, 1, -1, 1]); foot_y = 0.0838
+    tau = np.zeros((n, 12))
+    for s in range(n):
+        for i in range(4):
+            q_i = q[s, 3 * i:3 * i + 3]; dq_i = dq[s, 3 * i:3 * i + 3]
+            xyz_d = np.array([xs[s, i], side[i] * foot_y, zs[s, i]])
+            leg_q = rob.ComputeInverseKinematics(i, xyz_d)
+            t = -kp * (q_i - leg_q) - kd * dq_i
+            J, xyz = rob._compute_jacobian_and_position(q[s], i)
+            F = -kpC @ (xyz - xyz_d) - kdC @ (J @ dq_i)
+            t = t + J.T @ F
+            tau[s, 3 * i:3 * i + 3] = t
+    out.update(law_q=q, law_dq=dq, law_xs=xs, law_zs=zs, law_tau=tau)
+    np.savez_compressed(os.path.join(OUT, "hopf.npz"), **out)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "rollouts"]
+    if "urdf" in which:
+        gen_urdf()
+    if "analytic" in which:
+        gen_analytic()
+    if "obs" in which:
+        gen_obs_spaces()
+    if "hopf" in which:
+        gen_hopf()
+    if "rollouts" in which:
+        gen_rollouts()
+    print("golden fixtures written to", OUT)

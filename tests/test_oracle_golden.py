@@ -1,0 +1,129 @@
+"""The CPU oracle against the fixtures produced by the reference's own code
+(oracle/gen_golden.py).  Runs without a GPU."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import ROLLOUTS, load_golden
+from oracle import oracle as O
+
+TOL = dict(rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("tag", ["s1", "s0"])
+def test_pd_and_spring_torque(analytic, tag):
+    g = analytic
+    kp, kd, tm = g[f"{tag}_cfg_MOTOR_KP"], g[f"{tag}_cfg_MOTOR_KD"], g[f"{tag}_cfg_RL_TORQUE_LIMITS"]
+    q, qd, cmd = g[f"{tag}_q"], g[f"{tag}_qd"], g[f"{tag}_cmd"]
+    for i in range(len(q)):
+        np.testing.assert_allclose(O.pd_torque(kp, kd, tm, cmd[i], q[i], qd[i]), g[f"{tag}_tau_pd"][i], **TOL)
+        np.testing.assert_allclose(O.pd_torque(kp, kd, tm, g[f"{tag}_tcmd"][i], q[i], qd[i], torque_mode=True),
+                                   g[f"{tag}_tau_torque"][i], **TOL)
+        if tag == "s1":
+            np.testing.assert_allclose(
+                O.spring_torque(g["s1_cfg_SPRINGS_STIFFNESS"], g["s1_cfg_SPRINGS_DAMPING"],
+                                g["s1_cfg_SPRINGS_REST_ANGLE"], q[i], qd[i]), g["s1_tau_spring"][i], **TOL)
+
+
+def test_known_answers_survey_appendix_c(analytic):
+    # PD (-7.9,-8,-8)x4 and the PEA vector at q = INIT+0.1, qd = 0.5
+    g = analytic
+    np.testing.assert_allclose(g["s1_tau_pd"][1], [-7.9, -8.0, -8.0] * 4, atol=1e-12)
+    np.testing.assert_allclose(g["s1_tau_spring"][1],
+                               [-0, -2.15, 5.85, -2.15, -2.15, 5.85, -0, -2.15, 5.85, -2.15, -2.15, 5.85], atol=1e-12)
+    J, pos = O.fk_jacobian([0, np.pi / 4, -np.pi / 2], 0)
+    np.testing.assert_allclose(pos, [0, -0.0847, -0.30122749], atol=1e-8)
+    np.testing.assert_allclose(J, [[0, -0.30122749, -0.15061374], [0.30122749, 0, 0], [-0.0847, 0, -0.15061374]], atol=1e-8)
+
+
+@pytest.mark.parametrize("tag", ["s1", "s0"])
+def test_fk_jacobian_ik(analytic, tag):
+    g = analytic
+    q, qd = g[f"{tag}_q"], g[f"{tag}_qd"]
+    for i in range(len(q)):
+        for leg in range(4):
+            J, pos = O.fk_jacobian(q[i, 3 * leg:3 * leg + 3], leg)
+            np.testing.assert_allclose(J, g[f"{tag}_fk_J"][i, leg], **TOL)
+            np.testing.assert_allclose(pos, g[f"{tag}_fk_pos"][i, leg], **TOL)
+            np.testing.assert_allclose(J @ qd[i, 3 * leg:3 * leg + 3], g[f"{tag}_foot_vel"][i, leg], **TOL)
+            np.testing.assert_allclose(O.ik(g[f"{tag}_ik_xyz"][i, leg], leg), g[f"{tag}_ik_q"][i, leg], **TOL)
+            np.testing.assert_allclose(O.ik(pos, leg), g[f"{tag}_ik_of_fk"][i, leg], rtol=1e-7, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag", ["s1", "s0"])
+@pytest.mark.parametrize("ctrl", ["PD", "CARTESIAN_PD"])
+@pytest.mark.parametrize("am", ["DEFAULT", "SYMMETRIC", "SYMMETRIC_NO_HIP"])
+def test_action_to_command(analytic, tag, ctrl, am):
+    g = analytic
+    a, cmd = g[f"{tag}_{ctrl}_{am}_a"], g[f"{tag}_{ctrl}_{am}_cmd"]
+    for i in range(len(a)):
+        got = O.action_to_command(a[i], enable_springs=(tag == "s1"), control=ctrl, action_mode=am)
+        np.testing.assert_allclose(got, cmd[i], rtol=1e-9, atol=1e-9)
+
+
+def test_backflip_limits(analytic):
+    g = analytic
+    for i in range(len(g["backflip_PD_SYMMETRIC_a"])):
+        got = O.action_to_command(g["backflip_PD_SYMMETRIC_a"][i], True, "PD", "SYMMETRIC", task="BACKFLIP")
+        np.testing.assert_allclose(got, g["backflip_PD_SYMMETRIC_cmd"][i], **TOL)
+
+
+def test_orientation(analytic):
+    g = analytic
+    for i in range(len(g["orient_quat"])):
+        qt = g["orient_quat"][i]
+        np.testing.assert_allclose(O.rpy_from_quat(qt), g["orient_rpy"][i], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(O.backflip_pitch(qt, 0), g["orient_bf_pitch0"][i], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(O.backflip_pitch(qt, 1), g["orient_bf_pitch1"][i], rtol=1e-9, atol=1e-9)
+
+
+def test_butterworth_coefficients(analytic):
+    # SURVEY.md App. C
+    np.testing.assert_allclose(analytic["filter_b"], [0.00782021, 0.01564042, 0.00782021], atol=1e-8)
+    np.testing.assert_allclose(analytic["filter_a"], [1, -1.73472577, 0.7660066], atol=1e-8)
+
+
+def test_cpg(hopf):
+    for gait in ("TROT", "BOUND", "WALK", "PACE"):
+        p = hopf[f"{gait}_params"]
+        X = hopf[f"{gait}_X0"].copy()
+        for t in range(len(hopf[f"{gait}_X"])):
+            X, xs, zs = O.cpg_step(X, hopf[f"{gait}_PHI"], *p)
+            np.testing.assert_allclose(X, hopf[f"{gait}_X"][t], rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(xs, hopf[f"{gait}_xs"][t], rtol=1e-9, atol=1e-11)
+            np.testing.assert_allclose(zs, hopf[f"{gait}_zs"][t], rtol=1e-9, atol=1e-11)
+    for i in range(len(hopf["law_q"])):
+        tau = O.cpg_torque(hopf["law_xs"][i], hopf["law_zs"][i], hopf["law_q"][i], hopf["law_dq"][i], 0.0838,
+                           [150, 70, 70], [2, 0.5, 0.5], 2500.0, 40.0)
+        np.testing.assert_allclose(tau, hopf["law_tau"][i], rtol=1e-9, atol=1e-8)
+
+
+@pytest.mark.parametrize("name", ROLLOUTS)
+def test_rollout_matches_reference_env(name):
+    """qso_env_* (C) against the reference's QuadrupedGymEnv run over the same
+    oracle world: pins control flow, tasks, sensors and bookkeeping."""
+    g = load_golden(f"rollout_{name}.npz")
+    cfg = json.loads(str(g["cfg"]))
+    env = O.Env(enable_springs=cfg["enable_springs"], motor_control_mode=cfg["motor_control_mode"],
+                action_space_mode=cfg["action_space_mode"], task_env=cfg["task_env"],
+                observation_space_mode=cfg["observation_space_mode"],
+                enable_action_filter=cfg.get("enable_action_filter", False))
+    obs = env.reset(mu=float(g["mu"]))
+    np.testing.assert_allclose(env.world.get_state(), g["init_state"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(obs, g["init_obs"], rtol=1e-9, atol=1e-10)
+    for t in range(len(g["reward"])):
+        obs, r, d, tr = env.step(g["actions"][t])
+        np.testing.assert_allclose(env.world.get_state(), g["state"][t], rtol=1e-8, atol=1e-9, err_msg=f"step {t}")
+        np.testing.assert_allclose(obs, g["obs"][t], rtol=1e-8, atol=1e-9, err_msg=f"obs step {t}")
+        np.testing.assert_allclose(r, g["reward"][t], rtol=1e-8, atol=1e-10, err_msg=f"reward step {t}")
+        assert d == bool(g["done"][t]) and tr == bool(g["truncated"][t]), t
+        ts = env.task_state()
+        np.testing.assert_allclose(ts[23:27], g["foot_force"][t], rtol=1e-8, atol=1e-8)
+        np.testing.assert_array_equal(ts[19:23], g["foot_contact"][t])
+        np.testing.assert_allclose(env.torques()[0], g["tau"][t], rtol=1e-8, atol=1e-9)
+        if cfg["task_env"] != "NO_TASK":
+            gt = g["task"][t]
+            # switched, in_air, t_takeoff, init_h, max_flight, max_fwd, max_pitch, rel_max_h, max_dx, max_h
+            np.testing.assert_allclose([ts[0], ts[1], ts[2], ts[6], ts[8], ts[9], ts[10], ts[11], ts[12], ts[13]],
+                                       gt[:10], rtol=1e-8, atol=1e-10, err_msg=f"task step {t}")

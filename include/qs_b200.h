@@ -1,0 +1,217 @@
+/*
+ * qs_b200.h -- C ABI of the B200-native batched Go1(+PEA) simulator.
+ *
+ * This is the drop-in boundary for the hot path of
+ * francescovezzi/quadruped-springs: QuadrupedGymEnv.step / reset for N
+ * independent environments (reference: quadruped_spring/env/quadruped_gym_env.py).
+ * The reference is pure Python over pybullet and has no FFI of its own, so each
+ * entry point cites the reference Python interface it replaces; INTEGRATION.md
+ * shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C types only; every buffer is caller-owned unless stated; device
+ *     buffers are fp32 row-major [N, k] unless stated;
+ *   - int return: 0 = ok, negative = QS_ERR_*; qs_last_error() gives the text
+ *     (thread-local) -- replaces the reference's Python exceptions
+ *     (quadruped_gym_env.py:168, quadruped.py:75);
+ *   - every launch is asynchronous on the given cudaStream_t (passed as void*),
+ *     no host synchronisation inside qs_step / qs_reset;
+ *   - one handle per device, not re-entrant;
+ *   - there is NO CPU fallback: every call fails with QS_ERR_CUDA if no sm_100
+ *     device / driver is present.
+ */
+#ifndef QS_B200_H
+#define QS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QS_OK 0
+#define QS_ERR_ARG (-1)
+#define QS_ERR_CUDA (-2)
+#define QS_ERR_STATE (-3)
+
+#define QS_STATE_DIM 37 /* pos3 quat4(xyzw) linvel3 angvel3 q12 qd12 (world frame) */
+#define QS_MAX_OBS 32
+#define QS_TASK_DIM 32
+#define QS_STATS_DIM 16
+
+/* registry keys of the reference, as integers (string -> id mapping lives in
+ * the host layer and keeps the reference's names):
+ * control_interface/collection.py:21-49, tasks/task_collection.py:19-37,
+ * sensors/sensor_collection.py:92-105 */
+enum qs_control_mode { QS_CTRL_PD = 0, QS_CTRL_CARTESIAN_PD = 1, QS_CTRL_TORQUE = 2 };
+enum qs_action_mode { QS_ACT_DEFAULT = 0, QS_ACT_SYMMETRIC = 1, QS_ACT_SYMMETRIC_NO_HIP = 2 };
+enum qs_task {
+  QS_TASK_NO_TASK = 0,
+  QS_TASK_JUMPING_IN_PLACE = 1,
+  QS_TASK_JUMPING_FORWARD = 2,
+  QS_TASK_BACKFLIP = 3,
+  QS_TASK_JUMPING_IN_PLACE_PPO = 4,
+  QS_TASK_JUMPING_FORWARD_PPO = 5,
+  QS_TASK_BACKFLIP_PPO = 6,
+  QS_TASK_JUMPING_IN_PLACE_PPO_HP = 7,
+  QS_TASK_JUMPING_FORWARD_PPO_HP = 8
+};
+enum qs_obs_mode {
+  QS_OBS_ENCODER = 0,
+  QS_OBS_ENCODER_2,
+  QS_OBS_CARTESIAN_NO_IMU,
+  QS_OBS_ARS_BASIC,
+  QS_OBS_ARS_SENSOR,
+  QS_OBS_LANDING_SENSOR,
+  QS_OBS_PPO_BASIC,
+  QS_OBS_PPO_BASIC_X,
+  QS_OBS_PPO_BASIC_CONTACT,
+  QS_OBS_ARS_BACKFLIP,
+  QS_OBS_PPO_BACKFLIP,
+  QS_OBS_PPO_CONTINUOUS_JUMPING_FORWARD
+};
+
+/* Constructor arguments of QuadrupedGymEnv (quadruped_gym_env.py:52-70) plus the
+ * physics-engine parameters the reference sets on pybullet
+ * (quadruped_gym_env.py:301-309, quadruped.py:663-683).  Fill with
+ * qs_default_config() first. */
+typedef struct qs_config {
+  int32_t enable_springs;        /* enable_springs */
+  int32_t control_mode;          /* motor_control_mode */
+  int32_t action_mode;           /* action_space_mode */
+  int32_t task;                  /* task_env */
+  int32_t obs_mode;              /* observation_space_mode */
+  int32_t action_repeat;         /* action_repeat (10) */
+  int32_t is_rl_interface;       /* isRLGymInterface */
+  int32_t enable_action_filter;  /* enable_action_filter */
+  int32_t ground_randomizer;     /* env_randomizer_mode == GROUND_RANDOMIZER: mu ~ U[0.5,1) per reset */
+  int32_t settling_steps;        /* 2500 (quadruped_gym_env.py:115) */
+  int32_t enable_noise;          /* sensor noise (sensors/sensor.py:25-60) */
+  int32_t auto_reset;            /* reset finished envs inside qs_step (SB3 VecEnv behaviour) */
+  int32_t num_iterations;        /* int(300/action_repeat) unless overridden (>0) */
+  int32_t enable_limits;         /* joint-limit constraint rows */
+  int32_t body_contact_response; /* reserved: non-foot shapes are detected, not yet constrained */
+  int32_t block_size;            /* CUDA block size for the step kernel (0 = default) */
+  uint64_t seed;                 /* Philox key; streams are indexed by GLOBAL env id */
+  int64_t env_id_offset;         /* global id of local env 0 (multi-GPU sharding) */
+  double time_step;              /* 0.001; double so that sim_time > 10 s fires on control step 1001 like the reference */
+  double max_episode_time;       /* EPISODE_LENGTH = 10 s (quadruped_gym_env.py:35) */
+  float gravity_z;               /* -9.8 */
+  float mu_ground;               /* used when ground_randomizer == 0 */
+  float contact_erp, limit_erp, linear_slop, warmstart, residual_threshold;
+  float max_coord_vel;           /* 30.1 */
+  float breaking_threshold;      /* 0.02 */
+  float reserved0;
+} qs_config;
+
+typedef struct qs_env* qs_handle;
+
+/* device pointers into the handle-owned structure-of-arrays state; every array
+ * is [dim][N] (component-major, env-minor => coalesced).  Valid until
+ * qs_destroy.  Replaces the Quadruped accessor surface (quadruped.py:82-222). */
+typedef struct qs_state_ptrs {
+  float* state;        /* [37][N] */
+  float* tau_motor;    /* [12][N] last substep's clipped motor torque = GetMotorTorques() */
+  float* tau_spring;   /* [12][N] */
+  float* kp;           /* [12][N] per-env PD gains (quadruped_motor.py:45-99) */
+  float* kd;           /* [12][N] */
+  float* spring;       /* [9][N]  k3, b3, rest3 (springs.py:28-74) */
+  float* mu;           /* [N] ground friction */
+  float* foot_force;   /* [4][N] normal force of the last tick (quadruped.py:256) */
+  int32_t* contact;    /* [N] bits 0-3: foot in contact, bits 8-: invalid (non-foot) contact count */
+  float* task;         /* [QS_TASK_DIM][N] task state (tasks/task_base.py:40-59) */
+  float* last_action;  /* [12][N] */
+  int32_t* sim_steps;  /* [N] */
+  int32_t* env_steps;  /* [N] */
+  float* ep_return;    /* [N] */
+} qs_state_ptrs;
+
+void qs_default_config(qs_config* cfg);
+/* host-only helpers (no GPU needed): per-element sensor noise std of cfg->obs_mode
+ * (go1/configs_*.py:215-230 through sensors/robot_sensors.py), and the
+ * observation/action dimensions for a config. */
+int qs_obs_noise_std(const qs_config* cfg, float* out /*QS_MAX_OBS*/);
+int qs_config_obs_dim(const qs_config* cfg);
+int qs_config_action_dim(const qs_config* cfg);
+const char* qs_last_error(void);
+int qs_device_count(void);
+
+/* QuadrupedGymEnv.__init__ (quadruped_gym_env.py:52-155) for n_envs envs */
+int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out);
+/* QuadrupedGymEnv.close (quadruped_gym_env.py:337) */
+int qs_destroy(qs_handle h);
+int qs_action_dim(qs_handle h);
+int qs_obs_dim(qs_handle h);
+int qs_num_envs(qs_handle h);
+int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* out);
+
+/* QuadrupedGymEnv.reset (quadruped_gym_env.py:278-297): re-initialise and
+ * settle the envs whose mask byte is non-zero (all when mask == NULL); writes
+ * the first observation of those envs into obs[N, O] when obs != NULL. */
+int qs_reset(qs_handle h, const uint8_t* mask_dev, float* obs_dev, void* stream);
+
+/* QuadrupedGymEnv.step (quadruped_gym_env.py:227-256) for all N envs:
+ * actions [N, A] -> obs [N, O], reward [N], done [N], truncated [N]
+ * (infos["TimeLimit.truncated"]). */
+int qs_step(qs_handle h, const float* actions_dev, float* obs_dev, float* reward_dev,
+            uint8_t* done_dev, uint8_t* truncated_dev, void* stream);
+
+/* same call with HOST buffers (pinned or pageable): H2D of actions, the step,
+ * D2H of the four results, all on `stream`; returns after the stream is
+ * synchronised.  This is the end-to-end path a numpy caller (SB3 VecEnv) uses. */
+int qs_step_host(qs_handle h, const float* actions_host, float* obs_host, float* reward_host,
+                 uint8_t* done_host, uint8_t* truncated_host, void* stream);
+
+/* Quadruped.reset_desired_state / env.set_robot_desired_state
+ * (quadruped.py:521-525): overwrite the physical state [N,37] (row-major) */
+int qs_set_state(qs_handle h, const float* state_dev /*[N,37]*/, void* stream);
+int qs_get_state(qs_handle h, float* state_dev /*[N,37]*/, void* stream);
+/* the clean observation of the current state (SensorList.get_obs, sensor.py:101-105) */
+int qs_observe(qs_handle h, float* obs_dev, int with_noise, void* stream);
+
+/* TEST HOOK: advance n_ticks physics ticks (pybullet.stepSimulation,
+ * quadruped_gym_env.py:218-219) with fixed joint torques tau[N,12]; no task
+ * bookkeeping.  use_f64 != 0 runs the double-precision instantiation of the
+ * same kernel (algorithm check against the oracle, not a product path). */
+int qs_debug_ticks(qs_handle h, const float* tau_dev, int n_ticks, int use_f64, void* stream);
+
+/* ---- stand-alone analytic kernels (Quadruped / motor-model accessor surface) ---- */
+/* ActionWrapper._transform_action_to_motor_command (interface_base.py:162-164) */
+int qs_action_to_command(const qs_config* cfg, const float* actions_dev /*[N,A]*/,
+                         float* cmd_dev /*[N,12]*/, int n, void* stream);
+/* QuadrupedMotorModel.convert_to_torque + compute_spring_torques
+ * (quadruped_motor.py:45-104).  kp/kd/tau_max are [12] host arrays, spring9 =
+ * k3,b3,rest3 host array or NULL (no springs); outputs [N,12]. */
+int qs_pd_pea_torque(const float* cmd_dev, const float* q_dev, const float* qd_dev,
+                     const float* kp12, const float* kd12, const float* tau_max12,
+                     const float* spring9, int torque_mode, float* tau_motor_dev,
+                     float* tau_spring_dev, int n, void* stream);
+/* Quadruped.ComputeJacobianAndPosition + ComputeFeetPosAndVel
+ * (quadruped.py:348-397,440-449): q,qd [N,12] -> pos [N,12], J [N,4,9], vel [N,12] */
+int qs_fk_jacobian(const float* q_dev, const float* qd_dev, float* pos_dev, float* jac_dev,
+                   float* vel_dev, int n, void* stream);
+/* Quadruped.ComputeInverseKinematics (quadruped.py:399-438): xyz [N,12] -> q [N,12] */
+int qs_ik(const float* xyz_dev, float* q_dev, int n, void* stream);
+/* HopfNetwork.update (hopf_network.py:117-173) + the Cartesian impedance law of
+ * hopf_network.py:241-289.  X [N,8] (r[4], theta[4]) is updated in place;
+ * params9 = mu, omega_swing, omega_stance, coupling, dt, des_step_len,
+ * robot_height, ground_clearance, ground_penetration; phi16 row-major PHI;
+ * gains8 = kp3, kd3, kpCartesian, kdCartesian.  tau [N,12] out (may be NULL);
+ * xs, zs [N,4] out (may be NULL). */
+int qs_cpg_update(float* X_dev, const float* params9, const float* phi16, const float* q_dev,
+                  const float* qd_dev, const float* gains8, float foot_y, float* xs_dev,
+                  float* zs_dev, float* tau_dev, int n, void* stream);
+/* rollout statistics of this shard (EvaluationWrapper infos,
+ * evaluation_wrapper.py:43-53; task maxima, task_base.py:51-57): out[QS_STATS_DIM]
+ * floats on the device: count, finished episodes, sum/max of max_height,
+ * rel_max_height, max_forward_distance, max_flight_time, flip completion,
+ * return sum, length sum, terminated count. */
+int qs_reduce_stats(qs_handle h, float* out_dev, void* stream);
+
+/* number of kernels launched by this library since load (bench bookkeeping) */
+int64_t qs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

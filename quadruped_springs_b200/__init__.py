@@ -1,0 +1,10 @@
+"""quadruped_springs_b200: B200-native batched simulator for the hot path of
+francescovezzi/quadruped-springs (QuadrupedGymEnv.step for N independent Go1s)."""
+from .env import (  # noqa: F401
+    ActionInterfaceCollection, BatchedQuadruped, BatchedQuadrupedGymEnv, EnvRandomizerCollection,
+    MotorInterfaceCollection, SensorCollection, TaskCollection,
+)
+from .hopf_network import HopfNetwork  # noqa: F401
+from . import ops  # noqa: F401
+
+__all__ = ["BatchedQuadrupedGymEnv", "BatchedQuadruped", "HopfNetwork", "ops"]

@@ -1,0 +1,917 @@
+// qs_kernels.cu -- sm_100a kernels and the C ABI (include/qs_b200.h) of the
+// batched Go1(+PEA) simulator.  One env per thread: the whole control step
+// (action map -> [PD + PEA torque -> floating-base dynamics -> contact PGS ->
+// integration] x action_repeat -> task / reward / done -> observation) runs out
+// of registers; HBM is touched once per control step through SoA arrays
+// ([component][env], coalesced).  No tensor cores: per-env matrices are <= 6x6.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "qs_env.cuh"
+#include "qs_model_host.h"
+
+using namespace qs;
+
+// ============================================================================ args
+struct KernelArgs {
+  DeviceView D;
+  EnvCfg C;
+  RobotConst RC;
+  ModelConstT<float> M;
+  SolverConst SC;
+  double time_step_d, max_time_d;
+};
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return fail(QS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+  } while (0)
+
+// ============================================================================ kernels
+// settling / reset-time command: _convert_reference_to_command(get_init_pose())
+// (interface_base.py:68-72,182-200); also returns the settling action.
+__device__ __forceinline__ void settle_command(const EnvCfg& C, const RobotConst& RC, float* cmd, float* act12) {
+  if (C.is_rl) {
+    const bool cart = C.control_mode == QS_CTRL_CARTESIAN_PD;
+    const int sidx = cart ? 1 : 0;
+    float a12[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++)
+      a12[i] = cart ? command_to_action1(RC.nominal_foot[i], RC.cart_lo[i], RC.cart_hi[i])
+                    : command_to_action1(RC.init_angles[i], RC.ang_lo[i], RC.ang_hi[i]);
+    // _convert_to_actual_action_space (action_interface.py:17-18,41-44,67-74)
+#pragma unroll
+    for (int i = 0; i < 12; i++) act12[i] = 0.f;
+    if (C.action_mode == QS_ACT_DEFAULT) {
+#pragma unroll
+      for (int i = 0; i < 12; i++) act12[i] = a12[i];
+    } else if (C.action_mode == QS_ACT_SYMMETRIC) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) { act12[j] = a12[j]; act12[3 + j] = a12[6 + j]; }
+    } else {
+      if (sidx == 0) { act12[0] = a12[1]; act12[1] = a12[2]; act12[2] = a12[7]; act12[3] = a12[8]; }
+      else { act12[0] = a12[0]; act12[1] = a12[2]; act12[2] = a12[6]; act12[3] = a12[8]; }
+    }
+    float b12[12];
+    expand_action(C.action_mode, sidx, act12, b12);
+    action12_to_command(RC, C.control_mode, b12, cmd);
+  } else {
+    // settle_robot_by_pd (control_interface/utils.py:22-30): PD limits, DEFAULT space
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const float a = command_to_action1(RC.init_angles[i], RC.ang_lo[i], RC.ang_hi[i]);
+      cmd[i] = clampt(RC.ang_lo[i] + 0.5f * (a + 1.f) * (RC.ang_hi[i] - RC.ang_lo[i]), RC.ang_lo[i], RC.ang_hi[i]);
+      act12[i] = 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void finish_episode_stats(const DeviceView& D, int env, const float* ts, float ep_return,
+                                                     int ep_len, bool terminated, int task) {
+  const int n = D.n;
+  float* s = D.stats + env;
+  s[0 * n] += 1.f;
+  s[1 * n] += ts[TS_MAX_H];
+  s[2 * n] = fmaxf(s[2 * n], ts[TS_MAX_H]);
+  s[3 * n] += ts[TS_REL_MAX_H];
+  s[4 * n] += ts[TS_MAX_FWD];
+  s[5 * n] = fmaxf(s[5 * n], ts[TS_MAX_FWD]);
+  s[6 * n] += ts[TS_MAX_FLIGHT];
+  const float flip = (task == QS_TASK_BACKFLIP ? ts[TS_MAX_PITCH_BF] : ts[TS_MAX_PITCH]) / float(2 * QS_PI);
+  s[7 * n] += flip;
+  s[8 * n] += ep_return;
+  s[9 * n] += float(ep_len);
+  s[10 * n] += terminated ? 1.f : 0.f;
+}
+
+// -------------------------------------------------------------------- K1: step
+__global__ void __launch_bounds__(128)
+k_step(const __grid_constant__ KernelArgs A, const float* __restrict__ actions, float* __restrict__ obs,
+       float* __restrict__ reward, uint8_t* __restrict__ done, uint8_t* __restrict__ truncated,
+       int* __restrict__ reset_list, int* __restrict__ reset_count) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  const DeviceView& D = A.D;
+  const EnvCfg& C = A.C;
+  const int n = D.n;
+  if (env >= n) return;
+  const float dt = A.SC.dt;
+  EnvState<float> st;
+  ContactState<float> cs;
+  load_state(D, env, st, cs, dt);
+
+  // ---- action (quadruped_gym_env.py:229-234)
+  float act[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) act[i] = i < C.action_dim ? actions[size_t(env) * C.action_dim + i] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; i++) D.last_action[i * n + env] = act[i];
+  if (C.enable_filter) {  // utils/action_filter.py:110-121
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      if (i < C.action_dim) {
+        float* f = D.filt + env;
+        const float x0 = f[(0 * 12 + i) * n], x1 = f[(1 * 12 + i) * n];
+        const float y0 = f[(2 * 12 + i) * n], y1 = f[(3 * 12 + i) * n];
+        const float y = act[i] * A.RC.filt_b[0] + (x0 * A.RC.filt_b[1] + x1 * A.RC.filt_b[2]) -
+                        (y0 * A.RC.filt_a[1] + y1 * A.RC.filt_a[2]);
+        f[(1 * 12 + i) * n] = x0; f[(0 * 12 + i) * n] = act[i];
+        f[(3 * 12 + i) * n] = y0; f[(2 * 12 + i) * n] = y;
+        act[i] = y;
+      }
+    }
+  }
+  float cmd[12];
+  bool torque_mode = false;
+  if (C.is_rl) {
+    // _interpolate_actions (:187-205) is a no-op in the reference: step() overwrites
+    // _last_action with the current action before the substeps (:229-234).
+    float a12[12];
+    expand_action(C.action_mode, C.control_mode == QS_CTRL_CARTESIAN_PD ? 1 : 0, act, a12);
+    action12_to_command(A.RC, C.control_mode, a12, cmd);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; i++) cmd[i] = act[i];
+    torque_mode = C.control_mode == QS_CTRL_TORQUE;
+  }
+
+  // ---- action_repeat substeps (:236-237)
+  float tau_m[12], tau_s[12];
+  run_ticks(st, cs, cmd, torque_mode, C.action_repeat, env, D, C, A.RC, A.M, A.SC, tau_m, tau_s, true);
+  const int sim_steps = D.sim_steps[env] + C.action_repeat;
+  const int env_steps = D.env_steps[env] + 1;
+
+  // ---- task / reward / done (:239-251)
+  float Rb[9], rpy[3];
+  quat_to_R(st.quat, Rb);
+  rpy_from_quat(st.quat, rpy);
+  const float sim_time = float(double(sim_steps) * A.time_step_d);
+  float ts[QS_TASK_DIM];
+#pragma unroll
+  for (int i = 0; i < TS_END; i++) ts[i] = D.task[i * n + env];
+  float foot_force[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) foot_force[k] = (cs.mask >> k) & 1 ? cs.lam_n[k] / dt : 0.f;
+  task_on_step(ts, st, cs, tau_m, rpy, Rb, sim_time, C.task);
+  float r = task_reward(ts, st, foot_force, ts + TS_OLD_TAU0, tau_m, rpy, Rb, C.task);
+  const bool term = task_terminated(ts, st, cs, Rb, A.RC.fallen_height, C.task);
+  const bool dn = term || (double(sim_steps) * A.time_step_d > A.max_time_d);
+  if (dn) r += task_reward_end(ts, term, C.task);
+#pragma unroll
+  for (int i = 0; i < 12; i++) ts[TS_OLD_TAU0 + i] = tau_m[i];
+  const float ep_ret = D.ep_return[env] + r;
+
+  // ---- sensors (:253-254)
+  float o[QS_MAX_OBS];
+#pragma unroll
+  for (int i = 0; i < QS_MAX_OBS; i++) o[i] = 0.f;
+  observe(st, cs, ts, rpy, Rb, C.obs_mode, o);
+  const uint64_t gid = uint64_t(C.gid0 + env);
+  store_obs(obs + size_t(env) * C.obs_dim, o, C, A.RC, gid, D.reset_count[env], uint32_t(env_steps), C.enable_noise);
+  reward[env] = r;
+  done[env] = dn;
+  truncated[env] = dn && !term;
+
+  // ---- write back
+  store_state(D, env, st, cs, dt);
+#pragma unroll
+  for (int i = 0; i < 12; i++) { D.tau_motor[i * n + env] = tau_m[i]; D.tau_spring[i * n + env] = tau_s[i]; }
+#pragma unroll
+  for (int i = 0; i < TS_END; i++) D.task[i * n + env] = ts[i];
+  D.sim_steps[env] = sim_steps;
+  D.env_steps[env] = env_steps;
+  D.ep_return[env] = ep_ret;
+  if (dn) {
+    finish_episode_stats(D, env, ts, ep_ret, env_steps, term, C.task);
+    if (C.auto_reset) reset_list[atomicAdd(reset_count, 1)] = env;
+  }
+}
+
+// -------------------------------------------------------------------- K2: reset + settle
+// list == nullptr: thread i resets env i (all envs).  Otherwise thread i resets
+// env list[i] for i < *count (dense warps whatever the done pattern).
+__global__ void __launch_bounds__(128)
+k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, const int* __restrict__ count,
+        float* __restrict__ obs) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const DeviceView& D = A.D;
+  const EnvCfg& C = A.C;
+  const int n = D.n;
+  int env = tid;
+  if (list) {
+    if (tid >= *count) return;
+    env = list[tid];
+  } else if (tid >= n) {
+    return;
+  }
+  const float dt = A.SC.dt;
+  const uint64_t gid = uint64_t(C.gid0 + env);
+  const uint32_t epoch = D.reset_count[env] + 1;
+  D.reset_count[env] = epoch;
+  // env_randomizer.py:287-289: mu = 0.5 + 0.5 * U[0,1)
+  const float mu = C.ground_randomizer ? 0.5f + 0.5f * uniform1(C.seed, gid, epoch, 100) : C.mu_ground;
+  D.mu[env] = mu;
+  // a fresh Quadruped is built on every reset (quadruped_gym_env.py:299-319): default gains / springs
+#pragma unroll
+  for (int i = 0; i < 12; i++) { D.kp[i * n + env] = A.RC.kp[i]; D.kd[i * n + env] = A.RC.kd[i]; }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    D.spring[(0 + j) * n + env] = A.RC.spring_k[j];
+    D.spring[(3 + j) * n + env] = A.RC.spring_b[j];
+    D.spring[(6 + j) * n + env] = A.RC.spring_rest[j];
+  }
+  EnvState<float> st;
+  ContactState<float> cs;
+  st.pos[0] = 0.f; st.pos[1] = 0.f; st.pos[2] = 0.32f;  // INIT_POSITION, configs:23
+  st.quat[0] = st.quat[1] = st.quat[2] = 0.f; st.quat[3] = 1.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { st.vlin[i] = 0.f; st.vang[i] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < 12; i++) { st.q[i] = A.RC.init_angles[i]; st.qd[i] = 0.f; }
+  cs.mask = 0; cs.invalid = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) cs.lam_n[k] = 0.f;
+
+  float cmd[12], act12[12], tau_m[12], tau_s[12];
+  settle_command(C, A.RC, cmd, act12);
+  const int nsettle = C.is_rl ? C.settling_steps : 1500;
+  run_ticks(st, cs, cmd, false, nsettle, env, D, C, A.RC, A.M, A.SC, tau_m, tau_s, true);
+  if (nsettle == 0) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) { tau_m[i] = 0.f; tau_s[i] = 0.f; }
+  }
+
+  float Rb[9], rpy[3];
+  quat_to_R(st.quat, Rb);
+  rpy_from_quat(st.quat, rpy);
+  float ts[QS_TASK_DIM];
+#pragma unroll
+  for (int i = 0; i < TS_END; i++) ts[i] = D.task[i * n + env];
+  task_reset(ts, st, cs, tau_m, rpy, Rb, 0.f, C.task);
+#pragma unroll
+  for (int i = 0; i < TS_END; i++) D.task[i * n + env] = ts[i];
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    D.last_action[i * n + env] = act12[i];
+    D.tau_motor[i * n + env] = tau_m[i];
+    D.tau_spring[i * n + env] = tau_s[i];
+    // action_filter.py:123-127 init_history(last_action)
+    D.filt[(0 * 12 + i) * n + env] = act12[i]; D.filt[(1 * 12 + i) * n + env] = act12[i];
+    D.filt[(2 * 12 + i) * n + env] = act12[i]; D.filt[(3 * 12 + i) * n + env] = act12[i];
+  }
+  D.sim_steps[env] = 0;
+  D.env_steps[env] = 0;
+  D.ep_return[env] = 0.f;
+  store_state(D, env, st, cs, dt);
+  if (obs) {
+    float o[QS_MAX_OBS];
+#pragma unroll
+    for (int i = 0; i < QS_MAX_OBS; i++) o[i] = 0.f;
+    observe(st, cs, ts, rpy, Rb, C.obs_mode, o);
+    store_obs(obs + size_t(env) * C.obs_dim, o, C, A.RC, gid, epoch, 0u, C.enable_noise);
+  }
+}
+
+__global__ void k_compact(const uint8_t* __restrict__ mask, int n, int* __restrict__ list, int* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && mask[i]) list[atomicAdd(count, 1)] = i;
+}
+
+// -------------------------------------------------------------------- observe / state I/O
+__global__ void k_observe(const __grid_constant__ KernelArgs A, float* __restrict__ obs, int with_noise) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  const DeviceView& D = A.D;
+  if (env >= D.n) return;
+  EnvState<float> st;
+  ContactState<float> cs;
+  load_state(D, env, st, cs, A.SC.dt);
+  float Rb[9], rpy[3], ts[QS_TASK_DIM], o[QS_MAX_OBS];
+  quat_to_R(st.quat, Rb);
+  rpy_from_quat(st.quat, rpy);
+#pragma unroll
+  for (int i = 0; i < TS_END; i++) ts[i] = D.task[i * D.n + env];
+#pragma unroll
+  for (int i = 0; i < QS_MAX_OBS; i++) o[i] = 0.f;
+  observe(st, cs, ts, rpy, Rb, A.C.obs_mode, o);
+  store_obs(obs + size_t(env) * A.C.obs_dim, o, A.C, A.RC, uint64_t(A.C.gid0 + env), D.reset_count[env],
+            uint32_t(D.env_steps[env]) + 0x40000000u, with_noise != 0);
+}
+
+__global__ void k_set_state(DeviceView D, const float* __restrict__ src) {  // [N,37] -> SoA
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D.n * QS_STATE_DIM) return;
+  const int env = i / QS_STATE_DIM, c = i % QS_STATE_DIM;
+  D.state[c * D.n + env] = src[i];
+  if (c == 0) {  // a teleported robot has no contact history
+    D.contact[env] = 0;
+    for (int k = 0; k < 4; k++) D.foot_force[k * D.n + env] = 0.f;
+  }
+}
+__global__ void k_get_state(DeviceView D, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D.n * QS_STATE_DIM) return;
+  const int env = i / QS_STATE_DIM, c = i % QS_STATE_DIM;
+  dst[i] = D.state[c * D.n + env];
+}
+
+// -------------------------------------------------------------------- debug ticks (fp32 product / fp64 check)
+template <typename T> struct DebugArgs {
+  DeviceView D;
+  ModelConstT<T> M;
+  SolverConst SC;
+};
+template <typename T>
+__global__ void __launch_bounds__(128)
+k_debug_ticks(const __grid_constant__ DebugArgs<T> A, const float* __restrict__ tau, int n_ticks) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  const DeviceView& D = A.D;
+  if (env >= D.n) return;
+  EnvState<float> sf;
+  ContactState<float> cf;
+  load_state(D, env, sf, cf, A.SC.dt);
+  EnvState<T> st;
+  ContactState<T> cs;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { st.pos[i] = sf.pos[i]; st.vlin[i] = sf.vlin[i]; st.vang[i] = sf.vang[i]; }
+#pragma unroll
+  for (int i = 0; i < 4; i++) { st.quat[i] = sf.quat[i]; cs.lam_n[i] = cf.lam_n[i]; }
+#pragma unroll
+  for (int i = 0; i < 12; i++) { st.q[i] = sf.q[i]; st.qd[i] = sf.qd[i]; }
+  cs.mask = cf.mask; cs.invalid = cf.invalid;
+  T t12[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) t12[i] = T(tau[size_t(env) * 12 + i]);
+  const T mu = T(D.mu[env]);
+  for (int t = 0; t < n_ticks; t++) physics_tick<T>(st, t12, mu, cs, A.M, A.SC, true);
+#pragma unroll
+  for (int i = 0; i < 3; i++) { sf.pos[i] = float(st.pos[i]); sf.vlin[i] = float(st.vlin[i]); sf.vang[i] = float(st.vang[i]); }
+#pragma unroll
+  for (int i = 0; i < 4; i++) { sf.quat[i] = float(st.quat[i]); cf.lam_n[i] = float(cs.lam_n[i]); }
+#pragma unroll
+  for (int i = 0; i < 12; i++) { sf.q[i] = float(st.q[i]); sf.qd[i] = float(st.qd[i]); }
+  cf.mask = cs.mask; cf.invalid = cs.invalid;
+  store_state(D, env, sf, cf, A.SC.dt);
+}
+
+// -------------------------------------------------------------------- K3: analytic utilities
+__global__ void k_action_to_command(const __grid_constant__ RobotConst RC, int control_mode, int action_mode,
+                                    int adim, const float* __restrict__ a, float* __restrict__ cmd, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float act[12], a12[12], c[12];
+#pragma unroll
+  for (int j = 0; j < 12; j++) act[j] = j < adim ? a[size_t(i) * adim + j] : 0.f;
+  expand_action(action_mode, control_mode == QS_CTRL_CARTESIAN_PD ? 1 : 0, act, a12);
+  action12_to_command(RC, control_mode, a12, c);
+#pragma unroll
+  for (int j = 0; j < 12; j++) cmd[size_t(i) * 12 + j] = c[j];
+}
+
+struct TorqueArgs {
+  float kp[12], kd[12], tau_max[12], spring[9];
+  int has_spring, torque_mode;
+};
+__global__ void k_pd_pea(const __grid_constant__ TorqueArgs T, const float* __restrict__ cmd,
+                         const float* __restrict__ q, const float* __restrict__ qd, float* __restrict__ tau_m,
+                         float* __restrict__ tau_s, int n) {
+  // one thread per (env, leg)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 4) return;
+  const int leg = i & 3;
+  const size_t base = size_t(i >> 2) * 12 + 3 * leg;
+  float ql[3], qdl[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) { ql[j] = q[base + j]; qdl[j] = qd[base + j]; }
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+    tau_m[base + j] = pd_torque1(T.kp[3 * leg + j], T.kd[3 * leg + j], T.tau_max[3 * leg + j], cmd[base + j], ql[j],
+                                 qdl[j], T.torque_mode != 0);
+  if (tau_s) {
+    float ts3[3] = {0.f, 0.f, 0.f};
+    if (T.has_spring) spring_torque_leg(leg, T.spring, T.spring + 3, T.spring + 6, ql, qdl, ts3);
+#pragma unroll
+    for (int j = 0; j < 3; j++) tau_s[base + j] = ts3[j];
+  }
+}
+
+__global__ void k_fk(const float* __restrict__ q, const float* __restrict__ qd, float* __restrict__ pos,
+                     float* __restrict__ jac, float* __restrict__ vel, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 4) return;
+  const int leg = i & 3;
+  const size_t base = size_t(i >> 2) * 12 + 3 * leg;
+  float ql[3] = {q[base], q[base + 1], q[base + 2]}, p[3], J[9];
+  fk_jacobian(ql, leg, p, J);
+#pragma unroll
+  for (int j = 0; j < 3; j++) pos[base + j] = p[j];
+  if (jac) {
+#pragma unroll
+    for (int j = 0; j < 9; j++) jac[size_t(i) * 9 + j] = J[j];
+  }
+  if (vel && qd) {
+    const float d0 = qd[base], d1 = qd[base + 1], d2 = qd[base + 2];
+#pragma unroll
+    for (int a = 0; a < 3; a++) vel[base + a] = J[3 * a] * d0 + J[3 * a + 1] * d1 + J[3 * a + 2] * d2;
+  }
+}
+
+__global__ void k_ik(const float* __restrict__ xyz, float* __restrict__ q, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 4) return;
+  const int leg = i & 3;
+  const size_t base = size_t(i >> 2) * 12 + 3 * leg;
+  float x[3] = {xyz[base], xyz[base + 1], xyz[base + 2]}, o[3];
+  leg_ik(x, leg, o);
+#pragma unroll
+  for (int j = 0; j < 3; j++) q[base + j] = o[j];
+}
+
+// -------------------------------------------------------------------- K4: Hopf CPG + impedance law
+struct CpgArgs {
+  float p[9], phi[16], gains[8], foot_y;
+};
+__global__ void k_cpg(const __grid_constant__ CpgArgs P, float* __restrict__ X, const float* __restrict__ q,
+                      const float* __restrict__ qd, float* __restrict__ xs_o, float* __restrict__ zs_o,
+                      float* __restrict__ tau, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float mu = P.p[0], om_sw = P.p[1], om_st = P.p[2], coup = P.p[3], dt = P.p[4], dstep = P.p[5],
+              height = P.p[6], gc = P.p[7], gp = P.p[8];
+  float r0[4], th0[4], r1[4], th1[4], xs[4], zs[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { r0[k] = X[size_t(i) * 8 + k]; th0[k] = X[size_t(i) * 8 + 4 + k]; }
+  // hopf_network.py:137-173
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float rd = 50.f * (mu - r0[k] * r0[k]) * r0[k];
+    float thd = sinf(th0[k]) > 0.f ? om_sw : om_st;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (j != k) thd += r0[j] * coup * sinf(th0[j] - th0[k] - P.phi[4 * k + j]);
+    r1[k] = r0[k] + dt * rd;
+    float th = th0[k] + dt * thd;
+    th = fmodf(th, float(2 * QS_PI));
+    if (th < 0.f) th += float(2 * QS_PI);
+    th1[k] = th;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    X[size_t(i) * 8 + k] = r1[k];
+    X[size_t(i) * 8 + 4 + k] = th1[k];
+    float s, c;
+    sincosf(th1[k], &s, &c);
+    xs[k] = -dstep * r1[k] * c;                              // hopf_network.py:126-133
+    zs[k] = s > 0.f ? -height + gc * s : -height + gp * s;
+    if (xs_o) xs_o[size_t(i) * 4 + k] = xs[k];
+    if (zs_o) zs_o[size_t(i) * 4 + k] = zs[k];
+  }
+  if (!tau) return;
+  // hopf_network.py:241-289: joint PD on IK(xyz_d) + J^T (-Kp (x - x_d) - Kd J qd)
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const float xyz_d[3] = {xs[k], side_sign(k) * P.foot_y, zs[k]};
+    float qdes[3], ql[3], qdl[3], J[9], p[3];
+    leg_ik(xyz_d, k, qdes);
+#pragma unroll
+    for (int j = 0; j < 3; j++) { ql[j] = q[size_t(i) * 12 + 3 * k + j]; qdl[j] = qd[size_t(i) * 12 + 3 * k + j]; }
+    fk_jacobian(ql, k, p, J);
+    float F[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float dx = J[3 * a] * qdl[0] + J[3 * a + 1] * qdl[1] + J[3 * a + 2] * qdl[2];
+      F[a] = -P.gains[6] * (p[a] - xyz_d[a]) - P.gains[7] * dx;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      float t = -P.gains[j] * (ql[j] - qdes[j]) - P.gains[3 + j] * qdl[j];
+      t += J[j] * F[0] + J[3 + j] * F[1] + J[6 + j] * F[2];
+      tau[size_t(i) * 12 + 3 * k + j] = t;
+    }
+  }
+}
+
+// -------------------------------------------------------------------- K5: rollout statistics
+// block reduce with warp shuffles, one atomic per block and statistic
+__global__ void k_stats(DeviceView D, float* __restrict__ out) {
+  __shared__ float sm[QS_STATS_DIM][8];
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float v[QS_STATS_DIM];
+#pragma unroll
+  for (int i = 0; i < QS_STATS_DIM; i++) v[i] = 0.f;
+  if (env < D.n) {
+#pragma unroll
+    for (int i = 0; i < 11; i++) v[1 + i] = D.stats[i * D.n + env];
+    v[0] = 1.f;
+  }
+  // rows 3 and 6 of v (stats rows 2, 5) are maxima, everything else sums
+#pragma unroll
+  for (int i = 0; i < QS_STATS_DIM; i++) {
+    const bool is_max = (i == 3 || i == 6);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float t = __shfl_xor_sync(0xffffffffu, v[i], o);
+      v[i] = is_max ? fmaxf(v[i], t) : v[i] + t;
+    }
+    if (lane == 0) sm[i][warp] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < QS_STATS_DIM) {
+    const int i = threadIdx.x;
+    const bool is_max = (i == 3 || i == 6);
+    float a = sm[i][0];
+    for (int w = 1; w < (blockDim.x >> 5); w++) a = is_max ? fmaxf(a, sm[i][w]) : a + sm[i][w];
+    if (is_max) atomicMax(reinterpret_cast<int*>(out + i), __float_as_int(fmaxf(a, 0.f)));  // non-negative floats order as ints
+    else atomicAdd(out + i, a);
+  }
+}
+
+// ============================================================================ host side
+struct qs_env {
+  qs_config cfg;
+  int n, device;
+  KernelArgs args;
+  ModelConstT<double> model_d;
+  void* pool;       // one allocation backing every SoA array
+  size_t pool_bytes;
+  int* reset_list;
+  int* reset_count;
+  float* dev_actions;  // staging for qs_step_host
+  float* dev_obs;
+  float* dev_reward;
+  uint8_t* dev_done;
+  uint8_t* dev_trunc;
+  bool was_reset;
+};
+
+static inline unsigned grid_for(int n, int block) { return unsigned((n + block - 1) / block); }
+
+extern "C" {
+
+const char* qs_last_error(void) { return g_err.c_str(); }
+int64_t qs_launch_count(void) { return g_launches.load(); }
+
+int qs_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+void qs_default_config(qs_config* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->enable_springs = 0;                       // quadruped_gym_env.py:63
+  c->control_mode = QS_CTRL_PD;                // :57
+  c->action_mode = QS_ACT_SYMMETRIC;           // :60
+  c->task = QS_TASK_NO_TASK;                   // :58
+  c->obs_mode = QS_OBS_ENCODER;                // :59
+  c->action_repeat = 10;                       // :56
+  c->is_rl_interface = 1;                      // :54
+  c->enable_action_filter = 0;                 // :65
+  c->ground_randomizer = 1;                    // :66
+  c->settling_steps = 2500;                    // :115
+  c->enable_noise = 1;
+  c->auto_reset = 0;
+  c->num_iterations = 0;
+  c->enable_limits = 0;
+  c->body_contact_response = 0;
+  c->block_size = 0;
+  c->seed = 0;
+  c->env_id_offset = 0;
+  c->time_step = 0.001;                        // :55
+  c->max_episode_time = 10.0;                  // :35
+  c->gravity_z = -9.8f;                        // :309
+  c->mu_ground = 1.0f;
+  c->contact_erp = 0.08f;
+  c->limit_erp = 0.2f;
+  c->linear_slop = 1e-5f;
+  c->warmstart = 0.1f;
+  c->residual_threshold = 1e-7f;
+  c->max_coord_vel = 30.1f;                    // quadruped.py:678-683
+  c->breaking_threshold = 0.02f;
+}
+
+static int check_config(const qs_config* c) {
+  if (!c) return fail(QS_ERR_ARG, "config is NULL");
+  if (c->control_mode < 0 || c->control_mode > 2) return fail(QS_ERR_ARG, "unknown motor control mode");
+  if (c->action_mode < 0 || c->action_mode > 2) return fail(QS_ERR_ARG, "unknown action space mode");
+  if (c->task < 0 || c->task > QS_TASK_JUMPING_FORWARD_PPO_HP) return fail(QS_ERR_ARG, "unknown task");
+  if (c->obs_mode < 0 || c->obs_mode > QS_OBS_PPO_CONTINUOUS_JUMPING_FORWARD) return fail(QS_ERR_ARG, "unknown observation space mode");
+  if (c->action_repeat < 1 || c->action_repeat > 1000) return fail(QS_ERR_ARG, "action_repeat out of range");
+  if (c->control_mode == QS_CTRL_TORQUE && c->is_rl_interface)  // quadruped_gym_env.py:167-168
+    return fail(QS_ERR_ARG, "the motor control mode TORQUE not implemented yet for RL Gym interface.");
+  if (!(c->time_step > 0)) return fail(QS_ERR_ARG, "time_step must be positive");
+  return QS_OK;
+}
+
+int qs_config_obs_dim(const qs_config* c) { return c ? host::obs_dim_of(c->obs_mode) : QS_ERR_ARG; }
+int qs_config_action_dim(const qs_config* c) { return c ? host::action_dim_of(c->is_rl_interface, c->action_mode) : QS_ERR_ARG; }
+
+int qs_obs_noise_std(const qs_config* c, float* out) {
+  if (int e = check_config(c)) return e;
+  if (!out) return fail(QS_ERR_ARG, "out is NULL");
+  RobotConst R;
+  host::build_robot(*c, R);
+  std::memcpy(out, R.obs_noise, sizeof(float) * QS_MAX_OBS);
+  return QS_OK;
+}
+
+int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
+  if (int e = check_config(cfg)) return e;
+  if (!out) return fail(QS_ERR_ARG, "out handle is NULL");
+  if (n_envs <= 0) return fail(QS_ERR_ARG, "n_envs must be positive");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(QS_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)");
+  CUDA_TRY(cudaSetDevice(device));
+  qs_env* h = new (std::nothrow) qs_env();
+  if (!h) return fail(QS_ERR_STATE, "out of host memory");
+  std::memset(static_cast<void*>(h), 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->n = n_envs;
+  h->device = device;
+  KernelArgs& A = h->args;
+  host::build_robot(*cfg, A.RC);
+  host::build_model<float>(A.M, cfg->breaking_threshold);
+  host::build_model<double>(h->model_d, cfg->breaking_threshold);
+  A.SC.dt = float(cfg->time_step);
+  A.SC.gravity_z = cfg->gravity_z;
+  A.SC.contact_erp = cfg->contact_erp;
+  A.SC.limit_erp = cfg->limit_erp;
+  A.SC.linear_slop = cfg->linear_slop;
+  A.SC.warmstart = cfg->warmstart;
+  A.SC.residual_threshold = cfg->residual_threshold;
+  A.SC.max_coord_vel = cfg->max_coord_vel;
+  A.SC.mu_link = 1.0f;  // quadruped.py:670-676
+  A.SC.num_iterations = cfg->num_iterations > 0 ? cfg->num_iterations : 300 / cfg->action_repeat;  // quadruped_gym_env.py:113
+  A.SC.enable_limits = cfg->enable_limits;
+  A.time_step_d = cfg->time_step;
+  A.max_time_d = cfg->max_episode_time;
+  EnvCfg& C = A.C;
+  C.enable_springs = cfg->enable_springs; C.control_mode = cfg->control_mode; C.action_mode = cfg->action_mode;
+  C.task = cfg->task; C.obs_mode = cfg->obs_mode; C.action_repeat = cfg->action_repeat;
+  C.is_rl = cfg->is_rl_interface; C.enable_filter = cfg->enable_action_filter; C.enable_noise = cfg->enable_noise;
+  C.obs_dim = host::obs_dim_of(cfg->obs_mode);
+  C.action_dim = host::action_dim_of(cfg->is_rl_interface, cfg->action_mode);
+  C.settling_steps = cfg->settling_steps; C.ground_randomizer = cfg->ground_randomizer; C.auto_reset = cfg->auto_reset;
+  C.max_episode_time = float(cfg->max_episode_time); C.mu_ground = cfg->mu_ground;
+  C.seed = cfg->seed; C.gid0 = cfg->env_id_offset;
+
+  // one pool for all SoA arrays (4-byte elements), 256 B aligned segments
+  const size_t n = size_t(n_envs);
+  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1;
+  // rows of one array are contiguous with stride n floats; each array starts 256 B aligned
+  h->pool_bytes = rows * n * 4 + 64 * 256;
+  cudaError_t e = cudaMalloc(&h->pool, h->pool_bytes);
+  if (e != cudaSuccess) { delete h; return fail(QS_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+  cudaMemset(h->pool, 0, h->pool_bytes);
+  char* p = static_cast<char*>(h->pool);
+  auto carve = [&](size_t nrows) {
+    void* r = p;
+    size_t bytes = nrows * n * 4;
+    bytes = ((bytes + 255) / 256) * 256;
+    p += bytes;
+    return r;
+  };
+  DeviceView& D = A.D;
+  D.n = n_envs;
+  D.state = (float*)carve(37); D.tau_motor = (float*)carve(12); D.tau_spring = (float*)carve(12);
+  D.kp = (float*)carve(12); D.kd = (float*)carve(12); D.spring = (float*)carve(9); D.mu = (float*)carve(1);
+  D.foot_force = (float*)carve(4); D.contact = (int32_t*)carve(1); D.task = (float*)carve(QS_TASK_DIM);
+  D.last_action = (float*)carve(12); D.filt = (float*)carve(48); D.sim_steps = (int32_t*)carve(1);
+  D.env_steps = (int32_t*)carve(1); D.ep_return = (float*)carve(1); D.stats = (float*)carve(QS_STATS_DIM);
+  D.reset_count = (uint32_t*)carve(1);
+  if (size_t(p - static_cast<char*>(h->pool)) > h->pool_bytes) { cudaFree(h->pool); delete h; return fail(QS_ERR_STATE, "pool overflow"); }
+  e = cudaMalloc(&h->reset_list, (n + 1) * sizeof(int));
+  if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(QS_ERR_CUDA, "cudaMalloc reset list"); }
+  h->reset_count = h->reset_list + n;
+  cudaMemset(h->reset_list, 0, (n + 1) * sizeof(int));
+  *out = h;
+  return QS_OK;
+}
+
+int qs_destroy(qs_handle h) {
+  if (!h) return fail(QS_ERR_ARG, "handle is NULL");
+  cudaSetDevice(h->device);
+  cudaFree(h->pool);
+  cudaFree(h->reset_list);
+  if (h->dev_actions) cudaFree(h->dev_actions);
+  if (h->dev_obs) cudaFree(h->dev_obs);
+  if (h->dev_reward) cudaFree(h->dev_reward);
+  if (h->dev_done) cudaFree(h->dev_done);
+  delete h;
+  return QS_OK;
+}
+
+int qs_action_dim(qs_handle h) { return h ? h->args.C.action_dim : QS_ERR_ARG; }
+int qs_obs_dim(qs_handle h) { return h ? h->args.C.obs_dim : QS_ERR_ARG; }
+int qs_num_envs(qs_handle h) { return h ? h->n : QS_ERR_ARG; }
+
+int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* o) {
+  if (!h || !o) return fail(QS_ERR_ARG, "NULL argument");
+  const DeviceView& D = h->args.D;
+  o->state = D.state; o->tau_motor = D.tau_motor; o->tau_spring = D.tau_spring; o->kp = D.kp; o->kd = D.kd;
+  o->spring = D.spring; o->mu = D.mu; o->foot_force = D.foot_force; o->contact = D.contact; o->task = D.task;
+  o->last_action = D.last_action; o->sim_steps = D.sim_steps; o->env_steps = D.env_steps; o->ep_return = D.ep_return;
+  return QS_OK;
+}
+
+static int block_of(qs_handle h) { return h->cfg.block_size > 0 ? h->cfg.block_size : 128; }
+
+int qs_reset(qs_handle h, const uint8_t* mask, float* obs, void* stream) {
+  if (!h) return fail(QS_ERR_ARG, "handle is NULL");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int B = block_of(h);
+  if (mask) {
+    CUDA_TRY(cudaMemsetAsync(h->reset_count, 0, sizeof(int), s));
+    k_compact<<<grid_for(h->n, 256), 256, 0, s>>>(mask, h->n, h->reset_list, h->reset_count);
+    k_reset<<<grid_for(h->n, B), B, 0, s>>>(h->args, h->reset_list, h->reset_count, obs);
+    g_launches += 2;
+  } else {
+    k_reset<<<grid_for(h->n, B), B, 0, s>>>(h->args, nullptr, nullptr, obs);
+    g_launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  h->was_reset = true;
+  return QS_OK;
+}
+
+int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_t* done, uint8_t* truncated,
+            void* stream) {
+  if (!h) return fail(QS_ERR_ARG, "handle is NULL");
+  if (!actions || !obs || !reward || !done || !truncated) return fail(QS_ERR_ARG, "NULL buffer");
+  if (!h->was_reset) return fail(QS_ERR_STATE, "qs_step before qs_reset");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int B = block_of(h);
+  if (h->cfg.auto_reset) CUDA_TRY(cudaMemsetAsync(h->reset_count, 0, sizeof(int), s));
+  k_step<<<grid_for(h->n, B), B, 0, s>>>(h->args, actions, obs, reward, done, truncated, h->reset_list, h->reset_count);
+  g_launches += 1;
+  if (h->cfg.auto_reset) {
+    // finished envs restart inside the same call; their obs row becomes the first
+    // observation of the new episode (SB3 VecEnv convention)
+    k_reset<<<grid_for(h->n, B), B, 0, s>>>(h->args, h->reset_list, h->reset_count, obs);
+    g_launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_step_host(qs_handle h, const float* actions, float* obs, float* reward, uint8_t* done, uint8_t* truncated,
+                 void* stream) {
+  if (!h) return fail(QS_ERR_ARG, "handle is NULL");
+  if (!actions || !obs || !reward || !done || !truncated) return fail(QS_ERR_ARG, "NULL buffer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t n = size_t(h->n), A = size_t(h->args.C.action_dim), O = size_t(h->args.C.obs_dim);
+  if (!h->dev_actions) {
+    CUDA_TRY(cudaMalloc(&h->dev_actions, n * 12 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->dev_obs, n * QS_MAX_OBS * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->dev_reward, n * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&h->dev_done, 2 * n));
+    h->dev_trunc = h->dev_done + n;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->dev_actions, actions, n * A * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (int e = qs_step(h, h->dev_actions, h->dev_obs, h->dev_reward, h->dev_done, h->dev_trunc, stream)) return e;
+  CUDA_TRY(cudaMemcpyAsync(obs, h->dev_obs, n * O * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(reward, h->dev_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(done, h->dev_done, n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(truncated, h->dev_trunc, n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return QS_OK;
+}
+
+int qs_set_state(qs_handle h, const float* state, void* stream) {
+  if (!h || !state) return fail(QS_ERR_ARG, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_set_state<<<grid_for(h->n * QS_STATE_DIM, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(h->args.D, state);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+int qs_get_state(qs_handle h, float* state, void* stream) {
+  if (!h || !state) return fail(QS_ERR_ARG, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_get_state<<<grid_for(h->n * QS_STATE_DIM, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(h->args.D, state);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_observe(qs_handle h, float* obs, int with_noise, void* stream) {
+  if (!h || !obs) return fail(QS_ERR_ARG, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_observe<<<grid_for(h->n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(h->args, obs, with_noise);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_debug_ticks(qs_handle h, const float* tau, int n_ticks, int use_f64, void* stream) {
+  if (!h || !tau) return fail(QS_ERR_ARG, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (use_f64) {
+    DebugArgs<double> a;
+    a.D = h->args.D; a.M = h->model_d; a.SC = h->args.SC;
+    k_debug_ticks<double><<<grid_for(h->n, 128), 128, 0, s>>>(a, tau, n_ticks);
+  } else {
+    DebugArgs<float> a;
+    a.D = h->args.D; a.M = h->args.M; a.SC = h->args.SC;
+    k_debug_ticks<float><<<grid_for(h->n, 128), 128, 0, s>>>(a, tau, n_ticks);
+  }
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_action_to_command(const qs_config* cfg, const float* actions, float* cmd, int n, void* stream) {
+  if (int e = check_config(cfg)) return e;
+  if (!actions || !cmd || n <= 0) return fail(QS_ERR_ARG, "bad argument");
+  RobotConst R;
+  host::build_robot(*cfg, R);
+  const int adim = host::action_dim_of(1, cfg->action_mode);
+  k_action_to_command<<<grid_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(R, cfg->control_mode, cfg->action_mode,
+                                                                                     adim, actions, cmd, n);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_pd_pea_torque(const float* cmd, const float* q, const float* qd, const float* kp12, const float* kd12,
+                     const float* tau_max12, const float* spring9, int torque_mode, float* tau_motor,
+                     float* tau_spring, int n, void* stream) {
+  if (!cmd || !q || !qd || !kp12 || !kd12 || !tau_max12 || !tau_motor || n <= 0) return fail(QS_ERR_ARG, "bad argument");
+  TorqueArgs T;
+  std::memcpy(T.kp, kp12, sizeof T.kp);
+  std::memcpy(T.kd, kd12, sizeof T.kd);
+  std::memcpy(T.tau_max, tau_max12, sizeof T.tau_max);
+  T.has_spring = spring9 != nullptr;
+  if (spring9) std::memcpy(T.spring, spring9, sizeof T.spring); else std::memset(T.spring, 0, sizeof T.spring);
+  T.torque_mode = torque_mode;
+  k_pd_pea<<<grid_for(n * 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(T, cmd, q, qd, tau_motor, tau_spring, n);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_fk_jacobian(const float* q, const float* qd, float* pos, float* jac, float* vel, int n, void* stream) {
+  if (!q || !pos || n <= 0) return fail(QS_ERR_ARG, "bad argument");
+  k_fk<<<grid_for(n * 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(q, qd, pos, jac, vel, n);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_ik(const float* xyz, float* q, int n, void* stream) {
+  if (!xyz || !q || n <= 0) return fail(QS_ERR_ARG, "bad argument");
+  k_ik<<<grid_for(n * 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(xyz, q, n);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_cpg_update(float* X, const float* params9, const float* phi16, const float* q, const float* qd,
+                  const float* gains8, float foot_y, float* xs, float* zs, float* tau, int n, void* stream) {
+  if (!X || !params9 || !phi16 || n <= 0) return fail(QS_ERR_ARG, "bad argument");
+  if (tau && (!q || !qd || !gains8)) return fail(QS_ERR_ARG, "torque output needs q, qd and gains");
+  CpgArgs P;
+  std::memcpy(P.p, params9, sizeof P.p);
+  std::memcpy(P.phi, phi16, sizeof P.phi);
+  if (gains8) std::memcpy(P.gains, gains8, sizeof P.gains); else std::memset(P.gains, 0, sizeof P.gains);
+  P.foot_y = foot_y;
+  k_cpg<<<grid_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(P, X, q, qd, xs, zs, tau, n);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_reduce_stats(qs_handle h, float* out, void* stream) {
+  if (!h || !out) return fail(QS_ERR_ARG, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(out, 0, QS_STATS_DIM * sizeof(float), s));
+  k_stats<<<grid_for(h->n, 256), 256, 0, s>>>(h->args.D, out);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// qs_types.h -- POD types shared by host and device code of the product.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/qs_b200.h"
+
+namespace qs {
+
+// Robot-level constants of go1/configs_go1_{with,without}_springs.py (float).
+struct RobotConst {
+  float init_angles[12];           // configs:31-36
+  float ang_lo[12], ang_hi[12];    // RL_{LOWER,UPPER}_ANGLE_JOINT, configs_with:84-87 / without:80-83
+  float cart_lo[12], cart_hi[12];  // RL_{LOWER,UPPER}_CARTESIAN_POS, configs_with:90-96 / without:86-92
+  float nominal_foot[12];          // NOMINAL_FOOT_POS_LEG_FRAME, configs:69-71
+  float tau_max[12];               // RL_TORQUE_LIMITS, configs:100-101
+  float kp[12], kd[12];            // MOTOR_KP/KD, configs_with:106-107 / without:108-109
+  float spring_k[3], spring_b[3], spring_rest[3];  // configs_with:150-160
+  float fallen_height;             // IS_FALLEN_HEIGHT, configs:24
+  float obs_noise[QS_MAX_OBS];     // per-element sensor noise std of the selected obs mode
+  float filt_b[3], filt_a[3];      // Butterworth(2, 3 Hz) coefficients, action_filter.py:191-213
+};
+
+// Merged 13-body dynamics model of go1.urdf: fixed links folded into their
+// parents (base+trunk+imu -> body 0, calf+foot -> calf).  Inertia tensors follow
+// Bullet's collision-geometry rule.  Sym3 order: xx xy xz yy yz zz.
+template <typename T> struct ModelConstT {
+  T trunk_m, trunk_h[3], trunk_I[6];  // about the base origin, base axes
+  T hip_pos[4][3];                    // go1.urdf:112-118 (+ mirrored copies)
+  T thigh_off_y[4];                   // go1.urdf:164-170: (0, -+0.08, 0)
+  T link_len;                         // go1.urdf:191-197,218-222: 0.213
+  T body_m[4][3];                     // hip, thigh, calf(+foot)
+  T body_com[4][3][3];                // in the link frame
+  T body_Ic[4][3][6];                 // about the body's own COM, link axes
+  T foot_radius, foot_thresh;         // go1.urdf:230-236, relative breaking threshold
+  T trunk_half[3], trunk_thresh;      // collision shapes used for invalid-contact detection
+  T imu_pos[3], imu_half, imu_thresh;
+  T hip_r, hip_hl, hip_thresh;
+  T thigh_half[3], thigh_c[3], thigh_thresh;
+  T calf_half[3], calf_c[3], calf_thresh;
+  T joint_lo[3], joint_hi[3];         // go1.urdf limits per hip/thigh/calf
+};
+
+struct SolverConst {
+  float dt, gravity_z, contact_erp, limit_erp, linear_slop, warmstart, residual_threshold;
+  float max_coord_vel, mu_link;
+  int32_t num_iterations, enable_limits;
+};
+
+// Device view of the handle-owned SoA state (all arrays [dim][N]).
+struct DeviceView {
+  int32_t n;
+  float* state;
+  float* tau_motor;
+  float* tau_spring;
+  float* kp;
+  float* kd;
+  float* spring;
+  float* mu;
+  float* foot_force;  // [4][N]
+  int32_t* contact;   // [N]
+  float* task;        // [QS_TASK_DIM][N]
+  float* last_action; // [12][N]
+  float* filt;        // [4*12][N] xh0 xh1 yh0 yh1
+  int32_t* sim_steps;
+  int32_t* env_steps;
+  float* ep_return;
+  float* stats;       // [QS_STATS_DIM][N] finished-episode accumulators
+  uint32_t* reset_count; // [N] number of resets (RNG stream separation)
+};
+
+// task state slots (rows of DeviceView::task)
+enum TaskSlot {
+  TS_SWITCHED = 0, TS_IN_AIR, TS_T_TAKEOFF, TS_TAKEOFF_X, TS_TAKEOFF_Y, TS_TAKEOFF_Z, TS_INIT_HEIGHT,
+  TS_TAKEOFF_YAW, TS_MAX_FLIGHT, TS_MAX_FWD, TS_MAX_PITCH, TS_REL_MAX_H, TS_MAX_DX, TS_MAX_H,
+  TS_MAX_PITCH_BF, TS_OLD_FWD, TS_ACTUAL_FWD, TS_OLD_TAU0 /* ..+11 */, TS_END = TS_OLD_TAU0 + 12
+};
+static_assert(TS_END <= QS_TASK_DIM, "task state too large");
+
+}  // namespace qs

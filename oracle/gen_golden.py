@@ -130,10 +130,10 @@ def gen_analytic():
                      "RL_LOWER_CARTESIAN_POS", "RL_TORQUE_LIMITS", "MOTOR_KP", "MOTOR_KD", "NOMINAL_FOOT_POS_LEG_FRAME",
                      "IS_FALLEN_HEIGHT", "JOINT_ANGLES_NOISE", "JOINT_VELOCITIES_NOISE", "HEIGHT_NOISE", "PITCH_NOISE",
                      "VEL_LIN_NOISE", "VEL_ANG_NOISE", "PITCH_RATE_NOISE", "FEET_POS_NOISE", "FEET_VEL_NOISE"):
-            out[f"{tag}_cfg_{name}"] = np.asarray(getattr(cfg, name), dtype=np.float64)
+            out[f"{tag}_cfg_{name}"] = np.array(getattr(cfg, name), dtype=np.float64, copy=True)
         if springs:
             for name in ("SPRINGS_STIFFNESS", "SPRINGS_DAMPING", "SPRINGS_REST_ANGLE"):
-                out[f"{tag}_cfg_{name}"] = np.asarray(getattr(cfg, name), dtype=np.float64)
+                out[f"{tag}_cfg_{name}"] = np.array(getattr(cfg, name), dtype=np.float64, copy=True)
     # BACKFLIP limit mutation (motor_interface.py:20-22); do it LAST: it mutates module state
     e3 = make_env(enable_springs=True, task_env="BACKFLIP", observation_space_mode="ARS_BACKFLIP")
     e3.reset()
@@ -387,10 +387,12 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "rollouts"]
     if "urdf" in which:
         gen_urdf()
-    if "analytic" in which:
-        gen_analytic()
+    # NB: gen_analytic and the last rollout build a BACKFLIP env, which mutates the module-level
+    # RL_UPPER_ANGLE_JOINT for the rest of the process (App. D.7) -> everything else runs first.
     if "obs" in which:
         gen_obs_spaces()
+    if "analytic" in which:
+        gen_analytic()
     if "hopf" in which:
         gen_hopf()
     if "rollouts" in which:

@@ -1,0 +1,159 @@
+"""GPU behaviour tests of the batched env at BASELINE sizes: gym contract,
+auto-reset, time-limit truncation, determinism, shard invariance, sensor noise,
+rollout statistics (pytest -m gpu)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+JIP = dict(enable_springs=True, task_env="JUMPING_IN_PLACE", observation_space_mode="ARS_BASIC")
+
+
+@pytest.fixture(scope="module")
+def qs():
+    import quadruped_springs_b200 as m
+    return m
+
+
+def test_gym_contract_shapes_and_dtypes(qs):
+    env = qs.BatchedQuadrupedGymEnv(num_envs=4096, **JIP)
+    obs = env.reset()
+    assert obs.shape == (4096, 27) and obs.dtype == torch.float32 and obs.is_cuda
+    assert env.action_space.shape == (6,) and env.observation_space.shape == (27,)
+    a = torch.rand(4096, 6, device="cuda") * 2 - 1
+    obs, r, d, info = env.step(a)
+    assert r.shape == (4096,) and d.dtype == torch.bool and info["TimeLimit.truncated"].dtype == torch.bool
+    assert torch.isfinite(obs).all() and torch.isfinite(r).all()
+    assert (env.get_sim_time() == 0.01).all() or d.any()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(4096, 5, device="cuda"))
+    d_obs = env.get_observation_dict()
+    assert list(d_obs) == ["Encoder", "JointVelocity", "Pitch", "Height", "Base Linear Velocity z direction"]
+    with pytest.raises(ValueError):
+        qs.BatchedQuadrupedGymEnv(num_envs=2, motor_control_mode="TORQUE")          # quadruped_gym_env.py:167-168
+    with pytest.raises(ValueError):
+        qs.BatchedQuadrupedGymEnv(num_envs=2, observation_space_mode="ARS_HEIGHT")  # __init__.py:9 (undefined upstream)
+
+
+def test_full_size_random_rollout_stays_finite_and_resets(qs):
+    n = 65536
+    env = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=1, **JIP)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n_done = 0
+    for t in range(60):
+        a = torch.rand(n, 6, device="cuda", generator=g) * 2 - 1
+        obs, r, d, info = env.step(a)
+        n_done += int(d.sum())
+        # auto-reset: a finished env starts its next episode inside the same call
+        assert (env._views["sim_steps"][d] == 0).all() and (env._views["env_steps"][d] == 0).all()
+        assert (env._views["env_steps"][~d] > 0).all()
+    assert torch.isfinite(obs).all() and torch.isfinite(r).all()
+    S = env.get_state()
+    assert torch.isfinite(S).all()
+    assert (S[:, 3:7].norm(dim=1) - 1).abs().max() < 1e-4
+    assert (S[:, 25:37].abs() <= 30.1 + 1e-4).all()        # maxJointVelocity clamp (quadruped.py:678-683)
+    assert n_done > 0                                       # random actions do crash some robots within 60 steps
+    st = qs.stats.combine(env.rollout_stats()[None].cpu()) if hasattr(qs, "stats") else None
+    from quadruped_springs_b200 import stats
+    out = stats.gather_rollout_stats(env.rollout_stats())
+    assert out["num_envs"] == n and out["episodes"] == n_done
+    assert 0 < out["mean_length"] <= 60 and out["terminated_fraction"] == 1.0
+
+
+def test_time_limit_truncation_on_step_1001(qs):
+    # holding the settling action keeps the robot standing: the only way out is the 10 s limit,
+    # which the reference reaches on control step 1001 (`>` test, quadruped_gym_env.py:245)
+    env = qs.BatchedQuadrupedGymEnv(num_envs=32, auto_reset=False, enable_noise=False, **JIP)
+    env.reset()
+    a = env.get_last_action().clone()
+    for t in range(1, 1002):
+        obs, r, d, info = env.step(a)
+        if t <= 1000:
+            assert not d.any(), t
+    assert d.all() and info["TimeLimit.truncated"].all()
+    # sparse task: reward only at the end (alive bonus, robot_tasks.py:50-52), zero before
+    assert (r > 0).all() and (r < 0.2).all()
+
+
+def test_determinism_and_shard_invariance(qs):
+    n = 1024
+    acts = [torch.rand(n, 6, device="cuda", generator=torch.Generator(device="cuda").manual_seed(i)) * 2 - 1 for i in range(15)]
+
+    def run(offset, count, sl):
+        env = qs.BatchedQuadrupedGymEnv(num_envs=count, seed=7, env_id_offset=offset, **JIP)
+        out = [env.reset().clone()]
+        for a in acts:
+            obs, r, d, _ = env.step(a[sl].contiguous())
+            out.append(torch.cat([obs, r[:, None], d[:, None].float()], dim=1).clone())
+        return out
+
+    full = run(0, n, slice(0, n))
+    again = run(0, n, slice(0, n))
+    for x, y in zip(full, again):
+        assert torch.equal(x, y)                       # bit-identical replays
+    half = run(512, 512, slice(512, n))                # the second shard of a 2-GPU run
+    for x, y in zip(full, half):
+        assert torch.equal(x[512:], y)                 # RNG streams and results depend on the GLOBAL env id only
+
+
+def test_sensor_noise_statistics(qs):
+    n = 65536
+    env = qs.BatchedQuadrupedGymEnv(num_envs=n, auto_reset=False, seed=3, **JIP)
+    noisy = env.reset().clone()
+    clean = env.get_observation(with_noise=False)
+    diff = (noisy - clean).cpu().numpy()
+    std = qs.ops.obs_noise_std(enable_springs=True, observation_space_mode="ARS_BASIC")
+    np.testing.assert_allclose(diff.std(axis=0), std, rtol=0.03)          # sensor.py:25-32 N(0, sigma) per element
+    assert np.abs(diff.mean(axis=0) / std).max() < 0.03
+    c = np.corrcoef(diff[:, :6].T)
+    assert np.abs(c - np.eye(6)).max() < 0.03                             # independent across elements
+    a = env.get_last_action().clone()
+    o1 = env.step(a)[0].clone()
+    d1 = (o1 - env.get_observation(with_noise=False)).cpu().numpy()
+    assert np.abs(np.corrcoef(diff[:, 0], d1[:, 0])[0, 1]) < 0.03         # resampled every control step (:58-60)
+    quiet = qs.BatchedQuadrupedGymEnv(num_envs=64, enable_noise=False, auto_reset=False, **JIP)
+    o = quiet.reset()
+    assert torch.equal(o, quiet.get_observation(with_noise=False))
+
+
+def test_step_host_matches_device_step(qs):
+    n = 2048
+    e1 = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=5, **JIP)
+    e2 = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=5, **JIP)
+    e1.reset(); e2.reset()
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        a = rng.uniform(-1, 1, size=(n, 6)).astype(np.float32)
+        o, r, d, t = e1.step_host(a)
+        od, rd, dd, info = e2.step(torch.from_numpy(a).cuda())
+        assert np.array_equal(o, od.cpu().numpy()) and np.array_equal(r, rd.cpu().numpy())
+        assert np.array_equal(d.astype(bool), dd.cpu().numpy())
+
+
+def test_partial_reset_mask(qs):
+    env = qs.BatchedQuadrupedGymEnv(num_envs=256, auto_reset=False, enable_noise=False, **JIP)
+    env.reset()
+    a = torch.rand(256, 6, device="cuda") * 2 - 1
+    for _ in range(3):
+        env.step(a)
+    before = env.get_state().clone()
+    mask = torch.zeros(256, dtype=torch.bool, device="cuda")
+    mask[::3] = True
+    env.reset(mask)
+    after = env.get_state()
+    assert torch.equal(after[~mask], before[~mask])
+    assert (env._views["env_steps"][mask] == 0).all() and (env._views["env_steps"][~mask] == 3).all()
+    assert (after[mask, 2] - 0.328).abs().max() < 5e-3       # settled standing height with springs
+
+
+def test_per_env_gain_override(qs):
+    # landing wrappers swap PD gains at run time (landing_wrapper.py:21-33): gains are per-env tensors
+    env = qs.BatchedQuadrupedGymEnv(num_envs=8, auto_reset=False, enable_noise=False, **JIP)
+    env.reset()
+    env.robot.set_motor_gains(60.0, 1.5, env_ids=torch.tensor([1, 3], device="cuda"))
+    a = torch.full((8, 6), 0.5, device="cuda")
+    env.step(a)
+    tau = env.robot.GetMotorTorques()
+    assert torch.equal(tau[0], tau[2]) and not torch.equal(tau[0], tau[1]) and torch.equal(tau[1], tau[3])

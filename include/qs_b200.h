@@ -208,6 +208,13 @@ int qs_cpg_update(float* X_dev, const float* params9, const float* phi16, const 
  * return sum, length sum, terminated count. */
 int qs_reduce_stats(qs_handle h, float* out_dev, void* stream);
 
+/* measurement hooks (bench.py): device time of the last `last_k` step-kernel launches
+ * (CUDA events on the launching stream; synchronise first), and the algorithmic-work
+ * counters the step kernel keeps: out3 = {physics ticks, foot-contact ticks,
+ * contact x PGS-sweep count} summed over all envs since creation. */
+int qs_step_kernel_time(qs_handle h, int last_k, float* ms_sum);
+int qs_work_counters(qs_handle h, uint64_t* out3, void* stream);
+
 /* number of kernels launched by this library since load (bench bookkeeping) */
 int64_t qs_launch_count(void);
 

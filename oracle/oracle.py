@@ -78,6 +78,7 @@ def lib():
         "qso_world_set_mass": (None, [vp, C.c_int, C.c_double]),
         "qso_world_last_iterations": (C.c_int, [vp]),
         "qso_world_cone_clamped": (C.c_int, [vp]),
+        "qso_world_last_rows": (C.c_int, [vp, ip, ip]),
         "qso_world_mass_matrix": (None, [vp, dp]),
         "qso_world_bias": (None, [vp, dp, dp]),
         "qso_world_link_pose": (None, [vp, C.c_int, dp, dp]),
@@ -92,6 +93,7 @@ def lib():
         "qso_env_step": (None, [vp, dp, dp, dp, ip, ip]),
         "qso_env_get_task_state": (None, [vp, dp]),
         "qso_env_get_torques": (None, [vp, dp, dp]),
+        "qso_env_get_last_action": (None, [vp, dp]),
         "qso_env_set_gains": (None, [vp, dp, dp]),
         "qso_env_set_springs": (None, [vp, dp, dp, dp]),
         "qso_action_to_command": (None, [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp]),
@@ -215,6 +217,13 @@ class World:
         return self.L.qso_world_last_iterations(self.h)
 
     @property
+    def last_rows(self):
+        a = C.c_int()
+        b = C.c_int()
+        self.L.qso_world_last_rows(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    @property
     def cone_clamped(self):
         return self.L.qso_world_cone_clamped(self.h)
 
@@ -271,6 +280,11 @@ class Env:
         o, op = _out(32)
         self.L.qso_env_get_task_state(self.h, op)
         return o
+
+    def last_action(self):
+        o, op = _out(12)
+        self.L.qso_env_get_last_action(self.h, op)
+        return o[:self.action_dim]
 
     def torques(self):
         a, ap = _out(12)

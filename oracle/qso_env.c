@@ -335,6 +335,7 @@ void qso_env_set_springs(QsoEnv* e, const double* k, const double* b, const doub
   memcpy(e->rc.spring_b, b, 3 * sizeof(double));
   memcpy(e->rc.spring_rest, rest, 3 * sizeof(double));
 }
+void qso_env_get_last_action(const QsoEnv* e, double* a12) { memcpy(a12, e->last_action, sizeof e->last_action); }
 void qso_env_get_torques(const QsoEnv* e, double* tm, double* tsp) {
   memcpy(tm, e->tau_motor, sizeof e->tau_motor);
   memcpy(tsp, e->tau_spring, sizeof e->tau_spring);
@@ -660,8 +661,21 @@ void qso_env_reset(QsoEnv* e, double mu, double* obs) {
       apply_action(e, cmd, 0);
       qso_world_step(e->w);
     }
+    /* settling_action = _transform_motor_command_to_action(settling_command)
+     * (interface_base.py:196-200).  In CARTESIAN_PD mode settling_command holds
+     * JOINT ANGLES (it went through IK) but is scaled with the CARTESIAN limits,
+     * so the stored _last_action is (0, 1, -1) per leg: reproduced as is. */
+    double s12[12], sact[12];
+    if (cart) unscale_command(c->cart_lo, c->cart_hi, cmd, s12);
+    else unscale_command(c->ang_lo, c->ang_hi, cmd, s12);
+    if (e->cfg.action_mode == QSO_ACT_DEFAULT) memcpy(sact, s12, sizeof s12);
+    else if (e->cfg.action_mode == QSO_ACT_SYMMETRIC) { memcpy(sact, s12, 3 * sizeof(double)); memcpy(sact + 3, s12 + 6, 3 * sizeof(double)); }
+    else {
+      int s2 = 0;
+      for (int j = 0; j < 3; j++) if (j != sidx) { sact[s2] = s12[j]; sact[2 + s2] = s12[6 + j]; s2++; }
+    }
     memset(e->last_action, 0, sizeof e->last_action);
-    memcpy(e->last_action, act, adim * sizeof(double));
+    memcpy(e->last_action, sact, adim * sizeof(double));
   } else {
     /* settle_robot_by_pd (control_interface/utils.py:22-30): PD, DEFAULT space, 1500 ticks */
     double a12[12], cmd[12];

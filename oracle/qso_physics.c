@@ -89,6 +89,7 @@ struct QsoWorld {
   Row rows[MAXROWS];
   int last_iters;
   int cone_clamped;
+  int last_nlim, last_nnorm;
 };
 
 /* ------------------------------------------------------------------ utils */
@@ -377,6 +378,7 @@ void qso_world_set_mass(QsoWorld* w, int pyb, double mass) {
 }
 int qso_world_last_iterations(const QsoWorld* w) { return w->last_iters; }
 int qso_world_cone_clamped(const QsoWorld* w) { return w->cone_clamped; }
+int qso_world_last_rows(const QsoWorld* w, int* nlim, int* nnorm) { *nlim = w->last_nlim; *nnorm = w->last_nnorm; return w->last_nlim + 3 * w->last_nnorm; }
 
 /* ------------------------------------------------------------- kinematics */
 static void kinematics(QsoWorld* w) {
@@ -839,6 +841,8 @@ void qso_world_step(QsoWorld* w) {
     }
   }
   w->last_iters = it;
+  w->last_nlim = nlim;
+  w->last_nnorm = nnorm;
 
   /* 5. apply solver delta (clamped), remember impulses for reporting/warm start */
   apply_delta(w, dV, 1.0);

@@ -9,7 +9,7 @@
 namespace qs {
 
 // ---------------------------------------------------------------- Philox4x32-10
-QS_DEV void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+QS_DEVONLY void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -20,9 +20,9 @@ QS_DEV void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint3
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-QS_DEV float u01(uint32_t x) { return (float(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
+QS_DEVONLY float u01(uint32_t x) { return (float(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
 // four N(0,1) samples for (stream, step, block)
-QS_DEV void normal4(uint64_t seed, uint64_t gid, uint32_t epoch, uint32_t step, uint32_t blk, float* n) {
+QS_DEVONLY void normal4(uint64_t seed, uint64_t gid, uint32_t epoch, uint32_t step, uint32_t blk, float* n) {
   uint32_t r[4];
   philox4x32(uint32_t(gid), uint32_t(gid >> 32) ^ (blk << 16), step, epoch, uint32_t(seed), uint32_t(seed >> 32), r);
   float s, c;
@@ -33,7 +33,7 @@ QS_DEV void normal4(uint64_t seed, uint64_t gid, uint32_t epoch, uint32_t step, 
   sincospif(2.0f * u01(r[3]), &s, &c);
   n[2] = m * c; n[3] = m * s;
 }
-QS_DEV float uniform1(uint64_t seed, uint64_t gid, uint32_t epoch, uint32_t blk) {
+QS_DEVONLY float uniform1(uint64_t seed, uint64_t gid, uint32_t epoch, uint32_t blk) {
   uint32_t r[4];
   philox4x32(uint32_t(gid), uint32_t(gid >> 32) ^ (blk << 16), 0xFFFFFFFFu, epoch, uint32_t(seed), uint32_t(seed >> 32), r);
   return float(r[0] >> 8) * (1.0f / 16777216.0f);  // [0,1) like np.random.random
@@ -90,7 +90,7 @@ __device__ __forceinline__ void run_ticks(EnvState<float>& st, ContactState<floa
 // ---------------------------------------------------------------- task logic
 QS_DEV bool is_jump_task(int task) { return task != QS_TASK_NO_TASK; }
 
-QS_DEV float jumping_distance(const float* ts, const float* pos) {  // task_base.py:109-116
+QS_DEVONLY float jumping_distance(const float* ts, const float* pos) {  // task_base.py:109-116
   float s, c;
   sincosf(ts[TS_TAKEOFF_YAW], &s, &c);
   const float dx = pos[0] - ts[TS_TAKEOFF_X], dy = pos[1] - ts[TS_TAKEOFF_Y];
@@ -98,7 +98,7 @@ QS_DEV float jumping_distance(const float* ts, const float* pos) {  // task_base
 }
 
 // TaskJumping._on_step (task_base.py:61-107) + subclass overrides
-QS_DEV void task_on_step(float* ts, const EnvState<float>& st, const ContactState<float>& cs, const float* tau_m,
+QS_DEVONLY void task_on_step(float* ts, const EnvState<float>& st, const ContactState<float>& cs, const float* tau_m,
                          const float* rpy, const float* Rb, float sim_time, int task) {
   if (!is_jump_task(task)) return;
   const bool flying = (cs.mask & 15) == 0;
@@ -136,7 +136,7 @@ QS_DEV void task_on_step(float* ts, const EnvState<float>& st, const ContactStat
   }
 }
 
-QS_DEV bool task_terminated(const float* ts, const EnvState<float>& st, const ContactState<float>& cs,
+QS_DEVONLY bool task_terminated(const float* ts, const EnvState<float>& st, const ContactState<float>& cs,
                             const float* Rb, float fallen_height, int task) {
   if (!is_jump_task(task)) return false;
   const bool fallen_ground = st.pos[2] < fallen_height;  // task_base.py:123-124
@@ -147,7 +147,7 @@ QS_DEV bool task_terminated(const float* ts, const EnvState<float>& st, const Co
 
 // per-step reward (robot_tasks.py:334-344, 461-471, 783-800); 0 for the sparse tasks.
 // old_tau = torque of the previous control step, tau_m = of this one.
-QS_DEV float task_reward(const float* ts, const EnvState<float>& st, const float* foot_force, const float* old_tau,
+QS_DEVONLY float task_reward(const float* ts, const EnvState<float>& st, const float* foot_force, const float* old_tau,
                          const float* tau_m, const float* rpy, const float* Rb, int task) {
   float max_h_task, k_h;
   switch (task) {
@@ -183,7 +183,7 @@ QS_DEV float task_reward(const float* ts, const EnvState<float>& st, const float
 }
 
 // end-of-episode bonus / malus (robot_tasks.py:31-57, 70-99, 535-550, 349-358, 476-485, 802-809)
-QS_DEV float task_reward_end(const float* ts, bool term, int task) {
+QS_DEVONLY float task_reward_end(const float* ts, bool term, int task) {
   float r = 0.f;
   switch (task) {
     case QS_TASK_JUMPING_IN_PLACE: {
@@ -221,7 +221,7 @@ QS_DEV float task_reward_end(const float* ts, bool term, int task) {
 }
 
 // TaskJumping._reset (task_base.py:40-59): reset_params + one _on_step
-QS_DEV void task_reset(float* ts, const EnvState<float>& st, const ContactState<float>& cs, const float* tau_m,
+QS_DEVONLY void task_reset(float* ts, const EnvState<float>& st, const ContactState<float>& cs, const float* tau_m,
                        const float* rpy, const float* Rb, float sim_time, int task) {
   if (!is_jump_task(task)) return;
   const float keep_bf = ts[TS_MAX_PITCH_BF];  // BackFlip.max_pitch lives in __init__ only (robot_tasks.py:524)
@@ -240,7 +240,7 @@ QS_DEV void task_reset(float* ts, const EnvState<float>& st, const ContactState<
 // ---------------------------------------------------------------- sensors
 // SensorList.get_obs / get_noisy_obs (sensor.py:101-111) for the modes of
 // sensor_collection.py:18-105; obs is written row-major [N, O].
-QS_DEV void observe(const EnvState<float>& st, const ContactState<float>& cs, const float* ts, const float* rpy,
+QS_DEVONLY void observe(const EnvState<float>& st, const ContactState<float>& cs, const float* ts, const float* rpy,
                     const float* Rb, int obs_mode, float* o /*QS_MAX_OBS regs*/) {
   const float* q = st.q;
   const float* qd = st.qd;
@@ -292,7 +292,7 @@ QS_DEV void observe(const EnvState<float>& st, const ContactState<float>& cs, co
 }
 
 // add N(0, sigma) per element (sensor.py:25-32,46-52) and store the row
-QS_DEV void store_obs(float* obs_row, float* o, const EnvCfg& C, const RobotConst& RC, uint64_t gid, uint32_t epoch,
+QS_DEVONLY void store_obs(float* obs_row, float* o, const EnvCfg& C, const RobotConst& RC, uint64_t gid, uint32_t epoch,
                       uint32_t step, bool with_noise) {
   if (with_noise) {
 #pragma unroll
@@ -311,7 +311,7 @@ QS_DEV void store_obs(float* obs_row, float* o, const EnvCfg& C, const RobotCons
 }
 
 // ---------------------------------------------------------------- SoA load/store
-QS_DEV void load_state(const DeviceView& D, int env, EnvState<float>& st, ContactState<float>& cs, float dt) {
+QS_DEVONLY void load_state(const DeviceView& D, int env, EnvState<float>& st, ContactState<float>& cs, float dt) {
   const int n = D.n;
   const float* s = D.state + env;
 #pragma unroll
@@ -329,10 +329,12 @@ QS_DEV void load_state(const DeviceView& D, int env, EnvState<float>& st, Contac
   const int c = D.contact[env];
   cs.mask = c & 15;
   cs.invalid = c >> 8;
+  cs.work_contacts = 0;
+  cs.work_row_iters = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) cs.lam_n[k] = D.foot_force[k * n + env] * dt;
 }
-QS_DEV void store_state(const DeviceView& D, int env, const EnvState<float>& st, const ContactState<float>& cs, float dt) {
+QS_DEVONLY void store_state(const DeviceView& D, int env, const EnvState<float>& st, const ContactState<float>& cs, float dt) {
   const int n = D.n;
   float* s = D.state + env;
 #pragma unroll

@@ -70,6 +70,26 @@ __device__ __forceinline__ void settle_command(const EnvCfg& C, const RobotConst
     float b12[12];
     expand_action(C.action_mode, sidx, act12, b12);
     action12_to_command(RC, C.control_mode, b12, cmd);
+    // settling_action = _transform_motor_command_to_action(settling_command)
+    // (interface_base.py:196-200).  In CARTESIAN_PD mode the command holds JOINT
+    // ANGLES (it went through IK) yet is scaled with the CARTESIAN limits, so the
+    // reference stores (0, 1, -1) per leg as _last_action: reproduced as is.
+#pragma unroll
+    for (int i = 0; i < 12; i++)
+      a12[i] = cart ? command_to_action1(cmd[i], RC.cart_lo[i], RC.cart_hi[i])
+                    : command_to_action1(cmd[i], RC.ang_lo[i], RC.ang_hi[i]);
+#pragma unroll
+    for (int i = 0; i < 12; i++) act12[i] = 0.f;
+    if (C.action_mode == QS_ACT_DEFAULT) {
+#pragma unroll
+      for (int i = 0; i < 12; i++) act12[i] = a12[i];
+    } else if (C.action_mode == QS_ACT_SYMMETRIC) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) { act12[j] = a12[j]; act12[3 + j] = a12[6 + j]; }
+    } else {
+      if (sidx == 0) { act12[0] = a12[1]; act12[1] = a12[2]; act12[2] = a12[7]; act12[3] = a12[8]; }
+      else { act12[0] = a12[0]; act12[1] = a12[2]; act12[2] = a12[6]; act12[3] = a12[8]; }
+    }
   } else {
     // settle_robot_by_pd (control_interface/utils.py:22-30): PD limits, DEFAULT space
 #pragma unroll
@@ -195,6 +215,9 @@ k_step(const __grid_constant__ KernelArgs A, const float* __restrict__ actions, 
   D.sim_steps[env] = sim_steps;
   D.env_steps[env] = env_steps;
   D.ep_return[env] = ep_ret;
+  D.work[0 * n + env] += uint32_t(C.action_repeat);
+  D.work[1 * n + env] += uint32_t(cs.work_contacts);
+  D.work[2 * n + env] += uint32_t(cs.work_row_iters);
   if (dn) {
     finish_episode_stats(D, env, ts, ep_ret, env_steps, term, C.task);
     if (C.auto_reset) reset_list[atomicAdd(reset_count, 1)] = env;
@@ -242,7 +265,7 @@ k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, cons
   for (int i = 0; i < 3; i++) { st.vlin[i] = 0.f; st.vang[i] = 0.f; }
 #pragma unroll
   for (int i = 0; i < 12; i++) { st.q[i] = A.RC.init_angles[i]; st.qd[i] = 0.f; }
-  cs.mask = 0; cs.invalid = 0;
+  cs.mask = 0; cs.invalid = 0; cs.work_contacts = 0; cs.work_row_iters = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) cs.lam_n[k] = 0.f;
 
@@ -351,7 +374,7 @@ k_debug_ticks(const __grid_constant__ DebugArgs<T> A, const float* __restrict__ 
   for (int i = 0; i < 4; i++) { st.quat[i] = sf.quat[i]; cs.lam_n[i] = cf.lam_n[i]; }
 #pragma unroll
   for (int i = 0; i < 12; i++) { st.q[i] = sf.q[i]; st.qd[i] = sf.qd[i]; }
-  cs.mask = cf.mask; cs.invalid = cf.invalid;
+  cs.mask = cf.mask; cs.invalid = cf.invalid; cs.work_contacts = 0; cs.work_row_iters = 0;
   T t12[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) t12[i] = T(tau[size_t(env) * 12 + i]);
@@ -556,6 +579,11 @@ struct qs_env {
   uint8_t* dev_done;
   uint8_t* dev_trunc;
   bool was_reset;
+  // CUDA-event ring around k_step launches (roofline timing of the dominant kernel)
+  static constexpr int kRing = 512;
+  cudaEvent_t ev0[kRing], ev1[kRing];
+  bool ev_ready;
+  int64_t n_steps;
 };
 
 static inline unsigned grid_for(int n, int block) { return unsigned((n + block - 1) / block); }
@@ -675,7 +703,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
 
   // one pool for all SoA arrays (4-byte elements), 256 B aligned segments
   const size_t n = size_t(n_envs);
-  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1;
+  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1 + 3;
   // rows of one array are contiguous with stride n floats; each array starts 256 B aligned
   h->pool_bytes = rows * n * 4 + 64 * 256;
   cudaError_t e = cudaMalloc(&h->pool, h->pool_bytes);
@@ -697,6 +725,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   D.last_action = (float*)carve(12); D.filt = (float*)carve(48); D.sim_steps = (int32_t*)carve(1);
   D.env_steps = (int32_t*)carve(1); D.ep_return = (float*)carve(1); D.stats = (float*)carve(QS_STATS_DIM);
   D.reset_count = (uint32_t*)carve(1);
+  D.work = (uint32_t*)carve(3);
   if (size_t(p - static_cast<char*>(h->pool)) > h->pool_bytes) { cudaFree(h->pool); delete h; return fail(QS_ERR_STATE, "pool overflow"); }
   e = cudaMalloc(&h->reset_list, (n + 1) * sizeof(int));
   if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(QS_ERR_CUDA, "cudaMalloc reset list"); }
@@ -715,7 +744,44 @@ int qs_destroy(qs_handle h) {
   if (h->dev_obs) cudaFree(h->dev_obs);
   if (h->dev_reward) cudaFree(h->dev_reward);
   if (h->dev_done) cudaFree(h->dev_done);
+  if (h->ev_ready)
+    for (int i = 0; i < qs_env::kRing; i++) { cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); }
   delete h;
+  return QS_OK;
+}
+
+int qs_step_kernel_time(qs_handle h, int last_k, float* ms_sum) {
+  // sum of the device durations of the last `last_k` k_step launches (CUDA events on the
+  // launching stream); the stream must have been synchronised by the caller
+  if (!h || !ms_sum) return fail(QS_ERR_ARG, "NULL argument");
+  if (last_k <= 0 || last_k > qs_env::kRing || last_k > h->n_steps) return fail(QS_ERR_ARG, "last_k out of range");
+  float tot = 0.f;
+  for (int64_t i = h->n_steps - last_k; i < h->n_steps; i++) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0[i % qs_env::kRing], h->ev1[i % qs_env::kRing]));
+    tot += ms;
+  }
+  *ms_sum = tot;
+  return QS_OK;
+}
+
+int qs_work_counters(qs_handle h, uint64_t* out3, void* stream) {
+  // totals over all envs of (ticks, contact-ticks, contact-sweeps) executed by k_step so far; synchronises
+  if (!h || !out3) return fail(QS_ERR_ARG, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t n = size_t(h->n);
+  uint32_t* host = static_cast<uint32_t*>(std::malloc(3 * n * sizeof(uint32_t)));
+  if (!host) return fail(QS_ERR_STATE, "out of host memory");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemcpyAsync(host, h->args.D.work, 3 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { std::free(host); return fail(QS_ERR_CUDA, cudaGetErrorString(e)); }
+  for (int r = 0; r < 3; r++) {
+    uint64_t t = 0;
+    for (size_t i = 0; i < n; i++) t += host[r * n + i];
+    out3[r] = t;
+  }
+  std::free(host);
   return QS_OK;
 }
 
@@ -762,7 +828,15 @@ int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_
   CUDA_TRY(cudaSetDevice(h->device));
   const int B = block_of(h);
   if (h->cfg.auto_reset) CUDA_TRY(cudaMemsetAsync(h->reset_count, 0, sizeof(int), s));
+  if (!h->ev_ready) {
+    for (int i = 0; i < qs_env::kRing; i++) { CUDA_TRY(cudaEventCreate(&h->ev0[i])); CUDA_TRY(cudaEventCreate(&h->ev1[i])); }
+    h->ev_ready = true;
+  }
+  const int slot = int(h->n_steps % qs_env::kRing);
+  cudaEventRecord(h->ev0[slot], s);
   k_step<<<grid_for(h->n, B), B, 0, s>>>(h->args, actions, obs, reward, done, truncated, h->reset_list, h->reset_count);
+  cudaEventRecord(h->ev1[slot], s);
+  h->n_steps++;
   g_launches += 1;
   if (h->cfg.auto_reset) {
     // finished envs restart inside the same call; their obs row becomes the first

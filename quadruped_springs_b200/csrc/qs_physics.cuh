@@ -100,6 +100,8 @@ template <typename T> struct ContactState {
   T lam_n[4];   // normal impulse of the last tick per foot (N s); force = lam/dt
   int mask;     // bits 0-3: foot manifold point exists (quadruped.py:250-257)
   int invalid;  // number of non-foot shapes touching the ground (quadruped.py:243-249)
+  int work_contacts;   // sum over ticks of active foot contacts        } algorithmic-work counters
+  int work_row_iters;  // sum over ticks of contacts x PGS sweeps run   } (bench.py roofline)
 };
 
 template <typename T> struct LegKin {
@@ -163,7 +165,7 @@ template <typename T> QS_DEV T clamp_vel(T v, T mx) { return tmin(tmax(v, -mx), 
 // cs: in = previous tick's contact impulses (warm start), out = this tick's.
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__device__ void physics_tick(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
+__host__ __device__ void physics_tick(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
                              const ModelConstT<T>& M, const SolverConst& SC, bool detect_invalid) {
   const T dt = T(SC.dt);
   const T mcv = T(SC.max_coord_vel);
@@ -508,8 +510,11 @@ __device__ void physics_tick(EnvState<T>& st, const T* tau, T mu, ContactState<T
   if (active) {
     const T thr = T(SC.residual_threshold);
     const int iters = SC.num_iterations;
+    const int nact = (active & 1) + ((active >> 1) & 1) + ((active >> 2) & 1) + ((active >> 3) & 1);
+    cs.work_contacts += nact;
     for (int it = 0; it < iters; it++) {
       T res = T(0);
+      cs.work_row_iters += nact;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         if (!(active & (1 << k))) continue;

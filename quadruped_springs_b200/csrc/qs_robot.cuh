@@ -8,7 +8,8 @@
 
 #include "qs_types.h"
 
-#define QS_DEV __device__ __forceinline__
+#define QS_DEV __host__ __device__ __forceinline__
+#define QS_DEVONLY __device__ __forceinline__
 #define QS_PI 3.14159265358979323846
 
 namespace qs {

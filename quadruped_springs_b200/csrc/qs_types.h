@@ -66,6 +66,7 @@ struct DeviceView {
   float* ep_return;
   float* stats;       // [QS_STATS_DIM][N] finished-episode accumulators
   uint32_t* reset_count; // [N] number of resets (RNG stream separation)
+  uint32_t* work;        // [3][N] k_step work counters: ticks, contact-ticks, contact-sweeps
 };
 
 // task state slots (rows of DeviceView::task)

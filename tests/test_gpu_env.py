@@ -150,7 +150,8 @@ def test_partial_reset_mask(qs):
 
 def test_per_env_gain_override(qs):
     # landing wrappers swap PD gains at run time (landing_wrapper.py:21-33): gains are per-env tensors
-    env = qs.BatchedQuadrupedGymEnv(num_envs=8, auto_reset=False, enable_noise=False, **JIP)
+    env = qs.BatchedQuadrupedGymEnv(num_envs=8, auto_reset=False, enable_noise=False,
+                                    env_randomizer_mode="NO_RANDOMIZER", **JIP)
     env.reset()
     env.robot.set_motor_gains(60.0, 1.5, env_ids=torch.tensor([1, 3], device="cuda"))
     a = torch.full((8, 6), 0.5, device="cuda")

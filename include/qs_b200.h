@@ -90,7 +90,7 @@ typedef struct qs_config {
   int32_t auto_reset;            /* reset finished envs inside qs_step (SB3 VecEnv behaviour) */
   int32_t num_iterations;        /* int(300/action_repeat) unless overridden (>0) */
   int32_t enable_limits;         /* joint-limit constraint rows */
-  int32_t body_contact_response; /* reserved: non-foot shapes are detected, not yet constrained */
+  int32_t body_contact_response; /* non-foot shapes touching the ground are constrained too (general solver) */
   int32_t block_size;            /* CUDA block size for the step kernel (0 = default) */
   uint64_t seed;                 /* Philox key; streams are indexed by GLOBAL env id */
   int64_t env_id_offset;         /* global id of local env 0 (multi-GPU sharding) */

@@ -604,11 +604,11 @@ static void add_contact(QsoWorld* w, int link, int pt, const double* p, double d
   memcpy(c->pos, p, sizeof c->pos);
 }
 
-/* convex-vs-plane (btConvexPlaneCollisionAlgorithm): a manifold point exists
- * while the support point is closer than the link's contact breaking
- * threshold.  Boxes report every corner inside the threshold (the persistent
- * manifold Bullet accumulates over frames); cylinders the lowest rim point of
- * each cap. */
+/* convex-vs-plane (btConvexPlaneCollisionAlgorithm): ONE manifold point per
+ * shape and frame, the support vertex, while it is closer than the link's
+ * contact breaking threshold.  (Bullet's persistent manifold would also keep up
+ * to three older points of a box; every task of the reference ends the episode
+ * at the first non-foot contact, so that refinement is left out.) */
 static void collide(QsoWorld* w) {
   w->nC = 0;
   for (int i = 1; i < NL; i++) {
@@ -624,26 +624,23 @@ static void collide(QsoWorld* w) {
         add_contact(w, i, 0, p, d);
       }
     } else if (l->shape == SH_BOX) {
-      for (int s = 0; s < 8; s++) {
-        double loc[3] = {(s & 1 ? 1 : -1) * l->sdim[0], (s & 2 ? 1 : -1) * l->sdim[1],
-                         (s & 4 ? 1 : -1) * l->sdim[2]};
-        double p[3];
-        m3_v(w->Rw[i], loc, t);
-        for (int k = 0; k < 3; k++) p[k] = c[k] + t[k];
-        if (p[2] < l->thresh) add_contact(w, i, s, p, p[2]);
-      }
-    } else { /* cylinder, axis = link y */
+      /* support vertex in -z: corner with sign_i = -sign(R[2][i]) */
+      double loc[3], p[3];
+      for (int a = 0; a < 3; a++) loc[a] = (w->Rw[i][6 + a] > 0 ? -1.0 : 1.0) * l->sdim[a];
+      m3_v(w->Rw[i], loc, t);
+      for (int k = 0; k < 3; k++) p[k] = c[k] + t[k];
+      if (p[2] < l->thresh) add_contact(w, i, 0, p, p[2]);
+    } else { /* cylinder, axis = link y: lowest point of the lower rim */
       double a[3] = {w->Rw[i][1], w->Rw[i][4], w->Rw[i][7]};
       double dn[3] = {-a[2] * a[0], -a[2] * a[1], 1 - a[2] * a[2]}; /* z - (z.a)a */
       double n = sqrt(dot3(dn, dn));
       double rad[3];
       if (n > 1e-9) { for (int k = 0; k < 3; k++) rad[k] = -dn[k] / n * l->sdim[0]; }
       else { rad[0] = w->Rw[i][0] * l->sdim[0]; rad[1] = w->Rw[i][3] * l->sdim[0]; rad[2] = w->Rw[i][6] * l->sdim[0]; }
-      for (int s = 0; s < 2; s++) {
-        double p[3];
-        for (int k = 0; k < 3; k++) p[k] = c[k] + (s ? 1 : -1) * l->sdim[1] * a[k] + rad[k];
-        if (p[2] < l->thresh) add_contact(w, i, s, p, p[2]);
-      }
+      double sgn = a[2] > 0 ? -1.0 : 1.0;
+      double p[3];
+      for (int k = 0; k < 3; k++) p[k] = c[k] + sgn * l->sdim[1] * a[k] + rad[k];
+      if (p[2] < l->thresh) add_contact(w, i, 0, p, p[2]);
     }
   }
 }
@@ -796,7 +793,8 @@ void qso_world_step(QsoWorld* w) {
   memset(dV, 0, sizeof dV);
   for (int j = 0; j < nnorm; j++) { /* warm start of contact normals */
     Contact* ct = &w->C[nrm[j].contact];
-    if (w->prev_valid[ct->link][ct->pt]) {
+    /* warm start (m_warmstartingFactor) is kept for the foot contacts only */
+    if (w->L[ct->link].is_foot && w->prev_valid[ct->link][ct->pt]) {
       double imp = w->prev_lambda[ct->link][ct->pt] * P->warmstart;
       nrm[j].applied = imp;
       for (int k = 0; k < ND; k++) dV[k] += nrm[j].MinvJ[k] * imp;

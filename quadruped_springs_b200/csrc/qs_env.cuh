@@ -48,42 +48,72 @@ struct EnvCfg {
   int64_t gid0;
 };
 
-// ApplyAction + stepSimulation, n_ticks times (quadruped_gym_env.py:207-219,
-// quadruped.py:288-320).  cmd = desired joint angles (PD) or torques (TORQUE).
-__device__ __forceinline__ void run_ticks(EnvState<float>& st, ContactState<float>& cs, const float* cmd,
-                                          bool torque_mode, int n_ticks, int env, const DeviceView& D,
-                                          const EnvCfg& C, const RobotConst& RC, const ModelConstT<float>& M,
-                                          const SolverConst& SC, float* tau_m /*12 out*/, float* tau_s /*12 out*/,
-                                          bool detect_invalid_last) {
+// PD + PEA torque of one tick (quadruped.py:288-320, quadruped_motor.py:45-104)
+__device__ __forceinline__ void tick_torques(const EnvState<float>& st, const float* cmd, bool torque_mode, int env,
+                                             const DeviceView& D, const EnvCfg& C, const RobotConst& RC, const float* sk,
+                                             const float* sb, const float* sr, float* tau, float* tau_m, float* tau_s) {
   const int n = D.n;
-  const float mu = D.mu[env];
-  float sk[3], sb[3], sr[3];
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    const float kp = D.kp[i * n + env], kd = D.kd[i * n + env];
+    tau_m[i] = pd_torque1(kp, kd, RC.tau_max[i], cmd[i], st.q[i], st.qd[i], torque_mode);
+    tau[i] = tau_m[i];
+  }
+  if (C.enable_springs) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      spring_torque_leg(k, sk, sb, sr, st.q + 3 * k, st.qd + 3 * k, tau_s + 3 * k);
+#pragma unroll
+      for (int j = 0; j < 3; j++) tau[3 * k + j] += tau_s[3 * k + j];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; i++) tau_s[i] = 0.f;
+  }
+}
+
+QS_DEVONLY void load_springs(const DeviceView& D, int env, float* sk, float* sb, float* sr) {
+  const int n = D.n;
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     sk[j] = D.spring[(0 + j) * n + env];
     sb[j] = D.spring[(3 + j) * n + env];
     sr[j] = D.spring[(6 + j) * n + env];
   }
-  for (int t = 0; t < n_ticks; t++) {
+}
+
+// ApplyAction + stepSimulation for ticks [t0, n_ticks) (quadruped_gym_env.py:207-219).
+// cmd = desired joint angles (PD) or torques (TORQUE).  Returns n_ticks when all
+// ticks ran on the fast path, or the index of the tick that needs the general
+// solver (state untouched by that tick).
+__device__ __forceinline__ int run_ticks(EnvState<float>& st, ContactState<float>& cs, const float* cmd,
+                                         bool torque_mode, int t0, int n_ticks, int env, const DeviceView& D,
+                                         const EnvCfg& C, const RobotConst& RC, const ModelConstT<float>& M,
+                                         const SolverConst& SC, float* tau_m /*12 out*/, float* tau_s /*12 out*/,
+                                         bool detect_invalid_last) {
+  const float mu = D.mu[env];
+  float sk[3], sb[3], sr[3];
+  load_springs(D, env, sk, sb, sr);
+  for (int t = t0; t < n_ticks; t++) {
     float tau[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-      const float kp = D.kp[i * n + env], kd = D.kd[i * n + env];
-      tau_m[i] = pd_torque1(kp, kd, RC.tau_max[i], cmd[i], st.q[i], st.qd[i], torque_mode);
-      tau[i] = tau_m[i];
-    }
-    if (C.enable_springs) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        spring_torque_leg(k, sk, sb, sr, st.q + 3 * k, st.qd + 3 * k, tau_s + 3 * k);
-#pragma unroll
-        for (int j = 0; j < 3; j++) tau[3 * k + j] += tau_s[3 * k + j];
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 12; i++) tau_s[i] = 0.f;
-    }
-    physics_tick(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1));
+    tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s);
+    if (physics_tick(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1))) return t;
+  }
+  return n_ticks;
+}
+
+// same loop on the general solver (joint limits, every collision shape); rare path
+__device__ __noinline__ void run_ticks_general(EnvState<float>& st, ContactState<float>& cs, const float* cmd,
+                                               bool torque_mode, int t0, int n_ticks, int env, const DeviceView& D,
+                                               const EnvCfg& C, const RobotConst& RC, const ModelConstT<float>& M,
+                                               const SolverConst& SC, float* tau_m, float* tau_s) {
+  const float mu = D.mu[env];
+  float sk[3], sb[3], sr[3];
+  load_springs(D, env, sk, sb, sr);
+  for (int t = t0; t < n_ticks; t++) {
+    float tau[12];
+    tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s);
+    physics_tick_general(st, tau, mu, cs, M, SC);
   }
 }
 

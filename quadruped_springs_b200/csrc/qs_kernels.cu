@@ -6,6 +6,7 @@
 // ([component][env], coalesced).  No tensor cores: per-env matrices are <= 6x6.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -43,276 +44,7 @@ static int fail(int code, const std::string& msg) {
   } while (0)
 
 // ============================================================================ kernels
-// settling / reset-time command: _convert_reference_to_command(get_init_pose())
-// (interface_base.py:68-72,182-200); also returns the settling action.
-__device__ __forceinline__ void settle_command(const EnvCfg& C, const RobotConst& RC, float* cmd, float* act12) {
-  if (C.is_rl) {
-    const bool cart = C.control_mode == QS_CTRL_CARTESIAN_PD;
-    const int sidx = cart ? 1 : 0;
-    float a12[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++)
-      a12[i] = cart ? command_to_action1(RC.nominal_foot[i], RC.cart_lo[i], RC.cart_hi[i])
-                    : command_to_action1(RC.init_angles[i], RC.ang_lo[i], RC.ang_hi[i]);
-    // _convert_to_actual_action_space (action_interface.py:17-18,41-44,67-74)
-#pragma unroll
-    for (int i = 0; i < 12; i++) act12[i] = 0.f;
-    if (C.action_mode == QS_ACT_DEFAULT) {
-#pragma unroll
-      for (int i = 0; i < 12; i++) act12[i] = a12[i];
-    } else if (C.action_mode == QS_ACT_SYMMETRIC) {
-#pragma unroll
-      for (int j = 0; j < 3; j++) { act12[j] = a12[j]; act12[3 + j] = a12[6 + j]; }
-    } else {
-      if (sidx == 0) { act12[0] = a12[1]; act12[1] = a12[2]; act12[2] = a12[7]; act12[3] = a12[8]; }
-      else { act12[0] = a12[0]; act12[1] = a12[2]; act12[2] = a12[6]; act12[3] = a12[8]; }
-    }
-    float b12[12];
-    expand_action(C.action_mode, sidx, act12, b12);
-    action12_to_command(RC, C.control_mode, b12, cmd);
-    // settling_action = _transform_motor_command_to_action(settling_command)
-    // (interface_base.py:196-200).  In CARTESIAN_PD mode the command holds JOINT
-    // ANGLES (it went through IK) yet is scaled with the CARTESIAN limits, so the
-    // reference stores (0, 1, -1) per leg as _last_action: reproduced as is.
-#pragma unroll
-    for (int i = 0; i < 12; i++)
-      a12[i] = cart ? command_to_action1(cmd[i], RC.cart_lo[i], RC.cart_hi[i])
-                    : command_to_action1(cmd[i], RC.ang_lo[i], RC.ang_hi[i]);
-#pragma unroll
-    for (int i = 0; i < 12; i++) act12[i] = 0.f;
-    if (C.action_mode == QS_ACT_DEFAULT) {
-#pragma unroll
-      for (int i = 0; i < 12; i++) act12[i] = a12[i];
-    } else if (C.action_mode == QS_ACT_SYMMETRIC) {
-#pragma unroll
-      for (int j = 0; j < 3; j++) { act12[j] = a12[j]; act12[3 + j] = a12[6 + j]; }
-    } else {
-      if (sidx == 0) { act12[0] = a12[1]; act12[1] = a12[2]; act12[2] = a12[7]; act12[3] = a12[8]; }
-      else { act12[0] = a12[0]; act12[1] = a12[2]; act12[2] = a12[6]; act12[3] = a12[8]; }
-    }
-  } else {
-    // settle_robot_by_pd (control_interface/utils.py:22-30): PD limits, DEFAULT space
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-      const float a = command_to_action1(RC.init_angles[i], RC.ang_lo[i], RC.ang_hi[i]);
-      cmd[i] = clampt(RC.ang_lo[i] + 0.5f * (a + 1.f) * (RC.ang_hi[i] - RC.ang_lo[i]), RC.ang_lo[i], RC.ang_hi[i]);
-      act12[i] = 0.f;
-    }
-  }
-}
-
-__device__ __forceinline__ void finish_episode_stats(const DeviceView& D, int env, const float* ts, float ep_return,
-                                                     int ep_len, bool terminated, int task) {
-  const int n = D.n;
-  float* s = D.stats + env;
-  s[0 * n] += 1.f;
-  s[1 * n] += ts[TS_MAX_H];
-  s[2 * n] = fmaxf(s[2 * n], ts[TS_MAX_H]);
-  s[3 * n] += ts[TS_REL_MAX_H];
-  s[4 * n] += ts[TS_MAX_FWD];
-  s[5 * n] = fmaxf(s[5 * n], ts[TS_MAX_FWD]);
-  s[6 * n] += ts[TS_MAX_FLIGHT];
-  const float flip = (task == QS_TASK_BACKFLIP ? ts[TS_MAX_PITCH_BF] : ts[TS_MAX_PITCH]) / float(2 * QS_PI);
-  s[7 * n] += flip;
-  s[8 * n] += ep_return;
-  s[9 * n] += float(ep_len);
-  s[10 * n] += terminated ? 1.f : 0.f;
-}
-
-// -------------------------------------------------------------------- K1: step
-__global__ void __launch_bounds__(128)
-k_step(const __grid_constant__ KernelArgs A, const float* __restrict__ actions, float* __restrict__ obs,
-       float* __restrict__ reward, uint8_t* __restrict__ done, uint8_t* __restrict__ truncated,
-       int* __restrict__ reset_list, int* __restrict__ reset_count) {
-  const int env = blockIdx.x * blockDim.x + threadIdx.x;
-  const DeviceView& D = A.D;
-  const EnvCfg& C = A.C;
-  const int n = D.n;
-  if (env >= n) return;
-  const float dt = A.SC.dt;
-  EnvState<float> st;
-  ContactState<float> cs;
-  load_state(D, env, st, cs, dt);
-
-  // ---- action (quadruped_gym_env.py:229-234)
-  float act[12];
-#pragma unroll
-  for (int i = 0; i < 12; i++) act[i] = i < C.action_dim ? actions[size_t(env) * C.action_dim + i] : 0.f;
-#pragma unroll
-  for (int i = 0; i < 12; i++) D.last_action[i * n + env] = act[i];
-  if (C.enable_filter) {  // utils/action_filter.py:110-121
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-      if (i < C.action_dim) {
-        float* f = D.filt + env;
-        const float x0 = f[(0 * 12 + i) * n], x1 = f[(1 * 12 + i) * n];
-        const float y0 = f[(2 * 12 + i) * n], y1 = f[(3 * 12 + i) * n];
-        const float y = act[i] * A.RC.filt_b[0] + (x0 * A.RC.filt_b[1] + x1 * A.RC.filt_b[2]) -
-                        (y0 * A.RC.filt_a[1] + y1 * A.RC.filt_a[2]);
-        f[(1 * 12 + i) * n] = x0; f[(0 * 12 + i) * n] = act[i];
-        f[(3 * 12 + i) * n] = y0; f[(2 * 12 + i) * n] = y;
-        act[i] = y;
-      }
-    }
-  }
-  float cmd[12];
-  bool torque_mode = false;
-  if (C.is_rl) {
-    // _interpolate_actions (:187-205) is a no-op in the reference: step() overwrites
-    // _last_action with the current action before the substeps (:229-234).
-    float a12[12];
-    expand_action(C.action_mode, C.control_mode == QS_CTRL_CARTESIAN_PD ? 1 : 0, act, a12);
-    action12_to_command(A.RC, C.control_mode, a12, cmd);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 12; i++) cmd[i] = act[i];
-    torque_mode = C.control_mode == QS_CTRL_TORQUE;
-  }
-
-  // ---- action_repeat substeps (:236-237)
-  float tau_m[12], tau_s[12];
-  run_ticks(st, cs, cmd, torque_mode, C.action_repeat, env, D, C, A.RC, A.M, A.SC, tau_m, tau_s, true);
-  const int sim_steps = D.sim_steps[env] + C.action_repeat;
-  const int env_steps = D.env_steps[env] + 1;
-
-  // ---- task / reward / done (:239-251)
-  float Rb[9], rpy[3];
-  quat_to_R(st.quat, Rb);
-  rpy_from_quat(st.quat, rpy);
-  const float sim_time = float(double(sim_steps) * A.time_step_d);
-  float ts[QS_TASK_DIM];
-#pragma unroll
-  for (int i = 0; i < TS_END; i++) ts[i] = D.task[i * n + env];
-  float foot_force[4];
-#pragma unroll
-  for (int k = 0; k < 4; k++) foot_force[k] = (cs.mask >> k) & 1 ? cs.lam_n[k] / dt : 0.f;
-  task_on_step(ts, st, cs, tau_m, rpy, Rb, sim_time, C.task);
-  float r = task_reward(ts, st, foot_force, ts + TS_OLD_TAU0, tau_m, rpy, Rb, C.task);
-  const bool term = task_terminated(ts, st, cs, Rb, A.RC.fallen_height, C.task);
-  const bool dn = term || (double(sim_steps) * A.time_step_d > A.max_time_d);
-  if (dn) r += task_reward_end(ts, term, C.task);
-#pragma unroll
-  for (int i = 0; i < 12; i++) ts[TS_OLD_TAU0 + i] = tau_m[i];
-  const float ep_ret = D.ep_return[env] + r;
-
-  // ---- sensors (:253-254)
-  float o[QS_MAX_OBS];
-#pragma unroll
-  for (int i = 0; i < QS_MAX_OBS; i++) o[i] = 0.f;
-  observe(st, cs, ts, rpy, Rb, C.obs_mode, o);
-  const uint64_t gid = uint64_t(C.gid0 + env);
-  store_obs(obs + size_t(env) * C.obs_dim, o, C, A.RC, gid, D.reset_count[env], uint32_t(env_steps), C.enable_noise);
-  reward[env] = r;
-  done[env] = dn;
-  truncated[env] = dn && !term;
-
-  // ---- write back
-  store_state(D, env, st, cs, dt);
-#pragma unroll
-  for (int i = 0; i < 12; i++) { D.tau_motor[i * n + env] = tau_m[i]; D.tau_spring[i * n + env] = tau_s[i]; }
-#pragma unroll
-  for (int i = 0; i < TS_END; i++) D.task[i * n + env] = ts[i];
-  D.sim_steps[env] = sim_steps;
-  D.env_steps[env] = env_steps;
-  D.ep_return[env] = ep_ret;
-  D.work[0 * n + env] += uint32_t(C.action_repeat);
-  D.work[1 * n + env] += uint32_t(cs.work_contacts);
-  D.work[2 * n + env] += uint32_t(cs.work_row_iters);
-  if (dn) {
-    finish_episode_stats(D, env, ts, ep_ret, env_steps, term, C.task);
-    if (C.auto_reset) reset_list[atomicAdd(reset_count, 1)] = env;
-  }
-}
-
-// -------------------------------------------------------------------- K2: reset + settle
-// list == nullptr: thread i resets env i (all envs).  Otherwise thread i resets
-// env list[i] for i < *count (dense warps whatever the done pattern).
-__global__ void __launch_bounds__(128)
-k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, const int* __restrict__ count,
-        float* __restrict__ obs) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const DeviceView& D = A.D;
-  const EnvCfg& C = A.C;
-  const int n = D.n;
-  int env = tid;
-  if (list) {
-    if (tid >= *count) return;
-    env = list[tid];
-  } else if (tid >= n) {
-    return;
-  }
-  const float dt = A.SC.dt;
-  const uint64_t gid = uint64_t(C.gid0 + env);
-  const uint32_t epoch = D.reset_count[env] + 1;
-  D.reset_count[env] = epoch;
-  // env_randomizer.py:287-289: mu = 0.5 + 0.5 * U[0,1)
-  const float mu = C.ground_randomizer ? 0.5f + 0.5f * uniform1(C.seed, gid, epoch, 100) : C.mu_ground;
-  D.mu[env] = mu;
-  // a fresh Quadruped is built on every reset (quadruped_gym_env.py:299-319): default gains / springs
-#pragma unroll
-  for (int i = 0; i < 12; i++) { D.kp[i * n + env] = A.RC.kp[i]; D.kd[i * n + env] = A.RC.kd[i]; }
-#pragma unroll
-  for (int j = 0; j < 3; j++) {
-    D.spring[(0 + j) * n + env] = A.RC.spring_k[j];
-    D.spring[(3 + j) * n + env] = A.RC.spring_b[j];
-    D.spring[(6 + j) * n + env] = A.RC.spring_rest[j];
-  }
-  EnvState<float> st;
-  ContactState<float> cs;
-  st.pos[0] = 0.f; st.pos[1] = 0.f; st.pos[2] = 0.32f;  // INIT_POSITION, configs:23
-  st.quat[0] = st.quat[1] = st.quat[2] = 0.f; st.quat[3] = 1.f;
-#pragma unroll
-  for (int i = 0; i < 3; i++) { st.vlin[i] = 0.f; st.vang[i] = 0.f; }
-#pragma unroll
-  for (int i = 0; i < 12; i++) { st.q[i] = A.RC.init_angles[i]; st.qd[i] = 0.f; }
-  cs.mask = 0; cs.invalid = 0; cs.work_contacts = 0; cs.work_row_iters = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++) cs.lam_n[k] = 0.f;
-
-  float cmd[12], act12[12], tau_m[12], tau_s[12];
-  settle_command(C, A.RC, cmd, act12);
-  const int nsettle = C.is_rl ? C.settling_steps : 1500;
-  run_ticks(st, cs, cmd, false, nsettle, env, D, C, A.RC, A.M, A.SC, tau_m, tau_s, true);
-  if (nsettle == 0) {
-#pragma unroll
-    for (int i = 0; i < 12; i++) { tau_m[i] = 0.f; tau_s[i] = 0.f; }
-  }
-
-  float Rb[9], rpy[3];
-  quat_to_R(st.quat, Rb);
-  rpy_from_quat(st.quat, rpy);
-  float ts[QS_TASK_DIM];
-#pragma unroll
-  for (int i = 0; i < TS_END; i++) ts[i] = D.task[i * n + env];
-  task_reset(ts, st, cs, tau_m, rpy, Rb, 0.f, C.task);
-#pragma unroll
-  for (int i = 0; i < TS_END; i++) D.task[i * n + env] = ts[i];
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    D.last_action[i * n + env] = act12[i];
-    D.tau_motor[i * n + env] = tau_m[i];
-    D.tau_spring[i * n + env] = tau_s[i];
-    // action_filter.py:123-127 init_history(last_action)
-    D.filt[(0 * 12 + i) * n + env] = act12[i]; D.filt[(1 * 12 + i) * n + env] = act12[i];
-    D.filt[(2 * 12 + i) * n + env] = act12[i]; D.filt[(3 * 12 + i) * n + env] = act12[i];
-  }
-  D.sim_steps[env] = 0;
-  D.env_steps[env] = 0;
-  D.ep_return[env] = 0.f;
-  store_state(D, env, st, cs, dt);
-  if (obs) {
-    float o[QS_MAX_OBS];
-#pragma unroll
-    for (int i = 0; i < QS_MAX_OBS; i++) o[i] = 0.f;
-    observe(st, cs, ts, rpy, Rb, C.obs_mode, o);
-    store_obs(obs + size_t(env) * C.obs_dim, o, C, A.RC, gid, epoch, 0u, C.enable_noise);
-  }
-}
-
-__global__ void k_compact(const uint8_t* __restrict__ mask, int n, int* __restrict__ list, int* __restrict__ count) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && mask[i]) list[atomicAdd(count, 1)] = i;
-}
+#include "qs_step_kernels.cuh"
 
 // -------------------------------------------------------------------- observe / state I/O
 __global__ void k_observe(const __grid_constant__ KernelArgs A, float* __restrict__ obs, int with_noise) {
@@ -379,7 +111,8 @@ k_debug_ticks(const __grid_constant__ DebugArgs<T> A, const float* __restrict__ 
 #pragma unroll
   for (int i = 0; i < 12; i++) t12[i] = T(tau[size_t(env) * 12 + i]);
   const T mu = T(D.mu[env]);
-  for (int t = 0; t < n_ticks; t++) physics_tick<T>(st, t12, mu, cs, A.M, A.SC, true);
+  for (int t = 0; t < n_ticks; t++)
+    if (physics_tick<T>(st, t12, mu, cs, A.M, A.SC, true)) physics_tick_general<T>(st, t12, mu, cs, A.M, A.SC);
 #pragma unroll
   for (int i = 0; i < 3; i++) { sf.pos[i] = float(st.pos[i]); sf.vlin[i] = float(st.vlin[i]); sf.vang[i] = float(st.vang[i]); }
 #pragma unroll
@@ -571,8 +304,12 @@ struct qs_env {
   ModelConstT<double> model_d;
   void* pool;       // one allocation backing every SoA array
   size_t pool_bytes;
-  int* reset_list;
-  int* reset_count;
+  int* lists;          // slow | reset | refill[0] | refill[1], each (cap + 1) ints with the count last
+  int *slow_list, *reset_list, *refill_list[2];
+  int refill_cap, cur_refill, steps_since_refill, refill_interval;
+  cudaStream_t side;   // low-priority stream of the slot refills
+  cudaEvent_t ev_main, ev_refill_done[2];
+  bool refill_pending[2];
   float* dev_actions;  // staging for qs_step_host
   float* dev_obs;
   float* dev_reward;
@@ -617,8 +354,8 @@ void qs_default_config(qs_config* c) {
   c->enable_noise = 1;
   c->auto_reset = 0;
   c->num_iterations = 0;
-  c->enable_limits = 0;
-  c->body_contact_response = 0;
+  c->enable_limits = 1;
+  c->body_contact_response = 1;
   c->block_size = 0;
   c->seed = 0;
   c->env_id_offset = 0;
@@ -689,6 +426,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   A.SC.mu_link = 1.0f;  // quadruped.py:670-676
   A.SC.num_iterations = cfg->num_iterations > 0 ? cfg->num_iterations : 300 / cfg->action_repeat;  // quadruped_gym_env.py:113
   A.SC.enable_limits = cfg->enable_limits;
+  A.SC.body_response = cfg->body_contact_response;
   A.time_step_d = cfg->time_step;
   A.max_time_d = cfg->max_episode_time;
   EnvCfg& C = A.C;
@@ -703,7 +441,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
 
   // one pool for all SoA arrays (4-byte elements), 256 B aligned segments
   const size_t n = size_t(n_envs);
-  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1 + 3;
+  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1 + 3 + 12 + 1 + SLOT_ROWS + 1 + 1;
   // rows of one array are contiguous with stride n floats; each array starts 256 B aligned
   h->pool_bytes = rows * n * 4 + 64 * 256;
   cudaError_t e = cudaMalloc(&h->pool, h->pool_bytes);
@@ -726,11 +464,29 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   D.env_steps = (int32_t*)carve(1); D.ep_return = (float*)carve(1); D.stats = (float*)carve(QS_STATS_DIM);
   D.reset_count = (uint32_t*)carve(1);
   D.work = (uint32_t*)carve(3);
+  D.cmd = (float*)carve(12); D.resume_tick = (int32_t*)carve(1);
+  D.slot = (float*)carve(SLOT_ROWS); D.slot_contact = (int32_t*)carve(1); D.slot_epoch = (uint32_t*)carve(1);
   if (size_t(p - static_cast<char*>(h->pool)) > h->pool_bytes) { cudaFree(h->pool); delete h; return fail(QS_ERR_STATE, "pool overflow"); }
-  e = cudaMalloc(&h->reset_list, (n + 1) * sizeof(int));
-  if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(QS_ERR_CUDA, "cudaMalloc reset list"); }
-  h->reset_count = h->reset_list + n;
-  cudaMemset(h->reset_list, 0, (n + 1) * sizeof(int));
+  h->refill_cap = 2 * n_envs;
+  const size_t nints = 2 * (n + 1) + 2 * (size_t(h->refill_cap) + 1);
+  e = cudaMalloc(&h->lists, nints * sizeof(int));
+  if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(QS_ERR_CUDA, "cudaMalloc lists"); }
+  cudaMemset(h->lists, 0, nints * sizeof(int));
+  h->slow_list = h->lists;
+  h->reset_list = h->slow_list + n + 1;
+  h->refill_list[0] = h->reset_list + n + 1;
+  h->refill_list[1] = h->refill_list[0] + h->refill_cap + 1;
+  h->cur_refill = 0;
+  h->steps_since_refill = 0;
+  h->refill_interval = 16;
+  if (const char* v = std::getenv("QS_REFILL_INTERVAL")) h->refill_interval = std::max(1, std::atoi(v));
+  int lo_prio = 0, hi_prio = 0;
+  cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+  e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo_prio);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_refill_done[0], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_refill_done[1], cudaEventDisableTiming);
+  if (e != cudaSuccess) { cudaFree(h->pool); cudaFree(h->lists); delete h; return fail(QS_ERR_CUDA, "stream/event creation"); }
   *out = h;
   return QS_OK;
 }
@@ -738,8 +494,14 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
 int qs_destroy(qs_handle h) {
   if (!h) return fail(QS_ERR_ARG, "handle is NULL");
   cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->side);
+  cudaDeviceSynchronize();
+  cudaStreamDestroy(h->side);
+  cudaEventDestroy(h->ev_main);
+  cudaEventDestroy(h->ev_refill_done[0]);
+  cudaEventDestroy(h->ev_refill_done[1]);
   cudaFree(h->pool);
-  cudaFree(h->reset_list);
+  cudaFree(h->lists);
   if (h->dev_actions) cudaFree(h->dev_actions);
   if (h->dev_obs) cudaFree(h->dev_obs);
   if (h->dev_reward) cudaFree(h->dev_reward);
@@ -800,21 +562,51 @@ int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* o) {
 
 static int block_of(qs_handle h) { return h->cfg.block_size > 0 ? h->cfg.block_size : 128; }
 
+// launch the refill of the current list on the side stream and switch lists
+static int launch_refill(qs_handle h, cudaStream_t s, bool on_main) {
+  const int B = block_of(h);
+  const int cur = h->cur_refill;
+  cudaStream_t rs = on_main ? s : h->side;
+  if (!on_main) {
+    CUDA_TRY(cudaEventRecord(h->ev_main, s));
+    CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_main, 0));
+  }
+  k_refill<<<grid_for(h->refill_cap, B), B, 0, rs>>>(h->args, h->refill_list[cur], h->refill_cap);
+  CUDA_TRY(cudaMemsetAsync(h->refill_list[cur] + h->refill_cap, 0, sizeof(int), rs));
+  CUDA_TRY(cudaEventRecord(h->ev_refill_done[cur], rs));
+  h->refill_pending[cur] = true;
+  g_launches += 1;
+  h->cur_refill = cur ^ 1;
+  // the list we switch to must have been drained by its previous refill
+  if (h->refill_pending[h->cur_refill]) {
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_refill_done[h->cur_refill], 0));
+    h->refill_pending[h->cur_refill] = false;
+  }
+  h->steps_since_refill = 0;
+  return QS_OK;
+}
+
 int qs_reset(qs_handle h, const uint8_t* mask, float* obs, void* stream) {
   if (!h) return fail(QS_ERR_ARG, "handle is NULL");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(h->device));
   const int B = block_of(h);
+  int* rl = h->refill_list[h->cur_refill];
   if (mask) {
-    CUDA_TRY(cudaMemsetAsync(h->reset_count, 0, sizeof(int), s));
-    k_compact<<<grid_for(h->n, 256), 256, 0, s>>>(mask, h->n, h->reset_list, h->reset_count);
-    k_reset<<<grid_for(h->n, B), B, 0, s>>>(h->args, h->reset_list, h->reset_count, obs);
+    CUDA_TRY(cudaMemsetAsync(h->reset_list + h->n, 0, sizeof(int), s));
+    k_compact<<<grid_for(h->n, 256), 256, 0, s>>>(mask, h->n, h->reset_list);
+    k_reset<<<grid_for(h->n, B), B, 0, s>>>(h->args, h->reset_list, rl, h->refill_cap, obs);
     g_launches += 2;
   } else {
-    k_reset<<<grid_for(h->n, B), B, 0, s>>>(h->args, nullptr, nullptr, obs);
+    k_reset<<<grid_for(h->n, B), B, 0, s>>>(h->args, nullptr, rl, h->refill_cap, obs);
     g_launches += 1;
   }
   CUDA_TRY(cudaGetLastError());
+  if (h->cfg.auto_reset) {
+    // (re)fill the spare slots of the envs just reset, in stream order
+    if (int e = launch_refill(h, s, true)) return e;
+    CUDA_TRY(cudaGetLastError());
+  }
   h->was_reset = true;
   return QS_OK;
 }
@@ -827,22 +619,31 @@ int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(h->device));
   const int B = block_of(h);
-  if (h->cfg.auto_reset) CUDA_TRY(cudaMemsetAsync(h->reset_count, 0, sizeof(int), s));
+  // slow and reset lists are adjacent: clear both counts ... (counts sit at the end of each list)
+  CUDA_TRY(cudaMemsetAsync(h->slow_list + h->n, 0, sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(h->reset_list + h->n, 0, sizeof(int), s));
   if (!h->ev_ready) {
     for (int i = 0; i < qs_env::kRing; i++) { CUDA_TRY(cudaEventCreate(&h->ev0[i])); CUDA_TRY(cudaEventCreate(&h->ev1[i])); }
     h->ev_ready = true;
   }
+  StepIO io;
+  io.actions = actions; io.obs = obs; io.reward = reward; io.done = done; io.truncated = truncated;
+  io.slow_list = h->slow_list; io.reset_list = h->reset_list;
+  io.refill_list = h->refill_list[h->cur_refill]; io.refill_cap = h->refill_cap;
   const int slot = int(h->n_steps % qs_env::kRing);
   cudaEventRecord(h->ev0[slot], s);
-  k_step<<<grid_for(h->n, B), B, 0, s>>>(h->args, actions, obs, reward, done, truncated, h->reset_list, h->reset_count);
+  k_step<<<grid_for(h->n, B), B, 0, s>>>(h->args, io);
   cudaEventRecord(h->ev1[slot], s);
   h->n_steps++;
-  g_launches += 1;
+  // envs parked for the general solver (joint limits / body contacts): usually none
+  k_step_slow<<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io);
+  g_launches += 2;
   if (h->cfg.auto_reset) {
-    // finished envs restart inside the same call; their obs row becomes the first
-    // observation of the new episode (SB3 VecEnv convention)
-    k_reset<<<grid_for(h->n, B), B, 0, s>>>(h->args, h->reset_list, h->reset_count, obs);
+    // envs whose spare slot was not ready restart in place (usually none)
+    k_reset<<<grid_for(h->n, B), B, 0, s>>>(h->args, h->reset_list, io.refill_list, h->refill_cap, obs);
     g_launches += 1;
+    if (++h->steps_since_refill >= h->refill_interval)
+      if (int e = launch_refill(h, s, false)) return e;
   }
   CUDA_TRY(cudaGetLastError());
   return QS_OK;

@@ -160,223 +160,176 @@ QS_DEV void body_force(const SpI<T>& I, const T* Vw, const T* Vv, const T* Aw, c
 
 template <typename T> QS_DEV T clamp_vel(T v, T mx) { return tmin(tmax(v, -mx), mx); }
 
+
 // ------------------------------------------------------------------------------------------
-// One tick.  tau = joint torques applied this tick (motor + spring, already summed).
-// cs: in = previous tick's contact impulses (warm start), out = this tick's.
+// Shared pieces of a tick
 // ------------------------------------------------------------------------------------------
-template <typename T>
-__host__ __device__ void physics_tick(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
-                             const ModelConstT<T>& M, const SolverConst& SC, bool detect_invalid) {
-  const T dt = T(SC.dt);
-  const T mcv = T(SC.max_coord_vel);
-  T Rb[9];
-  quat_to_R(st.quat, Rb);
-  T wb[3], vb[3];
-  m3t_v(Rb, st.vang, wb);
-  m3t_v(Rb, st.vlin, vb);
-  const T nb[3] = {Rb[6], Rb[7], Rb[8]};  // world z in base coords
+template <typename T> struct TickCtx {
+  T Rb[9], wb[3], vb[3], nb[3], A0[3], wxv[3];
+  T tdir[3][3];  // contact frame in base coords: normal, t1 = -y_world, t2 = x_world (btPlaneSpace1 of (0,0,1))
+};
+
+template <typename T> QS_DEV void tick_ctx(const EnvState<T>& st, const SolverConst& SC, TickCtx<T>& X) {
+  quat_to_R(st.quat, X.Rb);
+  m3t_v(X.Rb, st.vang, X.wb);
+  m3t_v(X.Rb, st.vlin, X.vb);
   const T gacc = T(-SC.gravity_z);
-  const T A0[3] = {gacc * nb[0], gacc * nb[1], gacc * nb[2]};  // fictitious base acceleration
-  const T zero3[3] = {T(0), T(0), T(0)};
-  T wxv[3];
-  cross3(wb, vb, wxv);
-
-  // composite inertia of the whole robot and Newton-Euler base force, trunk first
-  SpI<T> tot;
-  tot.m = M.trunk_m;
 #pragma unroll
-  for (int i = 0; i < 3; i++) tot.h[i] = M.trunk_h[i];
-#pragma unroll
-  for (int i = 0; i < 6; i++) tot.I[i] = M.trunk_I[i];
-  T fb[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-  body_force(tot, wb, vb, zero3, A0, fb, fb + 3);
-
-  T S6[21];
-#pragma unroll
-  for (int i = 0; i < 21; i++) S6[i] = T(0);
-
-  // per-leg results kept for the later phases
-  T Bm[4][18];  // M_kk^-1 F_k            (3x6)
-  T ev[4][3];   // M_kk^-1 (tau - h) + B_lin (w x v)
-  T G[4][18];   // contact rows G, later Y = L^-1 G^T   (3 dirs x 6)
-  T H[4][6];    // J_kk M_kk^-1 J_kk^T (sym 3x3: nn n1 n2 11 12 22)
-  T W[4][9];    // M_kk^-1 J_kk^T, W[j*3+dir]
-  T cvel[4][3]; // J nu of the part that does not depend on the base solve
-  T gap[4];
-  int active = 0, invalid = 0;
-
-  const T tdir[3][3] = {{nb[0], nb[1], nb[2]}, {-Rb[3], -Rb[4], -Rb[5]}, {Rb[0], Rb[1], Rb[2]}};
-
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const T* q = st.q + 3 * k;
-    const T* qd = st.qd + 3 * k;
-    LegKin<T> K;
-    leg_kin(k, q, M, K);
-    // link rotations (link -> base)
-    const T RH[9] = {T(1), T(0), T(0), T(0), K.c1, -K.s1, T(0), K.s1, K.c1};
-    const T RT[9] = {K.c2, T(0), K.s2, K.s1 * K.s2, K.c1, -K.s1 * K.c2, -K.c1 * K.s2, K.s1, K.c1 * K.c2};
-    const T RC[9] = {K.c23, T(0), K.s23, K.s1 * K.s23, K.c1, -K.s1 * K.c23, -K.c1 * K.s23, K.s1, K.c1 * K.c23};
-    SpI<T> Ih, It, Ic;
-    body_spi(M.body_m[k][0], M.body_com[k][0], M.body_Ic[k][0], RH, K.r1, Ih);
-    body_spi(M.body_m[k][1], M.body_com[k][1], M.body_Ic[k][1], RT, K.r2, It);
-    body_spi(M.body_m[k][2], M.body_com[k][2], M.body_Ic[k][2], RC, K.r3, Ic);
-
-    // motion subspaces S_j = (a_j, r_j x a_j)
-    const T a1[3] = {T(1), T(0), T(0)};
-    T S1v[3], S2v[3], S3v[3];
-    cross3(K.r1, a1, S1v);
-    cross3(K.r2, K.a2, S2v);
-    cross3(K.r3, K.a2, S3v);
-
-    // ---- Newton-Euler bias (velocity products + gravity), individual bodies
-    T m1w[3], m1v[3], m2w[3], m2v[3], m3w[3], m3v[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      m1w[i] = a1[i] * qd[0]; m1v[i] = S1v[i] * qd[0];
-      m2w[i] = K.a2[i] * qd[1]; m2v[i] = S2v[i] * qd[1];
-      m3w[i] = K.a2[i] * qd[2]; m3v[i] = S3v[i] * qd[2];
-    }
-    T V1w[3], V1v[3], A1w[3], A1v[3];
-    cross3(wb, m1w, A1w);
-    cross3(wb, m1v, A1v);
-    cross3_add(vb, m1w, A1v);
-#pragma unroll
-    for (int i = 0; i < 3; i++) { V1w[i] = wb[i] + m1w[i]; V1v[i] = vb[i] + m1v[i]; A1v[i] += A0[i]; }
-    T V2w[3], V2v[3], A2w[3], A2v[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) { A2w[i] = A1w[i]; A2v[i] = A1v[i]; }
-    cross3_add(V1w, m2w, A2w);
-    cross3_add(V1w, m2v, A2v);
-    cross3_add(V1v, m2w, A2v);
-#pragma unroll
-    for (int i = 0; i < 3; i++) { V2w[i] = V1w[i] + m2w[i]; V2v[i] = V1v[i] + m2v[i]; }
-    T V3w[3], V3v[3], A3w[3], A3v[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) { A3w[i] = A2w[i]; A3v[i] = A2v[i]; }
-    cross3_add(V2w, m3w, A3w);
-    cross3_add(V2w, m3v, A3v);
-    cross3_add(V2v, m3w, A3v);
-#pragma unroll
-    for (int i = 0; i < 3; i++) { V3w[i] = V2w[i] + m3w[i]; V3v[i] = V2v[i] + m3v[i]; }
-
-    T f3n[3] = {T(0), T(0), T(0)}, f3l[3] = {T(0), T(0), T(0)};
-    body_force(Ic, V3w, V3v, A3w, A3v, f3n, f3l);
-    const T h3 = dot3(K.a2, f3n) + dot3(S3v, f3l);
-    body_force(It, V2w, V2v, A2w, A2v, f3n, f3l);  // now thigh + calf
-    const T h2 = dot3(K.a2, f3n) + dot3(S2v, f3l);
-    body_force(Ih, V1w, V1v, A1w, A1v, f3n, f3l);  // now the whole leg
-    const T h1 = f3n[0] + dot3(S1v, f3l);
-
-    // ---- composite inertias and joint-space blocks
-    spi_add(It, Ic);  // thigh + calf
-    spi_add(Ih, It);  // whole leg
-    T F1[6], F2[6], F3[6];
-    spi_apply(Ic, K.a2, S3v, F3, F3 + 3);
-    spi_apply(It, K.a2, S2v, F2, F2 + 3);
-    spi_apply(Ih, a1, S1v, F1, F1 + 3);
-    const T M33 = dot3(K.a2, F3) + dot3(S3v, F3 + 3);
-    const T M23 = dot3(K.a2, F3) + dot3(S2v, F3 + 3);
-    const T M13 = F3[0] + dot3(S1v, F3 + 3);
-    const T M22 = dot3(K.a2, F2) + dot3(S2v, F2 + 3);
-    const T M12 = F2[0] + dot3(S1v, F2 + 3);
-    const T M11 = F1[0] + dot3(S1v, F1 + 3);
-    // inverse of the symmetric 3x3 (adjugate)
-    const T c00 = M22 * M33 - M23 * M23, c01 = M13 * M23 - M12 * M33, c02 = M12 * M23 - M13 * M22;
-    const T c11 = M11 * M33 - M13 * M13, c12 = M12 * M13 - M11 * M23, c22 = M11 * M22 - M12 * M12;
-    const T idet = T(1) / (M11 * c00 + M12 * c01 + M13 * c02);
-    const T Mi[6] = {c00 * idet, c01 * idet, c02 * idet, c11 * idet, c12 * idet, c22 * idet};  // 00 01 02 11 12 22
-    const T t1 = tau[3 * k] - h1, t2 = tau[3 * k + 1] - h2, t3 = tau[3 * k + 2] - h3;
-    const T d0 = Mi[0] * t1 + Mi[1] * t2 + Mi[2] * t3;
-    const T d1 = Mi[1] * t1 + Mi[3] * t2 + Mi[4] * t3;
-    const T d2 = Mi[2] * t1 + Mi[4] * t2 + Mi[5] * t3;
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-      Bm[k][c] = Mi[0] * F1[c] + Mi[1] * F2[c] + Mi[2] * F3[c];
-      Bm[k][6 + c] = Mi[1] * F1[c] + Mi[3] * F2[c] + Mi[4] * F3[c];
-      Bm[k][12 + c] = Mi[2] * F1[c] + Mi[4] * F2[c] + Mi[5] * F3[c];
-    }
-    ev[k][0] = d0 + Bm[k][3] * wxv[0] + Bm[k][4] * wxv[1] + Bm[k][5] * wxv[2];
-    ev[k][1] = d1 + Bm[k][9] * wxv[0] + Bm[k][10] * wxv[1] + Bm[k][11] * wxv[2];
-    ev[k][2] = d2 + Bm[k][15] * wxv[0] + Bm[k][16] * wxv[1] + Bm[k][17] * wxv[2];
-    // Schur complement and base right-hand side
-#pragma unroll
-    for (int a = 0; a < 6; a++) {
-#pragma unroll
-      for (int b = a; b < 6; b++)
-        S6[s6(a, b)] -= F1[a] * Bm[k][b] + F2[a] * Bm[k][6 + b] + F3[a] * Bm[k][12 + b];
-      fb[a] += (a < 3 ? f3n[a] : f3l[a - 3]) + F1[a] * d0 + F2[a] * d1 + F3[a] * d2;
-    }
-    spi_add(tot, Ih);
-
-    // ---- collision detection on the poses at the start of the tick
-    gap[k] = st.pos[2] + dot3(nb, K.r4) - M.foot_radius;
-    if (gap[k] < M.foot_thresh) {
-      active |= 1 << k;
-      const T pc[3] = {K.r4[0] - M.foot_radius * nb[0], K.r4[1] - M.foot_radius * nb[1],
-                       K.r4[2] - M.foot_radius * nb[2]};
-      T Jk[3][3];
-#pragma unroll
-      for (int dd = 0; dd < 3; dd++) {
-        T Jb[6];
-        foot_jac_dir(K, pc, tdir[dd], Jb, Jk[dd]);
-#pragma unroll
-        for (int c = 0; c < 6; c++)
-          G[k][6 * dd + c] = Jb[c] - (Jk[dd][0] * Bm[k][c] + Jk[dd][1] * Bm[k][6 + c] + Jk[dd][2] * Bm[k][12 + c]);
-        W[k][0 * 3 + dd] = Mi[0] * Jk[dd][0] + Mi[1] * Jk[dd][1] + Mi[2] * Jk[dd][2];
-        W[k][1 * 3 + dd] = Mi[1] * Jk[dd][0] + Mi[3] * Jk[dd][1] + Mi[4] * Jk[dd][2];
-        W[k][2 * 3 + dd] = Mi[2] * Jk[dd][0] + Mi[4] * Jk[dd][1] + Mi[5] * Jk[dd][2];
-        cvel[k][dd] = Jb[0] * wb[0] + Jb[1] * wb[1] + Jb[2] * wb[2] + Jb[3] * vb[0] + Jb[4] * vb[1] + Jb[5] * vb[2] +
-                      Jk[dd][0] * (qd[0] + dt * ev[k][0]) + Jk[dd][1] * (qd[1] + dt * ev[k][1]) +
-                      Jk[dd][2] * (qd[2] + dt * ev[k][2]);
-      }
-#define QS_H(a, b) (Jk[a][0] * W[k][0 * 3 + b] + Jk[a][1] * W[k][1 * 3 + b] + Jk[a][2] * W[k][2 * 3 + b])
-      H[k][0] = QS_H(0, 0); H[k][1] = QS_H(0, 1); H[k][2] = QS_H(0, 2);
-      H[k][3] = QS_H(1, 1); H[k][4] = QS_H(1, 2); H[k][5] = QS_H(2, 2);
-#undef QS_H
-    }
-    if (detect_invalid) {
-      // non-foot shapes vs the plane: support-function distance below the link's
-      // contact breaking threshold (quadruped.py:243-249 -> invalid contact)
-      const T ch[3] = {K.r1[0], K.r1[1], K.r1[2]};
-      const T nz = dot3(nb, K.a2);
-      const T zh = st.pos[2] + dot3(nb, ch) - (abs_t(nz) * M.hip_hl + M.hip_r * sqrt_t(tmax(T(1) - nz * nz, T(0))));
-      invalid += zh < M.hip_thresh;
-      T c[3], zc;
-      m3_v(RT, M.thigh_c, c);
-      zc = st.pos[2] + dot3(nb, K.r2) + dot3(nb, c);
-      zc -= abs_t(nb[0] * RT[0] + nb[1] * RT[3] + nb[2] * RT[6]) * M.thigh_half[0] +
-            abs_t(nb[0] * RT[1] + nb[1] * RT[4] + nb[2] * RT[7]) * M.thigh_half[1] +
-            abs_t(nb[0] * RT[2] + nb[1] * RT[5] + nb[2] * RT[8]) * M.thigh_half[2];
-      invalid += zc < M.thigh_thresh;
-      m3_v(RC, M.calf_c, c);
-      zc = st.pos[2] + dot3(nb, K.r3) + dot3(nb, c);
-      zc -= abs_t(nb[0] * RC[0] + nb[1] * RC[3] + nb[2] * RC[6]) * M.calf_half[0] +
-            abs_t(nb[0] * RC[1] + nb[1] * RC[4] + nb[2] * RC[7]) * M.calf_half[1] +
-            abs_t(nb[0] * RC[2] + nb[1] * RC[5] + nb[2] * RC[8]) * M.calf_half[2];
-      invalid += zc < M.calf_thresh;
-    }
+  for (int i = 0; i < 3; i++) {
+    X.nb[i] = X.Rb[6 + i];          // world z in base coords
+    X.A0[i] = gacc * X.Rb[6 + i];   // fictitious base acceleration = -gravity
+    X.tdir[0][i] = X.Rb[6 + i];
+    X.tdir[1][i] = -X.Rb[3 + i];
+    X.tdir[2][i] = X.Rb[i];
   }
-  if (detect_invalid) {
-    T zt = st.pos[2] - (abs_t(nb[0]) * M.trunk_half[0] + abs_t(nb[1]) * M.trunk_half[1] + abs_t(nb[2]) * M.trunk_half[2]);
-    invalid += zt < M.trunk_thresh;
-    T zi = st.pos[2] + dot3(nb, M.imu_pos) - (abs_t(nb[0]) + abs_t(nb[1]) + abs_t(nb[2])) * M.imu_half;
-    invalid += zi < M.imu_thresh;
-  }
+  cross3(X.wb, X.vb, X.wxv);
+}
 
-  // ---- base: S = M_bb - sum F^T B, Cholesky, solve
-  {
-    const T* I = tot.I;
-    const T* h = tot.h;
-    S6[s6(0, 0)] += I[0]; S6[s6(0, 1)] += I[1]; S6[s6(0, 2)] += I[2];
-    S6[s6(1, 1)] += I[3]; S6[s6(1, 2)] += I[4]; S6[s6(2, 2)] += I[5];
-    // upper-right block [h]x
-    S6[s6(0, 4)] += -h[2]; S6[s6(0, 5)] += h[1];
-    S6[s6(1, 3)] += h[2];  S6[s6(1, 5)] += -h[0];
-    S6[s6(2, 3)] += -h[1]; S6[s6(2, 4)] += h[0];
-    S6[s6(3, 3)] += tot.m; S6[s6(4, 4)] += tot.m; S6[s6(5, 5)] += tot.m;
+template <typename T> QS_DEV void link_rotations(const LegKin<T>& K, T* RH, T* RT, T* RC) {
+  RH[0] = T(1); RH[1] = T(0); RH[2] = T(0); RH[3] = T(0); RH[4] = K.c1; RH[5] = -K.s1; RH[6] = T(0); RH[7] = K.s1; RH[8] = K.c1;
+  RT[0] = K.c2; RT[1] = T(0); RT[2] = K.s2; RT[3] = K.s1 * K.s2; RT[4] = K.c1; RT[5] = -K.s1 * K.c2;
+  RT[6] = -K.c1 * K.s2; RT[7] = K.s1; RT[8] = K.c1 * K.c2;
+  RC[0] = K.c23; RC[1] = T(0); RC[2] = K.s23; RC[3] = K.s1 * K.s23; RC[4] = K.c1; RC[5] = -K.s1 * K.c23;
+  RC[6] = -K.c1 * K.s23; RC[7] = K.s1; RC[8] = K.c1 * K.c23;
+}
+
+// Per-leg dynamics: joint-space inertia inverse Mi (sym 3x3: 00 01 02 11 12 22),
+// Bm = M_kk^-1 F_k (3x6), ev = M_kk^-1 (tau - h) + B_lin (w x v); accumulates the
+// Schur complement S6 -= F^T B, the base force fb += f_leg + F^T d and the
+// composite inertia tot += I_leg.
+template <typename T>
+QS_DEV void leg_dynamics(int k, const T* q, const T* qd, const T* tau3, const TickCtx<T>& X, const ModelConstT<T>& M,
+                         const LegKin<T>& K, const T* RH, const T* RT, const T* RC, T* Mi, T* Bm, T* ev, T* S6, T* fb,
+                         SpI<T>& tot) {
+  const T* wb = X.wb;
+  const T* vb = X.vb;
+  SpI<T> Ih, It, Ic;
+  body_spi(M.body_m[k][0], M.body_com[k][0], M.body_Ic[k][0], RH, K.r1, Ih);
+  body_spi(M.body_m[k][1], M.body_com[k][1], M.body_Ic[k][1], RT, K.r2, It);
+  body_spi(M.body_m[k][2], M.body_com[k][2], M.body_Ic[k][2], RC, K.r3, Ic);
+
+  // motion subspaces S_j = (a_j, r_j x a_j)
+  const T a1[3] = {T(1), T(0), T(0)};
+  T S1v[3], S2v[3], S3v[3];
+  cross3(K.r1, a1, S1v);
+  cross3(K.r2, K.a2, S2v);
+  cross3(K.r3, K.a2, S3v);
+
+  // ---- Newton-Euler bias (velocity products + gravity), individual bodies
+  T m1w[3], m1v[3], m2w[3], m2v[3], m3w[3], m3v[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    m1w[i] = a1[i] * qd[0]; m1v[i] = S1v[i] * qd[0];
+    m2w[i] = K.a2[i] * qd[1]; m2v[i] = S2v[i] * qd[1];
+    m3w[i] = K.a2[i] * qd[2]; m3v[i] = S3v[i] * qd[2];
   }
-  T Ld[6];  // reciprocal diagonal of L; S6 now holds L (L(i,j), j<=i at s6(j,i))
+  T V1w[3], V1v[3], A1w[3], A1v[3];
+  cross3(wb, m1w, A1w);
+  cross3(wb, m1v, A1v);
+  cross3_add(vb, m1w, A1v);
+#pragma unroll
+  for (int i = 0; i < 3; i++) { V1w[i] = wb[i] + m1w[i]; V1v[i] = vb[i] + m1v[i]; A1v[i] += X.A0[i]; }
+  T V2w[3], V2v[3], A2w[3], A2v[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { A2w[i] = A1w[i]; A2v[i] = A1v[i]; }
+  cross3_add(V1w, m2w, A2w);
+  cross3_add(V1w, m2v, A2v);
+  cross3_add(V1v, m2w, A2v);
+#pragma unroll
+  for (int i = 0; i < 3; i++) { V2w[i] = V1w[i] + m2w[i]; V2v[i] = V1v[i] + m2v[i]; }
+  T V3w[3], V3v[3], A3w[3], A3v[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { A3w[i] = A2w[i]; A3v[i] = A2v[i]; }
+  cross3_add(V2w, m3w, A3w);
+  cross3_add(V2w, m3v, A3v);
+  cross3_add(V2v, m3w, A3v);
+#pragma unroll
+  for (int i = 0; i < 3; i++) { V3w[i] = V2w[i] + m3w[i]; V3v[i] = V2v[i] + m3v[i]; }
+
+  T f3n[3] = {T(0), T(0), T(0)}, f3l[3] = {T(0), T(0), T(0)};
+  body_force(Ic, V3w, V3v, A3w, A3v, f3n, f3l);
+  const T h3 = dot3(K.a2, f3n) + dot3(S3v, f3l);
+  body_force(It, V2w, V2v, A2w, A2v, f3n, f3l);  // now thigh + calf
+  const T h2 = dot3(K.a2, f3n) + dot3(S2v, f3l);
+  body_force(Ih, V1w, V1v, A1w, A1v, f3n, f3l);  // now the whole leg
+  const T h1 = f3n[0] + dot3(S1v, f3l);
+
+  // ---- composite inertias and joint-space blocks
+  spi_add(It, Ic);  // thigh + calf
+  spi_add(Ih, It);  // whole leg
+  T F1[6], F2[6], F3[6];
+  spi_apply(Ic, K.a2, S3v, F3, F3 + 3);
+  spi_apply(It, K.a2, S2v, F2, F2 + 3);
+  spi_apply(Ih, a1, S1v, F1, F1 + 3);
+  const T M33 = dot3(K.a2, F3) + dot3(S3v, F3 + 3);
+  const T M23 = dot3(K.a2, F3) + dot3(S2v, F3 + 3);
+  const T M13 = F3[0] + dot3(S1v, F3 + 3);
+  const T M22 = dot3(K.a2, F2) + dot3(S2v, F2 + 3);
+  const T M12 = F2[0] + dot3(S1v, F2 + 3);
+  const T M11 = F1[0] + dot3(S1v, F1 + 3);
+  // inverse of the symmetric 3x3 (adjugate)
+  const T c00 = M22 * M33 - M23 * M23, c01 = M13 * M23 - M12 * M33, c02 = M12 * M23 - M13 * M22;
+  const T c11 = M11 * M33 - M13 * M13, c12 = M12 * M13 - M11 * M23, c22 = M11 * M22 - M12 * M12;
+  const T idet = T(1) / (M11 * c00 + M12 * c01 + M13 * c02);
+  Mi[0] = c00 * idet; Mi[1] = c01 * idet; Mi[2] = c02 * idet; Mi[3] = c11 * idet; Mi[4] = c12 * idet; Mi[5] = c22 * idet;
+  const T t1 = tau3[0] - h1, t2 = tau3[1] - h2, t3 = tau3[2] - h3;
+  const T d0 = Mi[0] * t1 + Mi[1] * t2 + Mi[2] * t3;
+  const T d1 = Mi[1] * t1 + Mi[3] * t2 + Mi[4] * t3;
+  const T d2 = Mi[2] * t1 + Mi[4] * t2 + Mi[5] * t3;
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    Bm[c] = Mi[0] * F1[c] + Mi[1] * F2[c] + Mi[2] * F3[c];
+    Bm[6 + c] = Mi[1] * F1[c] + Mi[3] * F2[c] + Mi[4] * F3[c];
+    Bm[12 + c] = Mi[2] * F1[c] + Mi[4] * F2[c] + Mi[5] * F3[c];
+  }
+  ev[0] = d0 + Bm[3] * X.wxv[0] + Bm[4] * X.wxv[1] + Bm[5] * X.wxv[2];
+  ev[1] = d1 + Bm[9] * X.wxv[0] + Bm[10] * X.wxv[1] + Bm[11] * X.wxv[2];
+  ev[2] = d2 + Bm[15] * X.wxv[0] + Bm[16] * X.wxv[1] + Bm[17] * X.wxv[2];
+#pragma unroll
+  for (int a = 0; a < 6; a++) {
+#pragma unroll
+    for (int b = a; b < 6; b++) S6[s6(a, b)] -= F1[a] * Bm[b] + F2[a] * Bm[6 + b] + F3[a] * Bm[12 + b];
+    fb[a] += (a < 3 ? f3n[a] : f3l[a - 3]) + F1[a] * d0 + F2[a] * d1 + F3[a] * d2;
+  }
+  spi_add(tot, Ih);
+}
+
+// support-function gap of the leg's non-foot shapes (hip cylinder, thigh box, calf box)
+template <typename T>
+QS_DEV void leg_shape_gaps(const EnvState<T>& st, const TickCtx<T>& X, const ModelConstT<T>& M, const LegKin<T>& K,
+                           const T* RT, const T* RC, T* zh, T* zt, T* zc) {
+  const T* nb = X.nb;
+  const T nz = dot3(nb, K.a2);
+  *zh = st.pos[2] + dot3(nb, K.r1) - (abs_t(nz) * M.hip_hl + M.hip_r * sqrt_t(tmax(T(1) - nz * nz, T(0))));
+  T c[3];
+  m3_v(RT, M.thigh_c, c);
+  *zt = st.pos[2] + dot3(nb, K.r2) + dot3(nb, c) -
+        (abs_t(nb[0] * RT[0] + nb[1] * RT[3] + nb[2] * RT[6]) * M.thigh_half[0] +
+         abs_t(nb[0] * RT[1] + nb[1] * RT[4] + nb[2] * RT[7]) * M.thigh_half[1] +
+         abs_t(nb[0] * RT[2] + nb[1] * RT[5] + nb[2] * RT[8]) * M.thigh_half[2]);
+  m3_v(RC, M.calf_c, c);
+  *zc = st.pos[2] + dot3(nb, K.r3) + dot3(nb, c) -
+        (abs_t(nb[0] * RC[0] + nb[1] * RC[3] + nb[2] * RC[6]) * M.calf_half[0] +
+         abs_t(nb[0] * RC[1] + nb[1] * RC[4] + nb[2] * RC[7]) * M.calf_half[1] +
+         abs_t(nb[0] * RC[2] + nb[1] * RC[5] + nb[2] * RC[8]) * M.calf_half[2]);
+}
+template <typename T>
+QS_DEV void trunk_shape_gaps(const EnvState<T>& st, const TickCtx<T>& X, const ModelConstT<T>& M, T* zt, T* zi) {
+  const T* nb = X.nb;
+  *zt = st.pos[2] - (abs_t(nb[0]) * M.trunk_half[0] + abs_t(nb[1]) * M.trunk_half[1] + abs_t(nb[2]) * M.trunk_half[2]);
+  *zi = st.pos[2] + dot3(nb, M.imu_pos) - (abs_t(nb[0]) + abs_t(nb[1]) + abs_t(nb[2])) * M.imu_half;
+}
+
+// base block: S6 += mat6(tot); in-place Cholesky (L(i,j), j<=i at s6(j,i)), Ld = 1/diag
+template <typename T> QS_DEV void base_factor(const SpI<T>& tot, T* S6, T* Ld) {
+  const T* I = tot.I;
+  const T* h = tot.h;
+  S6[s6(0, 0)] += I[0]; S6[s6(0, 1)] += I[1]; S6[s6(0, 2)] += I[2];
+  S6[s6(1, 1)] += I[3]; S6[s6(1, 2)] += I[4]; S6[s6(2, 2)] += I[5];
+  S6[s6(0, 4)] += -h[2]; S6[s6(0, 5)] += h[1];
+  S6[s6(1, 3)] += h[2];  S6[s6(1, 5)] += -h[0];
+  S6[s6(2, 3)] += -h[1]; S6[s6(2, 4)] += h[0];
+  S6[s6(3, 3)] += tot.m; S6[s6(4, 4)] += tot.m; S6[s6(5, 5)] += tot.m;
 #pragma unroll
   for (int j = 0; j < 6; j++) {
     T dj = S6[s6(j, j)];
@@ -393,44 +346,193 @@ __host__ __device__ void physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
       S6[s6(j, i)] = v * inv;
     }
   }
+}
+template <typename T> QS_DEV void chol_fwd(const T* S6, const T* Ld, T* g) {  // g <- L^-1 g
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    T v = g[i];
+#pragma unroll
+    for (int k2 = 0; k2 < i; k2++) v -= S6[s6(k2, i)] * g[k2];
+    g[i] = v * Ld[i];
+  }
+}
+template <typename T> QS_DEV void chol_bwd(const T* S6, const T* Ld, const T* y, T* x) {  // x = L^-T y
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    T v = y[i];
+#pragma unroll
+    for (int k2 = i + 1; k2 < 6; k2++) v -= S6[s6(i, k2)] * x[k2];
+    x[i] = v * Ld[i];
+  }
+}
+
+// unconstrained update v += dt a with Bullet's per-coordinate clamp (applyDeltaVeeMultiDof);
+// ab = classical base acceleration (spatial + w x v) in base coords
+template <typename T>
+QS_DEV bool base_velocity_update(EnvState<T>& st, const TickCtx<T>& X, const T* ab, T dt, T mcv, T* wb1, T* vb1) {
+  bool clamped = false;
+  T aw[3], av[3];
+  m3_v(X.Rb, ab, aw);
+  m3_v(X.Rb, ab + 3, av);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const T w1 = st.vang[i] + dt * aw[i], v1 = st.vlin[i] + dt * av[i];
+    st.vang[i] = clamp_vel(w1, mcv);
+    st.vlin[i] = clamp_vel(v1, mcv);
+    clamped |= (st.vang[i] != w1) | (st.vlin[i] != v1);
+  }
+  m3t_v(X.Rb, st.vang, wb1);
+  m3t_v(X.Rb, st.vlin, vb1);
+  return clamped;
+}
+
+// positions from the new velocities (btMultiBody::stepPositionsMultiDof)
+template <typename T> QS_DEV void integrate_positions(EnvState<T>& st, T dt) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) st.pos[i] += dt * st.vlin[i];
+  const T* om = st.vang;
+  T ang = sqrt_t(dot3(om, om));
+  if (ang * dt > T(0.25 * QS_PI)) ang = T(0.25 * QS_PI) / dt;
+  T sc, cw;
+  if (ang < T(0.001)) {
+    sc = T(0.5) * dt - dt * dt * dt * T(0.020833333333) * ang * ang;
+    T sdummy;
+    sincos_t(T(0.5) * ang * dt, &sdummy, &cw);
+  } else {
+    T sn;
+    sincos_t(T(0.5) * ang * dt, &sn, &cw);
+    sc = sn / ang;
+  }
+  const T ax = om[0] * sc, ay = om[1] * sc, az = om[2] * sc;
+  const T* q = st.quat;
+  const T nw = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
+  const T nx = cw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
+  const T ny = cw * q[1] - ax * q[2] + ay * q[3] + az * q[0];
+  const T nz = cw * q[2] + ax * q[1] - ay * q[0] + az * q[3];
+  const T inv = rsqrt_t(nx * nx + ny * ny + nz * nz + nw * nw);
+  st.quat[0] = nx * inv; st.quat[1] = ny * inv; st.quat[2] = nz * inv; st.quat[3] = nw * inv;
+#pragma unroll
+  for (int i = 0; i < 12; i++) st.q[i] += dt * st.qd[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// FAST tick: foot contacts only (the overwhelmingly common case), everything in registers.
+// tau = joint torques of this tick (motor + spring).  cs: in = previous tick's contact
+// impulses (warm start), out = this tick's.  Returns true WITHOUT touching the state when
+// the tick needs the general solver (a joint at its limit, or a non-foot shape on the
+// ground while SC.body_response is set); the caller then hands the env to physics_tick_general.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
+                                      const ModelConstT<T>& M, const SolverConst& SC, bool detect_invalid) {
+  const T dt = T(SC.dt);
+  const T mcv = T(SC.max_coord_vel);
+  TickCtx<T> X;
+  tick_ctx(st, SC, X);
+  const T* nb = X.nb;
+  const T* wb = X.wb;
+  const T* vb = X.vb;
+  const T zero3[3] = {T(0), T(0), T(0)};
+
+  // composite inertia of the whole robot and Newton-Euler base force, trunk first
+  SpI<T> tot;
+  tot.m = M.trunk_m;
+#pragma unroll
+  for (int i = 0; i < 3; i++) tot.h[i] = M.trunk_h[i];
+#pragma unroll
+  for (int i = 0; i < 6; i++) tot.I[i] = M.trunk_I[i];
+  T fb[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  body_force(tot, wb, vb, zero3, X.A0, fb, fb + 3);
+
+  T S6[21];
+#pragma unroll
+  for (int i = 0; i < 21; i++) S6[i] = T(0);
+
+  // per-leg results kept for the later phases
+  T Bm[4][18];  // M_kk^-1 F_k            (3x6)
+  T ev[4][3];   // M_kk^-1 (tau - h) + B_lin (w x v)
+  T G[4][18];   // contact rows G, later Y = L^-1 G^T   (3 dirs x 6)
+  T H[4][6];    // J_kk M_kk^-1 J_kk^T (sym 3x3: nn n1 n2 11 12 22)
+  T W[4][9];    // M_kk^-1 J_kk^T, W[j*3+dir]
+  T cvel[4][3]; // J nu of the part that does not depend on the base solve
+  T gap[4];
+  int active = 0, invalid = 0;
+  bool need_general = false;
+  const bool watch_shapes = detect_invalid || SC.body_response;
+
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const T* q = st.q + 3 * k;
+    const T* qd = st.qd + 3 * k;
+    LegKin<T> K;
+    leg_kin(k, q, M, K);
+    T RH[9], RT[9], RC[9], Mi[6];
+    link_rotations(K, RH, RT, RC);
+    leg_dynamics(k, q, qd, tau + 3 * k, X, M, K, RH, RT, RC, Mi, Bm[k], ev[k], S6, fb, tot);
+    if (SC.enable_limits) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) need_general |= (q[j] <= M.joint_lo[j]) | (q[j] >= M.joint_hi[j]);
+    }
+
+    // ---- collision detection on the poses at the start of the tick
+    gap[k] = st.pos[2] + dot3(nb, K.r4) - M.foot_radius;
+    if (gap[k] < M.foot_thresh) {
+      active |= 1 << k;
+      const T pc[3] = {K.r4[0] - M.foot_radius * nb[0], K.r4[1] - M.foot_radius * nb[1],
+                       K.r4[2] - M.foot_radius * nb[2]};
+      T Jk[3][3];
+#pragma unroll
+      for (int dd = 0; dd < 3; dd++) {
+        T Jb[6];
+        foot_jac_dir(K, pc, X.tdir[dd], Jb, Jk[dd]);
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+          G[k][6 * dd + c] = Jb[c] - (Jk[dd][0] * Bm[k][c] + Jk[dd][1] * Bm[k][6 + c] + Jk[dd][2] * Bm[k][12 + c]);
+        W[k][0 * 3 + dd] = Mi[0] * Jk[dd][0] + Mi[1] * Jk[dd][1] + Mi[2] * Jk[dd][2];
+        W[k][1 * 3 + dd] = Mi[1] * Jk[dd][0] + Mi[3] * Jk[dd][1] + Mi[4] * Jk[dd][2];
+        W[k][2 * 3 + dd] = Mi[2] * Jk[dd][0] + Mi[4] * Jk[dd][1] + Mi[5] * Jk[dd][2];
+        cvel[k][dd] = Jb[0] * wb[0] + Jb[1] * wb[1] + Jb[2] * wb[2] + Jb[3] * vb[0] + Jb[4] * vb[1] + Jb[5] * vb[2] +
+                      Jk[dd][0] * (qd[0] + dt * ev[k][0]) + Jk[dd][1] * (qd[1] + dt * ev[k][1]) +
+                      Jk[dd][2] * (qd[2] + dt * ev[k][2]);
+      }
+#define QS_H(a, b) (Jk[a][0] * W[k][0 * 3 + b] + Jk[a][1] * W[k][1 * 3 + b] + Jk[a][2] * W[k][2 * 3 + b])
+      H[k][0] = QS_H(0, 0); H[k][1] = QS_H(0, 1); H[k][2] = QS_H(0, 2);
+      H[k][3] = QS_H(1, 1); H[k][4] = QS_H(1, 2); H[k][5] = QS_H(2, 2);
+#undef QS_H
+    }
+    if (watch_shapes) {
+      // non-foot shapes vs the plane: support-function distance below the link's
+      // contact breaking threshold (quadruped.py:243-249 -> invalid contact)
+      T zh, zt, zc;
+      leg_shape_gaps(st, X, M, K, RT, RC, &zh, &zt, &zc);
+      invalid += (zh < M.hip_thresh) + (zt < M.thigh_thresh) + (zc < M.calf_thresh);
+    }
+  }
+  if (watch_shapes) {
+    T zt, zi;
+    trunk_shape_gaps(st, X, M, &zt, &zi);
+    invalid += (zt < M.trunk_thresh) + (zi < M.imu_thresh);
+    if (SC.body_response && invalid > 0) need_general = true;
+  }
+  if (need_general) return true;
+
+  // ---- base: S = M_bb - sum F^T B, Cholesky, solve
+  T Ld[6];
+  base_factor(tot, S6, Ld);
   T ab[6];
   {
     T y[6];
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-      T v = -fb[i];
-#pragma unroll
-      for (int k2 = 0; k2 < i; k2++) v -= S6[s6(k2, i)] * y[k2];
-      y[i] = v * Ld[i];
-    }
-#pragma unroll
-    for (int i = 5; i >= 0; i--) {
-      T v = y[i];
-#pragma unroll
-      for (int k2 = i + 1; k2 < 6; k2++) v -= S6[s6(i, k2)] * ab[k2];
-      ab[i] = v * Ld[i];
-    }
+    for (int i = 0; i < 6; i++) y[i] = -fb[i];
+    chol_fwd(S6, Ld, y);
+    chol_bwd(S6, Ld, y, ab);
   }
   // classical acceleration of the base origin: spatial + w x v
-  ab[3] += wxv[0]; ab[4] += wxv[1]; ab[5] += wxv[2];
+  ab[3] += X.wxv[0]; ab[4] += X.wxv[1]; ab[5] += X.wxv[2];
 
   // ---- v += dt a, clamped like btMultiBody::applyDeltaVeeMultiDof
-  bool base_clamped = false;
   T wb1[3], vb1[3];
-  {
-    T aw[3], av[3];
-    m3_v(Rb, ab, aw);
-    m3_v(Rb, ab + 3, av);
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      const T w1 = st.vang[i] + dt * aw[i], v1 = st.vlin[i] + dt * av[i];
-      st.vang[i] = clamp_vel(w1, mcv);
-      st.vlin[i] = clamp_vel(v1, mcv);
-      base_clamped |= (st.vang[i] != w1) | (st.vlin[i] != v1);
-    }
-    m3t_v(Rb, st.vang, wb1);
-    m3t_v(Rb, st.vlin, vb1);
-  }
+  const bool base_clamped = base_velocity_update(st, X, ab, dt, mcv, wb1, vb1);
   int leg_clamped = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -463,7 +565,7 @@ __host__ __device__ void physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
 #pragma unroll
       for (int dd = 0; dd < 3; dd++) {
         T Jb[6], Jk[3];
-        foot_jac_dir(K, pc, tdir[dd], Jb, Jk);
+        foot_jac_dir(K, pc, X.tdir[dd], Jb, Jk);
         rel[dd] = Jb[0] * wb1[0] + Jb[1] * wb1[1] + Jb[2] * wb1[2] + Jb[3] * vb1[0] + Jb[4] * vb1[1] + Jb[5] * vb1[2] +
                   Jk[0] * st.qd[3 * k] + Jk[1] * st.qd[3 * k + 1] + Jk[2] * st.qd[3 * k + 2];
       }
@@ -486,15 +588,10 @@ __host__ __device__ void physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
 #pragma unroll
     for (int dd = 0; dd < 3; dd++) {
       T* g = G[k] + 6 * dd;
+      chol_fwd(S6, Ld, g);
       T nn = T(0);
 #pragma unroll
-      for (int i = 0; i < 6; i++) {
-        T v = g[i];
-#pragma unroll
-        for (int k2 = 0; k2 < i; k2++) v -= S6[s6(k2, i)] * g[k2];
-        g[i] = v * Ld[i];
-        nn += g[i] * g[i];
-      }
+      for (int i = 0; i < 6; i++) nn += g[i] * g[i];
       dinv[k][dd] = T(1) / (nn + Hd[dd]);
     }
     // warm start of the normal impulse (Bullet m_warmstartingFactor)
@@ -558,16 +655,10 @@ __host__ __device__ void physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
     }
     // ---- apply: base twist change L^-T z, joint change W lam - B dnu_b
     T dnu[6];
-#pragma unroll
-    for (int i = 5; i >= 0; i--) {
-      T v = z[i];
-#pragma unroll
-      for (int k2 = i + 1; k2 < 6; k2++) v -= S6[s6(i, k2)] * dnu[k2];
-      dnu[i] = v * Ld[i];
-    }
+    chol_bwd(S6, Ld, z, dnu);
     T dw[3], dv[3];
-    m3_v(Rb, dnu, dw);
-    m3_v(Rb, dnu + 3, dv);
+    m3_v(X.Rb, dnu, dw);
+    m3_v(X.Rb, dnu + 3, dv);
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       st.vang[i] = clamp_vel(st.vang[i] + dw[i], mcv);
@@ -589,35 +680,310 @@ __host__ __device__ void physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
   cs.invalid = invalid;
 #pragma unroll
   for (int k = 0; k < 4; k++) cs.lam_n[k] = lam[k][0];
+  integrate_positions(st, dt);
+  return false;
+}
 
-  // ---- integrate positions with the new velocities (btMultiBody::stepPositionsMultiDof)
+// ------------------------------------------------------------------------------------------
+// GENERAL tick (rare path): joint-limit rows, one contact point per collision shape
+// (trunk, imu, hips, thighs, calves, feet) with normal + 2 friction rows each, solved by
+// the same reduced-space PGS with one extra 3-vector per leg:
+//   w_r = Y_r . z + Jk_r . delta_leg(r),   z += Y_r dI,   delta_leg += M_kk^-1 Jk_r^T dI.
+// Row order is the oracle's (Bullet's): limits (alternating direction), all normals in
+// link order (trunk, imu, then hip/thigh/calf/foot per leg), all friction cones.
+// Rows live in local memory: this runs for the handful of envs the fast tick hands over.
+// ------------------------------------------------------------------------------------------
+constexpr int QS_MAX_CONTACTS = 17;
+constexpr int QS_MAX_LIMITS = 12;
+
+template <typename T> struct GenRow {
+  T Y[6], Jk[3], Wk[3], dinv, rhs, lam;
+  int leg;  // -1: base only
+};
+
+template <typename T>
+QS_DEV void gen_build_row(GenRow<T>& r, int leg, const T* Jb, const T* Jk, const T* Mi, const T* Bm, const T* S6,
+                          const T* Ld, const T* wb1, const T* vb1, const T* qd_leg, T* rel_out) {
+  r.leg = leg;
+  T rel = T(0);
+  if (Jb) rel = Jb[0] * wb1[0] + Jb[1] * wb1[1] + Jb[2] * wb1[2] + Jb[3] * vb1[0] + Jb[4] * vb1[1] + Jb[5] * vb1[2];
 #pragma unroll
-  for (int i = 0; i < 3; i++) st.pos[i] += dt * st.vlin[i];
-  {
-    const T* om = st.vang;
-    T ang = sqrt_t(dot3(om, om));
-    if (ang * dt > T(0.25 * QS_PI)) ang = T(0.25 * QS_PI) / dt;
-    T sc, cw;
-    if (ang < T(0.001)) {
-      sc = T(0.5) * dt - dt * dt * dt * T(0.020833333333) * ang * ang;
-      T sdummy;
-      sincos_t(T(0.5) * ang * dt, &sdummy, &cw);
-    } else {
-      T sn;
-      sincos_t(T(0.5) * ang * dt, &sn, &cw);
-      sc = sn / ang;
-    }
-    const T ax = om[0] * sc, ay = om[1] * sc, az = om[2] * sc;
-    const T* q = st.quat;
-    const T nw = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
-    const T nx = cw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
-    const T ny = cw * q[1] - ax * q[2] + ay * q[3] + az * q[0];
-    const T nz = cw * q[2] + ax * q[1] - ay * q[0] + az * q[3];
-    const T inv = rsqrt_t(nx * nx + ny * ny + nz * nz + nw * nw);
-    st.quat[0] = nx * inv; st.quat[1] = ny * inv; st.quat[2] = nz * inv; st.quat[3] = nw * inv;
+  for (int c = 0; c < 6; c++) r.Y[c] = Jb ? Jb[c] : T(0);
+  T hdiag = T(0);
+  if (leg >= 0) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) r.Jk[j] = Jk[j];
+    r.Wk[0] = Mi[0] * Jk[0] + Mi[1] * Jk[1] + Mi[2] * Jk[2];
+    r.Wk[1] = Mi[1] * Jk[0] + Mi[3] * Jk[1] + Mi[4] * Jk[2];
+    r.Wk[2] = Mi[2] * Jk[0] + Mi[4] * Jk[1] + Mi[5] * Jk[2];
+#pragma unroll
+    for (int c = 0; c < 6; c++) r.Y[c] -= Jk[0] * Bm[c] + Jk[1] * Bm[6 + c] + Jk[2] * Bm[12 + c];
+    hdiag = Jk[0] * r.Wk[0] + Jk[1] * r.Wk[1] + Jk[2] * r.Wk[2];
+    rel += Jk[0] * qd_leg[0] + Jk[1] * qd_leg[1] + Jk[2] * qd_leg[2];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 3; j++) { r.Jk[j] = T(0); r.Wk[j] = T(0); }
   }
+  chol_fwd(S6, Ld, r.Y);
+  T nn = T(0);
 #pragma unroll
-  for (int i = 0; i < 12; i++) st.q[i] += dt * st.qd[i];
+  for (int c = 0; c < 6; c++) nn += r.Y[c] * r.Y[c];
+  r.dinv = T(1) / (nn + hdiag);
+  r.lam = T(0);
+  *rel_out = rel;
+}
+
+template <typename T> QS_DEV T gen_row_w(const GenRow<T>& r, const T* z, const T (*delta)[3]) {
+  T w = T(0);
+#pragma unroll
+  for (int c = 0; c < 6; c++) w += r.Y[c] * z[c];
+  if (r.leg >= 0) w += r.Jk[0] * delta[r.leg][0] + r.Jk[1] * delta[r.leg][1] + r.Jk[2] * delta[r.leg][2];
+  return w;
+}
+template <typename T> QS_DEV void gen_row_apply(const GenRow<T>& r, T dI, T* z, T (*delta)[3]) {
+#pragma unroll
+  for (int c = 0; c < 6; c++) z[c] += r.Y[c] * dI;
+  if (r.leg >= 0) { delta[r.leg][0] += r.Wk[0] * dI; delta[r.leg][1] += r.Wk[1] * dI; delta[r.leg][2] += r.Wk[2] * dI; }
+}
+
+// Jacobian of a point pc on body `level` (0 hip, 1 thigh, 2 calf/foot) of a leg
+template <typename T>
+QS_DEV void body_point_jac(const LegKin<T>& K, int level, const T* pc, const T* d, T* Jb, T* Jk) {
+  foot_jac_dir(K, pc, d, Jb, Jk);
+  if (level < 2) Jk[2] = T(0);
+  if (level < 1) Jk[1] = T(0);
+}
+
+template <typename T>
+__host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
+                                              const ModelConstT<T>& M, const SolverConst& SC) {
+  const T dt = T(SC.dt);
+  const T mcv = T(SC.max_coord_vel);
+  TickCtx<T> X;
+  tick_ctx(st, SC, X);
+  const T* nb = X.nb;
+  const T zero3[3] = {T(0), T(0), T(0)};
+  SpI<T> tot;
+  tot.m = M.trunk_m;
+  for (int i = 0; i < 3; i++) tot.h[i] = M.trunk_h[i];
+  for (int i = 0; i < 6; i++) tot.I[i] = M.trunk_I[i];
+  T fb[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  body_force(tot, X.wb, X.vb, zero3, X.A0, fb, fb + 3);
+  T S6[21];
+  for (int i = 0; i < 21; i++) S6[i] = T(0);
+  T Bm[4][18], ev[4][3], Mi[4][6];
+  LegKin<T> K[4];
+  // contact candidates in link order; level -1 = trunk body
+  struct Cand { int leg, level, foot; T pc[3]; T gap; };
+  Cand cand[QS_MAX_CONTACTS];
+  int ncand = 0, invalid = 0, active = 0;
+  // trunk box and imu box (link order: trunk, imu come first)
+  {
+    T zt, zi;
+    trunk_shape_gaps(st, X, M, &zt, &zi);
+    if (zt < M.trunk_thresh) {
+      Cand& c = cand[ncand++];
+      c.leg = -1; c.level = -1; c.foot = 0; c.gap = zt;
+      for (int a = 0; a < 3; a++) c.pc[a] = (nb[a] > T(0) ? -M.trunk_half[a] : M.trunk_half[a]);
+      invalid++;
+    }
+    if (zi < M.imu_thresh) {
+      Cand& c = cand[ncand++];
+      c.leg = -1; c.level = -1; c.foot = 0; c.gap = zi;
+      for (int a = 0; a < 3; a++) c.pc[a] = M.imu_pos[a] + (nb[a] > T(0) ? -M.imu_half : M.imu_half);
+      invalid++;
+    }
+  }
+  for (int k = 0; k < 4; k++) {
+    leg_kin(k, st.q + 3 * k, M, K[k]);
+    T RH[9], RT[9], RC[9];
+    link_rotations(K[k], RH, RT, RC);
+    leg_dynamics(k, st.q + 3 * k, st.qd + 3 * k, tau + 3 * k, X, M, K[k], RH, RT, RC, Mi[k], Bm[k], ev[k], S6, fb, tot);
+    T zh, zt, zc;
+    leg_shape_gaps(st, X, M, K[k], RT, RC, &zh, &zt, &zc);
+    if (zh < M.hip_thresh) {  // lowest point of the lower rim of the hip cylinder (axis a2)
+      Cand& c = cand[ncand++];
+      c.leg = k; c.level = 0; c.foot = 0; c.gap = zh;
+      const T nz = dot3(nb, K[k].a2);
+      T dn[3] = {nb[0] - nz * K[k].a2[0], nb[1] - nz * K[k].a2[1], nb[2] - nz * K[k].a2[2]};
+      const T n2 = dot3(dn, dn);
+      T rad[3];
+      if (n2 > T(1e-18)) { const T sc = M.hip_r * rsqrt_t(n2); for (int a = 0; a < 3; a++) rad[a] = -dn[a] * sc; }
+      else { rad[0] = M.hip_r; rad[1] = T(0); rad[2] = T(0); }
+      const T sg = nz > T(0) ? T(-1) : T(1);
+      for (int a = 0; a < 3; a++) c.pc[a] = K[k].r1[a] + sg * M.hip_hl * K[k].a2[a] + rad[a];
+      invalid++;
+    }
+    if (zt < M.thigh_thresh || zc < M.calf_thresh) {
+      for (int b = 0; b < 2; b++) {
+        const bool hit = b == 0 ? (zt < M.thigh_thresh) : (zc < M.calf_thresh);
+        if (!hit) continue;
+        const T* R = b == 0 ? RT : RC;
+        const T* half = b == 0 ? M.thigh_half : M.calf_half;
+        const T* cen = b == 0 ? M.thigh_c : M.calf_c;
+        const T* org = b == 0 ? K[k].r2 : K[k].r3;
+        Cand& c = cand[ncand++];
+        c.leg = k; c.level = 1 + b; c.foot = 0; c.gap = b == 0 ? zt : zc;
+        T loc[3];
+        for (int a = 0; a < 3; a++) {
+          const T nza = nb[0] * R[a] + nb[1] * R[3 + a] + nb[2] * R[6 + a];
+          loc[a] = cen[a] + (nza > T(0) ? -half[a] : half[a]);
+        }
+        T w3[3];
+        m3_v(R, loc, w3);
+        for (int a = 0; a < 3; a++) c.pc[a] = org[a] + w3[a];
+        invalid++;
+      }
+    }
+    const T gf = st.pos[2] + dot3(nb, K[k].r4) - M.foot_radius;
+    if (gf < M.foot_thresh) {
+      Cand& c = cand[ncand++];
+      c.leg = k; c.level = 2; c.foot = 1; c.gap = gf;
+      for (int a = 0; a < 3; a++) c.pc[a] = K[k].r4[a] - M.foot_radius * nb[a];
+      active |= 1 << k;
+    }
+  }
+  T Ld[6];
+  base_factor(tot, S6, Ld);
+  T ab[6];
+  {
+    T y[6];
+    for (int i = 0; i < 6; i++) y[i] = -fb[i];
+    chol_fwd(S6, Ld, y);
+    chol_bwd(S6, Ld, y, ab);
+  }
+  ab[3] += X.wxv[0]; ab[4] += X.wxv[1]; ab[5] += X.wxv[2];
+  T wb1[3], vb1[3];
+  base_velocity_update(st, X, ab, dt, mcv, wb1, vb1);
+  for (int k = 0; k < 4; k++)
+    for (int j = 0; j < 3; j++) {
+      T acc = ev[k][j];
+      for (int c = 0; c < 6; c++) acc -= Bm[k][6 * j + c] * ab[c];
+      st.qd[3 * k + j] = clamp_vel(st.qd[3 * k + j] + dt * acc, mcv);
+    }
+
+  // ---- rows
+  GenRow<T> lim[QS_MAX_LIMITS];
+  GenRow<T> nrm[QS_MAX_CONTACTS];
+  GenRow<T> fr[2 * QS_MAX_CONTACTS];
+  int nlim = 0, nn = 0;
+  if (SC.enable_limits) {
+    for (int k = 0; k < 4; k++)
+      for (int j = 0; j < 3; j++)
+        for (int side = 0; side < 2; side++) {
+          const T qv = st.q[3 * k + j];
+          const T pen = side ? M.joint_hi[j] - qv : qv - M.joint_lo[j];
+          if (pen > T(0)) continue;
+          T Jk[3] = {T(0), T(0), T(0)};
+          Jk[j] = side ? T(-1) : T(1);
+          T rel;
+          gen_build_row(lim[nlim], k, (const T*)nullptr, Jk, Mi[k], Bm[k], S6, Ld, wb1, vb1, st.qd + 3 * k, &rel);
+          lim[nlim].rhs = -pen * T(SC.limit_erp) / dt - rel;
+          nlim++;
+        }
+  }
+  int foot_of_row[QS_MAX_CONTACTS];
+  for (int c = 0; c < ncand; c++) {
+    const Cand& cd = cand[c];
+    if (!cd.foot && !SC.body_response) continue;
+    foot_of_row[nn] = cd.foot ? cd.leg : -1;
+    for (int dd = 0; dd < 3; dd++) {
+      T Jb[6], Jk[3] = {T(0), T(0), T(0)};
+      if (cd.leg >= 0) body_point_jac(K[cd.leg], cd.level, cd.pc, X.tdir[dd], Jb, Jk);
+      else { cross3(cd.pc, X.tdir[dd], Jb); Jb[3] = X.tdir[dd][0]; Jb[4] = X.tdir[dd][1]; Jb[5] = X.tdir[dd][2]; }
+      GenRow<T>& r = dd == 0 ? nrm[nn] : fr[2 * nn + dd - 1];
+      T rel;
+      const int lg = cd.leg;
+      gen_build_row(r, lg, Jb, Jk, lg >= 0 ? Mi[lg] : (const T*)nullptr, lg >= 0 ? Bm[lg] : (const T*)nullptr, S6, Ld,
+                    wb1, vb1, lg >= 0 ? st.qd + 3 * lg : (const T*)nullptr, &rel);
+      if (dd == 0) {
+        const T dist = cd.gap + T(SC.linear_slop);
+        T pos_err = T(0), vel_err = -rel;
+        if (dist > T(0)) vel_err -= dist / dt; else pos_err = -dist * T(SC.contact_erp) / dt;
+        r.rhs = pos_err + vel_err;
+      } else {
+        r.rhs = -rel;
+      }
+    }
+    nn++;
+  }
+  T z[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  T delta[4][3];
+  for (int k = 0; k < 4; k++) delta[k][0] = delta[k][1] = delta[k][2] = T(0);
+  for (int r = 0; r < nn; r++) {  // warm start, feet only
+    const int f = foot_of_row[r];
+    if (f >= 0 && (cs.mask & (1 << f))) {
+      const T imp = cs.lam_n[f] * T(SC.warmstart);
+      nrm[r].lam = imp;
+      gen_row_apply(nrm[r], imp, z, delta);
+    }
+  }
+  if (nlim + nn > 0) {
+    const T thr = T(SC.residual_threshold);
+    for (int it = 0; it < SC.num_iterations; it++) {
+      T res = T(0);
+      for (int j = 0; j < nlim; j++) {
+        GenRow<T>& r = lim[(it & 1) ? j : nlim - 1 - j];
+        T dI = (r.rhs - gen_row_w(r, z, delta)) * r.dinv;
+        const T sum = r.lam + dI;
+        if (sum < T(0)) { dI = -r.lam; r.lam = T(0); }
+        else if (sum > T(100)) { dI = T(100) - r.lam; r.lam = T(100); }
+        else r.lam = sum;
+        gen_row_apply(r, dI, z, delta);
+        const T dv = dI / r.dinv;
+        res = tmax(res, dv * dv);
+      }
+      for (int j = 0; j < nn; j++) {
+        GenRow<T>& r = nrm[j];
+        T dI = (r.rhs - gen_row_w(r, z, delta)) * r.dinv;
+        const T sum = r.lam + dI;
+        if (sum < T(0)) { dI = -r.lam; r.lam = T(0); } else r.lam = sum;
+        gen_row_apply(r, dI, z, delta);
+        const T dv = dI / r.dinv;
+        res = tmax(res, dv * dv);
+      }
+      for (int j = 0; j < nn; j++) {
+        GenRow<T>& a = fr[2 * j];
+        GenRow<T>& b = fr[2 * j + 1];
+        T sa = a.lam + (a.rhs - gen_row_w(a, z, delta)) * a.dinv;
+        T sb = b.lam + (b.rhs - gen_row_w(b, z, delta)) * b.dinv;
+        const T limf = mu * T(SC.mu_link) * nrm[j].lam;
+        const T r2 = sa * sa + sb * sb;
+        if (r2 >= limf * limf) {
+          const T sc = r2 > T(0) ? limf * rsqrt_t(r2) : T(0);
+          sa *= sc; sb *= sc;
+        }
+        const T dIa = sa - a.lam, dIb = sb - b.lam;
+        a.lam = sa; b.lam = sb;
+        gen_row_apply(a, dIa, z, delta);
+        gen_row_apply(b, dIb, z, delta);
+        const T ra = dIa / a.dinv, rb = dIb / b.dinv;
+        res = tmax(res, ra * ra + rb * rb);
+      }
+      if (res <= thr) break;
+    }
+    T dnu[6];
+    chol_bwd(S6, Ld, z, dnu);
+    T dw[3], dv[3];
+    m3_v(X.Rb, dnu, dw);
+    m3_v(X.Rb, dnu + 3, dv);
+    for (int i = 0; i < 3; i++) {
+      st.vang[i] = clamp_vel(st.vang[i] + dw[i], mcv);
+      st.vlin[i] = clamp_vel(st.vlin[i] + dv[i], mcv);
+    }
+    for (int k = 0; k < 4; k++)
+      for (int j = 0; j < 3; j++) {
+        T acc = delta[k][j];
+        for (int c = 0; c < 6; c++) acc -= Bm[k][6 * j + c] * dnu[c];
+        st.qd[3 * k + j] = clamp_vel(st.qd[3 * k + j] + acc, mcv);
+      }
+  }
+  cs.mask = active;
+  cs.invalid = invalid;
+  for (int k = 0; k < 4; k++) cs.lam_n[k] = T(0);
+  for (int r = 0; r < nn; r++)
+    if (foot_of_row[r] >= 0) cs.lam_n[foot_of_row[r]] = nrm[r].lam;
+  integrate_positions(st, dt);
 }
 
 }  // namespace qs

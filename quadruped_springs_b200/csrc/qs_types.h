@@ -43,7 +43,7 @@ template <typename T> struct ModelConstT {
 struct SolverConst {
   float dt, gravity_z, contact_erp, limit_erp, linear_slop, warmstart, residual_threshold;
   float max_coord_vel, mu_link;
-  int32_t num_iterations, enable_limits;
+  int32_t num_iterations, enable_limits, body_response;
 };
 
 // Device view of the handle-owned SoA state (all arrays [dim][N]).
@@ -67,6 +67,11 @@ struct DeviceView {
   float* stats;       // [QS_STATS_DIM][N] finished-episode accumulators
   uint32_t* reset_count; // [N] number of resets (RNG stream separation)
   uint32_t* work;        // [3][N] k_step work counters: ticks, contact-ticks, contact-sweeps
+  float* cmd;            // [12][N] motor command of the current control step (slow-path hand-over)
+  int32_t* resume_tick;  // [N] tick at which the fast kernel handed the env to the general solver
+  float* slot;           // [66][N] spare settled state of the NEXT episode (see qs_step_kernels.cuh)
+  int32_t* slot_contact; // [N]
+  uint32_t* slot_epoch;  // [N] episode number the slot was settled for (0 = empty)
 };
 
 // task state slots (rows of DeviceView::task)

@@ -51,7 +51,7 @@ def tick_parity(n_ticks, contact, use_f64, n=256, seed=0):
     contact_bits = env._views["contact"].cpu().numpy()
     ff = env._views["foot_force"].cpu().numpy().T
     ref = np.zeros_like(S)
-    w = O.World(enable_limits=0, body_contact_response=0)
+    w = O.World()
     refc = np.zeros(n, dtype=int)
     reff = np.zeros((n, 4))
     iters = []

@@ -193,12 +193,13 @@ int qs_fk_jacobian(const float* q_dev, const float* qd_dev, float* pos_dev, floa
 /* Quadruped.ComputeInverseKinematics (quadruped.py:399-438): xyz [N,12] -> q [N,12] */
 int qs_ik(const float* xyz_dev, float* q_dev, int n, void* stream);
 /* HopfNetwork.update (hopf_network.py:117-173) + the Cartesian impedance law of
- * hopf_network.py:241-289.  X [N,8] (r[4], theta[4]) is updated in place;
+ * hopf_network.py:241-289.  X [N,8] float64 (r[4], theta[4]) is updated in place
+ * (float64 because the reference starts every phase ON the sin(theta) > 0 switch);
  * params9 = mu, omega_swing, omega_stance, coupling, dt, des_step_len,
  * robot_height, ground_clearance, ground_penetration; phi16 row-major PHI;
  * gains8 = kp3, kd3, kpCartesian, kdCartesian.  tau [N,12] out (may be NULL);
  * xs, zs [N,4] out (may be NULL). */
-int qs_cpg_update(float* X_dev, const float* params9, const float* phi16, const float* q_dev,
+int qs_cpg_update(double* X_dev, const double* params9, const double* phi16, const float* q_dev,
                   const float* qd_dev, const float* gains8, float foot_y, float* xs_dev,
                   float* zs_dev, float* tau_dev, int n, void* stream);
 /* rollout statistics of this shard (EvaluationWrapper infos,

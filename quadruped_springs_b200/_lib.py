@@ -101,7 +101,7 @@ EXPORTS = {
                                                                                 C.c_int, C.c_void_p]),
     "qs_fk_jacobian": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_void_p]),
     "qs_ik": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
-    "qs_cpg_update": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p,
+    "qs_cpg_update": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p, C.c_void_p,
                                 C.POINTER(C.c_float), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_void_p]),
     "qs_reduce_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

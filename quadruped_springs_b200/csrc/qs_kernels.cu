@@ -197,41 +197,45 @@ __global__ void k_ik(const float* __restrict__ xyz, float* __restrict__ q, int n
 }
 
 // -------------------------------------------------------------------- K4: Hopf CPG + impedance law
+// The oscillator state is kept in float64: the reference starts every phase exactly at 0 / +-pi,
+// i.e. ON the swing/stance switch `sin(theta) > 0` (hopf_network.py:150-153), where a float32 pi
+// would flip the branch.  It is ~60 FLOP per env and tick; the torque law below is fp32.
 struct CpgArgs {
-  float p[9], phi[16], gains[8], foot_y;
+  double p[9], phi[16];
+  float gains[8], foot_y;
 };
-__global__ void k_cpg(const __grid_constant__ CpgArgs P, float* __restrict__ X, const float* __restrict__ q,
+__global__ void k_cpg(const __grid_constant__ CpgArgs P, double* __restrict__ X, const float* __restrict__ q,
                       const float* __restrict__ qd, float* __restrict__ xs_o, float* __restrict__ zs_o,
                       float* __restrict__ tau, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float mu = P.p[0], om_sw = P.p[1], om_st = P.p[2], coup = P.p[3], dt = P.p[4], dstep = P.p[5],
-              height = P.p[6], gc = P.p[7], gp = P.p[8];
-  float r0[4], th0[4], r1[4], th1[4], xs[4], zs[4];
+  const double mu = P.p[0], om_sw = P.p[1], om_st = P.p[2], coup = P.p[3], dt = P.p[4], dstep = P.p[5],
+               height = P.p[6], gc = P.p[7], gp = P.p[8];
+  double r0[4], th0[4], r1[4], th1[4];
+  float xs[4], zs[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) { r0[k] = X[size_t(i) * 8 + k]; th0[k] = X[size_t(i) * 8 + 4 + k]; }
   // hopf_network.py:137-173
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const float rd = 50.f * (mu - r0[k] * r0[k]) * r0[k];
-    float thd = sinf(th0[k]) > 0.f ? om_sw : om_st;
+    const double rd = 50.0 * (mu - r0[k] * r0[k]) * r0[k];
+    double thd = sin(th0[k]) > 0.0 ? om_sw : om_st;
 #pragma unroll
     for (int j = 0; j < 4; j++)
-      if (j != k) thd += r0[j] * coup * sinf(th0[j] - th0[k] - P.phi[4 * k + j]);
+      if (j != k) thd += r0[j] * coup * sin(th0[j] - th0[k] - P.phi[4 * k + j]);
     r1[k] = r0[k] + dt * rd;
-    float th = th0[k] + dt * thd;
-    th = fmodf(th, float(2 * QS_PI));
-    if (th < 0.f) th += float(2 * QS_PI);
+    double th = fmod(th0[k] + dt * thd, 2 * QS_PI);
+    if (th < 0.0) th += 2 * QS_PI;  // numpy % is a floored modulo
     th1[k] = th;
   }
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     X[size_t(i) * 8 + k] = r1[k];
     X[size_t(i) * 8 + 4 + k] = th1[k];
-    float s, c;
-    sincosf(th1[k], &s, &c);
-    xs[k] = -dstep * r1[k] * c;                              // hopf_network.py:126-133
-    zs[k] = s > 0.f ? -height + gc * s : -height + gp * s;
+    double s, c;
+    sincos(th1[k], &s, &c);
+    xs[k] = float(-dstep * r1[k] * c);                              // hopf_network.py:126-133
+    zs[k] = float(s > 0.0 ? -height + gc * s : -height + gp * s);
     if (xs_o) xs_o[size_t(i) * 4 + k] = xs[k];
     if (zs_o) zs_o[size_t(i) * 4 + k] = zs[k];
   }
@@ -763,7 +767,7 @@ int qs_ik(const float* xyz, float* q, int n, void* stream) {
   return QS_OK;
 }
 
-int qs_cpg_update(float* X, const float* params9, const float* phi16, const float* q, const float* qd,
+int qs_cpg_update(double* X, const double* params9, const double* phi16, const float* q, const float* qd,
                   const float* gains8, float foot_y, float* xs, float* zs, float* tau, int n, void* stream) {
   if (!X || !params9 || !phi16 || n <= 0) return fail(QS_ERR_ARG, "bad argument");
   if (tau && (!q || !qd || !gains8)) return fail(QS_ERR_ARG, "torque output needs q, qd and gains");

@@ -31,9 +31,10 @@ class HopfNetwork:
         g = torch.Generator(device="cpu")
         if seed is not None:
             g.manual_seed(seed)
-        X = torch.zeros(num_envs, 2, 4)
-        X[:, 0, :] = torch.rand(num_envs, 4, generator=g) * 0.1      # hopf_network.py:63-64
-        X[:, 1, :] = torch.as_tensor(self.PHI[0, :], dtype=torch.float32)
+        # float64 state: the phases start exactly on the swing/stance switch (see csrc K4)
+        X = torch.zeros(num_envs, 2, 4, dtype=torch.float64)
+        X[:, 0, :] = torch.rand(num_envs, 4, generator=g, dtype=torch.float64) * 0.1      # hopf_network.py:63-64
+        X[:, 1, :] = torch.as_tensor(self.PHI[0, :], dtype=torch.float64)
         self.X = X.to(self.device).contiguous()
         self._ground_clearance, self._ground_penetration = ground_clearance, ground_penetration
         self._robot_height, self._des_step_len = robot_height, des_step_len
@@ -54,8 +55,8 @@ class HopfNetwork:
     def _params(self):
         coupling = self._coupling_strength if self._couple else 0.0
         p = np.array([self._mu, self._omega_swing, self._omega_stance, coupling, self._dt, self._des_step_len,
-                      self._robot_height, self._ground_clearance, self._ground_penetration], dtype=np.float32)
-        phi = np.ascontiguousarray(self.PHI.reshape(16), dtype=np.float32)
+                      self._robot_height, self._ground_clearance, self._ground_penetration], dtype=np.float64)
+        phi = np.ascontiguousarray(self.PHI.reshape(16), dtype=np.float64)
         return p, phi
 
     def update(self, q=None, qd=None, kp=(150, 70, 70), kd=(2, 0.5, 0.5), kp_cartesian=2500.0, kd_cartesian=40.0,
@@ -76,7 +77,7 @@ class HopfNetwork:
             gains_p = gains.ctypes.data_as(C.POINTER(C.c_float))
         Xf = self.X.view(n, 8)
         _lib.check(self._L.qs_cpg_update(
-            _p(Xf), p.ctypes.data_as(C.POINTER(C.c_float)), phi.ctypes.data_as(C.POINTER(C.c_float)), _p(q), _p(qd),
+            _p(Xf), p.ctypes.data_as(C.POINTER(C.c_double)), phi.ctypes.data_as(C.POINTER(C.c_double)), _p(q), _p(qd),
             gains_p, float(foot_y), _p(xs), _p(zs), _p(tau), n,
             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         if tau is None:

@@ -90,16 +90,22 @@ __device__ __forceinline__ int run_ticks(EnvState<float>& st, ContactState<float
                                          bool torque_mode, int t0, int n_ticks, int env, const DeviceView& D,
                                          const EnvCfg& C, const RobotConst& RC, const ModelConstT<float>& M,
                                          const SolverConst& SC, float* tau_m /*12 out*/, float* tau_s /*12 out*/,
-                                         bool detect_invalid_last) {
+                                         bool detect_invalid_last, const Scratch<float>& scr) {
   const float mu = D.mu[env];
   float sk[3], sb[3], sr[3];
   load_springs(D, env, sk, sb, sr);
+  int bail = n_ticks;
   for (int t = t0; t < n_ticks; t++) {
-    float tau[12];
-    tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s);
-    if (physics_tick(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1))) return t;
+    // keep the warps of the block in lockstep: the tick is several times larger than the
+    // instruction cache, so warps that run it together share every fetched line
+    __syncthreads();
+    if (bail == n_ticks) {
+      float tau[12];
+      tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s);
+      if (physics_tick(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1), scr)) bail = t;
+    }
   }
-  return n_ticks;
+  return bail;
 }
 
 // same loop on the general solver (joint limits, every collision shape); rare path

@@ -90,7 +90,7 @@ template <typename T> struct DebugArgs {
   SolverConst SC;
 };
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 k_debug_ticks(const __grid_constant__ DebugArgs<T> A, const float* __restrict__ tau, int n_ticks) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   const DeviceView& D = A.D;
@@ -111,8 +111,10 @@ k_debug_ticks(const __grid_constant__ DebugArgs<T> A, const float* __restrict__ 
 #pragma unroll
   for (int i = 0; i < 12; i++) t12[i] = T(tau[size_t(env) * 12 + i]);
   const T mu = T(D.mu[env]);
+  extern __shared__ unsigned char qs_smem_raw[];
+  const Scratch<T> scr{reinterpret_cast<T*>(qs_smem_raw) + threadIdx.x, int(blockDim.x)};
   for (int t = 0; t < n_ticks; t++)
-    if (physics_tick<T>(st, t12, mu, cs, A.M, A.SC, true)) physics_tick_general<T>(st, t12, mu, cs, A.M, A.SC);
+    if (physics_tick<T>(st, t12, mu, cs, A.M, A.SC, true, scr)) physics_tick_general<T>(st, t12, mu, cs, A.M, A.SC);
 #pragma unroll
   for (int i = 0; i < 3; i++) { sf.pos[i] = float(st.pos[i]); sf.vlin[i] = float(st.vlin[i]); sf.vang[i] = float(st.vang[i]); }
 #pragma unroll
@@ -308,12 +310,9 @@ struct qs_env {
   ModelConstT<double> model_d;
   void* pool;       // one allocation backing every SoA array
   size_t pool_bytes;
-  int* lists;          // slow | reset | refill[0] | refill[1], each (cap + 1) ints with the count last
-  int *slow_list, *reset_list, *refill_list[2];
-  int refill_cap, cur_refill, steps_since_refill, refill_interval;
-  cudaStream_t side;   // low-priority stream of the slot refills
-  cudaEvent_t ev_main, ev_refill_done[2];
-  bool refill_pending[2];
+  int* lists;          // slow (n + 1) | reset (n + 1) | refill (2 * cap + 1), counts last
+  int *slow_list, *reset_list, *refill_list;
+  int refill_cap, refill_threshold;
   float* dev_actions;  // staging for qs_step_host
   float* dev_obs;
   float* dev_reward;
@@ -328,6 +327,8 @@ struct qs_env {
 };
 
 static inline unsigned grid_for(int n, int block) { return unsigned((n + block - 1) / block); }
+static int block_of(qs_handle h) { return h->cfg.block_size > 0 ? std::min(h->cfg.block_size, 256) : 128; }
+static size_t smem_of(int block) { return size_t(block) * QS_TICK_SCRATCH * sizeof(float); }
 
 extern "C" {
 
@@ -445,7 +446,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
 
   // one pool for all SoA arrays (4-byte elements), 256 B aligned segments
   const size_t n = size_t(n_envs);
-  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1 + 3 + 12 + 1 + SLOT_ROWS + 1 + 1;
+  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1 + 3 + 12 + 1 + QS_SLOTS * (SLOT_ROWS + 1 + 1);
   // rows of one array are contiguous with stride n floats; each array starts 256 B aligned
   h->pool_bytes = rows * n * 4 + 64 * 256;
   cudaError_t e = cudaMalloc(&h->pool, h->pool_bytes);
@@ -469,28 +470,31 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   D.reset_count = (uint32_t*)carve(1);
   D.work = (uint32_t*)carve(3);
   D.cmd = (float*)carve(12); D.resume_tick = (int32_t*)carve(1);
-  D.slot = (float*)carve(SLOT_ROWS); D.slot_contact = (int32_t*)carve(1); D.slot_epoch = (uint32_t*)carve(1);
+  D.slot = (float*)carve(QS_SLOTS * SLOT_ROWS); D.slot_contact = (int32_t*)carve(QS_SLOTS); D.slot_epoch = (uint32_t*)carve(QS_SLOTS);
   if (size_t(p - static_cast<char*>(h->pool)) > h->pool_bytes) { cudaFree(h->pool); delete h; return fail(QS_ERR_STATE, "pool overflow"); }
-  h->refill_cap = 2 * n_envs;
-  const size_t nints = 2 * (n + 1) + 2 * (size_t(h->refill_cap) + 1);
+  h->refill_cap = 2 * QS_SLOTS * n_envs;
+  // a refill runs when one full wave of settle blocks is pending (148 SMs x 2 blocks x 128 threads),
+  // or half the envs for small batches
+  h->refill_threshold = std::max(1, std::min(n_envs / 2, 148 * 2 * 128));
+  if (const char* v = std::getenv("QS_REFILL_THRESHOLD")) h->refill_threshold = std::max(1, std::atoi(v));
+  const size_t nints = 2 * (n + 1) + 2 * size_t(h->refill_cap) + 1;
   e = cudaMalloc(&h->lists, nints * sizeof(int));
   if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(QS_ERR_CUDA, "cudaMalloc lists"); }
   cudaMemset(h->lists, 0, nints * sizeof(int));
   h->slow_list = h->lists;
   h->reset_list = h->slow_list + n + 1;
-  h->refill_list[0] = h->reset_list + n + 1;
-  h->refill_list[1] = h->refill_list[0] + h->refill_cap + 1;
-  h->cur_refill = 0;
-  h->steps_since_refill = 0;
-  h->refill_interval = 16;
-  if (const char* v = std::getenv("QS_REFILL_INTERVAL")) h->refill_interval = std::max(1, std::atoi(v));
-  int lo_prio = 0, hi_prio = 0;
-  cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
-  e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo_prio);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_refill_done[0], cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_refill_done[1], cudaEventDisableTiming);
-  if (e != cudaSuccess) { cudaFree(h->pool); cudaFree(h->lists); delete h; return fail(QS_ERR_CUDA, "stream/event creation"); }
+  h->refill_list = h->reset_list + n + 1;
+  {
+    const int max_smem = int(smem_of(256));
+    e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_refill, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_debug_ticks<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   int(64 * QS_TICK_SCRATCH * sizeof(double)));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_debug_ticks<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   int(64 * QS_TICK_SCRATCH * sizeof(float)));
+    if (e != cudaSuccess) { cudaFree(h->pool); cudaFree(h->lists); delete h; return fail(QS_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
+  }
   *out = h;
   return QS_OK;
 }
@@ -498,12 +502,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
 int qs_destroy(qs_handle h) {
   if (!h) return fail(QS_ERR_ARG, "handle is NULL");
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->side);
   cudaDeviceSynchronize();
-  cudaStreamDestroy(h->side);
-  cudaEventDestroy(h->ev_main);
-  cudaEventDestroy(h->ev_refill_done[0]);
-  cudaEventDestroy(h->ev_refill_done[1]);
   cudaFree(h->pool);
   cudaFree(h->lists);
   if (h->dev_actions) cudaFree(h->dev_actions);
@@ -551,6 +550,19 @@ int qs_work_counters(qs_handle h, uint64_t* out3, void* stream) {
   return QS_OK;
 }
 
+int qs_debug_counters(qs_handle h, int32_t* out3, void* stream) {
+  // {envs handed to the general solver, envs reset in place (no spare slot ready), refill entries pending}
+  // as left by the last qs_step; synchronises
+  if (!h || !out3) return fail(QS_ERR_ARG, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemcpyAsync(out3 + 0, h->slow_list + h->n, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(out3 + 1, h->reset_list + h->n, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(out3 + 2, h->refill_list + 2 * h->refill_cap, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return QS_OK;
+}
+
 int qs_action_dim(qs_handle h) { return h ? h->args.C.action_dim : QS_ERR_ARG; }
 int qs_obs_dim(qs_handle h) { return h ? h->args.C.obs_dim : QS_ERR_ARG; }
 int qs_num_envs(qs_handle h) { return h ? h->n : QS_ERR_ARG; }
@@ -564,29 +576,15 @@ int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* o) {
   return QS_OK;
 }
 
-static int block_of(qs_handle h) { return h->cfg.block_size > 0 ? h->cfg.block_size : 128; }
 
-// launch the refill of the current list on the side stream and switch lists
-static int launch_refill(qs_handle h, cudaStream_t s, bool on_main) {
+// pre-settle queued episodes; a no-op kernel pair unless `threshold` entries are pending
+static int launch_refill(qs_handle h, cudaStream_t s, int threshold, float* obs) {
   const int B = block_of(h);
-  const int cur = h->cur_refill;
-  cudaStream_t rs = on_main ? s : h->side;
-  if (!on_main) {
-    CUDA_TRY(cudaEventRecord(h->ev_main, s));
-    CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_main, 0));
-  }
-  k_refill<<<grid_for(h->refill_cap, B), B, 0, rs>>>(h->args, h->refill_list[cur], h->refill_cap);
-  CUDA_TRY(cudaMemsetAsync(h->refill_list[cur] + h->refill_cap, 0, sizeof(int), rs));
-  CUDA_TRY(cudaEventRecord(h->ev_refill_done[cur], rs));
-  h->refill_pending[cur] = true;
-  g_launches += 1;
-  h->cur_refill = cur ^ 1;
-  // the list we switch to must have been drained by its previous refill
-  if (h->refill_pending[h->cur_refill]) {
-    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_refill_done[h->cur_refill], 0));
-    h->refill_pending[h->cur_refill] = false;
-  }
-  h->steps_since_refill = 0;
+  int* urgent = h->reset_list + h->n;  // in qs_step the reset-list counter counts urgent entries
+  k_refill<<<grid_for(h->refill_cap, B), B, smem_of(B), s>>>(h->args, h->refill_list, h->refill_cap, threshold, urgent, obs);
+  k_refill_done<<<1, 1, 0, s>>>(h->refill_list, h->refill_cap, threshold, urgent);
+  g_launches += 2;
+  CUDA_TRY(cudaGetLastError());
   return QS_OK;
 }
 
@@ -595,21 +593,21 @@ int qs_reset(qs_handle h, const uint8_t* mask, float* obs, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(h->device));
   const int B = block_of(h);
-  int* rl = h->refill_list[h->cur_refill];
+  int* rl = h->refill_list;
   if (mask) {
     CUDA_TRY(cudaMemsetAsync(h->reset_list + h->n, 0, sizeof(int), s));
     k_compact<<<grid_for(h->n, 256), 256, 0, s>>>(mask, h->n, h->reset_list);
-    k_reset<<<grid_for(h->n, B), B, 0, s>>>(h->args, h->reset_list, rl, h->refill_cap, obs);
+    k_reset<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, h->reset_list, rl, h->refill_cap, obs);
     g_launches += 2;
   } else {
-    k_reset<<<grid_for(h->n, B), B, 0, s>>>(h->args, nullptr, rl, h->refill_cap, obs);
+    k_reset<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, nullptr, rl, h->refill_cap, obs);
     g_launches += 1;
   }
   CUDA_TRY(cudaGetLastError());
   if (h->cfg.auto_reset) {
     // (re)fill the spare slots of the envs just reset, in stream order
-    if (int e = launch_refill(h, s, true)) return e;
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemsetAsync(h->reset_list + h->n, 0, sizeof(int), s));
+    if (int e = launch_refill(h, s, 1, obs)) return e;
   }
   h->was_reset = true;
   return QS_OK;
@@ -633,21 +631,19 @@ int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_
   StepIO io;
   io.actions = actions; io.obs = obs; io.reward = reward; io.done = done; io.truncated = truncated;
   io.slow_list = h->slow_list; io.reset_list = h->reset_list;
-  io.refill_list = h->refill_list[h->cur_refill]; io.refill_cap = h->refill_cap;
+  io.refill_list = h->refill_list; io.refill_cap = h->refill_cap;
   const int slot = int(h->n_steps % qs_env::kRing);
   cudaEventRecord(h->ev0[slot], s);
-  k_step<<<grid_for(h->n, B), B, 0, s>>>(h->args, io);
+  k_step<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
   cudaEventRecord(h->ev1[slot], s);
   h->n_steps++;
   // envs parked for the general solver (joint limits / body contacts): usually none
   k_step_slow<<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io);
   g_launches += 2;
   if (h->cfg.auto_reset) {
-    // envs whose spare slot was not ready restart in place (usually none)
-    k_reset<<<grid_for(h->n, B), B, 0, s>>>(h->args, h->reset_list, io.refill_list, h->refill_cap, obs);
-    g_launches += 1;
-    if (++h->steps_since_refill >= h->refill_interval)
-      if (int e = launch_refill(h, s, false)) return e;
+    // pre-settle queued episodes when a full wave is pending; also starts, right now, the episodes of
+    // envs that finished without a ready slot (urgent entries; rare)
+    if (int e = launch_refill(h, s, h->refill_threshold, obs)) return e;
   }
   CUDA_TRY(cudaGetLastError());
   return QS_OK;
@@ -710,11 +706,11 @@ int qs_debug_ticks(qs_handle h, const float* tau, int n_ticks, int use_f64, void
   if (use_f64) {
     DebugArgs<double> a;
     a.D = h->args.D; a.M = h->model_d; a.SC = h->args.SC;
-    k_debug_ticks<double><<<grid_for(h->n, 128), 128, 0, s>>>(a, tau, n_ticks);
+    k_debug_ticks<double><<<grid_for(h->n, 64), 64, 64 * QS_TICK_SCRATCH * sizeof(double), s>>>(a, tau, n_ticks);
   } else {
     DebugArgs<float> a;
     a.D = h->args.D; a.M = h->args.M; a.SC = h->args.SC;
-    k_debug_ticks<float><<<grid_for(h->n, 128), 128, 0, s>>>(a, tau, n_ticks);
+    k_debug_ticks<float><<<grid_for(h->n, 64), 64, 64 * QS_TICK_SCRATCH * sizeof(float), s>>>(a, tau, n_ticks);
   }
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());

@@ -270,7 +270,7 @@ QS_DEV void leg_dynamics(int k, const T* q, const T* qd, const T* tau3, const Ti
   // inverse of the symmetric 3x3 (adjugate)
   const T c00 = M22 * M33 - M23 * M23, c01 = M13 * M23 - M12 * M33, c02 = M12 * M23 - M13 * M22;
   const T c11 = M11 * M33 - M13 * M13, c12 = M12 * M13 - M11 * M23, c22 = M11 * M22 - M12 * M12;
-  const T idet = T(1) / (M11 * c00 + M12 * c01 + M13 * c02);
+  const T idet = div_t(T(1), M11 * c00 + M12 * c01 + M13 * c02);
   Mi[0] = c00 * idet; Mi[1] = c01 * idet; Mi[2] = c02 * idet; Mi[3] = c11 * idet; Mi[4] = c12 * idet; Mi[5] = c22 * idet;
   const T t1 = tau3[0] - h1, t2 = tau3[1] - h2, t3 = tau3[2] - h3;
   const T d0 = Mi[0] * t1 + Mi[1] * t2 + Mi[2] * t3;
@@ -392,7 +392,7 @@ template <typename T> QS_DEV void integrate_positions(EnvState<T>& st, T dt) {
   for (int i = 0; i < 3; i++) st.pos[i] += dt * st.vlin[i];
   const T* om = st.vang;
   T ang = sqrt_t(dot3(om, om));
-  if (ang * dt > T(0.25 * QS_PI)) ang = T(0.25 * QS_PI) / dt;
+  if (ang * dt > T(0.25 * QS_PI)) ang = div_t(T(0.25 * QS_PI), dt);
   T sc, cw;
   if (ang < T(0.001)) {
     sc = T(0.5) * dt - dt * dt * dt * T(0.020833333333) * ang * ang;
@@ -401,7 +401,7 @@ template <typename T> QS_DEV void integrate_positions(EnvState<T>& st, T dt) {
   } else {
     T sn;
     sincos_t(T(0.5) * ang * dt, &sn, &cw);
-    sc = sn / ang;
+    sc = div_t(sn, ang);
   }
   const T ax = om[0] * sc, ay = om[1] * sc, az = om[2] * sc;
   const T* q = st.quat;
@@ -416,22 +416,50 @@ template <typename T> QS_DEV void integrate_positions(EnvState<T>& st, T dt) {
 }
 
 // ------------------------------------------------------------------------------------------
-// FAST tick: foot contacts only (the overwhelmingly common case), everything in registers.
+// FAST tick: foot contacts only (the overwhelmingly common case).
+//
+// Code-size discipline: the per-leg work is ONE rolled loop body (the instruction cache, not
+// the FP32 pipe, bounded the fully unrolled version: ncu showed ~85% "no instruction" stalls),
+// so per-leg results that later phases need go through a small per-thread scratch area
+// (shared memory in the kernels, [slot][thread] layout => conflict-free); the PGS rows of the
+// four feet live in registers because the sweep loop re-reads them up to 30 times.
+//
 // tau = joint torques of this tick (motor + spring).  cs: in = previous tick's contact
 // impulses (warm start), out = this tick's.  Returns true WITHOUT touching the state when
 // the tick needs the general solver (a joint at its limit, or a non-foot shape on the
 // ground while SC.body_response is set); the caller then hands the env to physics_tick_general.
 // ------------------------------------------------------------------------------------------
+constexpr int QS_LEG_SCRATCH = 18 + 3 + 6 + 6 + 9 + 9;      // Bm, ev, Mi, sincos, W, (q, qd, tau)
+constexpr int QS_TICK_SCRATCH = 4 * QS_LEG_SCRATCH;          // floats per thread
+
+template <typename T> struct Scratch {
+  T* p;        // this thread's first element
+  int stride;  // elements between consecutive slots of one thread
+  QS_DEV T& operator()(int leg, int slot) const { return p[(leg * QS_LEG_SCRATCH + slot) * stride]; }
+};
+enum { SCR_BM = 0, SCR_EV = 18, SCR_MI = 21, SCR_SC = 27, SCR_W = 33, SCR_Q = 42, SCR_QD = 45, SCR_TAU = 48 };
+
+template <typename T> QS_DEV void leg_kin_from_sc(int k, const T* sc, const ModelConstT<T>& M, LegKin<T>& K) {
+  K.s1 = sc[0]; K.c1 = sc[1]; K.s2 = sc[2]; K.c2 = sc[3]; K.s23 = sc[4]; K.c23 = sc[5];
+  K.a2[0] = T(0); K.a2[1] = K.c1; K.a2[2] = K.s1;
+  const T l = M.link_len, dy = M.thigh_off_y[k];
+#pragma unroll
+  for (int i = 0; i < 3; i++) K.r1[i] = M.hip_pos[k][i];
+  K.r2[0] = K.r1[0]; K.r2[1] = K.r1[1] + dy * K.c1; K.r2[2] = K.r1[2] + dy * K.s1;
+  K.r3[0] = K.r2[0] - l * K.s2; K.r3[1] = K.r2[1] + l * K.s1 * K.c2; K.r3[2] = K.r2[2] - l * K.c1 * K.c2;
+  K.r4[0] = K.r3[0] - l * K.s23; K.r4[1] = K.r3[1] + l * K.s1 * K.c23; K.r4[2] = K.r3[2] - l * K.c1 * K.c23;
+}
+
 template <typename T>
 __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
-                                      const ModelConstT<T>& M, const SolverConst& SC, bool detect_invalid) {
+                                      const ModelConstT<T>& M, const SolverConst& SC, bool detect_invalid,
+                                      const Scratch<T>& scr) {
   const T dt = T(SC.dt);
+  const T idt = div_t(T(1), dt);
   const T mcv = T(SC.max_coord_vel);
   TickCtx<T> X;
   tick_ctx(st, SC, X);
   const T* nb = X.nb;
-  const T* wb = X.wb;
-  const T* vb = X.vb;
   const T zero3[3] = {T(0), T(0), T(0)};
 
   // composite inertia of the whole robot and Newton-Euler base force, trunk first
@@ -442,64 +470,52 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
 #pragma unroll
   for (int i = 0; i < 6; i++) tot.I[i] = M.trunk_I[i];
   T fb[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-  body_force(tot, wb, vb, zero3, X.A0, fb, fb + 3);
-
+  body_force(tot, X.wb, X.vb, zero3, X.A0, fb, fb + 3);
   T S6[21];
 #pragma unroll
   for (int i = 0; i < 21; i++) S6[i] = T(0);
 
-  // per-leg results kept for the later phases
-  T Bm[4][18];  // M_kk^-1 F_k            (3x6)
-  T ev[4][3];   // M_kk^-1 (tau - h) + B_lin (w x v)
-  T G[4][18];   // contact rows G, later Y = L^-1 G^T   (3 dirs x 6)
-  T H[4][6];    // J_kk M_kk^-1 J_kk^T (sym 3x3: nn n1 n2 11 12 22)
-  T W[4][9];    // M_kk^-1 J_kk^T, W[j*3+dir]
-  T cvel[4][3]; // J nu of the part that does not depend on the base solve
-  T gap[4];
   int active = 0, invalid = 0;
   bool need_general = false;
   const bool watch_shapes = detect_invalid || SC.body_response;
 
+  // joint state and torques go through the scratch so that the rolled loops can index them by leg
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const T* q = st.q + 3 * k;
-    const T* qd = st.qd + 3 * k;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      scr(k, SCR_Q + j) = st.q[3 * k + j];
+      scr(k, SCR_QD + j) = st.qd[3 * k + j];
+      scr(k, SCR_TAU + j) = tau[3 * k + j];
+    }
+  }
+
+  // ---- pass A: one rolled loop over the legs
+#pragma unroll 1
+  for (int k = 0; k < 4; k++) {
+    const T q[3] = {scr(k, SCR_Q), scr(k, SCR_Q + 1), scr(k, SCR_Q + 2)};
+    const T qd[3] = {scr(k, SCR_QD), scr(k, SCR_QD + 1), scr(k, SCR_QD + 2)};
+    const T tk[3] = {scr(k, SCR_TAU), scr(k, SCR_TAU + 1), scr(k, SCR_TAU + 2)};
     LegKin<T> K;
     leg_kin(k, q, M, K);
-    T RH[9], RT[9], RC[9], Mi[6];
+    T RH[9], RT[9], RC[9], Mi[6], Bm[18], ev[3];
     link_rotations(K, RH, RT, RC);
-    leg_dynamics(k, q, qd, tau + 3 * k, X, M, K, RH, RT, RC, Mi, Bm[k], ev[k], S6, fb, tot);
+    leg_dynamics(k, q, qd, tk, X, M, K, RH, RT, RC, Mi, Bm, ev, S6, fb, tot);
+#pragma unroll
+    for (int i = 0; i < 18; i++) scr(k, SCR_BM + i) = Bm[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) scr(k, SCR_EV + i) = ev[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) scr(k, SCR_MI + i) = Mi[i];
+    scr(k, SCR_SC + 0) = K.s1; scr(k, SCR_SC + 1) = K.c1; scr(k, SCR_SC + 2) = K.s2;
+    scr(k, SCR_SC + 3) = K.c2; scr(k, SCR_SC + 4) = K.s23; scr(k, SCR_SC + 5) = K.c23;
     if (SC.enable_limits) {
 #pragma unroll
       for (int j = 0; j < 3; j++) need_general |= (q[j] <= M.joint_lo[j]) | (q[j] >= M.joint_hi[j]);
     }
-
-    // ---- collision detection on the poses at the start of the tick
-    gap[k] = st.pos[2] + dot3(nb, K.r4) - M.foot_radius;
-    if (gap[k] < M.foot_thresh) {
-      active |= 1 << k;
-      const T pc[3] = {K.r4[0] - M.foot_radius * nb[0], K.r4[1] - M.foot_radius * nb[1],
-                       K.r4[2] - M.foot_radius * nb[2]};
-      T Jk[3][3];
-#pragma unroll
-      for (int dd = 0; dd < 3; dd++) {
-        T Jb[6];
-        foot_jac_dir(K, pc, X.tdir[dd], Jb, Jk[dd]);
-#pragma unroll
-        for (int c = 0; c < 6; c++)
-          G[k][6 * dd + c] = Jb[c] - (Jk[dd][0] * Bm[k][c] + Jk[dd][1] * Bm[k][6 + c] + Jk[dd][2] * Bm[k][12 + c]);
-        W[k][0 * 3 + dd] = Mi[0] * Jk[dd][0] + Mi[1] * Jk[dd][1] + Mi[2] * Jk[dd][2];
-        W[k][1 * 3 + dd] = Mi[1] * Jk[dd][0] + Mi[3] * Jk[dd][1] + Mi[4] * Jk[dd][2];
-        W[k][2 * 3 + dd] = Mi[2] * Jk[dd][0] + Mi[4] * Jk[dd][1] + Mi[5] * Jk[dd][2];
-        cvel[k][dd] = Jb[0] * wb[0] + Jb[1] * wb[1] + Jb[2] * wb[2] + Jb[3] * vb[0] + Jb[4] * vb[1] + Jb[5] * vb[2] +
-                      Jk[dd][0] * (qd[0] + dt * ev[k][0]) + Jk[dd][1] * (qd[1] + dt * ev[k][1]) +
-                      Jk[dd][2] * (qd[2] + dt * ev[k][2]);
-      }
-#define QS_H(a, b) (Jk[a][0] * W[k][0 * 3 + b] + Jk[a][1] * W[k][1 * 3 + b] + Jk[a][2] * W[k][2 * 3 + b])
-      H[k][0] = QS_H(0, 0); H[k][1] = QS_H(0, 1); H[k][2] = QS_H(0, 2);
-      H[k][3] = QS_H(1, 1); H[k][4] = QS_H(1, 2); H[k][5] = QS_H(2, 2);
-#undef QS_H
-    }
+    // collision detection on the poses at the start of the tick
+    const T gap = st.pos[2] + dot3(nb, K.r4) - M.foot_radius;
+    if (gap < M.foot_thresh) active |= 1 << k;
     if (watch_shapes) {
       // non-foot shapes vs the plane: support-function distance below the link's
       // contact breaking threshold (quadruped.py:243-249 -> invalid contact)
@@ -532,79 +548,94 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
 
   // ---- v += dt a, clamped like btMultiBody::applyDeltaVeeMultiDof
   T wb1[3], vb1[3];
-  const bool base_clamped = base_velocity_update(st, X, ab, dt, mcv, wb1, vb1);
-  int leg_clamped = 0;
-#pragma unroll
+  base_velocity_update(st, X, ab, dt, mcv, wb1, vb1);
+#pragma unroll 1
   for (int k = 0; k < 4; k++) {
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-      T acc = ev[k][j];
+      T acc = scr(k, SCR_EV + j);
 #pragma unroll
-      for (int c = 0; c < 6; c++) acc -= Bm[k][6 * j + c] * ab[c];
-      const T v1 = st.qd[3 * k + j] + dt * acc;
-      st.qd[3 * k + j] = clamp_vel(v1, mcv);
-      if (st.qd[3 * k + j] != v1) leg_clamped |= 1 << k;
+      for (int c = 0; c < 6; c++) acc -= scr(k, SCR_BM + 6 * j + c) * ab[c];
+      scr(k, SCR_QD + j) = clamp_vel(scr(k, SCR_QD + j) + dt * acc, mcv);
     }
   }
 
-  // ---- contact rows: right-hand sides, Y = L^-1 G^T, diagonal
-  T rhs[4][3], dinv[4][3], lam[4][3];
-  T z[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-  const T db[6] = {wb1[0] - wb[0], wb1[1] - wb[1], wb1[2] - wb[2], vb1[0] - vb[0], vb1[1] - vb[1], vb1[2] - vb[2]};
+  if (active) {
+    // ---- contact rows of the active feet (rolled loop), results routed into registers
+    T Y[4][18], H[4][6], rhs[4][3], dinv[4][3], lam[4][3];
+    T z[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    lam[k][0] = lam[k][1] = lam[k][2] = T(0);
-    if (!(active & (1 << k))) continue;
-    T rel[3];
-    if (base_clamped || (leg_clamped & (1 << k))) {
-      // rare: a velocity clamp fired, evaluate J nu* directly
+    for (int k = 0; k < 4; k++) lam[k][0] = lam[k][1] = lam[k][2] = T(0);
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+      if (!(active & (1 << k))) continue;
+      T sc[6], Mi[6], Bm[18];
+#pragma unroll
+      for (int i = 0; i < 6; i++) { sc[i] = scr(k, SCR_SC + i); Mi[i] = scr(k, SCR_MI + i); }
+#pragma unroll
+      for (int i = 0; i < 18; i++) Bm[i] = scr(k, SCR_BM + i);
       LegKin<T> K;
-      leg_kin(k, st.q + 3 * k, M, K);
+      leg_kin_from_sc(k, sc, M, K);
+      const T gap = st.pos[2] + dot3(nb, K.r4) - M.foot_radius;
       const T pc[3] = {K.r4[0] - M.foot_radius * nb[0], K.r4[1] - M.foot_radius * nb[1],
                        K.r4[2] - M.foot_radius * nb[2]};
+      const T qk[3] = {scr(k, SCR_QD), scr(k, SCR_QD + 1), scr(k, SCR_QD + 2)};
+      T y[18], h[6], r3[3], di[3], Jk[3][3], Wl[9];
 #pragma unroll
       for (int dd = 0; dd < 3; dd++) {
-        T Jb[6], Jk[3];
-        foot_jac_dir(K, pc, X.tdir[dd], Jb, Jk);
-        rel[dd] = Jb[0] * wb1[0] + Jb[1] * wb1[1] + Jb[2] * wb1[2] + Jb[3] * vb1[0] + Jb[4] * vb1[1] + Jb[5] * vb1[2] +
-                  Jk[0] * st.qd[3 * k] + Jk[1] * st.qd[3 * k + 1] + Jk[2] * st.qd[3 * k + 2];
+        T Jb[6];
+        foot_jac_dir(K, pc, X.tdir[dd], Jb, Jk[dd]);
+        // J nu* evaluated directly on the updated velocities
+        r3[dd] = Jb[0] * wb1[0] + Jb[1] * wb1[1] + Jb[2] * wb1[2] + Jb[3] * vb1[0] + Jb[4] * vb1[1] + Jb[5] * vb1[2] +
+                 Jk[dd][0] * qk[0] + Jk[dd][1] * qk[1] + Jk[dd][2] * qk[2];
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+          y[6 * dd + c] = Jb[c] - (Jk[dd][0] * Bm[c] + Jk[dd][1] * Bm[6 + c] + Jk[dd][2] * Bm[12 + c]);
+        Wl[0 * 3 + dd] = Mi[0] * Jk[dd][0] + Mi[1] * Jk[dd][1] + Mi[2] * Jk[dd][2];
+        Wl[1 * 3 + dd] = Mi[1] * Jk[dd][0] + Mi[3] * Jk[dd][1] + Mi[4] * Jk[dd][2];
+        Wl[2 * 3 + dd] = Mi[2] * Jk[dd][0] + Mi[4] * Jk[dd][1] + Mi[5] * Jk[dd][2];
       }
-    } else {
+#define QS_H(a, b) (Jk[a][0] * Wl[0 * 3 + b] + Jk[a][1] * Wl[1 * 3 + b] + Jk[a][2] * Wl[2 * 3 + b])
+      h[0] = QS_H(0, 0); h[1] = QS_H(0, 1); h[2] = QS_H(0, 2);
+      h[3] = QS_H(1, 1); h[4] = QS_H(1, 2); h[5] = QS_H(2, 2);
+#undef QS_H
+#pragma unroll
+      for (int i = 0; i < 9; i++) scr(k, SCR_W + i) = Wl[i];
+      const T dist = gap + T(SC.linear_slop);
+      T pos_err = T(0), vel_err = -r3[0];
+      if (dist > T(0)) vel_err -= dist * idt; else pos_err = -dist * T(SC.contact_erp) * idt;
+      r3[0] = pos_err + vel_err;
+      r3[1] = -r3[1];
+      r3[2] = -r3[2];
+      const T hd[3] = {h[0], h[3], h[5]};
 #pragma unroll
       for (int dd = 0; dd < 3; dd++) {
-        T r = cvel[k][dd];
+        chol_fwd(S6, Ld, y + 6 * dd);
+        T nn = T(0);
 #pragma unroll
-        for (int c = 0; c < 6; c++) r += G[k][6 * dd + c] * db[c];
-        rel[dd] = r;
+        for (int i = 0; i < 6; i++) nn += y[6 * dd + i] * y[6 * dd + i];
+        di[dd] = div_t(T(1), nn + hd[dd]);
       }
-    }
-    const T dist = gap[k] + T(SC.linear_slop);
-    T pos_err = T(0), vel_err = -rel[0];
-    if (dist > T(0)) vel_err -= dist / dt; else pos_err = -dist * T(SC.contact_erp) / dt;
-    rhs[k][0] = pos_err + vel_err;
-    rhs[k][1] = -rel[1];
-    rhs[k][2] = -rel[2];
-    const T Hd[3] = {H[k][0], H[k][3], H[k][5]};
+      // warm start of the normal impulse (Bullet m_warmstartingFactor)
+      T l0 = T(0);
+      if (cs.mask & (1 << k)) {
+        l0 = cs.lam_n[k] * T(SC.warmstart);
 #pragma unroll
-    for (int dd = 0; dd < 3; dd++) {
-      T* g = G[k] + 6 * dd;
-      chol_fwd(S6, Ld, g);
-      T nn = T(0);
-#pragma unroll
-      for (int i = 0; i < 6; i++) nn += g[i] * g[i];
-      dinv[k][dd] = T(1) / (nn + Hd[dd]);
+        for (int i = 0; i < 6; i++) z[i] += y[i] * l0;
+      }
+      // route into the register file (static indices only)
+#define QS_ROUTE(KK)                                                                    \
+  case KK: {                                                                            \
+    _Pragma("unroll") for (int i = 0; i < 18; i++) Y[KK][i] = y[i];                      \
+    _Pragma("unroll") for (int i = 0; i < 6; i++) H[KK][i] = h[i];                       \
+    _Pragma("unroll") for (int i = 0; i < 3; i++) { rhs[KK][i] = r3[i]; dinv[KK][i] = di[i]; } \
+    lam[KK][0] = l0;                                                                    \
+  } break;
+      switch (k) { QS_ROUTE(0) QS_ROUTE(1) QS_ROUTE(2) default: QS_ROUTE(3) }
+#undef QS_ROUTE
     }
-    // warm start of the normal impulse (Bullet m_warmstartingFactor)
-    if (cs.mask & (1 << k)) {
-      const T imp = cs.lam_n[k] * T(SC.warmstart);
-      lam[k][0] = imp;
-#pragma unroll
-      for (int i = 0; i < 6; i++) z[i] += G[k][i] * imp;
-    }
-  }
 
-  // ---- projected Gauss-Seidel (rows: normals of all feet, then friction cones)
-  if (active) {
+    // ---- projected Gauss-Seidel (rows: normals of all feet, then friction cones)
     const T thr = T(SC.residual_threshold);
     const int iters = SC.num_iterations;
     const int nact = (active & 1) + ((active >> 1) & 1) + ((active >> 2) & 1) + ((active >> 3) & 1);
@@ -615,23 +646,23 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         if (!(active & (1 << k))) continue;
-        const T* Y = G[k];
+        const T* Yn = Y[k];
         T w = H[k][0] * lam[k][0] + H[k][1] * lam[k][1] + H[k][2] * lam[k][2];
 #pragma unroll
-        for (int i = 0; i < 6; i++) w += Y[i] * z[i];
+        for (int i = 0; i < 6; i++) w += Yn[i] * z[i];
         T dI = (rhs[k][0] - w) * dinv[k][0];
         const T sum = lam[k][0] + dI;
         if (sum < T(0)) { dI = -lam[k][0]; lam[k][0] = T(0); } else lam[k][0] = sum;
 #pragma unroll
-        for (int i = 0; i < 6; i++) z[i] += Y[i] * dI;
-        const T dv = dI / dinv[k][0];
+        for (int i = 0; i < 6; i++) z[i] += Yn[i] * dI;
+        const T dv = div_t(dI, dinv[k][0]);
         res = tmax(res, dv * dv);
       }
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         if (!(active & (1 << k))) continue;
-        const T* Ya = G[k] + 6;
-        const T* Yb = G[k] + 12;
+        const T* Ya = Y[k] + 6;
+        const T* Yb = Y[k] + 12;
         T wa = H[k][1] * lam[k][0] + H[k][3] * lam[k][1] + H[k][4] * lam[k][2];
         T wbb = H[k][2] * lam[k][0] + H[k][4] * lam[k][1] + H[k][5] * lam[k][2];
 #pragma unroll
@@ -641,14 +672,14 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
         const T lim = mu * T(SC.mu_link) * lam[k][0];
         const T r2 = sa * sa + sb * sb;
         if (r2 >= lim * lim) {
-          const T sc = r2 > T(0) ? lim * rsqrt_t(r2) : T(0);
-          sa *= sc; sb *= sc;
+          const T sc2 = r2 > T(0) ? lim * rsqrt_t(r2) : T(0);
+          sa *= sc2; sb *= sc2;
         }
         const T dIa = sa - lam[k][1], dIb = sb - lam[k][2];
         lam[k][1] = sa; lam[k][2] = sb;
 #pragma unroll
         for (int i = 0; i < 6; i++) z[i] += Ya[i] * dIa + Yb[i] * dIb;
-        const T ra = dIa / dinv[k][1], rb = dIb / dinv[k][2];
+        const T ra = div_t(dIa, dinv[k][1]), rb = div_t(dIb, dinv[k][2]);
         res = tmax(res, ra * ra + rb * rb);
       }
       if (res <= thr) break;
@@ -666,20 +697,29 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
+      const bool on = active & (1 << k);
 #pragma unroll
       for (int j = 0; j < 3; j++) {
         T acc = T(0);
 #pragma unroll
-        for (int c = 0; c < 6; c++) acc -= Bm[k][6 * j + c] * dnu[c];
-        if (active & (1 << k)) acc += W[k][3 * j] * lam[k][0] + W[k][3 * j + 1] * lam[k][1] + W[k][3 * j + 2] * lam[k][2];
-        st.qd[3 * k + j] = clamp_vel(st.qd[3 * k + j] + acc, mcv);
+        for (int c = 0; c < 6; c++) acc -= scr(k, SCR_BM + 6 * j + c) * dnu[c];
+        if (on) acc += scr(k, SCR_W + 3 * j) * lam[k][0] + scr(k, SCR_W + 3 * j + 1) * lam[k][1] +
+                       scr(k, SCR_W + 3 * j + 2) * lam[k][2];
+        st.qd[3 * k + j] = clamp_vel(scr(k, SCR_QD + j) + acc, mcv);
       }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) cs.lam_n[k] = lam[k][0];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      cs.lam_n[k] = T(0);
+#pragma unroll
+      for (int j = 0; j < 3; j++) st.qd[3 * k + j] = scr(k, SCR_QD + j);
     }
   }
   cs.mask = active;
   cs.invalid = invalid;
-#pragma unroll
-  for (int k = 0; k < 4; k++) cs.lam_n[k] = lam[k][0];
   integrate_positions(st, dt);
   return false;
 }

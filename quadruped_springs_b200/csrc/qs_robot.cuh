@@ -31,6 +31,17 @@ QS_DEV double asin_t(double x) { return asin(x); }
 QS_DEV float exp_t(float x) { return expf(x); }
 QS_DEV double exp_t(double x) { return exp(x); }
 QS_DEV float abs_t(float x) { return fabsf(x); }
+// division on the hot path: fp32 device code uses the 2-instruction approximate divide (<= 2 ulp,
+// no IEEE slow-path subroutine: the slow paths alone were ~10% of the tick's code size); the
+// fp64 check instantiation and host code divide exactly
+QS_DEV float div_t(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fdividef(a, b);
+#else
+  return a / b;
+#endif
+}
+QS_DEV double div_t(double a, double b) { return a / b; }
 QS_DEV double abs_t(double x) { return fabs(x); }
 
 // leg geometry used by the reference's analytic kinematics

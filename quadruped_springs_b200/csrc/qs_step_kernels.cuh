@@ -11,10 +11,12 @@
 //
 // Auto-reset without stalls: the state an env starts its next episode from is a pure
 // function of (seed, global env id, episode number): mu ~ U[0.5,1) from Philox, then the
-// reference's 2500 settle ticks.  k_refill computes it ahead of time into a per-env slot in
-// large, dense batches on a low-priority side stream; a finished env just copies its slot
-// inside k_step.  If the slot is not ready the env falls back to k_reset in place -- same
-// numbers either way, so results do not depend on scheduling.
+// reference's 2500 settle ticks.  Each env owns a ring of QS_SLOTS spare slots holding its
+// next episodes' settled states; a finished env copies its slot inside k_step and queues an
+// (env, episode) refill entry.  k_refill is launched after every step but returns at once
+// unless a machine-filling batch of entries is pending, so the 2500-tick settles always run
+// as dense, full-occupancy launches.  If a slot is not ready the env falls back to k_reset in
+// place -- same numbers either way, so results never depend on scheduling or sharding.
 #pragma once
 
 // settling / reset-time command: _convert_reference_to_command(get_init_pose())
@@ -101,13 +103,17 @@ struct StepIO {
   uint8_t* truncated;
   int* slow_list;    // envs parked for the general solver, slow_list[n] = count
   int* reset_list;   // envs that must be reset in place,   reset_list[n] = count
-  int* refill_list;  // envs whose spare slot was consumed, refill_list[refill_cap] = count
+  int* refill_list;  // (env, episode) pairs to pre-settle, refill_list[2 * refill_cap] = count
   int refill_cap;
 };
 
-__device__ __forceinline__ void refill_push(int* list, int cap, int env) {
-  const int i = atomicAdd(list + cap, 1);
-  if (i < cap) list[i] = env;  // an overflowing entry is only a missed prefetch: the env falls back to k_reset
+constexpr int QS_SLOTS = 2;
+constexpr uint32_t QS_URGENT = 0x80000000u;  // refill entry flag: settle AND start the episode now (no slot was ready)
+
+__device__ __forceinline__ void refill_push(int* list, int cap, int env, uint32_t epoch) {
+  const int i = atomicAdd(list + 2 * cap, 1);
+  // an overflowing entry is only a missed prefetch: the env falls back to k_reset
+  if (i < cap) { list[2 * i] = env; list[2 * i + 1] = int(epoch); }
 }
 
 // ---- spare slot of an env: the settled state its next episode starts from
@@ -118,7 +124,8 @@ __device__ __forceinline__ void slot_store(const DeviceView& D, int env, const E
                                            const ContactState<float>& cs, const float* tau_m, const float* tau_s,
                                            float mu, uint32_t epoch, float dt) {
   const int n = D.n;
-  float* s = D.slot + env;
+  const int sl = int(epoch % QS_SLOTS);
+  float* s = D.slot + size_t(sl) * SLOT_ROWS * n + env;
 #pragma unroll
   for (int i = 0; i < 3; i++) s[i * n] = st.pos[i];
 #pragma unroll
@@ -136,15 +143,15 @@ __device__ __forceinline__ void slot_store(const DeviceView& D, int env, const E
 #pragma unroll
   for (int k = 0; k < 4; k++) s[(61 + k) * n] = cs.lam_n[k] / dt;
   s[65 * n] = mu;
-  D.slot_contact[env] = (cs.mask & 15) | (cs.invalid << 8);
-  __threadfence();  // data before the epoch tag: a concurrent k_step either sees a complete slot or none
-  *reinterpret_cast<volatile uint32_t*>(D.slot_epoch + env) = epoch;
+  D.slot_contact[sl * n + env] = (cs.mask & 15) | (cs.invalid << 8);
+  D.slot_epoch[sl * n + env] = epoch;
 }
 
-__device__ __forceinline__ void slot_load(const DeviceView& D, int env, EnvState<float>& st, ContactState<float>& cs,
-                                          float* tau_m, float* tau_s, float* mu, float dt) {
+__device__ __forceinline__ void slot_load(const DeviceView& D, int env, uint32_t epoch, EnvState<float>& st,
+                                          ContactState<float>& cs, float* tau_m, float* tau_s, float* mu, float dt) {
   const int n = D.n;
-  const float* s = D.slot + env;
+  const int sl = int(epoch % QS_SLOTS);
+  const float* s = D.slot + size_t(sl) * SLOT_ROWS * n + env;
 #pragma unroll
   for (int i = 0; i < 3; i++) st.pos[i] = __ldcg(s + i * n);
 #pragma unroll
@@ -162,7 +169,7 @@ __device__ __forceinline__ void slot_load(const DeviceView& D, int env, EnvState
 #pragma unroll
   for (int k = 0; k < 4; k++) cs.lam_n[k] = __ldcg(s + (61 + k) * n) * dt;
   *mu = __ldcg(s + 65 * n);
-  const int c = __ldcg(D.slot_contact + env);
+  const int c = __ldcg(D.slot_contact + sl * n + env);
   cs.mask = c & 15;
   cs.invalid = c >> 8;
   cs.work_contacts = 0;
@@ -173,10 +180,15 @@ __device__ __forceinline__ void slot_load(const DeviceView& D, int env, EnvState
 // (quadruped_gym_env.py:278-289,323-327; env_randomizer.py:287-289).
 __device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint64_t gid, uint32_t epoch,
                                              EnvState<float>& st, ContactState<float>& cs, float* tau_m, float* tau_s,
-                                             float* mu_out) {
+                                             float* mu_out, const Scratch<float>& scr, bool need) {
+  // `need` = this thread really settles; the others only keep the block's barriers matched.
+  // Must be called by every thread of the block.
+  if (!__syncthreads_or(need)) return;
   const EnvCfg& C = A.C;
   const float mu = C.ground_randomizer ? 0.5f + 0.5f * uniform1(C.seed, gid, epoch, 100) : C.mu_ground;
-  *mu_out = mu;
+  if (need) *mu_out = mu;
+  EnvState<float> st_keep = st;  // a thread that does not need the settle gets its state back untouched
+  ContactState<float> cs_keep = cs;
   st.pos[0] = 0.f; st.pos[1] = 0.f; st.pos[2] = 0.32f;  // INIT_POSITION, configs:23
   st.quat[0] = st.quat[1] = st.quat[2] = 0.f; st.quat[3] = 1.f;
 #pragma unroll
@@ -198,6 +210,7 @@ __device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint6
 #pragma unroll
   for (int j = 0; j < 3; j++) { sk[j] = A.RC.spring_k[j]; sb[j] = A.RC.spring_b[j]; sr[j] = A.RC.spring_rest[j]; }
   for (int t = 0; t < nsettle; t++) {
+    __syncthreads();  // lockstep across the block (see run_ticks)
     float tau[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
@@ -212,8 +225,9 @@ __device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint6
         for (int j = 0; j < 3; j++) tau[3 * k + j] += tau_s[3 * k + j];
       }
     }
-    physics_tick(st, tau, mu, cs, A.M, SCs, t == nsettle - 1);
+    if (need) physics_tick(st, tau, mu, cs, A.M, SCs, t == nsettle - 1, scr);
   }
+  if (!need) { st = st_keep; cs = cs_keep; }
 }
 
 // Everything QuadrupedGymEnv.reset does after the settle (quadruped_gym_env.py:282-297),
@@ -309,18 +323,23 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
 #pragma unroll
     for (int i = 0; i < TS_END; i++) D.task[i * n + env] = ts[i];  // BackFlip.max_pitch survives resets
     const uint32_t epoch = D.reset_count[env] + 1;
-    const uint32_t have = *reinterpret_cast<volatile uint32_t*>(D.slot_epoch + env);
-    if (have == epoch) {
-      __threadfence();
+    uint32_t* tag = D.slot_epoch + int(epoch % QS_SLOTS) * n + env;
+    if (*tag == epoch) {
       float tm[12], tsp[12], mu;
-      slot_load(D, env, st, cs, tm, tsp, &mu, dt);
-      D.slot_epoch[env] = 0;
-      refill_push(io.refill_list, io.refill_cap, env);
+      slot_load(D, env, epoch, st, cs, tm, tsp, &mu, dt);
+      *tag = 0;
+      refill_push(io.refill_list, io.refill_cap, env, epoch + QS_SLOTS);  // the freed slot's next tenant
       begin_episode(A, env, epoch, mu, st, cs, tm, tsp, io.obs);
     } else {
-      // spare slot not ready: exact in-place reset right after this kernel (same numbers)
+      // no spare slot ready: an urgent refill entry makes k_refill (launched right after this kernel)
+      // settle this episode now and start it; same numbers as the prefetched path
       store_state(D, env, st, cs, dt);
-      io.reset_list[atomicAdd(io.reset_list + n, 1)] = env;
+      refill_push(io.refill_list, io.refill_cap, env, epoch | QS_URGENT);
+#pragma unroll
+      for (int d = 1; d <= QS_SLOTS; d++)  // and its (empty or stale) ring is rebuilt in the same launch
+        if (D.slot_epoch[int((epoch + d) % QS_SLOTS) * n + env] != epoch + d)
+          refill_push(io.refill_list, io.refill_cap, env, epoch + d);
+      atomicAdd(io.reset_list + n, 1);  // urgent counter (forces the refill to run)
     }
     return;
   }
@@ -341,13 +360,16 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
 }
 
 // -------------------------------------------------------------------- K1: step
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256, 1)
 k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
-  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const DeviceView& D = A.D;
   const EnvCfg& C = A.C;
   const int n = D.n;
-  if (env >= n) return;
+  // threads past the end shadow the last env (block-wide barriers inside run_ticks need every
+  // thread); they compute the same thing and write nothing
+  const bool live = tid < n;
+  const int env = live ? tid : n - 1;
   const float dt = A.SC.dt;
   EnvState<float> st;
   ContactState<float> cs;
@@ -357,8 +379,10 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
   float act[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) act[i] = i < C.action_dim ? io.actions[size_t(env) * C.action_dim + i] : 0.f;
+  if (live) {
 #pragma unroll
-  for (int i = 0; i < 12; i++) D.last_action[i * n + env] = act[i];
+    for (int i = 0; i < 12; i++) D.last_action[i * n + env] = act[i];
+  }
   if (C.enable_filter) {  // utils/action_filter.py:110-121
 #pragma unroll
     for (int i = 0; i < 12; i++) {
@@ -368,8 +392,10 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
         const float y0 = f[(2 * 12 + i) * n], y1 = f[(3 * 12 + i) * n];
         const float y = act[i] * A.RC.filt_b[0] + (x0 * A.RC.filt_b[1] + x1 * A.RC.filt_b[2]) -
                         (y0 * A.RC.filt_a[1] + y1 * A.RC.filt_a[2]);
-        f[(1 * 12 + i) * n] = x0; f[(0 * 12 + i) * n] = act[i];
-        f[(3 * 12 + i) * n] = y0; f[(2 * 12 + i) * n] = y;
+        if (live) {
+          f[(1 * 12 + i) * n] = x0; f[(0 * 12 + i) * n] = act[i];
+          f[(3 * 12 + i) * n] = y0; f[(2 * 12 + i) * n] = y;
+        }
         act[i] = y;
       }
     }
@@ -390,7 +416,10 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
 
   // ---- action_repeat substeps (:236-237)
   float tau_m[12], tau_s[12];
-  const int t_done = run_ticks(st, cs, cmd, torque_mode, 0, C.action_repeat, env, D, C, A.RC, A.M, A.SC, tau_m, tau_s, true);
+  extern __shared__ float qs_smem[];
+  const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
+  const int t_done = run_ticks(st, cs, cmd, torque_mode, 0, C.action_repeat, env, D, C, A.RC, A.M, A.SC, tau_m, tau_s, true, scr);
+  if (!live) return;
   if (t_done < C.action_repeat) {
     // park the env (state as of the start of tick t_done) for the general solver
     store_state(D, env, st, cs, dt);
@@ -428,52 +457,89 @@ k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io) {
 // -------------------------------------------------------------------- K2: reset + settle
 // list == nullptr: thread i resets env i (all envs).  Otherwise thread i resets env list[i]
 // for i < list[n] (dense warps whatever the done pattern).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256, 1)
 k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, int* __restrict__ refill_list,
         int refill_cap, float* __restrict__ obs) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const DeviceView& D = A.D;
   const int n = D.n;
-  int env = tid;
-  if (list) {
-    if (tid >= list[n]) return;
-    env = list[tid];
-  } else if (tid >= n) {
-    return;
-  }
+  const int count = list ? list[n] : n;
+  if (count == 0) return;                       // uniform over the grid
+  if (blockIdx.x * blockDim.x >= count) return;  // uniform over the block
+  const bool live = tid < count;                 // stragglers shadow the last entry and write nothing
+  const int idx = live ? tid : count - 1;
+  const int env = list ? list[idx] : idx;
   const uint64_t gid = uint64_t(A.C.gid0 + env);
   const uint32_t epoch = D.reset_count[env] + 1;
   EnvState<float> st;
   ContactState<float> cs;
   float tau_m[12], tau_s[12], mu;
-  const uint32_t have = *reinterpret_cast<volatile uint32_t*>(D.slot_epoch + env);
-  if (have == epoch) {
-    __threadfence();
-    slot_load(D, env, st, cs, tau_m, tau_s, &mu, A.SC.dt);
+  uint32_t* tag = D.slot_epoch + int(epoch % QS_SLOTS) * n + env;
+  const bool have = *tag == epoch;
+  extern __shared__ float qs_smem[];
+  const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
+  float tm2[12], ts2[12];
+  settle_fresh(A, env, gid, epoch, st, cs, tm2, ts2, &mu, scr, !have);
+  if (have) {
+    slot_load(D, env, epoch, st, cs, tau_m, tau_s, &mu, A.SC.dt);
   } else {
-    settle_fresh(A, env, gid, epoch, st, cs, tau_m, tau_s, &mu);
+#pragma unroll
+    for (int i = 0; i < 12; i++) { tau_m[i] = tm2[i]; tau_s[i] = ts2[i]; }
   }
-  if (A.C.auto_reset && have != epoch + 1) {  // spare slot consumed, empty or stale: queue a refill
-    D.slot_epoch[env] = 0;
-    refill_push(refill_list, refill_cap, env);
+  if (!live) return;
+  if (A.C.auto_reset) {
+    if (have) *tag = 0;
+    // every future episode within the ring must be present or queued (duplicates are skipped by k_refill)
+#pragma unroll
+    for (int d = 1; d <= QS_SLOTS; d++) {
+      const uint32_t e = epoch + d;
+      if (D.slot_epoch[int(e % QS_SLOTS) * n + env] != e) refill_push(refill_list, refill_cap, env, e);
+    }
   }
   begin_episode(A, env, epoch, mu, st, cs, tau_m, tau_s, obs);
 }
 
-// pre-settle the next episode of the listed envs into their spare slots
-__global__ void __launch_bounds__(128)
-k_refill(const __grid_constant__ KernelArgs A, const int* __restrict__ list, int cap) {
+// pre-settle queued (env, episode) pairs into the envs' spare slots.  Launched after every
+// step: returns immediately unless at least `threshold` entries are pending or an entry is
+// urgent (an env finished without a ready slot: its episode is settled and started here).
+__global__ void __launch_bounds__(256, 1)
+k_refill(const __grid_constant__ KernelArgs A, const int* __restrict__ list, int cap, int threshold,
+         const int* __restrict__ urgent_count, float* __restrict__ obs) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const DeviceView& D = A.D;
-  if (tid >= min(list[cap], cap)) return;
-  const int env = list[tid];
-  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(D.reset_count + env) + 1;
-  if (*reinterpret_cast<volatile uint32_t*>(D.slot_epoch + env) == epoch) return;  // duplicate entry
+  const int n = D.n;
+  const int count = min(list[2 * cap], cap);
+  if ((count < threshold && *urgent_count == 0) || count == 0) return;  // uniform over the grid
+  if (blockIdx.x * blockDim.x >= count) return;                          // uniform over the block
+  const bool live = tid < count;
+  const int i = live ? tid : count - 1;
+  const int env = list[2 * i];
+  const uint32_t raw = uint32_t(list[2 * i + 1]);
+  const bool urgent = (raw & QS_URGENT) != 0;
+  const uint32_t epoch = raw & ~QS_URGENT;
+  // skip duplicates and entries that became stale (the env moved past that episode)
+  const bool need = urgent ? (D.reset_count[env] + 1 == epoch)
+                           : (D.slot_epoch[int(epoch % QS_SLOTS) * n + env] != epoch && epoch > D.reset_count[env]);
   EnvState<float> st;
   ContactState<float> cs;
-  float tau_m[12], tau_s[12], mu;
-  settle_fresh(A, env, uint64_t(A.C.gid0 + env), epoch, st, cs, tau_m, tau_s, &mu);
-  slot_store(D, env, st, cs, tau_m, tau_s, mu, epoch, A.SC.dt);
+  float tau_m[12], tau_s[12], mu = 0.f;
+  extern __shared__ float qs_smem[];
+  const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
+  settle_fresh(A, env, uint64_t(A.C.gid0 + env), epoch, st, cs, tau_m, tau_s, &mu, scr, need);
+  if (!live || !need) return;
+  if (urgent) {
+    begin_episode(A, env, epoch, mu, st, cs, tau_m, tau_s, obs);
+  } else {
+    slot_store(D, env, st, cs, tau_m, tau_s, mu, epoch, A.SC.dt);
+  }
+}
+// clears the queue after a refill that ran (same trigger condition)
+__global__ void k_refill_done(int* __restrict__ list, int cap, int threshold, int* __restrict__ urgent_count) {
+  const int count = min(list[2 * cap], cap);
+  if ((count >= threshold || *urgent_count > 0) && count > 0) {
+    list[2 * cap] = 0;
+    *urgent_count = 0;
+  }
 }
 
 __global__ void k_compact(const uint8_t* __restrict__ mask, int n, int* __restrict__ list) {

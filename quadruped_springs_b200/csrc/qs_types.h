@@ -69,9 +69,9 @@ struct DeviceView {
   uint32_t* work;        // [3][N] k_step work counters: ticks, contact-ticks, contact-sweeps
   float* cmd;            // [12][N] motor command of the current control step (slow-path hand-over)
   int32_t* resume_tick;  // [N] tick at which the fast kernel handed the env to the general solver
-  float* slot;           // [66][N] spare settled state of the NEXT episode (see qs_step_kernels.cuh)
-  int32_t* slot_contact; // [N]
-  uint32_t* slot_epoch;  // [N] episode number the slot was settled for (0 = empty)
+  float* slot;           // [slots][66][N] settled states of the next episodes (see qs_step_kernels.cuh)
+  int32_t* slot_contact; // [slots][N]
+  uint32_t* slot_epoch;  // [slots][N] episode number the slot was settled for (0 = empty)
 };
 
 // task state slots (rows of DeviceView::task)

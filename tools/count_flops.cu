@@ -88,7 +88,8 @@ static Counts run(int n_contacts, int sweeps, bool springs, Counts* torque_only)
       for (int j = 0; j < 3; j++) tau[3 * k + j] += ts[j];
     }
   if (torque_only) *torque_only = {g_add, g_mul, g_div, g_sqrt, g_trig};
-  physics_tick<Cnt>(st, tau, Cnt(0.8), cs, M, SC, false);
+  static Cnt scratch[QS_TICK_SCRATCH];
+  physics_tick<Cnt>(st, tau, Cnt(0.8), cs, M, SC, false, Scratch<Cnt>{scratch, 1});
   int got = __builtin_popcount(cs.mask);
   if (got != n_contacts) std::fprintf(stderr, "WARNING: wanted %d contacts, got %d\n", n_contacts, got);
   return {g_add, g_mul, g_div, g_sqrt, g_trig};

@@ -156,6 +156,10 @@ int qs_reset(qs_handle h, const uint8_t* mask_dev, float* obs_dev, void* stream)
 int qs_step(qs_handle h, const float* actions_dev, float* obs_dev, float* reward_dev,
             uint8_t* done_dev, uint8_t* truncated_dev, void* stream);
 
+/* qs_reset with HOST buffers: mask_host [N] bytes or NULL (all), obs_host [N, O] or NULL;
+ * synchronises the stream. */
+int qs_reset_host(qs_handle h, const uint8_t* mask_host, float* obs_host, void* stream);
+
 /* same call with HOST buffers (pinned or pageable): H2D of actions, the step,
  * D2H of the four results, all on `stream`; returns after the stream is
  * synchronised.  This is the end-to-end path a numpy caller (SB3 VecEnv) uses. */

@@ -92,6 +92,7 @@ EXPORTS = {
     "qs_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qs_step": (C.c_int, [C.c_void_p] * 7),
     "qs_step_host": (C.c_int, [C.c_void_p] * 7),
+    "qs_reset_host": (C.c_int, [C.c_void_p] * 4),
     "qs_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "qs_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "qs_observe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -649,13 +649,8 @@ int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_
   return QS_OK;
 }
 
-int qs_step_host(qs_handle h, const float* actions, float* obs, float* reward, uint8_t* done, uint8_t* truncated,
-                 void* stream) {
-  if (!h) return fail(QS_ERR_ARG, "handle is NULL");
-  if (!actions || !obs || !reward || !done || !truncated) return fail(QS_ERR_ARG, "NULL buffer");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CUDA_TRY(cudaSetDevice(h->device));
-  const size_t n = size_t(h->n), A = size_t(h->args.C.action_dim), O = size_t(h->args.C.obs_dim);
+static int ensure_staging(qs_handle h) {
+  const size_t n = size_t(h->n);
   if (!h->dev_actions) {
     CUDA_TRY(cudaMalloc(&h->dev_actions, n * 12 * sizeof(float)));
     CUDA_TRY(cudaMalloc(&h->dev_obs, n * QS_MAX_OBS * sizeof(float)));
@@ -663,6 +658,31 @@ int qs_step_host(qs_handle h, const float* actions, float* obs, float* reward, u
     CUDA_TRY(cudaMalloc(&h->dev_done, 2 * n));
     h->dev_trunc = h->dev_done + n;
   }
+  return QS_OK;
+}
+
+int qs_reset_host(qs_handle h, const uint8_t* mask, float* obs, void* stream) {
+  if (!h) return fail(QS_ERR_ARG, "handle is NULL");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (int e = ensure_staging(h)) return e;
+  const size_t n = size_t(h->n), O = size_t(h->args.C.obs_dim);
+  if (mask) CUDA_TRY(cudaMemcpyAsync(h->dev_done, mask, n, cudaMemcpyHostToDevice, s));
+  if (obs && mask) CUDA_TRY(cudaMemcpyAsync(h->dev_obs, obs, n * O * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (int e = qs_reset(h, mask ? h->dev_done : nullptr, obs ? h->dev_obs : nullptr, stream)) return e;
+  if (obs) CUDA_TRY(cudaMemcpyAsync(obs, h->dev_obs, n * O * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return QS_OK;
+}
+
+int qs_step_host(qs_handle h, const float* actions, float* obs, float* reward, uint8_t* done, uint8_t* truncated,
+                 void* stream) {
+  if (!h) return fail(QS_ERR_ARG, "handle is NULL");
+  if (!actions || !obs || !reward || !done || !truncated) return fail(QS_ERR_ARG, "NULL buffer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t n = size_t(h->n), A = size_t(h->args.C.action_dim), O = size_t(h->args.C.obs_dim);
+  if (int e0 = ensure_staging(h)) return e0;
   CUDA_TRY(cudaMemcpyAsync(h->dev_actions, actions, n * A * sizeof(float), cudaMemcpyHostToDevice, s));
   if (int e = qs_step(h, h->dev_actions, h->dev_obs, h->dev_reward, h->dev_done, h->dev_trunc, stream)) return e;
   CUDA_TRY(cudaMemcpyAsync(obs, h->dev_obs, n * O * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -736,7 +736,7 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
 constexpr int QS_MAX_CONTACTS = 17;
 constexpr int QS_MAX_LIMITS = 12;
 
-template <typename T> struct GenRow {
+template <typename T> struct alignas(16) GenRow {
   T Y[6], Jk[3], Wk[3], dinv, rhs, lam;
   int leg;  // -1: base only
 };

@@ -494,6 +494,17 @@ class BatchedQuadrupedGymEnv:
         infos = {"TimeLimit.truncated": self._trunc.bool()}
         return self._obs, self._reward, self._done.bool(), infos
 
+    def reset_host(self, mask_np=None):
+        """numpy twin of reset(): returns the host observation array [N, O]"""
+        out = np.zeros((self.num_envs, self.obs_dim), np.float32)
+        m = None
+        if mask_np is not None:
+            m = np.ascontiguousarray(mask_np, dtype=np.uint8)
+            out[:] = self._obs.cpu().numpy()
+        _lib.check(self._L.qs_reset_host(self._h, m.ctypes.data_as(C.c_void_p) if m is not None else None,
+                                         out.ctypes.data_as(C.c_void_p), _stream_ptr(self.device)))
+        return out
+
     def step_host(self, action_np, out=None):
         """End-to-end numpy path (what an SB3 VecEnv adapter calls): host action
         [N, A] float32 -> host (obs, reward, done, truncated); copies are inside."""

@@ -132,6 +132,14 @@ def test_step_host_matches_device_step(qs):
         assert np.array_equal(d.astype(bool), dd.cpu().numpy())
 
 
+def test_reset_host_matches_device_reset(qs):
+    e1 = qs.BatchedQuadrupedGymEnv(num_envs=128, seed=9, auto_reset=False, **JIP)
+    e2 = qs.BatchedQuadrupedGymEnv(num_envs=128, seed=9, auto_reset=False, **JIP)
+    o1 = e1.reset_host()
+    o2 = e2.reset()
+    assert np.array_equal(o1, o2.cpu().numpy())
+
+
 def test_partial_reset_mask(qs):
     env = qs.BatchedQuadrupedGymEnv(num_envs=256, auto_reset=False, enable_noise=False, **JIP)
     env.reset()

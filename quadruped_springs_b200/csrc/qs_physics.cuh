@@ -736,54 +736,54 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
 constexpr int QS_MAX_CONTACTS = 17;
 constexpr int QS_MAX_LIMITS = 12;
 
+// A general row in dense form over u = [z(6), delta_leg0(3), ..., delta_leg3(3)]:
+//   w = a . u,  u += b dI   with a = [Y, Jk in the leg's slot], b = [Y, M_kk^-1 Jk^T in the leg's slot].
+// Dense rows cost twice the FMAs of the sparse form but keep u in registers with static indices, which
+// is what matters here: this path is bound by the latency of ONE thread's dependent chain.
 template <typename T> struct alignas(16) GenRow {
-  T Y[6], Jk[3], Wk[3], dinv, rhs, lam;
-  int leg;  // -1: base only
+  T a[18], b[18], dinv, rhs, lam, pad;
 };
 
 template <typename T>
 QS_DEV void gen_build_row(GenRow<T>& r, int leg, const T* Jb, const T* Jk, const T* Mi, const T* Bm, const T* S6,
                           const T* Ld, const T* wb1, const T* vb1, const T* qd_leg, T* rel_out) {
-  r.leg = leg;
   T rel = T(0);
   if (Jb) rel = Jb[0] * wb1[0] + Jb[1] * wb1[1] + Jb[2] * wb1[2] + Jb[3] * vb1[0] + Jb[4] * vb1[1] + Jb[5] * vb1[2];
+  T Y[6];
 #pragma unroll
-  for (int c = 0; c < 6; c++) r.Y[c] = Jb ? Jb[c] : T(0);
+  for (int c = 0; c < 6; c++) Y[c] = Jb ? Jb[c] : T(0);
+#pragma unroll
+  for (int c = 6; c < 18; c++) { r.a[c] = T(0); r.b[c] = T(0); }
   T hdiag = T(0);
   if (leg >= 0) {
+    const T W0 = Mi[0] * Jk[0] + Mi[1] * Jk[1] + Mi[2] * Jk[2];
+    const T W1 = Mi[1] * Jk[0] + Mi[3] * Jk[1] + Mi[4] * Jk[2];
+    const T W2 = Mi[2] * Jk[0] + Mi[4] * Jk[1] + Mi[5] * Jk[2];
 #pragma unroll
-    for (int j = 0; j < 3; j++) r.Jk[j] = Jk[j];
-    r.Wk[0] = Mi[0] * Jk[0] + Mi[1] * Jk[1] + Mi[2] * Jk[2];
-    r.Wk[1] = Mi[1] * Jk[0] + Mi[3] * Jk[1] + Mi[4] * Jk[2];
-    r.Wk[2] = Mi[2] * Jk[0] + Mi[4] * Jk[1] + Mi[5] * Jk[2];
-#pragma unroll
-    for (int c = 0; c < 6; c++) r.Y[c] -= Jk[0] * Bm[c] + Jk[1] * Bm[6 + c] + Jk[2] * Bm[12 + c];
-    hdiag = Jk[0] * r.Wk[0] + Jk[1] * r.Wk[1] + Jk[2] * r.Wk[2];
+    for (int c = 0; c < 6; c++) Y[c] -= Jk[0] * Bm[c] + Jk[1] * Bm[6 + c] + Jk[2] * Bm[12 + c];
+    hdiag = Jk[0] * W0 + Jk[1] * W1 + Jk[2] * W2;
     rel += Jk[0] * qd_leg[0] + Jk[1] * qd_leg[1] + Jk[2] * qd_leg[2];
-  } else {
-#pragma unroll
-    for (int j = 0; j < 3; j++) { r.Jk[j] = T(0); r.Wk[j] = T(0); }
+    r.a[6 + 3 * leg] = Jk[0]; r.a[7 + 3 * leg] = Jk[1]; r.a[8 + 3 * leg] = Jk[2];
+    r.b[6 + 3 * leg] = W0; r.b[7 + 3 * leg] = W1; r.b[8 + 3 * leg] = W2;
   }
-  chol_fwd(S6, Ld, r.Y);
+  chol_fwd(S6, Ld, Y);
   T nn = T(0);
 #pragma unroll
-  for (int c = 0; c < 6; c++) nn += r.Y[c] * r.Y[c];
-  r.dinv = T(1) / (nn + hdiag);
+  for (int c = 0; c < 6; c++) { nn += Y[c] * Y[c]; r.a[c] = Y[c]; r.b[c] = Y[c]; }
+  r.dinv = div_t(T(1), nn + hdiag);
   r.lam = T(0);
   *rel_out = rel;
 }
 
-template <typename T> QS_DEV T gen_row_w(const GenRow<T>& r, const T* z, const T (*delta)[3]) {
-  T w = T(0);
+template <typename T> QS_DEV T gen_row_w(const GenRow<T>& r, const T* u) {
+  T w0 = T(0), w1 = T(0), w2 = T(0);
 #pragma unroll
-  for (int c = 0; c < 6; c++) w += r.Y[c] * z[c];
-  if (r.leg >= 0) w += r.Jk[0] * delta[r.leg][0] + r.Jk[1] * delta[r.leg][1] + r.Jk[2] * delta[r.leg][2];
-  return w;
+  for (int c = 0; c < 18; c += 3) { w0 += r.a[c] * u[c]; w1 += r.a[c + 1] * u[c + 1]; w2 += r.a[c + 2] * u[c + 2]; }
+  return (w0 + w1) + w2;
 }
-template <typename T> QS_DEV void gen_row_apply(const GenRow<T>& r, T dI, T* z, T (*delta)[3]) {
+template <typename T> QS_DEV void gen_row_apply(const GenRow<T>& r, T dI, T* u) {
 #pragma unroll
-  for (int c = 0; c < 6; c++) z[c] += r.Y[c] * dI;
-  if (r.leg >= 0) { delta[r.leg][0] += r.Wk[0] * dI; delta[r.leg][1] += r.Wk[1] * dI; delta[r.leg][2] += r.Wk[2] * dI; }
+  for (int c = 0; c < 18; c++) u[c] += r.b[c] * dI;
 }
 
 // Jacobian of a point pc on body `level` (0 hip, 1 thigh, 2 calf/foot) of a leg
@@ -947,15 +947,15 @@ __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T m
     }
     nn++;
   }
-  T z[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
-  T delta[4][3];
-  for (int k = 0; k < 4; k++) delta[k][0] = delta[k][1] = delta[k][2] = T(0);
+  T u[18];
+#pragma unroll
+  for (int c = 0; c < 18; c++) u[c] = T(0);
   for (int r = 0; r < nn; r++) {  // warm start, feet only
     const int f = foot_of_row[r];
     if (f >= 0 && (cs.mask & (1 << f))) {
       const T imp = cs.lam_n[f] * T(SC.warmstart);
       nrm[r].lam = imp;
-      gen_row_apply(nrm[r], imp, z, delta);
+      gen_row_apply(nrm[r], imp, u);
     }
   }
   if (nlim + nn > 0) {
@@ -964,46 +964,46 @@ __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T m
       T res = T(0);
       for (int j = 0; j < nlim; j++) {
         GenRow<T>& r = lim[(it & 1) ? j : nlim - 1 - j];
-        T dI = (r.rhs - gen_row_w(r, z, delta)) * r.dinv;
+        T dI = (r.rhs - gen_row_w(r, u)) * r.dinv;
         const T sum = r.lam + dI;
         if (sum < T(0)) { dI = -r.lam; r.lam = T(0); }
         else if (sum > T(100)) { dI = T(100) - r.lam; r.lam = T(100); }
         else r.lam = sum;
-        gen_row_apply(r, dI, z, delta);
-        const T dv = dI / r.dinv;
+        gen_row_apply(r, dI, u);
+        const T dv = div_t(dI, r.dinv);
         res = tmax(res, dv * dv);
       }
       for (int j = 0; j < nn; j++) {
         GenRow<T>& r = nrm[j];
-        T dI = (r.rhs - gen_row_w(r, z, delta)) * r.dinv;
+        T dI = (r.rhs - gen_row_w(r, u)) * r.dinv;
         const T sum = r.lam + dI;
         if (sum < T(0)) { dI = -r.lam; r.lam = T(0); } else r.lam = sum;
-        gen_row_apply(r, dI, z, delta);
-        const T dv = dI / r.dinv;
+        gen_row_apply(r, dI, u);
+        const T dv = div_t(dI, r.dinv);
         res = tmax(res, dv * dv);
       }
       for (int j = 0; j < nn; j++) {
-        GenRow<T>& a = fr[2 * j];
-        GenRow<T>& b = fr[2 * j + 1];
-        T sa = a.lam + (a.rhs - gen_row_w(a, z, delta)) * a.dinv;
-        T sb = b.lam + (b.rhs - gen_row_w(b, z, delta)) * b.dinv;
+        GenRow<T>& ra = fr[2 * j];
+        GenRow<T>& rb = fr[2 * j + 1];
+        T sa = ra.lam + (ra.rhs - gen_row_w(ra, u)) * ra.dinv;
+        T sb = rb.lam + (rb.rhs - gen_row_w(rb, u)) * rb.dinv;
         const T limf = mu * T(SC.mu_link) * nrm[j].lam;
         const T r2 = sa * sa + sb * sb;
         if (r2 >= limf * limf) {
           const T sc = r2 > T(0) ? limf * rsqrt_t(r2) : T(0);
           sa *= sc; sb *= sc;
         }
-        const T dIa = sa - a.lam, dIb = sb - b.lam;
-        a.lam = sa; b.lam = sb;
-        gen_row_apply(a, dIa, z, delta);
-        gen_row_apply(b, dIb, z, delta);
-        const T ra = dIa / a.dinv, rb = dIb / b.dinv;
-        res = tmax(res, ra * ra + rb * rb);
+        const T dIa = sa - ra.lam, dIb = sb - rb.lam;
+        ra.lam = sa; rb.lam = sb;
+        gen_row_apply(ra, dIa, u);
+        gen_row_apply(rb, dIb, u);
+        const T qa = div_t(dIa, ra.dinv), qb = div_t(dIb, rb.dinv);
+        res = tmax(res, qa * qa + qb * qb);
       }
       if (res <= thr) break;
     }
     T dnu[6];
-    chol_bwd(S6, Ld, z, dnu);
+    chol_bwd(S6, Ld, u, dnu);
     T dw[3], dv[3];
     m3_v(X.Rb, dnu, dw);
     m3_v(X.Rb, dnu + 3, dv);
@@ -1011,9 +1011,11 @@ __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T m
       st.vang[i] = clamp_vel(st.vang[i] + dw[i], mcv);
       st.vlin[i] = clamp_vel(st.vlin[i] + dv[i], mcv);
     }
+#pragma unroll
     for (int k = 0; k < 4; k++)
+#pragma unroll
       for (int j = 0; j < 3; j++) {
-        T acc = delta[k][j];
+        T acc = u[6 + 3 * k + j];
         for (int c = 0; c < 6; c++) acc -= Bm[k][6 * j + c] * dnu[c];
         st.qd[3 * k + j] = clamp_vel(st.qd[3 * k + j] + acc, mcv);
       }

@@ -124,6 +124,8 @@ typedef struct qs_state_ptrs {
   int32_t* sim_steps;  /* [N] */
   int32_t* env_steps;  /* [N] */
   float* ep_return;    /* [N] */
+  uint8_t* custom_gains; /* [N] set non-zero after writing kp/kd of an env: the kernels then read its gains from
+                          * the arrays instead of the config constants; cleared by every reset of that env */
 } qs_state_ptrs;
 
 void qs_default_config(qs_config* cfg);

@@ -90,6 +90,7 @@ struct QsoWorld {
   int last_iters;
   int cone_clamped;
   int last_nlim, last_nnorm;
+  double max_fric_ratio; /* running max of |f_t| / (lambda_n) demanded before the cone projection */
 };
 
 /* ------------------------------------------------------------------ utils */
@@ -378,6 +379,7 @@ void qso_world_set_mass(QsoWorld* w, int pyb, double mass) {
 }
 int qso_world_last_iterations(const QsoWorld* w) { return w->last_iters; }
 int qso_world_cone_clamped(const QsoWorld* w) { return w->cone_clamped; }
+double qso_world_max_fric_ratio(QsoWorld* w, int reset) { double r = w->max_fric_ratio; if (reset) w->max_fric_ratio = 0; return r; }
 int qso_world_last_rows(const QsoWorld* w, int* nlim, int* nnorm) { *nlim = w->last_nlim; *nnorm = w->last_nnorm; return w->last_nlim + 3 * w->last_nnorm; }
 
 /* ------------------------------------------------------------- kinematics */
@@ -823,6 +825,11 @@ void qso_world_step(QsoWorld* w) {
         for (int k = 0; k < ND; k++) { dva += a->J[k] * dV[k]; dvb += b->J[k] * dV[k]; }
         double dIa = a->rhs - dva * a->dinv, dIb = b->rhs - dvb * b->dinv;
         double sa = a->applied + dIa, sb = b->applied + dIb;
+        {
+          double dem = sqrt(sa * sa + sb * sb);
+          double rat = nrm[j].applied > 0 ? dem / nrm[j].applied : (dem > 0 ? 1e30 : 0);
+          if (rat > w->max_fric_ratio) w->max_fric_ratio = rat;
+        }
         if (sa * sa + sb * sb >= lim_imp * lim_imp) {
           double rr = sqrt(sa * sa + sb * sb);
           double sc = rr > 0 ? lim_imp / rr : 0;

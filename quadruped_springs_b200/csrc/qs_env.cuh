@@ -51,14 +51,21 @@ struct EnvCfg {
 // PD + PEA torque of one tick (quadruped.py:288-320, quadruped_motor.py:45-104)
 __device__ __forceinline__ void tick_torques(const EnvState<float>& st, const float* cmd, bool torque_mode, int env,
                                              const DeviceView& D, const EnvCfg& C, const RobotConst& RC, const float* sk,
-                                             const float* sb, const float* sr, float* tau, float* tau_m, float* tau_s) {
+                                             const float* sb, const float* sr, float* tau, float* tau_m, float* tau_s,
+                                             bool custom_gains) {
   const int n = D.n;
+  if (custom_gains) {  // gains swapped at run time for this env (landing wrappers, landing_wrapper.py:21-33)
 #pragma unroll
-  for (int i = 0; i < 12; i++) {
-    const float kp = D.kp[i * n + env], kd = D.kd[i * n + env];
-    tau_m[i] = pd_torque1(kp, kd, RC.tau_max[i], cmd[i], st.q[i], st.qd[i], torque_mode);
-    tau[i] = tau_m[i];
+    for (int i = 0; i < 12; i++) {
+      const float kp = D.kp[i * n + env], kd = D.kd[i * n + env];
+      tau_m[i] = pd_torque1(kp, kd, RC.tau_max[i], cmd[i], st.q[i], st.qd[i], torque_mode);
+    }
+  } else {             // config gains straight from the constant bank: no global loads on the per-tick path
+#pragma unroll
+    for (int i = 0; i < 12; i++) tau_m[i] = pd_torque1(RC.kp[i], RC.kd[i], RC.tau_max[i], cmd[i], st.q[i], st.qd[i], torque_mode);
   }
+#pragma unroll
+  for (int i = 0; i < 12; i++) tau[i] = tau_m[i];
   if (C.enable_springs) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -92,6 +99,7 @@ __device__ __forceinline__ int run_ticks(EnvState<float>& st, ContactState<float
                                          const SolverConst& SC, float* tau_m /*12 out*/, float* tau_s /*12 out*/,
                                          bool detect_invalid_last, const Scratch<float>& scr) {
   const float mu = D.mu[env];
+  const bool custom = D.custom_gains[env] != 0;
   float sk[3], sb[3], sr[3];
   load_springs(D, env, sk, sb, sr);
   int bail = n_ticks;
@@ -101,7 +109,7 @@ __device__ __forceinline__ int run_ticks(EnvState<float>& st, ContactState<float
     __syncthreads();
     if (bail == n_ticks) {
       float tau[12];
-      tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s);
+      tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s, custom);
       if (physics_tick(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1), scr)) bail = t;
     }
   }
@@ -114,11 +122,12 @@ __device__ __noinline__ void run_ticks_general(EnvState<float>& st, ContactState
                                                const EnvCfg& C, const RobotConst& RC, const ModelConstT<float>& M,
                                                const SolverConst& SC, float* tau_m, float* tau_s) {
   const float mu = D.mu[env];
+  const bool custom = D.custom_gains[env] != 0;
   float sk[3], sb[3], sr[3];
   load_springs(D, env, sk, sb, sr);
   for (int t = t0; t < n_ticks; t++) {
     float tau[12];
-    tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s);
+    tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s, custom);
     physics_tick_general(st, tau, mu, cs, M, SC);
   }
 }

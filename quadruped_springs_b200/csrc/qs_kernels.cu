@@ -446,7 +446,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
 
   // one pool for all SoA arrays (4-byte elements), 256 B aligned segments
   const size_t n = size_t(n_envs);
-  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1 + 3 + 12 + 1 + QS_SLOTS * (SLOT_ROWS + 1 + 1);
+  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1 + 3 + 12 + 1 + 1 + QS_SLOTS * (SLOT_ROWS + 1 + 1);
   // rows of one array are contiguous with stride n floats; each array starts 256 B aligned
   h->pool_bytes = rows * n * 4 + 64 * 256;
   cudaError_t e = cudaMalloc(&h->pool, h->pool_bytes);
@@ -470,6 +470,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   D.reset_count = (uint32_t*)carve(1);
   D.work = (uint32_t*)carve(3);
   D.cmd = (float*)carve(12); D.resume_tick = (int32_t*)carve(1);
+  D.custom_gains = (uint8_t*)carve(1);
   D.slot = (float*)carve(QS_SLOTS * SLOT_ROWS); D.slot_contact = (int32_t*)carve(QS_SLOTS); D.slot_epoch = (uint32_t*)carve(QS_SLOTS);
   if (size_t(p - static_cast<char*>(h->pool)) > h->pool_bytes) { cudaFree(h->pool); delete h; return fail(QS_ERR_STATE, "pool overflow"); }
   h->refill_cap = 2 * QS_SLOTS * n_envs;
@@ -573,6 +574,7 @@ int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* o) {
   o->state = D.state; o->tau_motor = D.tau_motor; o->tau_spring = D.tau_spring; o->kp = D.kp; o->kd = D.kd;
   o->spring = D.spring; o->mu = D.mu; o->foot_force = D.foot_force; o->contact = D.contact; o->task = D.task;
   o->last_action = D.last_action; o->sim_steps = D.sim_steps; o->env_steps = D.env_steps; o->ep_return = D.ep_return;
+  o->custom_gains = D.custom_gains;
   return QS_OK;
 }
 

@@ -112,9 +112,9 @@ template <typename T> struct LegKin {
 
 template <typename T> QS_DEV void leg_kin(int k, const T* q, const ModelConstT<T>& M, LegKin<T>& K) {
   T s3, c3;
-  sincos_t(q[0], &K.s1, &K.c1);
-  sincos_t(q[1], &K.s2, &K.c2);
-  sincos_t(q[2], &s3, &c3);
+  sincos_tick(q[0], &K.s1, &K.c1);
+  sincos_tick(q[1], &K.s2, &K.c2);
+  sincos_tick(q[2], &s3, &c3);
   K.c23 = K.c2 * c3 - K.s2 * s3;
   K.s23 = K.s2 * c3 + K.c2 * s3;
   K.a2[0] = T(0); K.a2[1] = K.c1; K.a2[2] = K.s1;

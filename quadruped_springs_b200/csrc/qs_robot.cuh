@@ -42,6 +42,16 @@ QS_DEV float div_t(float a, float b) {
 #endif
 }
 QS_DEV double div_t(double a, double b) { return a / b; }
+// sin/cos of a joint angle inside the physics tick: |x| <= pi, so the 2-MUFU approximation (abs error
+// < 5e-7) is within fp32 rounding of the dynamics; the analytic accessor kernels keep the exact sincosf
+QS_DEV void sincos_tick(float x, float* s, float* c) {
+#ifdef __CUDA_ARCH__
+  __sincosf(x, s, c);
+#else
+  sincosf(x, s, c);
+#endif
+}
+QS_DEV void sincos_tick(double x, double* s, double* c) { sincos(x, s, c); }
 QS_DEV double abs_t(double x) { return fabs(x); }
 
 // leg geometry used by the reference's analytic kinematics

@@ -241,6 +241,7 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
   const float dt = A.SC.dt;
   D.reset_count[env] = epoch;
   D.mu[env] = mu;
+  D.custom_gains[env] = 0;
 #pragma unroll
   for (int i = 0; i < 12; i++) { D.kp[i * n + env] = A.RC.kp[i]; D.kd[i * n + env] = A.RC.kd[i]; }
 #pragma unroll

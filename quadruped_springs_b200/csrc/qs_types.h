@@ -69,6 +69,7 @@ struct DeviceView {
   uint32_t* work;        // [3][N] k_step work counters: ticks, contact-ticks, contact-sweeps
   float* cmd;            // [12][N] motor command of the current control step (slow-path hand-over)
   int32_t* resume_tick;  // [N] tick at which the fast kernel handed the env to the general solver
+  uint8_t* custom_gains; // [N] non-zero: read kp/kd of this env from the arrays instead of the config constants
   float* slot;           // [slots][66][N] settled states of the next episodes (see qs_step_kernels.cuh)
   int32_t* slot_contact; // [slots][N]
   uint32_t* slot_epoch;  // [slots][N] episode number the slot was settled for (0 = empty)

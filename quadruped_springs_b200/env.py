@@ -202,9 +202,11 @@ class BatchedQuadruped:
         if env_ids is None:
             v["kp"][:] = kp[:, None]
             v["kd"][:] = kd[:, None]
+            v["custom_gains"][:] = 1
         else:
             v["kp"][:, env_ids] = kp[:, None]
             v["kd"][:, env_ids] = kd[:, None]
+            v["custom_gains"][env_ids] = 1
 
     def get_spring_nominal_params(self):
         sp = self._env._views["spring"]
@@ -445,6 +447,7 @@ class BatchedQuadrupedGymEnv:
             "last_action": _view(ptrs.last_action, (12, n), "<f4", dev),
             "sim_steps": _view(ptrs.sim_steps, (n,), "<i4", dev), "env_steps": _view(ptrs.env_steps, (n,), "<i4", dev),
             "ep_return": _view(ptrs.ep_return, (n,), "<f4", dev),
+            "custom_gains": _view(ptrs.custom_gains, (n,), "|u1", dev),
         }
         self.robot = BatchedQuadruped(self)
         self.task = _Task(self)

@@ -44,6 +44,11 @@ inline Cnt atan2_t(Cnt y, Cnt x) { g_trig++; return Cnt(std::atan2(y.v, x.v)); }
 inline Cnt asin_t(Cnt x) { g_trig++; return Cnt(std::asin(x.v)); }
 inline Cnt exp_t(Cnt x) { g_trig++; return Cnt(std::exp(x.v)); }
 
+namespace qs {  // overloads of the hot-path helpers for the counting type (declared before the templates)
+inline void sincos_tick(Cnt x, Cnt* s, Cnt* c) { sincos_t(x, s, c); }
+inline Cnt div_t(Cnt a, Cnt b) { return a / b; }
+}  // namespace qs
+
 #include "../quadruped_springs_b200/csrc/qs_physics.cuh"
 #include "../quadruped_springs_b200/csrc/qs_model_host.h"
 

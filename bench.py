@@ -214,7 +214,7 @@ def run_ours(args):
              torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory())
     np_act = [a.numpy() for a in h_act]
     np_out = tuple(x.numpy() for x in h_out)
-    e2e_steps = max(min(args.steps, 50), 5)
+    e2e_steps = max(min(args.steps, 200), 5)   # long enough to contain the periodic settle batches
     for i in range(2):
         env.step_host(np_act[i % n_act], np_out)
     barrier()

@@ -5,6 +5,6 @@ from .env import (  # noqa: F401
     MotorInterfaceCollection, SensorCollection, TaskCollection,
 )
 from .hopf_network import HopfNetwork  # noqa: F401
-from . import ops  # noqa: F401
+from . import ops, stats  # noqa: F401
 
 __all__ = ["BatchedQuadrupedGymEnv", "BatchedQuadruped", "HopfNetwork", "ops"]

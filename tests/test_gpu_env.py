@@ -55,9 +55,7 @@ def test_full_size_random_rollout_stays_finite_and_resets(qs):
     assert (S[:, 3:7].norm(dim=1) - 1).abs().max() < 1e-4
     assert (S[:, 25:37].abs() <= 30.1 + 1e-4).all()        # maxJointVelocity clamp (quadruped.py:678-683)
     assert n_done > 0                                       # random actions do crash some robots within 60 steps
-    st = qs.stats.combine(env.rollout_stats()[None].cpu()) if hasattr(qs, "stats") else None
-    from quadruped_springs_b200 import stats
-    out = stats.gather_rollout_stats(env.rollout_stats())
+    out = qs.stats.gather_rollout_stats(env.rollout_stats())
     assert out["num_envs"] == n and out["episodes"] == n_done
     assert 0 < out["mean_length"] <= 60 and out["terminated_fraction"] == 1.0
 
@@ -166,3 +164,64 @@ def test_per_env_gain_override(qs):
     env.step(a)
     tau = env.robot.GetMotorTorques()
     assert torch.equal(tau[0], tau[2]) and not torch.equal(tau[0], tau[1]) and torch.equal(tau[1], tau[3])
+
+
+def test_config2_no_springs_4096(qs):
+    """BASELINE config 2: PEA off, jumping in place, 4096 envs, fixed-seed random actions"""
+    env = qs.BatchedQuadrupedGymEnv(num_envs=4096, enable_springs=False, task_env="JUMPING_IN_PLACE",
+                                    observation_space_mode="ARS_BASIC", seed=0)
+    obs = env.reset()
+    assert (env.robot.GetBasePosition()[:, 2] - 0.309).abs().max() < 5e-3     # settled height without springs
+    assert (env.robot.GetSpringTorques() == 0).all()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ret = torch.zeros(4096, device="cuda")
+    for _ in range(150):
+        obs, r, d, info = env.step(torch.rand(4096, 6, device="cuda", generator=g) * 2 - 1)
+        ret += r
+    assert torch.isfinite(obs).all() and torch.isfinite(ret).all()
+    out = qs.stats.gather_rollout_stats(env.rollout_stats())
+    assert out["episodes"] > 100 and 0.2 < out["mean_max_height"] < 1.5
+
+
+def test_config4_cpg_torque_mode_matches_oracle_and_trots(qs):
+    """BASELINE config 4: HopfNetwork + Cartesian impedance in TORQUE mode, action_repeat = 1
+    (hopf_network.py:176-289): first against the oracle tick by tick, then 4096 robots trotting."""
+    from oracle import oracle as O
+    n = 4
+    env = qs.BatchedQuadrupedGymEnv(num_envs=n, isRLGymInterface=False, action_repeat=1, motor_control_mode="TORQUE",
+                                    enable_springs=True, auto_reset=False, enable_noise=False,
+                                    env_randomizer_mode="NO_RANDOMIZER", solver=dict(mu_ground=0.8))
+    env.reset()
+    assert env.action_dim == 12
+    ref = O.Env(enable_springs=True, motor_control_mode="TORQUE", isRLGymInterface=False, action_repeat=1)
+    ref.reset(mu=0.8)
+    np.testing.assert_allclose(env.get_state()[0].cpu().numpy(), ref.world.get_state(), atol=1e-3)  # settle_robot_by_pd
+    cpg = qs.HopfNetwork(num_envs=n, gait="TROT", omega_swing=16 * np.pi, omega_stance=4 * np.pi, seed=1)
+    X = cpg.X[0].cpu().numpy().copy()
+    PHI = cpg.PHI
+    for t in range(150):
+        xs, zs, tau = cpg.update(env.robot.GetMotorAngles(), env.robot.GetMotorVelocities())
+        s = ref.world.get_state()
+        X, rx, rz = O.cpg_step(X, PHI, 2, 16 * np.pi, 4 * np.pi, 1, 0.001, 0.04, 0.25, 0.05, 0.01)
+        rtau = O.cpg_torque(rx, rz, s[13:25], s[25:37], 0.0838, [150, 70, 70], [2, 0.5, 0.5], 2500.0, 40.0)
+        env.step(tau)
+        ref.step(rtau)
+        if t < 40:   # the impedance gains (2500 N/m) amplify fp32 differences quickly; hold the first 40 ms tightly
+            np.testing.assert_allclose(env.get_state()[0].cpu().numpy()[:25], ref.world.get_state()[:25], atol=2e-3)
+    assert abs(float(env.get_state()[0, 2]) - ref.world.get_state()[2]) < 0.02
+    # at size: robots keep walking forward and stay up
+    sys_path = __import__("sys").path
+    sys_path.insert(0, __import__("os").path.join(__import__("conftest").ROOT, "examples"))
+    import cpg_trot
+    env2, _ = cpg_trot.main(4096, 1500)
+    pos = env2.robot.GetBasePosition()
+    assert torch.isfinite(pos).all()
+    assert float(pos[:, 2].mean()) > 0.2 and float((pos[:, 2] > 0.15).float().mean()) > 0.95
+    assert float(pos[:, 0].mean()) > 0.05     # moved forward in 1.5 s of trotting
+
+
+def test_config5_policy_in_the_loop(qs):
+    sys_path = __import__("sys").path
+    sys_path.insert(0, __import__("os").path.join(__import__("conftest").ROOT, "examples"))
+    import policy_rollout
+    policy_rollout.main(2048, 40)

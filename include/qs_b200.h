@@ -36,7 +36,7 @@ extern "C" {
 
 #define QS_STATE_DIM 37 /* pos3 quat4(xyzw) linvel3 angvel3 q12 qd12 (world frame) */
 #define QS_MAX_OBS 32
-#define QS_TASK_DIM 32
+#define QS_TASK_DIM 48
 #define QS_STATS_DIM 16
 
 /* registry keys of the reference, as integers (string -> id mapping lives in
@@ -54,7 +54,11 @@ enum qs_task {
   QS_TASK_JUMPING_FORWARD_PPO = 5,
   QS_TASK_BACKFLIP_PPO = 6,
   QS_TASK_JUMPING_IN_PLACE_PPO_HP = 7,
-  QS_TASK_JUMPING_FORWARD_PPO_HP = 8
+  QS_TASK_JUMPING_FORWARD_PPO_HP = 8,
+  QS_TASK_CONTINUOUS_JUMPING_FORWARD = 9,      /* robot_tasks.py:102-131 */
+  QS_TASK_CONTINUOUS_JUMPING_FORWARD2 = 10,    /* robot_tasks.py:134-166 */
+  QS_TASK_CONTINUOUS_JUMPING_FORWARD3 = 11,    /* robot_tasks.py:169-212 */
+  QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO = 12  /* robot_tasks.py:553-698 */
 };
 enum qs_obs_mode {
   QS_OBS_ENCODER = 0,

@@ -266,7 +266,9 @@ def rollout(name, cfg, actions, seed, world_params=None):
         g = lambda n, d=0.0: float(getattr(T, n, d))
         return np.array([g("_switched_controller"), g("_all_feet_in_the_air"), g("_time_take_off"), g("_init_height"),
                          g("_max_flight_time"), g("_max_forward_distance"), g("_max_pitch"), g("_relative_max_height"),
-                         g("_max_delta_x"), g("_max_height"), g("max_pitch"), g("old_fwd"), g("actual_fwd")])
+                         g("_max_delta_x"), g("_max_height"), g("max_pitch"), g("old_fwd"), g("actual_fwd"),
+                         g("is_jumping"), g("cumulative_fwd"), g("cumulative_flight_time"), g("jump_counter"),
+                         g("good_jump_counter"), g("first_jump"), g("max_jump_height"), g("end_jump")])
 
     init_task = task_vec()
     n_done = 0
@@ -284,10 +286,14 @@ def rollout(name, cfg, actions, seed, world_params=None):
         rec["foot_force"].append(np.asarray(ff, dtype=np.float64))
         rec["foot_contact"].append(np.asarray(fc, dtype=np.float64))
         rec["task"].append(task_vec())
+        if hasattr(T, "fwd_array"):
+            jumps = np.stack([np.asarray(T.fwd_array, dtype=np.float64), np.asarray(T.performance_array, dtype=np.float64)])
         if d:
             n_done += 1
             break
     out = {k: np.asarray(v) for k, v in rec.items()}
+    if hasattr(T, "fwd_array"):
+        out["jumps"] = jumps
     out.update(actions=np.asarray(actions)[: len(out["reward"])], mu=mu, init_state=init_state, init_obs=init_obs,
                init_last_action=init_last_action, init_task=init_task,
                cfg=json.dumps(cfg), world_params=json.dumps(world_params or {}))
@@ -331,6 +337,78 @@ def gen_rollouts():
     # BACKFLIP mutates RL_UPPER_ANGLE_JOINT for the rest of the process (App. D.7): keep it last
     rollout("backflip", dict(base, task_env="BACKFLIP", observation_space_mode="ARS_BACKFLIP"),
             jump_actions(6, 160, rng, amp=1.0), seed=13)
+
+
+def ref_mu(cfg, seed):
+    """Ground friction the reference draws for this (cfg, seed) -- the same calls rollout() makes."""
+    np.random.seed(seed)
+    env = make_env(**cfg)
+    env.reset()
+    return float(env._pybullet_client._mu_ground)
+
+
+def hop_actions(cfg, n, seed, mu, amp=0.8, lean=0.2, thp=0.0, kp_pitch=4.0, crouch_n=15, push_n=8):
+    """Repeated hops for the continuous-jumping tasks.  The action sequence comes from a small
+    closed-loop crouch/push/recover automaton run once on the CPU oracle (pitch feedback on the
+    calf command); the recorded sequence is then replayed open loop through the reference."""
+    import math
+    from oracle import oracle as O
+    e = O.Env(**cfg)
+    e.reset(mu=mu)
+    rng = np.random.default_rng(seed)
+    phase, cnt, acts, lands, done, was_air = 0, 0, [], 0, False, False
+    for _ in range(n):
+        st, ts = e.world.get_state(), e.task_state()
+        pitch = math.asin(max(-1.0, min(1.0, 2 * (st[6] * st[4] - st[5] * st[3]))))
+        if phase == 0:
+            th, ca, cnt = 0.6 + lean, -0.6, cnt + 1
+            if cnt >= crouch_n:
+                phase, cnt = 1, 0
+        elif phase == 1:
+            th, ca, cnt = thp * amp, amp, cnt + 1
+            if cnt >= push_n:
+                phase, cnt = 2, 0
+        else:
+            th, ca, cnt = 0.2, -0.2, cnt + 1
+            if cnt >= 25 and ts[1] < 0.5:
+                phase, cnt = 0, 0
+        d = kp_pitch * pitch
+        a = np.clip(np.array([0, th, ca - d, 0, th, ca + d]) + rng.normal(size=6) * 0.02, -1, 1)
+        acts.append(a)
+        done = e.step(a)[2]
+        air = e.task_state()[1] > 0.5
+        lands += int(was_air and not air)
+        was_air = air
+        if done:
+            break
+    return np.asarray(acts), done, lands
+
+
+def gen_rollouts_continuous():
+    """Continuous-jumping task family (task_base.py:222-400, robot_tasks.py:102-212,553-698)."""
+    base = dict(enable_springs=True, motor_control_mode="PD", action_space_mode="SYMMETRIC",
+                observation_space_mode="PPO_CONTINUOUS_JUMPING_FORWARD")
+    runs = [("cjf", "CONTINUOUS_JUMPING_FORWARD", True), ("cjf2", "CONTINUOUS_JUMPING_FORWARD2", True),
+            ("cjf3", "CONTINUOUS_JUMPING_FORWARD3", True), ("cjf_ppo", "CONTINUOUS_JUMPING_FORWARD_PPO", True),
+            ("cjf3_random", "CONTINUOUS_JUMPING_FORWARD3", False), ("cjf_ppo_random", "CONTINUOUS_JUMPING_FORWARD_PPO", False)]
+    sweep = [dict(amp=a, lean=le, thp=t, kp_pitch=k) for k in (4.0, 2.0) for a in (0.8, 0.6, 1.0)
+             for le in (0.2, 0.4) for t in (0.0, -0.2)]
+    for i, (name, task, hop) in enumerate(runs):
+        cfg = dict(base, task_env=task)
+        if not hop:
+            acts = np.random.default_rng(40 + i).uniform(-1, 1, size=(120, 6))
+        else:
+            # first automaton setting whose episode ends (crash) after >= 4 landings within 320 steps:
+            # exercises first-jump skipping, the per-jump arrays and the end-of-episode reward
+            mu, best = ref_mu(cfg, 20 + i), None
+            for kw in sweep:
+                acts, done, lands = hop_actions(cfg, 320, seed=40 + i, mu=mu, **kw)
+                if best is None or (done and lands > best[1]):
+                    best = (acts, lands if done else -1)
+                if done and lands >= 4:
+                    break
+            acts = best[0]
+        rollout(name, cfg, acts, seed=20 + i)
 
 
 # ----------------------------------------------------------------------------- CPG
@@ -384,7 +462,7 @@ def gen_hopf():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "rollouts"]
+    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "continuous", "rollouts"]
     if "urdf" in which:
         gen_urdf()
     # NB: gen_analytic and the last rollout build a BACKFLIP env, which mutates the module-level
@@ -395,6 +473,8 @@ if __name__ == "__main__":
         gen_analytic()
     if "hopf" in which:
         gen_hopf()
+    if "continuous" in which:
+        gen_rollouts_continuous()
     if "rollouts" in which:
         gen_rollouts()
     print("golden fixtures written to", OUT)

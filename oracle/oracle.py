@@ -15,7 +15,8 @@ _LIB = None
 TASKS = {
     "NO_TASK": 0, "JUMPING_IN_PLACE": 1, "JUMPING_FORWARD": 2, "BACKFLIP": 3,
     "JUMPING_IN_PLACE_PPO": 4, "JUMPING_FORWARD_PPO": 5, "BACKFLIP_PPO": 6,
-    "JUMPING_IN_PLACE_PPO_HP": 7, "JUMPING_FORWARD_PPO_HP": 8,
+    "JUMPING_IN_PLACE_PPO_HP": 7, "JUMPING_FORWARD_PPO_HP": 8, "CONTINUOUS_JUMPING_FORWARD": 9,
+    "CONTINUOUS_JUMPING_FORWARD2": 10, "CONTINUOUS_JUMPING_FORWARD3": 11, "CONTINUOUS_JUMPING_FORWARD_PPO": 12,
 }
 CONTROL = {"PD": 0, "CARTESIAN_PD": 1, "TORQUE": 2}
 ACTION = {"DEFAULT": 0, "SYMMETRIC": 1, "SYMMETRIC_NO_HIP": 2}
@@ -92,6 +93,7 @@ def lib():
         "qso_env_reset": (None, [vp, C.c_double, dp]),
         "qso_env_step": (None, [vp, dp, dp, dp, ip, ip]),
         "qso_env_get_task_state": (None, [vp, dp]),
+        "qso_env_get_jump_arrays": (None, [vp, dp]),
         "qso_env_get_torques": (None, [vp, dp, dp]),
         "qso_env_get_last_action": (None, [vp, dp]),
         "qso_env_set_gains": (None, [vp, dp, dp]),
@@ -280,6 +282,13 @@ class Env:
         o, op = _out(32)
         self.L.qso_env_get_task_state(self.h, op)
         return o
+
+    def jump_arrays(self):
+        """(fwd[n], perf[n], [jump_counter, good_jump_counter, first_jump, max_jump_height, end_jump]) of the continuous-jumping tasks (task_base.py:340-353)."""
+        o, op = _out(1030)
+        self.L.qso_env_get_jump_arrays(self.h, op)
+        n = int(o[0])
+        return o[6:6 + n].copy(), o[518:518 + n].copy(), o[1:6].copy()
 
     def last_action(self):
         o, op = _out(12)

@@ -15,6 +15,7 @@
 #include <string.h>
 
 #define PI 3.14159265358979323846
+#define QSO_MAX_JUMPS 512 /* a jump needs >= 2 control steps and an episode has <= 1000 */
 
 /* ------------------------------------------------------------ constants */
 /* go1/configs_go1_with_springs.py:56-58 */
@@ -268,6 +269,10 @@ typedef struct {
   double pos[3], vel[3], rpy[3];
   double max_pitch_bf; /* BackFlip.max_pitch: set in __init__ only (robot_tasks.py:524) */
   double old_fwd, actual_fwd;
+  /* continuous jumping (task_base.py:222-400) */
+  int is_jumping, first_jump, end_jump, jump_counter, good_jump_counter, n_jumps;
+  double cumulative_fwd, cumulative_flight_time, max_jump_height;
+  double fwd_arr[QSO_MAX_JUMPS], perf_arr[QSO_MAX_JUMPS];
 } TaskState;
 
 struct QsoEnv {
@@ -390,6 +395,29 @@ static double jumping_distance(const QsoEnv* e) { /* task_base.py:109-116 */
   return x > 0 ? x : 0;
 }
 
+/* task families: 0 = TaskJumping, 1 = TaskContinuousJumping, 2 = TaskContinuousJumping2 */
+static int task_family(int t) {
+  if (t == QSO_TASK_CONTINUOUS_JUMPING_FORWARD || t == QSO_TASK_CONTINUOUS_JUMPING_FORWARD2) return 1;
+  if (t == QSO_TASK_CONTINUOUS_JUMPING_FORWARD3 || t == QSO_TASK_CONTINUOUS_JUMPING_FORWARD_PPO) return 2;
+  return 0;
+}
+static void cont2_params(int t, double* jump_limit, double* height_limit, double* bound) {
+  if (t == QSO_TASK_CONTINUOUS_JUMPING_FORWARD3) { *jump_limit = 0.6; *height_limit = 0.45; *bound = 0.7; } /* robot_tasks.py:172-177 */
+  else { *jump_limit = 0.6; *height_limit = 0.5; *bound = 0.85; } /* robot_tasks.py:553-561, task_base.py:280-287 */
+}
+static double entropy_fwd(const TaskState* t) { /* task_base.py:365-373 */
+  double sum = 0;
+  for (int i = 0; i < t->n_jumps; i++) sum += t->fwd_arr[i];
+  if (t->jump_counter == 0 || sum < 0.05) return 0;
+  int size = t->n_jumps < 3 ? 3 : t->n_jumps;
+  double h = 0;
+  for (int i = 0; i < t->n_jumps; i++) {
+    double p = t->fwd_arr[i] / sum;
+    if (p != 0) h -= p * log2(p);
+  }
+  return h / log2((double)size);
+}
+
 static void task_on_step(QsoEnv* e) { /* task_base.py:61-107 */
   TaskState* t = &e->ts;
   if (!is_jump_task(e->cfg.task)) return;
@@ -408,25 +436,83 @@ static void task_on_step(QsoEnv* e) { /* task_base.py:61-107 */
   if (fabs(z) > t->max_height) t->max_height = fabs(z);
   if (fabs(t->pos[0]) > t->max_delta_x) t->max_delta_x = fabs(t->pos[0]);
   if (fabs(t->rpy[1]) > t->max_pitch) t->max_pitch = fabs(t->rpy[1]);
-  if (is_flying(e)) {
-    if (!t->in_air) {
-      t->in_air = 1;
-      t->t_takeoff = sim_time(e);
-      memcpy(t->pose_takeoff, t->pos, sizeof t->pos);
-      memcpy(t->rpy_takeoff, t->rpy, sizeof t->rpy);
+  const int fam = task_family(e->cfg.task);
+  const int jumping_now = is_flying(e) && st[9] / 9.81 > 0.06; /* detect_jumping, task_base.py:236-241 */
+  if (fam == 0) {
+    if (is_flying(e)) {
+      if (!t->in_air) {
+        t->in_air = 1;
+        t->t_takeoff = sim_time(e);
+        memcpy(t->pose_takeoff, t->pos, sizeof t->pos);
+        memcpy(t->rpy_takeoff, t->rpy, sizeof t->rpy);
+      } else {
+        double d = jumping_distance(e);
+        if (d > t->max_fwd) t->max_fwd = d;
+      }
     } else {
-      double d = jumping_distance(e);
-      if (d > t->max_fwd) t->max_fwd = d;
+      if (t->in_air) {
+        double ft = sim_time(e) - t->t_takeoff;
+        if (ft > t->max_flight_time) t->max_flight_time = ft;
+        double d = jumping_distance(e);
+        if (d > t->max_fwd) t->max_fwd = d;
+        t->in_air = 0;
+      } else {
+        t->max_fwd = 0; /* task_base.py:106-107 */
+      }
     }
-  } else {
-    if (t->in_air) {
+  } else if (fam == 1) { /* TaskContinuousJumping._compute_jumping_info, task_base.py:243-262 */
+    const double jump_limit = 0.5;
+    const double time_limit = e->cfg.task == QSO_TASK_CONTINUOUS_JUMPING_FORWARD ? 0.15 : 0.35; /* robot_tasks.py:105-106,139-140 */
+    if (is_flying(e)) {
+      if (!t->in_air) {
+        t->in_air = 1;
+        t->t_takeoff = sim_time(e);
+        memcpy(t->pose_takeoff, t->pos, sizeof t->pos);
+        memcpy(t->rpy_takeoff, t->rpy, sizeof t->rpy);
+        t->is_jumping = jumping_now;
+      }
+    } else if (t->in_air) {
       double ft = sim_time(e) - t->t_takeoff;
       if (ft > t->max_flight_time) t->max_flight_time = ft;
       double d = jumping_distance(e);
       if (d > t->max_fwd) t->max_fwd = d;
+      t->cumulative_fwd += t->max_fwd < jump_limit ? t->max_fwd : jump_limit;           /* update_end_jump :264-266 */
+      t->cumulative_flight_time += t->max_flight_time < time_limit ? t->max_flight_time : time_limit;
       t->in_air = 0;
-    } else {
-      t->max_fwd = 0; /* task_base.py:106-107 */
+      t->is_jumping = 0;
+    }
+  } else { /* TaskContinuousJumping2._compute_jumping_info, task_base.py:319-338 */
+    double jump_limit, height_limit, bound;
+    cont2_params(e->cfg.task, &jump_limit, &height_limit, &bound);
+    t->end_jump = 0;
+    if (is_flying(e)) {
+      if (!t->in_air) {
+        t->in_air = 1;
+        t->t_takeoff = sim_time(e);
+        memcpy(t->pose_takeoff, t->pos, sizeof t->pos);
+        memcpy(t->rpy_takeoff, t->rpy, sizeof t->rpy);
+        t->is_jumping = jumping_now;
+        t->max_jump_height = 0; /* set to z, then restart_jump_performance_variables() zeroes it (:326-330) */
+      } else if (t->pos[2] > t->max_jump_height) {
+        t->max_jump_height = t->pos[2];
+      }
+    } else if (t->in_air) {
+      double ft = sim_time(e) - t->t_takeoff;
+      if (ft > t->max_flight_time) t->max_flight_time = ft;
+      if (!t->first_jump) { /* update_end_jump :340-353 */
+        t->jump_counter++;
+        double d = jumping_distance(e);
+        double fwd = d < jump_limit ? d : jump_limit;
+        double hh = t->max_jump_height < height_limit ? t->max_jump_height : height_limit;
+        double perf = 0.7 * fwd / jump_limit + 0.3 * hh / height_limit;
+        if (perf >= bound) t->good_jump_counter++;
+        if (t->n_jumps < QSO_MAX_JUMPS) { t->fwd_arr[t->n_jumps] = fwd; t->perf_arr[t->n_jumps] = perf; t->n_jumps++; }
+        t->end_jump = 1;
+      } else {
+        t->first_jump = 0;
+      }
+      t->in_air = 0;
+      t->is_jumping = 0;
     }
   }
   int task = e->cfg.task;
@@ -452,6 +538,7 @@ static void task_reset(QsoEnv* e) { /* task_base.py:40-59 */
   double keep_bf = t->max_pitch_bf;
   memset(t, 0, sizeof *t);
   t->max_pitch_bf = keep_bf;
+  t->first_jump = 1;
   t->t_takeoff = sim_time(e);
   memcpy(t->pose_takeoff, st, sizeof t->pose_takeoff);
   t->init_height = st[2];
@@ -553,6 +640,44 @@ static double task_reward_end(QsoEnv* e) {
       return term ? 0.0 : 0.05 * (t->max_fwd + t->max_height) / 2;
     case QSO_TASK_BACKFLIP_PPO: /* robot_tasks.py:802-809 */
       return term ? 0.0 : 0.2 * (0.7 * t->max_pitch / 5 + 0.3 * t->max_height) / 2;
+    case QSO_TASK_CONTINUOUS_JUMPING_FORWARD: { /* robot_tasks.py:112-131 */
+      double a = t->cumulative_flight_time / 0.15, b = t->cumulative_fwd / 0.5, bm = (a + b) / 2;
+      r += 0.25 * a; r += 0.5 * b;
+      r += a * 0.25 * exp(-t->max_pitch * t->max_pitch / (0.15 * 0.15));
+      if (!term) r += 0.1 * bm;
+      return r;
+    }
+    case QSO_TASK_CONTINUOUS_JUMPING_FORWARD2: { /* robot_tasks.py:146-166 */
+      double a = (t->max_flight_time < 0.35 ? t->max_flight_time : 0.35) / 0.35;
+      double b = (t->max_fwd < 0.5 ? t->max_fwd : 0.5) / 0.5, bm = (a + b) / 2;
+      r += 0.25 * a; r += 0.5 * b;
+      r += b * 0.15 * exp(-(t->max_pitch * t->max_pitch / (0.15 * 0.15)));
+      r += 0.4 * (sim_time(e) / 10.0) * bm;
+      if (!term) r += 0.2 * bm;
+      return r;
+    }
+    case QSO_TASK_CONTINUOUS_JUMPING_FORWARD3: { /* robot_tasks.py:183-212 */
+      int size = t->n_jumps < 3 ? 3 : t->n_jumps;
+      double sum = 0, mx = t->n_jumps < 3 ? 0.0 : t->perf_arr[0]; /* np.max over the zero-padded array */
+      for (int i = 0; i < t->n_jumps; i++) { sum += t->perf_arr[i]; if (t->perf_arr[i] > mx) mx = t->perf_arr[i]; }
+      double avg = sum / size;
+      double rew_entropy = exp((entropy_fwd(t) - 1) / 0.3), rew_avg = 0;
+      rew_avg += avg * 0.15 * exp(-t->max_pitch * t->max_pitch / (0.15 * 0.15));
+      rew_avg += avg * 0.4 * (sim_time(e) / 10.0);
+      rew_avg += avg * rew_entropy * 0.2;
+      rew_avg += avg * 0.25;
+      r = 0.8 * rew_avg + 0.2 * mx;
+      r += 0.1 * t->good_jump_counter;
+      if (!term) r += 0.2 * avg;
+      return r;
+    }
+    case QSO_TASK_CONTINUOUS_JUMPING_FORWARD_PPO: { /* robot_tasks.py:687-698 */
+      int size = t->n_jumps < 3 ? 3 : t->n_jumps;
+      double sum = 0;
+      for (int i = 0; i < t->n_jumps; i++) sum += t->perf_arr[i];
+      double rr = (sum / size) * exp((entropy_fwd(t) - 1) / 0.3);
+      return term ? rr - 1 : rr;
+    }
     default: return 0;
   }
 }
@@ -569,6 +694,13 @@ void qso_env_get_task_state(const QsoEnv* e, double* o) {
   o[17] = e->n_valid; o[18] = e->n_invalid;
   for (int k = 0; k < 4; k++) { o[19 + k] = e->foot_contact[k]; o[23 + k] = e->foot_force[k]; }
   o[27] = (double)e->sim_steps; o[28] = (double)e->env_steps;
+  o[29] = t->is_jumping; o[30] = t->cumulative_fwd; o[31] = t->cumulative_flight_time;
+}
+void qso_env_get_jump_arrays(const QsoEnv* e, double* o) {
+  const TaskState* t = &e->ts;
+  o[0] = t->n_jumps;
+  o[1] = t->jump_counter; o[2] = t->good_jump_counter; o[3] = t->first_jump; o[4] = t->max_jump_height; o[5] = t->end_jump;
+  for (int i = 0; i < QSO_MAX_JUMPS; i++) { o[6 + i] = t->fwd_arr[i]; o[6 + QSO_MAX_JUMPS + i] = t->perf_arr[i]; }
 }
 
 /* ---- sensors (sensors/robot_sensors.py, sensors/sensor_collection.py:18-105) ---- */
@@ -616,7 +748,7 @@ static void observe(QsoEnv* e, double* obs) {
       PUTN(q, 12); PUTN(qd, 12); PUT(pos[2]); PUT(v[2]); PUT(qso_backflip_pitch(quat, e->ts.switched));
       PUT(landing); break;
     case QSO_OBS_PPO_CONTINUOUS_JUMPING_FORWARD:
-      PUTN(q, 12); PUTN(qd, 12); PUT(pos[2]); PUT(v[2]); PUT(rpy[1]); PUT(landing); PUT(0.0); break;
+      PUTN(q, 12); PUTN(qd, 12); PUT(pos[2]); PUT(v[2]); PUT(rpy[1]); PUT(landing); PUT((double)e->ts.is_jumping); break;
   }
 #undef PUT
 #undef PUTN

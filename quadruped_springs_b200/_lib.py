@@ -19,7 +19,7 @@ NVCC_FLAGS = [
 ]
 
 QS_MAX_OBS = 32
-QS_TASK_DIM = 32
+QS_TASK_DIM = 48
 QS_STATS_DIM = 16
 QS_STATE_DIM = 37
 

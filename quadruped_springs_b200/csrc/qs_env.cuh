@@ -134,6 +134,14 @@ __device__ __noinline__ void run_ticks_general(EnvState<float>& st, ContactState
 
 // ---------------------------------------------------------------- task logic
 QS_DEV bool is_jump_task(int task) { return task != QS_TASK_NO_TASK; }
+// 0 = TaskJumping, 1 = TaskContinuousJumping, 2 = TaskContinuousJumping2 (task_base.py:222,280)
+QS_DEV int task_family(int task) {
+  if (task == QS_TASK_CONTINUOUS_JUMPING_FORWARD || task == QS_TASK_CONTINUOUS_JUMPING_FORWARD2) return 1;
+  if (task == QS_TASK_CONTINUOUS_JUMPING_FORWARD3 || task == QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO) return 2;
+  return 0;
+}
+// rows of DeviceView::task this task reads and writes
+QS_DEV int task_slots(int task) { return task_family(task) ? int(TS_END) : int(TS_END_BASIC); }
 
 QS_DEVONLY float jumping_distance(const float* ts, const float* pos) {  // task_base.py:109-116
   float s, c;
@@ -153,22 +161,67 @@ QS_DEVONLY void task_on_step(float* ts, const EnvState<float>& st, const Contact
   ts[TS_MAX_H] = fmaxf(ts[TS_MAX_H], fabsf(z));
   ts[TS_MAX_DX] = fmaxf(ts[TS_MAX_DX], fabsf(st.pos[0]));
   ts[TS_MAX_PITCH] = fmaxf(ts[TS_MAX_PITCH], fabsf(rpy[1]));
-  if (flying) {
-    if (ts[TS_IN_AIR] == 0.f) {
-      ts[TS_IN_AIR] = 1.f;
-      ts[TS_T_TAKEOFF] = sim_time;
-      ts[TS_TAKEOFF_X] = st.pos[0]; ts[TS_TAKEOFF_Y] = st.pos[1]; ts[TS_TAKEOFF_Z] = st.pos[2];
-      ts[TS_TAKEOFF_YAW] = rpy[2];
+  const int fam = task_family(task);
+  if (fam == 0) {
+    if (flying) {
+      if (ts[TS_IN_AIR] == 0.f) {
+        ts[TS_IN_AIR] = 1.f;
+        ts[TS_T_TAKEOFF] = sim_time;
+        ts[TS_TAKEOFF_X] = st.pos[0]; ts[TS_TAKEOFF_Y] = st.pos[1]; ts[TS_TAKEOFF_Z] = st.pos[2];
+        ts[TS_TAKEOFF_YAW] = rpy[2];
+      } else {
+        ts[TS_MAX_FWD] = fmaxf(ts[TS_MAX_FWD], jumping_distance(ts, st.pos));
+      }
     } else {
-      ts[TS_MAX_FWD] = fmaxf(ts[TS_MAX_FWD], jumping_distance(ts, st.pos));
+      if (ts[TS_IN_AIR] != 0.f) {
+        ts[TS_MAX_FLIGHT] = fmaxf(ts[TS_MAX_FLIGHT], sim_time - ts[TS_T_TAKEOFF]);
+        ts[TS_MAX_FWD] = fmaxf(ts[TS_MAX_FWD], jumping_distance(ts, st.pos));
+        ts[TS_IN_AIR] = 0.f;
+      } else {
+        ts[TS_MAX_FWD] = 0.f;  // task_base.py:106-107
+      }
     }
   } else {
-    if (ts[TS_IN_AIR] != 0.f) {
+    // TaskContinuousJumping(2)._compute_jumping_info (task_base.py:243-262, 319-338)
+    const bool cj2 = fam == 2;
+    ts[TS_END_JUMP] = 0.f;
+    if (flying) {
+      if (ts[TS_IN_AIR] == 0.f) {
+        ts[TS_IN_AIR] = 1.f;
+        ts[TS_T_TAKEOFF] = sim_time;
+        ts[TS_TAKEOFF_X] = st.pos[0]; ts[TS_TAKEOFF_Y] = st.pos[1]; ts[TS_TAKEOFF_Z] = st.pos[2];
+        ts[TS_TAKEOFF_YAW] = rpy[2];
+        ts[TS_IS_JUMPING] = st.vlin[2] / 9.81f > 0.06f ? 1.f : 0.f;  // detect_jumping, :236-241
+        ts[TS_MAX_JUMP_H] = 0.f;  // set to z, then zeroed by restart_jump_performance_variables (:326-330)
+      } else if (cj2) {
+        ts[TS_MAX_JUMP_H] = fmaxf(ts[TS_MAX_JUMP_H], st.pos[2]);
+      }
+    } else if (ts[TS_IN_AIR] != 0.f) {
       ts[TS_MAX_FLIGHT] = fmaxf(ts[TS_MAX_FLIGHT], sim_time - ts[TS_T_TAKEOFF]);
-      ts[TS_MAX_FWD] = fmaxf(ts[TS_MAX_FWD], jumping_distance(ts, st.pos));
+      const float d = jumping_distance(ts, st.pos);
+      if (!cj2) {  // update_end_jump :264-266
+        const float time_limit = task == QS_TASK_CONTINUOUS_JUMPING_FORWARD ? 0.15f : 0.35f;  // robot_tasks.py:105-106,139-140
+        ts[TS_MAX_FWD] = fmaxf(ts[TS_MAX_FWD], d);
+        ts[TS_CUM_FWD] += fminf(ts[TS_MAX_FWD], 0.5f);
+        ts[TS_CUM_FLIGHT] += fminf(ts[TS_MAX_FLIGHT], time_limit);
+      } else if (ts[TS_FIRST_JUMP] == 0.f) {  // update_end_jump :340-353
+        const bool t3 = task == QS_TASK_CONTINUOUS_JUMPING_FORWARD3;  // robot_tasks.py:172-177 / 553-561
+        const float jump_limit = 0.6f, height_limit = t3 ? 0.45f : 0.5f, bound = t3 ? 0.7f : 0.85f;
+        const float fwd = fminf(d, jump_limit);
+        const float perf = 0.7f * fwd / jump_limit + 0.3f * fminf(ts[TS_MAX_JUMP_H], height_limit) / height_limit;
+        ts[TS_JUMP_COUNT] += 1.f;
+        if (perf >= bound) ts[TS_GOOD_JUMPS] += 1.f;
+        ts[TS_SUM_FWD] += fwd;
+        ts[TS_SUM_FLOG] += fwd > 0.f ? fwd * log2f(fwd) : 0.f;
+        ts[TS_SUM_PERF] += perf;
+        ts[TS_MAX_PERF] = ts[TS_JUMP_COUNT] == 1.f ? perf : fmaxf(ts[TS_MAX_PERF], perf);
+        ts[TS_LAST_PERF] = perf;
+        ts[TS_END_JUMP] = 1.f;
+      } else {
+        ts[TS_FIRST_JUMP] = 0.f;
+      }
       ts[TS_IN_AIR] = 0.f;
-    } else {
-      ts[TS_MAX_FWD] = 0.f;  // task_base.py:106-107
+      ts[TS_IS_JUMPING] = 0.f;
     }
   }
   if (task == QS_TASK_BACKFLIP)  // robot_tasks.py:527-530
@@ -228,7 +281,7 @@ QS_DEVONLY float task_reward(const float* ts, const EnvState<float>& st, const f
 }
 
 // end-of-episode bonus / malus (robot_tasks.py:31-57, 70-99, 535-550, 349-358, 476-485, 802-809)
-QS_DEVONLY float task_reward_end(const float* ts, bool term, int task) {
+QS_DEVONLY float task_reward_end(const float* ts, bool term, int task, float sim_time, float max_ep_time) {
   float r = 0.f;
   switch (task) {
     case QS_TASK_JUMPING_IN_PLACE: {
@@ -261,6 +314,40 @@ QS_DEVONLY float task_reward_end(const float* ts, bool term, int task) {
     case QS_TASK_JUMPING_FORWARD_PPO:
     case QS_TASK_JUMPING_FORWARD_PPO_HP: return term ? 0.f : 0.05f * (ts[TS_MAX_FWD] + ts[TS_MAX_H]) / 2.f;
     case QS_TASK_BACKFLIP_PPO: return term ? 0.f : 0.2f * (0.7f * ts[TS_MAX_PITCH] / 5.f + 0.3f * ts[TS_MAX_H]) / 2.f;
+    case QS_TASK_CONTINUOUS_JUMPING_FORWARD: {  // robot_tasks.py:112-131
+      const float a = ts[TS_CUM_FLIGHT] / 0.15f, b = ts[TS_CUM_FWD] / 0.5f;
+      r += 0.25f * a; r += 0.5f * b;
+      r += a * 0.25f * expf(-ts[TS_MAX_PITCH] * ts[TS_MAX_PITCH] / (0.15f * 0.15f));
+      if (!term) r += 0.1f * (a + b) / 2.f;
+      return r;
+    }
+    case QS_TASK_CONTINUOUS_JUMPING_FORWARD2: {  // robot_tasks.py:146-166
+      const float a = fminf(ts[TS_MAX_FLIGHT], 0.35f) / 0.35f, b = fminf(ts[TS_MAX_FWD], 0.5f) / 0.5f, bm = (a + b) / 2.f;
+      r += 0.25f * a; r += 0.5f * b;
+      r += b * 0.15f * expf(-(ts[TS_MAX_PITCH] * ts[TS_MAX_PITCH] / (0.15f * 0.15f)));
+      r += 0.4f * (sim_time / max_ep_time) * bm;
+      if (!term) r += 0.2f * bm;
+      return r;
+    }
+    case QS_TASK_CONTINUOUS_JUMPING_FORWARD3:      // robot_tasks.py:183-212
+    case QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO: {  // robot_tasks.py:687-698
+      const float n = ts[TS_JUMP_COUNT], size = fmaxf(n, 3.f);  // arrays are zero-padded to >= 3 entries
+      const float avg = ts[TS_SUM_PERF] / size;
+      float entropy = 0.f;  // get_entropy_fwd, task_base.py:376-383: -sum p log2 p / log2(size), p = f / S
+      if (n > 0.f && ts[TS_SUM_FWD] >= 0.05f)
+        entropy = (log2f(ts[TS_SUM_FWD]) - ts[TS_SUM_FLOG] / ts[TS_SUM_FWD]) / log2f(size);
+      const float rew_entropy = expf((entropy - 1.f) / 0.3f);
+      if (task == QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO) return avg * rew_entropy - (term ? 1.f : 0.f);
+      const float mx = n < 3.f ? fmaxf(n > 0.f ? ts[TS_MAX_PERF] : 0.f, 0.f) : ts[TS_MAX_PERF];
+      float rew_avg = avg * 0.15f * expf(-ts[TS_MAX_PITCH] * ts[TS_MAX_PITCH] / (0.15f * 0.15f));
+      rew_avg += avg * 0.4f * (sim_time / max_ep_time);
+      rew_avg += avg * rew_entropy * 0.2f;
+      rew_avg += avg * 0.25f;
+      r = 0.8f * rew_avg + 0.2f * mx;
+      r += 0.1f * ts[TS_GOOD_JUMPS];
+      if (!term) r += 0.2f * avg;
+      return r;
+    }
     default: return 0.f;
   }
 }
@@ -273,6 +360,7 @@ QS_DEVONLY void task_reset(float* ts, const EnvState<float>& st, const ContactSt
 #pragma unroll
   for (int i = 0; i < TS_END; i++) ts[i] = 0.f;
   ts[TS_MAX_PITCH_BF] = keep_bf;
+  ts[TS_FIRST_JUMP] = 1.f;
   ts[TS_T_TAKEOFF] = sim_time;
   ts[TS_TAKEOFF_X] = st.pos[0]; ts[TS_TAKEOFF_Y] = st.pos[1]; ts[TS_TAKEOFF_Z] = st.pos[2];
   ts[TS_INIT_HEIGHT] = st.pos[2];
@@ -286,12 +374,13 @@ QS_DEVONLY void task_reset(float* ts, const EnvState<float>& st, const ContactSt
 // SensorList.get_obs / get_noisy_obs (sensor.py:101-111) for the modes of
 // sensor_collection.py:18-105; obs is written row-major [N, O].
 QS_DEVONLY void observe(const EnvState<float>& st, const ContactState<float>& cs, const float* ts, const float* rpy,
-                    const float* Rb, int obs_mode, float* o /*QS_MAX_OBS regs*/) {
+                    const float* Rb, int obs_mode, int task, float* o /*QS_MAX_OBS regs*/) {
   const float* q = st.q;
   const float* qd = st.qd;
   float wl[3];
   m3t_v(Rb, st.vang, wl);  // quadruped.py:141-170
   const float landing = ts[TS_SWITCHED];
+  const float jumping = task_family(task) ? ts[TS_IS_JUMPING] : 0.f;  // the attribute exists on those tasks only
   int n = 0;
 #define PUT(x) o[n++] = (x)
 #define PUT12(p) _Pragma("unroll") for (int _i = 0; _i < 12; _i++) o[n++] = (p)[_i]
@@ -330,7 +419,7 @@ QS_DEVONLY void observe(const EnvState<float>& st, const ContactState<float>& cs
     case QS_OBS_PPO_BACKFLIP:
       PUT12(q); PUT12(qd); PUT(st.pos[2]); PUT(st.vlin[2]); PUT(backflip_pitch(Rb, landing != 0.f)); PUT(landing); break;
     default:  // QS_OBS_PPO_CONTINUOUS_JUMPING_FORWARD: is_jumping only exists on the continuous tasks
-      PUT12(q); PUT12(qd); PUT(st.pos[2]); PUT(st.vlin[2]); PUT(rpy[1]); PUT(landing); PUT(0.f); break;
+      PUT12(q); PUT12(qd); PUT(st.pos[2]); PUT(st.vlin[2]); PUT(rpy[1]); PUT(landing); PUT(jumping); break;
   }
 #undef PUT
 #undef PUT12

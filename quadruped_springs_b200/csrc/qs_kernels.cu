@@ -58,10 +58,10 @@ __global__ void k_observe(const __grid_constant__ KernelArgs A, float* __restric
   quat_to_R(st.quat, Rb);
   rpy_from_quat(st.quat, rpy);
 #pragma unroll
-  for (int i = 0; i < TS_END; i++) ts[i] = D.task[i * D.n + env];
+  for (int i = 0; i < TS_END; i++) ts[i] = i < task_slots(A.C.task) ? D.task[i * D.n + env] : 0.f;
 #pragma unroll
   for (int i = 0; i < QS_MAX_OBS; i++) o[i] = 0.f;
-  observe(st, cs, ts, rpy, Rb, A.C.obs_mode, o);
+  observe(st, cs, ts, rpy, Rb, A.C.obs_mode, A.C.task, o);
   store_obs(obs + size_t(env) * A.C.obs_dim, o, A.C, A.RC, uint64_t(A.C.gid0 + env), D.reset_count[env],
             uint32_t(D.env_steps[env]) + 0x40000000u, with_noise != 0);
 }
@@ -381,7 +381,7 @@ static int check_config(const qs_config* c) {
   if (!c) return fail(QS_ERR_ARG, "config is NULL");
   if (c->control_mode < 0 || c->control_mode > 2) return fail(QS_ERR_ARG, "unknown motor control mode");
   if (c->action_mode < 0 || c->action_mode > 2) return fail(QS_ERR_ARG, "unknown action space mode");
-  if (c->task < 0 || c->task > QS_TASK_JUMPING_FORWARD_PPO_HP) return fail(QS_ERR_ARG, "unknown task");
+  if (c->task < 0 || c->task > QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO) return fail(QS_ERR_ARG, "unknown task");
   if (c->obs_mode < 0 || c->obs_mode > QS_OBS_PPO_CONTINUOUS_JUMPING_FORWARD) return fail(QS_ERR_ARG, "unknown observation space mode");
   if (c->action_repeat < 1 || c->action_repeat > 1000) return fail(QS_ERR_ARG, "action_repeat out of range");
   if (c->control_mode == QS_CTRL_TORQUE && c->is_rl_interface)  // quadruped_gym_env.py:167-168

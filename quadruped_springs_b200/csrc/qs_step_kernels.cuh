@@ -257,10 +257,10 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
   rpy_from_quat(st.quat, rpy);
   float ts[QS_TASK_DIM];
 #pragma unroll
-  for (int i = 0; i < TS_END; i++) ts[i] = D.task[i * n + env];
+  for (int i = 0; i < TS_END; i++) ts[i] = i < task_slots(C.task) ? D.task[i * n + env] : 0.f;
   task_reset(ts, st, cs, tau_m, rpy, Rb, 0.f, C.task);
 #pragma unroll
-  for (int i = 0; i < TS_END; i++) D.task[i * n + env] = ts[i];
+  for (int i = 0; i < TS_END; i++) if (i < task_slots(C.task)) D.task[i * n + env] = ts[i];
 #pragma unroll
   for (int i = 0; i < 12; i++) {
     D.last_action[i * n + env] = act12[i];
@@ -278,7 +278,7 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
     float o[QS_MAX_OBS];
 #pragma unroll
     for (int i = 0; i < QS_MAX_OBS; i++) o[i] = 0.f;
-    observe(st, cs, ts, rpy, Rb, C.obs_mode, o);
+    observe(st, cs, ts, rpy, Rb, C.obs_mode, C.task, o);
     store_obs(obs + size_t(env) * C.obs_dim, o, C, A.RC, uint64_t(C.gid0 + env), epoch, 0u, C.enable_noise);
   }
 }
@@ -298,7 +298,7 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   const float sim_time = float(double(sim_steps) * A.time_step_d);
   float ts[QS_TASK_DIM];
 #pragma unroll
-  for (int i = 0; i < TS_END; i++) ts[i] = D.task[i * n + env];
+  for (int i = 0; i < TS_END; i++) ts[i] = i < task_slots(C.task) ? D.task[i * n + env] : 0.f;
   float foot_force[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) foot_force[k] = (cs.mask >> k) & 1 ? cs.lam_n[k] / dt : 0.f;
@@ -306,7 +306,7 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   float r = task_reward(ts, st, foot_force, ts + TS_OLD_TAU0, tau_m, rpy, Rb, C.task);
   const bool term = task_terminated(ts, st, cs, Rb, A.RC.fallen_height, C.task);
   const bool dn = term || (double(sim_steps) * A.time_step_d > A.max_time_d);
-  if (dn) r += task_reward_end(ts, term, C.task);
+  if (dn) r += task_reward_end(ts, term, C.task, sim_time, C.max_episode_time);
 #pragma unroll
   for (int i = 0; i < 12; i++) ts[TS_OLD_TAU0 + i] = tau_m[i];
   const float ep_ret = D.ep_return[env] + r;
@@ -322,7 +322,7 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
     // the finished env starts its next episode inside the same call; its obs row becomes the
     // first observation of that episode (SB3 VecEnv convention)
 #pragma unroll
-    for (int i = 0; i < TS_END; i++) D.task[i * n + env] = ts[i];  // BackFlip.max_pitch survives resets
+    for (int i = 0; i < TS_END; i++) if (i < task_slots(C.task)) D.task[i * n + env] = ts[i];  // BackFlip.max_pitch survives resets
     const uint32_t epoch = D.reset_count[env] + 1;
     uint32_t* tag = D.slot_epoch + int(epoch % QS_SLOTS) * n + env;
     if (*tag == epoch) {
@@ -348,13 +348,13 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   float o[QS_MAX_OBS];
 #pragma unroll
   for (int i = 0; i < QS_MAX_OBS; i++) o[i] = 0.f;
-  observe(st, cs, ts, rpy, Rb, C.obs_mode, o);
+  observe(st, cs, ts, rpy, Rb, C.obs_mode, C.task, o);
   store_obs(io.obs + size_t(env) * C.obs_dim, o, C, A.RC, gid, D.reset_count[env], uint32_t(env_steps), C.enable_noise);
   store_state(D, env, st, cs, dt);
 #pragma unroll
   for (int i = 0; i < 12; i++) { D.tau_motor[i * n + env] = tau_m[i]; D.tau_spring[i * n + env] = tau_s[i]; }
 #pragma unroll
-  for (int i = 0; i < TS_END; i++) D.task[i * n + env] = ts[i];
+  for (int i = 0; i < TS_END; i++) if (i < task_slots(C.task)) D.task[i * n + env] = ts[i];
   D.sim_steps[env] = sim_steps;
   D.env_steps[env] = env_steps;
   D.ep_return[env] = ep_ret;

@@ -79,7 +79,11 @@ struct DeviceView {
 enum TaskSlot {
   TS_SWITCHED = 0, TS_IN_AIR, TS_T_TAKEOFF, TS_TAKEOFF_X, TS_TAKEOFF_Y, TS_TAKEOFF_Z, TS_INIT_HEIGHT,
   TS_TAKEOFF_YAW, TS_MAX_FLIGHT, TS_MAX_FWD, TS_MAX_PITCH, TS_REL_MAX_H, TS_MAX_DX, TS_MAX_H,
-  TS_MAX_PITCH_BF, TS_OLD_FWD, TS_ACTUAL_FWD, TS_OLD_TAU0 /* ..+11 */, TS_END = TS_OLD_TAU0 + 12
+  TS_MAX_PITCH_BF, TS_OLD_FWD, TS_ACTUAL_FWD, TS_OLD_TAU0 /* ..+11 */, TS_END_BASIC = TS_OLD_TAU0 + 12,
+  // continuous-jumping tasks only (task_base.py:222-400).  The reference keeps per-jump arrays; the
+  // end-of-episode reward needs only their count, sum, max and the entropy sums S = sum f, Q = sum f log2 f.
+  TS_IS_JUMPING = TS_END_BASIC, TS_CUM_FWD, TS_CUM_FLIGHT, TS_FIRST_JUMP, TS_JUMP_COUNT, TS_GOOD_JUMPS, TS_MAX_JUMP_H,
+  TS_SUM_FWD, TS_SUM_FLOG, TS_SUM_PERF, TS_MAX_PERF, TS_LAST_PERF, TS_END_JUMP, TS_END
 };
 static_assert(TS_END <= QS_TASK_DIM, "task state too large");
 

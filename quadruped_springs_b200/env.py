@@ -41,10 +41,11 @@ class _Collection:
 # control_interface/collection.py:21-49
 MotorInterfaceCollection = lambda: _Collection("motor control mode", ["PD", "CARTESIAN_PD", "TORQUE"])
 ActionInterfaceCollection = lambda: _Collection("action space mode", ["DEFAULT", "SYMMETRIC", "SYMMETRIC_NO_HIP"])
-# tasks/task_collection.py:19-37 (demo / continuous tasks are out of scope: SURVEY.md section 2 #8)
+# tasks/task_collection.py:19-37 (the *_DEMO tasks replay recorded trajectories on the host: SURVEY.md section 2 #8)
 TaskCollection = lambda: _Collection("task", [
     "NO_TASK", "JUMPING_IN_PLACE", "JUMPING_FORWARD", "BACKFLIP", "JUMPING_IN_PLACE_PPO", "JUMPING_FORWARD_PPO",
-    "BACKFLIP_PPO", "JUMPING_IN_PLACE_PPO_HP", "JUMPING_FORWARD_PPO_HP"])
+    "BACKFLIP_PPO", "JUMPING_IN_PLACE_PPO_HP", "JUMPING_FORWARD_PPO_HP", "CONTINUOUS_JUMPING_FORWARD",
+    "CONTINUOUS_JUMPING_FORWARD2", "CONTINUOUS_JUMPING_FORWARD3", "CONTINUOUS_JUMPING_FORWARD_PPO"])
 # sensors/sensor_collection.py:92-105
 SensorCollection = lambda: _Collection("sensor package", list(SENSOR_SETS))
 # env_randomizers/env_randomizer_collection.py:15-21 (mass/spring randomizers: SURVEY.md 8f "next")
@@ -309,6 +310,9 @@ _TASK_FIELDS = {  # reference attribute name -> task-state slot (csrc/qs_types.h
     "_switched_controller": 0, "_all_feet_in_the_air": 1, "_time_take_off": 2, "_init_height": 6,
     "_max_flight_time": 8, "_max_forward_distance": 9, "_max_pitch": 10, "_relative_max_height": 11,
     "_max_delta_x": 12, "_max_height": 13, "max_pitch": 14, "old_fwd": 15, "actual_fwd": 16,
+    # continuous-jumping tasks (task_base.py:222-400)
+    "is_jumping": 29, "cumulative_fwd": 30, "cumulative_flight_time": 31, "first_jump": 32, "jump_counter": 33,
+    "good_jump_counter": 34, "max_jump_height": 35, "end_jump": 41,
 }
 
 
@@ -330,6 +334,22 @@ class _Task:
 
     def is_switched_controller(self):
         return self._env._views["task"][0] != 0
+
+    def get_jumping(self):                           # task_base.py:277,355
+        return self._env._views["task"][29] != 0
+
+    def get_cumulative_fwd(self):                    # task_base.py:358 (sum of the per-jump fwd array)
+        return self._env._views["task"][36]
+
+    def get_avg_performance(self):                   # task_base.py:392-399 (zero-padded to >= 3 jumps)
+        t = self._env._views["task"]
+        return t[38] / t[33].clamp_min(3)
+
+    def get_entropy_fwd(self):                       # task_base.py:376-383
+        t = self._env._views["task"]
+        n, S, Q = t[33], t[36], t[37]
+        ent = (torch.log2(S.clamp_min(1e-30)) - Q / S.clamp_min(1e-30)) / torch.log2(n.clamp_min(3))
+        return torch.where((n > 0) & (S >= 0.05), ent, torch.zeros_like(ent))
 
     def compute_jumping_distance(self):              # task_base.py:109-116
         t = self._env._views["task"]

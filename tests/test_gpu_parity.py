@@ -435,4 +435,22 @@ def test_rollout_teacher_forced_matches_reference_env(qs, name):
             np.testing.assert_allclose(env.robot.GetMotorTorques()[0].cpu().numpy(), g["tau"][t], rtol=1e-3, atol=5e-2)
         ninv = int(env.robot.GetContactInfo()[1][0])
         assert (ninv > 0) == (int(g["n_invalid"][t]) > 0), t
+        if cfg["task_env"].startswith("CONTINUOUS") and contact_now == ref_bits:
+            gt = g["task"][t]  # [13:] is_jumping, cum_fwd, cum_flight | jump_counter, good_jumps, first_jump, max_jump_h, end_jump
+            T = env.task
+            assert float(T.is_jumping[0]) == gt[13], t
+            if cfg["task_env"] in ("CONTINUOUS_JUMPING_FORWARD", "CONTINUOUS_JUMPING_FORWARD2"):
+                assert float(T.cumulative_fwd[0]) == pytest.approx(gt[14], abs=2e-3), t
+                assert float(T.cumulative_flight_time[0]) == pytest.approx(gt[15], abs=1e-5), t
+            else:
+                assert [float(T.jump_counter[0]), float(T.good_jump_counter[0]), float(T.first_jump[0])] == list(gt[16:19]), t
+                assert float(T.max_jump_height[0]) == pytest.approx(gt[19], abs=1e-3), t
     assert bool(g["done"][-1]) == bool(d[0])
+    if "jumps" in g.files and len(g["jumps"][0]):
+        # the kernels keep sums instead of the reference's per-jump arrays (csrc/qs_types.h TaskSlot)
+        fwd, perf = g["jumps"]
+        assert float(env.task.get_cumulative_fwd()[0]) == pytest.approx(fwd.sum(), abs=2e-3)
+        assert float(env.task.get_avg_performance()[0]) == pytest.approx(perf.sum() / max(len(perf), 3), abs=2e-3)
+        p = np.concatenate([fwd, np.zeros(max(0, 3 - len(fwd)))]) / max(fwd.sum(), 1e-30)
+        ent = 0.0 if fwd.sum() < 0.05 else float(-(p[p > 0] * np.log2(p[p > 0])).sum() / np.log2(len(p)))
+        assert float(env.task.get_entropy_fwd()[0]) == pytest.approx(ent, abs=2e-2)

@@ -127,3 +127,13 @@ def test_rollout_matches_reference_env(name):
             # switched, in_air, t_takeoff, init_h, max_flight, max_fwd, max_pitch, rel_max_h, max_dx, max_h
             np.testing.assert_allclose([ts[0], ts[1], ts[2], ts[6], ts[8], ts[9], ts[10], ts[11], ts[12], ts[13]],
                                        gt[:10], rtol=1e-8, atol=1e-10, err_msg=f"task step {t}")
+            if cfg["task_env"].startswith("CONTINUOUS"):
+                # is_jumping, cumulative_fwd, cumulative_flight_time | jump_counter, good_jumps, first_jump, max_jump_h, end_jump
+                fwd, perf, cnt = env.jump_arrays()
+                np.testing.assert_allclose(ts[29:32], gt[13:16], rtol=1e-8, atol=1e-10, err_msg=f"continuous step {t}")
+                if cfg["task_env"] in ("CONTINUOUS_JUMPING_FORWARD3", "CONTINUOUS_JUMPING_FORWARD_PPO"):
+                    np.testing.assert_allclose(cnt, gt[16:21], rtol=1e-8, atol=1e-10, err_msg=f"jump counters step {t}")
+    if "jumps" in g.files:
+        fwd, perf, _ = env.jump_arrays()
+        np.testing.assert_allclose(fwd, g["jumps"][0], rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(perf, g["jumps"][1], rtol=1e-8, atol=1e-10)

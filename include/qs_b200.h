@@ -225,9 +225,10 @@ int qs_reduce_stats(qs_handle h, float* out_dev, void* stream);
  * contact x PGS-sweep count} summed over all envs since creation. */
 int qs_step_kernel_time(qs_handle h, int last_k, float* ms_sum);
 int qs_work_counters(qs_handle h, uint64_t* out3, void* stream);
-/* diagnostics of the last qs_step: {envs handed to the general solver, envs reset in place because no
- * pre-settled slot was ready, refill entries pending}; synchronises the stream */
-int qs_debug_counters(qs_handle h, int32_t* out3, void* stream);
+/* diagnostics of the last qs_step: out4 = {envs handed to the general solver, envs whose next episode was
+ * settled on the spot because no settled slot was ready, entries on the settle conveyor, ticks of its last
+ * slice}; synchronises the stream */
+int qs_debug_counters(qs_handle h, int32_t* out4, void* stream);
 
 /* number of kernels launched by this library since load (bench bookkeeping) */
 int64_t qs_launch_count(void);

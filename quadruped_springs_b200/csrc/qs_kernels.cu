@@ -310,9 +310,13 @@ struct qs_env {
   ModelConstT<double> model_d;
   void* pool;       // one allocation backing every SoA array
   size_t pool_bytes;
-  int* lists;          // slow (n + 1) | reset (n + 1) | refill (2 * cap + 1), counts last
-  int *slow_list, *reset_list, *refill_list;
-  int refill_cap, refill_threshold;
+  int* lists;          // slow (n + 1) | reset (n + 1) | urgent (2 n) | conveyor fifo, tick, wip, control words
+  int *slow_list, *reset_list;
+  Conveyor cv;
+  int wave_blocks;     // settle blocks resident at once (SMs x 2)
+  int slice_min, slice_max;
+  cudaStream_t bg;     // the conveyor's slices run here, next to k_step_slow on the caller's stream
+  cudaEvent_t ev_fork, ev_join;
   float* dev_actions;  // staging for qs_step_host
   float* dev_obs;
   float* dev_reward;
@@ -473,23 +477,48 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   D.custom_gains = (uint8_t*)carve(1);
   D.slot = (float*)carve(QS_SLOTS * SLOT_ROWS); D.slot_contact = (int32_t*)carve(QS_SLOTS); D.slot_epoch = (uint32_t*)carve(QS_SLOTS);
   if (size_t(p - static_cast<char*>(h->pool)) > h->pool_bytes) { cudaFree(h->pool); delete h; return fail(QS_ERR_STATE, "pool overflow"); }
-  h->refill_cap = 2 * QS_SLOTS * n_envs;
-  // a refill runs when one full wave of settle blocks is pending (148 SMs x 2 blocks x 128 threads),
-  // or half the envs for small batches
-  h->refill_threshold = std::max(1, std::min(n_envs / 2, 148 * 2 * 128));
-  if (const char* v = std::getenv("QS_REFILL_THRESHOLD")) h->refill_threshold = std::max(1, std::atoi(v));
-  const size_t nints = 2 * (n + 1) + 2 * size_t(h->refill_cap) + 1;
-  e = cudaMalloc(&h->lists, nints * sizeof(int));
-  if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(QS_ERR_CUDA, "cudaMalloc lists"); }
-  cudaMemset(h->lists, 0, nints * sizeof(int));
-  h->slow_list = h->lists;
-  h->reset_list = h->slow_list + n + 1;
-  h->refill_list = h->reset_list + n + 1;
+  {
+    // settle conveyor: window = one wave of settle blocks (2 per SM); the queue holds every ring entry
+    // of every env several times over (duplicates after explicit resets)
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(QS_ERR_CUDA, "cudaGetDeviceProperties"); }
+    const int B = block_of(h);
+    h->wave_blocks = prop.multiProcessorCount * std::max(1, 256 / B);
+    Conveyor& cv = h->cv;
+    cv.width = h->wave_blocks * B;
+    size_t cap = 1024;
+    while (cap < 4 * size_t(QS_SLOTS) * n) cap <<= 1;
+    cv.cap_mask = uint32_t(cap - 1);
+    h->slice_min = 8;
+    h->slice_max = 1 << 20;  // no cap: the slice follows the demand
+    if (const char* v = std::getenv("QS_SETTLE_SLICE_MIN")) h->slice_min = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("QS_SETTLE_SLICE_MAX")) h->slice_max = std::max(h->slice_min, std::atoi(v));
+    const size_t w = size_t(cv.width);
+    const size_t nints = 2 * (n + 1) + 2 * n + 2 * cap + cap + (WIP_ROWS + 1) * w + CV_CTL_WORDS;
+    e = cudaMalloc(&h->lists, nints * sizeof(int));
+    if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(QS_ERR_CUDA, "cudaMalloc lists"); }
+    cudaMemset(h->lists, 0, nints * sizeof(int));
+    h->slow_list = h->lists;
+    h->reset_list = h->slow_list + n + 1;
+    cv.urgent_list = h->reset_list + n + 1;
+    cv.fifo = cv.urgent_list + 2 * n;
+    cv.tick = cv.fifo + 2 * cap;
+    cv.wip = reinterpret_cast<float*>(cv.tick + cap);
+    cv.wip_contact = reinterpret_cast<int*>(cv.wip + WIP_ROWS * w);
+    cv.ctl = reinterpret_cast<uint32_t*>(cv.wip_contact + w);
+    cudaMemset(cv.tick, 0xff, cap * sizeof(int));  // CV_DONE: nothing queued
+    e = cudaStreamCreateWithFlags(&h->bg, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    if (e != cudaSuccess) { cudaFree(h->pool); cudaFree(h->lists); delete h; return fail(QS_ERR_CUDA, "stream / event creation"); }
+  }
   {
     const int max_smem = int(smem_of(256));
     e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_refill, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_settle_urgent, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_settle_slice, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_debug_ticks<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    int(64 * QS_TICK_SCRATCH * sizeof(double)));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_debug_ticks<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -506,6 +535,9 @@ int qs_destroy(qs_handle h) {
   cudaDeviceSynchronize();
   cudaFree(h->pool);
   cudaFree(h->lists);
+  cudaStreamDestroy(h->bg);
+  cudaEventDestroy(h->ev_fork);
+  cudaEventDestroy(h->ev_join);
   if (h->dev_actions) cudaFree(h->dev_actions);
   if (h->dev_obs) cudaFree(h->dev_obs);
   if (h->dev_reward) cudaFree(h->dev_reward);
@@ -551,16 +583,19 @@ int qs_work_counters(qs_handle h, uint64_t* out3, void* stream) {
   return QS_OK;
 }
 
-int qs_debug_counters(qs_handle h, int32_t* out3, void* stream) {
-  // {envs handed to the general solver, envs reset in place (no spare slot ready), refill entries pending}
-  // as left by the last qs_step; synchronises
+int qs_debug_counters(qs_handle h, int32_t* out3, void* stream) {  // out3: 4 counters
+  // {envs handed to the general solver, envs started on the urgent path (no settled slot was ready),
+  // conveyor entries in flight, ticks of the last slice} as left by the last qs_step; synchronises
   if (!h || !out3) return fail(QS_ERR_ARG, "NULL argument");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaMemcpyAsync(out3 + 0, h->slow_list + h->n, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(out3 + 1, h->reset_list + h->n, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(out3 + 2, h->refill_list + 2 * h->refill_cap, sizeof(int), cudaMemcpyDeviceToHost, s));
+  uint32_t ctl[CV_CTL_WORDS];
+  CUDA_TRY(cudaMemcpyAsync(ctl, h->cv.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  out3[1] = int32_t(ctl[CV_URGENT_LAST]);
+  out3[2] = int32_t(ctl[CV_HEAD] - ctl[CV_TAIL]);
+  out3[3] = int32_t(ctl[CV_SLICE]);
   return QS_OK;
 }
 
@@ -579,13 +614,22 @@ int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* o) {
 }
 
 
-// pre-settle queued episodes; a no-op kernel pair unless `threshold` entries are pending
-static int launch_refill(qs_handle h, cudaStream_t s, int threshold, float* obs) {
+// One turn of the settle conveyor.  In qs_step it runs on the second stream, forked after k_step and
+// joined before the urgent pass, so that the slice shares the GPU with k_step_slow (a few latency-bound
+// blocks); `flush` runs the whole window to completion in stream order (reset-time prefill).
+static int launch_conveyor(qs_handle h, cudaStream_t s, int flush) {
   const int B = block_of(h);
-  int* urgent = h->reset_list + h->n;  // in qs_step the reset-list counter counts urgent entries
-  k_refill<<<grid_for(h->refill_cap, B), B, smem_of(B), s>>>(h->args, h->refill_list, h->refill_cap, threshold, urgent, obs);
-  k_refill_done<<<1, 1, 0, s>>>(h->refill_list, h->refill_cap, threshold, urgent);
-  g_launches += 2;
+  const int nsettle = h->cfg.is_rl_interface ? h->cfg.settling_steps : 1500;
+  k_conveyor_ctl<<<1, 1024, 0, s>>>(h->cv, flush ? nullptr : h->slow_list + h->n, 64, h->wave_blocks, B, nsettle,
+                                    h->slice_min, h->slice_max, flush);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+static int launch_slice(qs_handle h, cudaStream_t s) {
+  const int B = block_of(h);
+  k_settle_slice<<<h->wave_blocks, B, smem_of(B), s>>>(h->args, h->cv);
+  g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return QS_OK;
 }
@@ -595,21 +639,24 @@ int qs_reset(qs_handle h, const uint8_t* mask, float* obs, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(h->device));
   const int B = block_of(h);
-  int* rl = h->refill_list;
   if (mask) {
     CUDA_TRY(cudaMemsetAsync(h->reset_list + h->n, 0, sizeof(int), s));
     k_compact<<<grid_for(h->n, 256), 256, 0, s>>>(mask, h->n, h->reset_list);
-    k_reset<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, h->reset_list, rl, h->refill_cap, obs);
+    k_reset<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, h->reset_list, h->cv, obs);
     g_launches += 2;
   } else {
-    k_reset<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, nullptr, rl, h->refill_cap, obs);
+    k_reset<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, nullptr, h->cv, obs);
     g_launches += 1;
   }
   CUDA_TRY(cudaGetLastError());
   if (h->cfg.auto_reset) {
-    // (re)fill the spare slots of the envs just reset, in stream order
-    CUDA_TRY(cudaMemsetAsync(h->reset_list + h->n, 0, sizeof(int), s));
-    if (int e = launch_refill(h, s, 1, obs)) return e;
+    // settle the rings of the envs just reset, in stream order: every queued entry, one window at a time
+    const size_t entries = size_t(QS_SLOTS) * size_t(h->n);
+    const int rounds = int((entries + size_t(h->cv.width) - 1) / size_t(h->cv.width));
+    for (int r = 0; r < rounds; r++) {
+      if (int e = launch_conveyor(h, s, 1)) return e;
+      if (int e = launch_slice(h, s)) return e;
+    }
   }
   h->was_reset = true;
   return QS_OK;
@@ -623,29 +670,38 @@ int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(h->device));
   const int B = block_of(h);
-  // slow and reset lists are adjacent: clear both counts ... (counts sit at the end of each list)
   CUDA_TRY(cudaMemsetAsync(h->slow_list + h->n, 0, sizeof(int), s));
-  CUDA_TRY(cudaMemsetAsync(h->reset_list + h->n, 0, sizeof(int), s));
   if (!h->ev_ready) {
     for (int i = 0; i < qs_env::kRing; i++) { CUDA_TRY(cudaEventCreate(&h->ev0[i])); CUDA_TRY(cudaEventCreate(&h->ev1[i])); }
     h->ev_ready = true;
   }
   StepIO io;
   io.actions = actions; io.obs = obs; io.reward = reward; io.done = done; io.truncated = truncated;
-  io.slow_list = h->slow_list; io.reset_list = h->reset_list;
-  io.refill_list = h->refill_list; io.refill_cap = h->refill_cap;
+  io.slow_list = h->slow_list;
+  io.cv = h->cv;
   const int slot = int(h->n_steps % qs_env::kRing);
   cudaEventRecord(h->ev0[slot], s);
   k_step<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
   cudaEventRecord(h->ev1[slot], s);
   h->n_steps++;
-  // envs parked for the general solver (joint limits / body contacts): usually none
+  if (h->cfg.auto_reset) {
+    // conveyor turn: bookkeeping in stream order, then the slice on the second stream next to k_step_slow
+    if (int e = launch_conveyor(h, s, 0)) return e;
+    CUDA_TRY(cudaEventRecord(h->ev_fork, s));
+  }
+  // envs parked for the general solver (joint limits / body contacts); launched before the slice so
+  // that its few blocks are placed first
   k_step_slow<<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io);
   g_launches += 2;
   if (h->cfg.auto_reset) {
-    // pre-settle queued episodes when a full wave is pending; also starts, right now, the episodes of
-    // envs that finished without a ready slot (urgent entries; rare)
-    if (int e = launch_refill(h, s, h->refill_threshold, obs)) return e;
+    CUDA_TRY(cudaStreamWaitEvent(h->bg, h->ev_fork, 0));
+    if (int e = launch_slice(h, h->bg)) return e;
+    CUDA_TRY(cudaEventRecord(h->ev_join, h->bg));
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
+    // envs that finished without a settled slot (rare): settled and started now
+    k_settle_urgent<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, h->cv, obs);
+    k_urgent_clear<<<1, 1, 0, s>>>(h->cv);
+    g_launches += 2;
   }
   CUDA_TRY(cudaGetLastError());
   return QS_OK;

@@ -7,16 +7,20 @@
 //                (a handful of envs per step: launched for N, exits on `count`).
 //   k_reset      in-place reset + 2500-tick settle (exact QuadrupedGymEnv.reset), for a
 //                mask / list / all envs.
-//   k_refill     pre-settles the NEXT episode of envs whose spare slot is empty.
+//   k_settle_slice / k_conveyor_ctl   the settle conveyor: episodes settled ahead of time.
+//   k_settle_urgent                   an episode nobody settled in time (rare).
 //
 // Auto-reset without stalls: the state an env starts its next episode from is a pure
 // function of (seed, global env id, episode number): mu ~ U[0.5,1) from Philox, then the
-// reference's 2500 settle ticks.  Each env owns a ring of QS_SLOTS spare slots holding its
-// next episodes' settled states; a finished env copies its slot inside k_step and queues an
-// (env, episode) refill entry.  k_refill is launched after every step but returns at once
-// unless a machine-filling batch of entries is pending, so the 2500-tick settles always run
-// as dense, full-occupancy launches.  If a slot is not ready the env falls back to k_reset in
-// place -- same numbers either way, so results never depend on scheduling or sharding.
+// reference's 2500 settle ticks.  Each env owns a ring of QS_SLOTS slots holding its next
+// episodes' settled states; a finished env copies its slot inside k_step and queues the
+// slot's next tenant on the conveyor.  Every control step the conveyor advances all its
+// entries by a slice of ticks (k_settle_slice, on a second stream, next to the few
+// latency-bound blocks of k_step_slow), saving the unfinished ones bit-exactly in between, so
+// the settles run as one dense wave and their cost hides behind the step's serial tail.
+// If a slot is not ready in time the episode is settled start to end at the end of the step
+// (k_settle_urgent) -- same numbers either way, so results never depend on scheduling,
+// slicing or sharding.
 #pragma once
 
 // settling / reset-time command: _convert_reference_to_command(get_init_pose())
@@ -95,6 +99,28 @@ __device__ __forceinline__ void finish_episode_stats(const DeviceView& D, int en
   s[10 * n] += terminated ? 1.f : 0.f;
 }
 
+constexpr int QS_SLOTS = 4;  // settled episodes kept ahead per env (ring indexed by episode number)
+
+// ---- settle conveyor: the queue of (env, episode) pairs whose settled start state is computed
+// ahead of time, a slice of ticks per control step, on a second stream next to k_step_slow.
+//   fifo[2 * (i & cap_mask)] = {env, episode} of entry i; entries are pushed at `head` and retire at `tail`
+//   tick[i & cap_mask]       = settle ticks already done for entry i (CV_DONE: finished or dropped)
+//   wip[row][i % width]      = state of entry i between slices (raw floats: slicing is bit-invisible)
+// The first `active` entries after `tail` run `slice` ticks in k_settle_slice; k_conveyor_ctl picks both.
+enum { CV_HEAD = 0, CV_TAIL, CV_ACTIVE, CV_SLICE, CV_URGENT, CV_URGENT_LAST, CV_PREV_HEAD, CV_DEMAND, CV_CTL_WORDS = 8 };
+constexpr int CV_DONE = -1;
+constexpr int WIP_ROWS = 37 + 4;  // state | normal impulses (warm start); + contact mask (int row)
+struct Conveyor {
+  int* fifo;
+  int* tick;
+  float* wip;
+  int* wip_contact;
+  uint32_t* ctl;
+  int* urgent_list;  // (env, episode) pairs that must be settled and started NOW; count in ctl[CV_URGENT]
+  uint32_t cap_mask;
+  int width;
+};
+
 struct StepIO {
   const float* actions;
   float* obs;
@@ -102,23 +128,41 @@ struct StepIO {
   uint8_t* done;
   uint8_t* truncated;
   int* slow_list;    // envs parked for the general solver, slow_list[n] = count
-  int* reset_list;   // envs that must be reset in place,   reset_list[n] = count
-  int* refill_list;  // (env, episode) pairs to pre-settle, refill_list[2 * refill_cap] = count
-  int refill_cap;
+  Conveyor cv;
 };
 
-constexpr int QS_SLOTS = 2;
-constexpr uint32_t QS_URGENT = 0x80000000u;  // refill entry flag: settle AND start the episode now (no slot was ready)
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
-__device__ __forceinline__ void refill_push(int* list, int cap, int env, uint32_t epoch) {
-  const int i = atomicAdd(list + 2 * cap, 1);
-  // an overflowing entry is only a missed prefetch: the env falls back to k_reset
-  if (i < cap) { list[2 * i] = env; list[2 * i + 1] = int(epoch); }
+__device__ __forceinline__ void conveyor_push(const Conveyor& cv, int env, uint32_t epoch) {
+  const uint32_t i = atomicAdd(cv.ctl + CV_HEAD, 1u);
+  const uint32_t tail = *reinterpret_cast<volatile uint32_t*>(cv.ctl + CV_TAIL);
+  // a full queue only loses a prefetch: the position keeps its retired entry and the env takes the urgent path
+  if (i - tail > cv.cap_mask) return;
+  const uint32_t pos = i & cv.cap_mask;
+  cv.fifo[2 * pos] = env;
+  cv.fifo[2 * pos + 1] = int(epoch);
+  cv.tick[pos] = 0;
+}
+__device__ __forceinline__ void urgent_push(const Conveyor& cv, int env, uint32_t epoch) {
+  const uint32_t i = atomicAdd(cv.ctl + CV_URGENT, 1u);
+  cv.urgent_list[2 * i] = env;  // at most one per env and step
+  cv.urgent_list[2 * i + 1] = int(epoch);
 }
 
 // ---- spare slot of an env: the settled state its next episode starts from
 // rows: state 37 | tau_motor 12 | tau_spring 12 | foot_force 4 | mu 1   (floats), contact, epoch (ints)
 constexpr int SLOT_ROWS = 37 + 12 + 12 + 4 + 1;
+
+__device__ __forceinline__ bool slot_ready(const DeviceView& D, int env, uint32_t epoch) {
+  return ld_acquire(D.slot_epoch + int(epoch % QS_SLOTS) * D.n + env) == epoch;
+}
 
 __device__ __forceinline__ void slot_store(const DeviceView& D, int env, const EnvState<float>& st,
                                            const ContactState<float>& cs, const float* tau_m, const float* tau_s,
@@ -144,7 +188,51 @@ __device__ __forceinline__ void slot_store(const DeviceView& D, int env, const E
   for (int k = 0; k < 4; k++) s[(61 + k) * n] = cs.lam_n[k] / dt;
   s[65 * n] = mu;
   D.slot_contact[sl * n + env] = (cs.mask & 15) | (cs.invalid << 8);
-  D.slot_epoch[sl * n + env] = epoch;
+  st_release(D.slot_epoch + sl * n + env, epoch);  // readers on the other stream see the rows before the tag
+}
+
+// state of a settle between two slices (bit-exact round trip)
+__device__ __forceinline__ void wip_store(const Conveyor& cv, int col, const EnvState<float>& st, const ContactState<float>& cs) {
+  const int w = cv.width;
+  float* s = cv.wip + col;
+#pragma unroll
+  for (int i = 0; i < 3; i++) s[i * w] = st.pos[i];
+#pragma unroll
+  for (int i = 0; i < 4; i++) s[(3 + i) * w] = st.quat[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) s[(7 + i) * w] = st.vlin[i];
+#pragma unroll
+  for (int i = 0; i < 3; i++) s[(10 + i) * w] = st.vang[i];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[(13 + i) * w] = st.q[i];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[(25 + i) * w] = st.qd[i];
+#pragma unroll
+  for (int k = 0; k < 4; k++) s[(37 + k) * w] = cs.lam_n[k];
+  cv.wip_contact[col] = (cs.mask & 15) | (cs.invalid << 8);
+}
+__device__ __forceinline__ void wip_load(const Conveyor& cv, int col, EnvState<float>& st, ContactState<float>& cs) {
+  const int w = cv.width;
+  const float* s = cv.wip + col;
+#pragma unroll
+  for (int i = 0; i < 3; i++) st.pos[i] = s[i * w];
+#pragma unroll
+  for (int i = 0; i < 4; i++) st.quat[i] = s[(3 + i) * w];
+#pragma unroll
+  for (int i = 0; i < 3; i++) st.vlin[i] = s[(7 + i) * w];
+#pragma unroll
+  for (int i = 0; i < 3; i++) st.vang[i] = s[(10 + i) * w];
+#pragma unroll
+  for (int i = 0; i < 12; i++) st.q[i] = s[(13 + i) * w];
+#pragma unroll
+  for (int i = 0; i < 12; i++) st.qd[i] = s[(25 + i) * w];
+#pragma unroll
+  for (int k = 0; k < 4; k++) cs.lam_n[k] = s[(37 + k) * w];
+  const int c = cv.wip_contact[col];
+  cs.mask = c & 15;
+  cs.invalid = c >> 8;
+  cs.work_contacts = 0;
+  cs.work_row_iters = 0;
 }
 
 __device__ __forceinline__ void slot_load(const DeviceView& D, int env, uint32_t epoch, EnvState<float>& st,
@@ -176,28 +264,30 @@ __device__ __forceinline__ void slot_load(const DeviceView& D, int env, uint32_t
   cs.work_row_iters = 0;
 }
 
-// A fresh robot settled for episode `epoch` of global env `gid`
-// (quadruped_gym_env.py:278-289,323-327; env_randomizer.py:287-289).
-__device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint64_t gid, uint32_t epoch,
-                                             EnvState<float>& st, ContactState<float>& cs, float* tau_m, float* tau_s,
-                                             float* mu_out, const Scratch<float>& scr, bool need) {
-  // `need` = this thread really settles; the others only keep the block's barriers matched.
-  // Must be called by every thread of the block.
-  if (!__syncthreads_or(need)) return;
-  const EnvCfg& C = A.C;
-  const float mu = C.ground_randomizer ? 0.5f + 0.5f * uniform1(C.seed, gid, epoch, 100) : C.mu_ground;
-  if (need) *mu_out = mu;
-  EnvState<float> st_keep = st;  // a thread that does not need the settle gets its state back untouched
-  ContactState<float> cs_keep = cs;
-  st.pos[0] = 0.f; st.pos[1] = 0.f; st.pos[2] = 0.32f;  // INIT_POSITION, configs:23
+// The robot as reset() spawns it (quadruped_gym_env.py:278-289, configs:23)
+__device__ __forceinline__ void fresh_state(const KernelArgs& A, EnvState<float>& st, ContactState<float>& cs) {
+  st.pos[0] = 0.f; st.pos[1] = 0.f; st.pos[2] = 0.32f;  // INIT_POSITION
   st.quat[0] = st.quat[1] = st.quat[2] = 0.f; st.quat[3] = 1.f;
 #pragma unroll
   for (int i = 0; i < 3; i++) { st.vlin[i] = 0.f; st.vang[i] = 0.f; }
 #pragma unroll
-  for (int i = 0; i < 12; i++) { st.q[i] = A.RC.init_angles[i]; st.qd[i] = 0.f; tau_m[i] = 0.f; tau_s[i] = 0.f; }
+  for (int i = 0; i < 12; i++) { st.q[i] = A.RC.init_angles[i]; st.qd[i] = 0.f; }
   cs.mask = 0; cs.invalid = 0; cs.work_contacts = 0; cs.work_row_iters = 0;
 #pragma unroll
   for (int k = 0; k < 4; k++) cs.lam_n[k] = 0.f;
+}
+__device__ __forceinline__ float episode_mu(const EnvCfg& C, uint64_t gid, uint32_t epoch) {  // env_randomizer.py:287-289
+  return C.ground_randomizer ? 0.5f + 0.5f * uniform1(C.seed, gid, epoch, 100) : C.mu_ground;
+}
+__device__ __forceinline__ int settle_length(const EnvCfg& C) { return C.is_rl ? C.settling_steps : 1500; }
+
+// Settle ticks [t0, t1) of the reset (control_interface/interface_base.py:182-200), at most `span` of them.
+// Every thread of the block runs the same `span` iterations (one barrier each, see run_ticks);
+// a thread works while t < t1.
+__device__ __forceinline__ void settle_ticks(const KernelArgs& A, EnvState<float>& st, ContactState<float>& cs, float mu,
+                                             int t0, int t1, int span, float* tau_m, float* tau_s,
+                                             const Scratch<float>& scr) {
+  const EnvCfg& C = A.C;
   float cmd[12], act12[12];
   settle_command(C, A.RC, cmd, act12);
   // a fresh Quadruped has the default gains / springs (quadruped_gym_env.py:299-319); the settle
@@ -205,17 +295,19 @@ __device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint6
   SolverConst SCs = A.SC;
   SCs.enable_limits = 0;
   SCs.body_response = 0;
-  const int nsettle = C.is_rl ? C.settling_steps : 1500;
+  const int nsettle = settle_length(C);
   float sk[3], sb[3], sr[3];
 #pragma unroll
   for (int j = 0; j < 3; j++) { sk[j] = A.RC.spring_k[j]; sb[j] = A.RC.spring_b[j]; sr[j] = A.RC.spring_rest[j]; }
-  for (int t = 0; t < nsettle; t++) {
+  for (int i = 0; i < span; i++) {
     __syncthreads();  // lockstep across the block (see run_ticks)
+    const int t = t0 + i;
+    if (t >= t1) continue;
     float tau[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
-      tau_m[i] = pd_torque1(A.RC.kp[i], A.RC.kd[i], A.RC.tau_max[i], cmd[i], st.q[i], st.qd[i], false);
-      tau[i] = tau_m[i];
+    for (int i2 = 0; i2 < 12; i2++) {
+      tau_m[i2] = pd_torque1(A.RC.kp[i2], A.RC.kd[i2], A.RC.tau_max[i2], cmd[i2], st.q[i2], st.qd[i2], false);
+      tau[i2] = tau_m[i2];
     }
     if (C.enable_springs) {
 #pragma unroll
@@ -225,8 +317,26 @@ __device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint6
         for (int j = 0; j < 3; j++) tau[3 * k + j] += tau_s[3 * k + j];
       }
     }
-    if (need) physics_tick(st, tau, mu, cs, A.M, SCs, t == nsettle - 1, scr);
+    physics_tick(st, tau, mu, cs, A.M, SCs, t == nsettle - 1, scr);
   }
+}
+
+// A fresh robot settled for episode `epoch` of global env `gid`, start to end.
+__device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint64_t gid, uint32_t epoch,
+                                             EnvState<float>& st, ContactState<float>& cs, float* tau_m, float* tau_s,
+                                             float* mu_out, const Scratch<float>& scr, bool need) {
+  // `need` = this thread really settles; the others only keep the block's barriers matched.
+  // Must be called by every thread of the block.
+  if (!__syncthreads_or(need)) return;
+  const float mu = episode_mu(A.C, gid, epoch);
+  if (need) *mu_out = mu;
+  EnvState<float> st_keep = st;  // a thread that does not need the settle gets its state back untouched
+  ContactState<float> cs_keep = cs;
+  fresh_state(A, st, cs);
+#pragma unroll
+  for (int i = 0; i < 12; i++) { tau_m[i] = 0.f; tau_s[i] = 0.f; }
+  const int nsettle = settle_length(A.C);
+  settle_ticks(A, st, cs, mu, 0, need ? nsettle : 0, nsettle, tau_m, tau_s, scr);
   if (!need) { st = st_keep; cs = cs_keep; }
 }
 
@@ -324,23 +434,17 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
 #pragma unroll
     for (int i = 0; i < TS_END; i++) if (i < task_slots(C.task)) D.task[i * n + env] = ts[i];  // BackFlip.max_pitch survives resets
     const uint32_t epoch = D.reset_count[env] + 1;
-    uint32_t* tag = D.slot_epoch + int(epoch % QS_SLOTS) * n + env;
-    if (*tag == epoch) {
+    if (slot_ready(D, env, epoch)) {
       float tm[12], tsp[12], mu;
       slot_load(D, env, epoch, st, cs, tm, tsp, &mu, dt);
-      *tag = 0;
-      refill_push(io.refill_list, io.refill_cap, env, epoch + QS_SLOTS);  // the freed slot's next tenant
+      D.slot_epoch[int(epoch % QS_SLOTS) * n + env] = 0;
+      conveyor_push(io.cv, env, epoch + QS_SLOTS);  // the freed slot's next tenant
       begin_episode(A, env, epoch, mu, st, cs, tm, tsp, io.obs);
     } else {
-      // no spare slot ready: an urgent refill entry makes k_refill (launched right after this kernel)
+      // no spare slot ready: an urgent entry makes k_settle_urgent (launched at the end of this step)
       // settle this episode now and start it; same numbers as the prefetched path
       store_state(D, env, st, cs, dt);
-      refill_push(io.refill_list, io.refill_cap, env, epoch | QS_URGENT);
-#pragma unroll
-      for (int d = 1; d <= QS_SLOTS; d++)  // and its (empty or stale) ring is rebuilt in the same launch
-        if (D.slot_epoch[int((epoch + d) % QS_SLOTS) * n + env] != epoch + d)
-          refill_push(io.refill_list, io.refill_cap, env, epoch + d);
-      atomicAdd(io.reset_list + n, 1);  // urgent counter (forces the refill to run)
+      urgent_push(io.cv, env, epoch);
     }
     return;
   }
@@ -459,8 +563,8 @@ k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io) {
 // list == nullptr: thread i resets env i (all envs).  Otherwise thread i resets env list[i]
 // for i < list[n] (dense warps whatever the done pattern).
 __global__ void __launch_bounds__(256, 1)
-k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, int* __restrict__ refill_list,
-        int refill_cap, float* __restrict__ obs) {
+k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, const Conveyor cv,
+        float* __restrict__ obs) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const DeviceView& D = A.D;
   const int n = D.n;
@@ -475,8 +579,7 @@ k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, int*
   EnvState<float> st;
   ContactState<float> cs;
   float tau_m[12], tau_s[12], mu;
-  uint32_t* tag = D.slot_epoch + int(epoch % QS_SLOTS) * n + env;
-  const bool have = *tag == epoch;
+  const bool have = slot_ready(D, env, epoch);
   extern __shared__ float qs_smem[];
   const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
   float tm2[12], ts2[12];
@@ -489,57 +592,133 @@ k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, int*
   }
   if (!live) return;
   if (A.C.auto_reset) {
-    if (have) *tag = 0;
-    // every future episode within the ring must be present or queued (duplicates are skipped by k_refill)
+    if (have) D.slot_epoch[int(epoch % QS_SLOTS) * n + env] = 0;
+    // every future episode within the ring must be present or queued (a duplicate of an entry already
+    // on the conveyor settles twice and stores the same rows)
 #pragma unroll
-    for (int d = 1; d <= QS_SLOTS; d++) {
-      const uint32_t e = epoch + d;
-      if (D.slot_epoch[int(e % QS_SLOTS) * n + env] != e) refill_push(refill_list, refill_cap, env, e);
-    }
+    for (int d = 1; d <= QS_SLOTS; d++)
+      if (!slot_ready(D, env, epoch + d)) conveyor_push(cv, env, epoch + d);
   }
   begin_episode(A, env, epoch, mu, st, cs, tau_m, tau_s, obs);
 }
 
-// pre-settle queued (env, episode) pairs into the envs' spare slots.  Launched after every
-// step: returns immediately unless at least `threshold` entries are pending or an entry is
-// urgent (an env finished without a ready slot: its episode is settled and started here).
+// Episodes of envs that finished without a ready slot: settled start to end and started, in stream
+// order at the end of the step.  Exits at once when there is none (the usual case).
 __global__ void __launch_bounds__(256, 1)
-k_refill(const __grid_constant__ KernelArgs A, const int* __restrict__ list, int cap, int threshold,
-         const int* __restrict__ urgent_count, float* __restrict__ obs) {
+k_settle_urgent(const __grid_constant__ KernelArgs A, const Conveyor cv, float* __restrict__ obs) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const DeviceView& D = A.D;
-  const int n = D.n;
-  const int count = min(list[2 * cap], cap);
-  if ((count < threshold && *urgent_count == 0) || count == 0) return;  // uniform over the grid
-  if (blockIdx.x * blockDim.x >= count) return;                          // uniform over the block
+  const int count = int(cv.ctl[CV_URGENT]);
+  if (blockIdx.x * blockDim.x >= count) return;  // uniform over the block
   const bool live = tid < count;
   const int i = live ? tid : count - 1;
-  const int env = list[2 * i];
-  const uint32_t raw = uint32_t(list[2 * i + 1]);
-  const bool urgent = (raw & QS_URGENT) != 0;
-  const uint32_t epoch = raw & ~QS_URGENT;
-  // skip duplicates and entries that became stale (the env moved past that episode)
-  const bool need = urgent ? (D.reset_count[env] + 1 == epoch)
-                           : (D.slot_epoch[int(epoch % QS_SLOTS) * n + env] != epoch && epoch > D.reset_count[env]);
+  const int env = cv.urgent_list[2 * i];
+  const uint32_t epoch = uint32_t(cv.urgent_list[2 * i + 1]);
   EnvState<float> st;
   ContactState<float> cs;
   float tau_m[12], tau_s[12], mu = 0.f;
   extern __shared__ float qs_smem[];
   const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
-  settle_fresh(A, env, uint64_t(A.C.gid0 + env), epoch, st, cs, tau_m, tau_s, &mu, scr, need);
-  if (!live || !need) return;
-  if (urgent) {
-    begin_episode(A, env, epoch, mu, st, cs, tau_m, tau_s, obs);
-  } else {
-    slot_store(D, env, st, cs, tau_m, tau_s, mu, epoch, A.SC.dt);
-  }
+  settle_fresh(A, env, uint64_t(A.C.gid0 + env), epoch, st, cs, tau_m, tau_s, &mu, scr, live);
+  if (!live) return;
+  // its ring: the slot of this episode never became ready, the others may be missing too
+#pragma unroll
+  for (int d = 1; d <= QS_SLOTS; d++)
+    if (!slot_ready(D, env, epoch + d)) conveyor_push(cv, env, epoch + d);
+  begin_episode(A, env, epoch, mu, st, cs, tau_m, tau_s, obs);
 }
-// clears the queue after a refill that ran (same trigger condition)
-__global__ void k_refill_done(int* __restrict__ list, int cap, int threshold, int* __restrict__ urgent_count) {
-  const int count = min(list[2 * cap], cap);
-  if ((count >= threshold || *urgent_count > 0) && count > 0) {
-    list[2 * cap] = 0;
-    *urgent_count = 0;
+__global__ void k_urgent_clear(Conveyor cv) {
+  cv.ctl[CV_URGENT_LAST] = cv.ctl[CV_URGENT];
+  cv.ctl[CV_URGENT] = 0;
+}
+
+// Conveyor bookkeeping, once per step between k_step and the slice: retire the finished entries at
+// the tail, then choose how many entries run (`lanes` = what fits next to this step's k_step_slow
+// blocks) and for how many ticks.  The slice length follows the demand (entries pushed per step,
+// smoothed): with d episodes ending per step, nsettle * d / slice entries are in flight, and the slice
+// is chosen so that they fill ~90 % of one wave -- the settles then run as a dense launch whatever
+// the episode length.  Entries beyond the window (start-up, bursts) or flush != 0 run the window to
+// completion at once.
+__global__ void k_conveyor_ctl(Conveyor cv, const int* __restrict__ slow_count, int slow_block, int wave_blocks,
+                               int block, int nsettle, int s_min, int s_max, int flush) {
+  __shared__ uint32_t first_live;
+  const uint32_t head = cv.ctl[CV_HEAD];
+  uint32_t tail = cv.ctl[CV_TAIL];
+  const uint32_t span = min(head - tail, uint32_t(cv.width));
+  if (threadIdx.x == 0) first_live = span;
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < span; j += blockDim.x)
+    if (cv.tick[(tail + j) & cv.cap_mask] != CV_DONE) { atomicMin(&first_live, j); break; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  tail += first_live;
+  const uint32_t pending = head - tail;
+  int lanes = cv.width;
+  if (slow_count && !flush) {
+    const int reserve = (*slow_count + slow_block - 1) / slow_block;  // one settle block displaced per slow block
+    lanes = max(block, min(cv.width, (wave_blocks - reserve) * block));
+  }
+  const uint32_t active = min(pending, uint32_t(lanes));
+  int slice = nsettle;
+  if (!flush) {
+    float demand = __uint_as_float(cv.ctl[CV_DEMAND]);
+    demand += (float(head - cv.ctl[CV_PREV_HEAD]) - demand) * 0.125f;
+    cv.ctl[CV_DEMAND] = __float_as_uint(demand);
+    const float target = 0.9f * float(lanes);
+    float want = float(nsettle) * demand / target;
+    if (float(active) > 0.97f * float(lanes)) want *= 1.5f;  // nearly full: catch up before a backlog forms
+    slice = max(s_min, min(s_max, int(ceilf(want))));
+    if (pending > uint32_t(lanes)) slice = nsettle;
+  }
+  cv.ctl[CV_PREV_HEAD] = head;
+  cv.ctl[CV_TAIL] = tail;
+  cv.ctl[CV_ACTIVE] = active;
+  cv.ctl[CV_SLICE] = uint32_t(slice);
+}
+
+// One slice of the conveyor: entry tail + j advances by ctl[CV_SLICE] settle ticks; an entry that
+// reaches the end of its settle stores the episode's slot and retires.
+__global__ void __launch_bounds__(256, 1)
+k_settle_slice(const __grid_constant__ KernelArgs A, const Conveyor cv) {
+  const DeviceView& D = A.D;
+  const int n = D.n;
+  const int active = int(cv.ctl[CV_ACTIVE]);
+  if (blockIdx.x * blockDim.x >= active) return;  // uniform over the block
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = j < active;
+  const uint32_t idx = cv.ctl[CV_TAIL] + uint32_t(live ? j : active - 1);
+  const uint32_t pos = idx & cv.cap_mask;
+  const int span = int(cv.ctl[CV_SLICE]);
+  const int env = cv.fifo[2 * pos];
+  const uint32_t epoch = uint32_t(cv.fifo[2 * pos + 1]);
+  const int t0 = cv.tick[pos];
+  bool need = live && t0 != CV_DONE;
+  // stale (the env went past that episode on the urgent path) or already stored by a duplicate
+  if (need && (epoch <= D.reset_count[env] || slot_ready(D, env, epoch))) {
+    cv.tick[pos] = CV_DONE;
+    need = false;
+  }
+  const int nsettle = settle_length(A.C);
+  const int col = int(idx % uint32_t(cv.width));
+  EnvState<float> st;
+  ContactState<float> cs;
+  float tau_m[12], tau_s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) { tau_m[i] = 0.f; tau_s[i] = 0.f; }
+  fresh_state(A, st, cs);
+  if (need && t0 > 0) wip_load(cv, col, st, cs);
+  const float mu = episode_mu(A.C, uint64_t(A.C.gid0 + env), epoch);
+  const int t1 = need ? min(t0 + span, nsettle) : 0;
+  extern __shared__ float qs_smem[];
+  const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
+  settle_ticks(A, st, cs, mu, t0, t1, span, tau_m, tau_s, scr);
+  if (!need) return;
+  if (t1 == nsettle) {
+    slot_store(D, env, st, cs, tau_m, tau_s, mu, epoch, A.SC.dt);
+    cv.tick[pos] = CV_DONE;
+  } else {
+    wip_store(cv, col, st, cs);
+    cv.tick[pos] = t1;
   }
 }
 

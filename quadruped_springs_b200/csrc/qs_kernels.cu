@@ -490,7 +490,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     size_t cap = 1024;
     while (cap < 4 * size_t(QS_SLOTS) * n) cap <<= 1;
     cv.cap_mask = uint32_t(cap - 1);
-    h->slice_min = 8;
+    h->slice_min = 4;
     h->slice_max = 1 << 20;  // no cap: the slice follows the demand
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MIN")) h->slice_min = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MAX")) h->slice_max = std::max(h->slice_min, std::atoi(v));
@@ -620,7 +620,7 @@ int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* o) {
 static int launch_conveyor(qs_handle h, cudaStream_t s, int flush) {
   const int B = block_of(h);
   const int nsettle = h->cfg.is_rl_interface ? h->cfg.settling_steps : 1500;
-  k_conveyor_ctl<<<1, 1024, 0, s>>>(h->cv, flush ? nullptr : h->slow_list + h->n, 64, h->wave_blocks, B, nsettle,
+  k_conveyor_ctl<<<1, 1024, 0, s>>>(h->cv, flush ? nullptr : h->slow_list + h->n, 64, h->wave_blocks, B, h->n, nsettle,
                                     h->slice_min, h->slice_max, flush);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());

@@ -107,7 +107,11 @@ constexpr int QS_SLOTS = 4;  // settled episodes kept ahead per env (ring indexe
 //   tick[i & cap_mask]       = settle ticks already done for entry i (CV_DONE: finished or dropped)
 //   wip[row][i % width]      = state of entry i between slices (raw floats: slicing is bit-invisible)
 // The first `active` entries after `tail` run `slice` ticks in k_settle_slice; k_conveyor_ctl picks both.
-enum { CV_HEAD = 0, CV_TAIL, CV_ACTIVE, CV_SLICE, CV_URGENT, CV_URGENT_LAST, CV_PREV_HEAD, CV_DEMAND, CV_CTL_WORDS = 8 };
+enum {
+  CV_HEAD = 0, CV_TAIL, CV_ACTIVE, CV_SLICE, CV_URGENT, CV_URGENT_LAST, CV_PREV_HEAD, CV_DEMAND,
+  // ring pressure: slots consumed this step, and how many of those envs found their next slot missing
+  CV_TAKEN, CV_LOW2, CV_EMA_TAKEN, CV_EMA_LOW2, CV_PRESS, CV_CTL_WORDS = 16
+};
 constexpr int CV_DONE = -1;
 constexpr int WIP_ROWS = 37 + 4;  // state | normal impulses (warm start); + contact mask (int row)
 struct Conveyor {
@@ -439,6 +443,8 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
       slot_load(D, env, epoch, st, cs, tm, tsp, &mu, dt);
       D.slot_epoch[int(epoch % QS_SLOTS) * n + env] = 0;
       conveyor_push(io.cv, env, epoch + QS_SLOTS);  // the freed slot's next tenant
+      atomicAdd(io.cv.ctl + CV_TAKEN, 1u);           // feedback for the slice length (k_conveyor_ctl)
+      if (!slot_ready(D, env, epoch + 1)) atomicAdd(io.cv.ctl + CV_LOW2, 1u);
       begin_episode(A, env, epoch, mu, st, cs, tm, tsp, io.obs);
     } else {
       // no spare slot ready: an urgent entry makes k_settle_urgent (launched at the end of this step)
@@ -637,10 +643,11 @@ __global__ void k_urgent_clear(Conveyor cv) {
 // blocks) and for how many ticks.  The slice length follows the demand (entries pushed per step,
 // smoothed): with d episodes ending per step, nsettle * d / slice entries are in flight, and the slice
 // is chosen so that they fill ~90 % of one wave -- the settles then run as a dense launch whatever
-// the episode length.  Entries beyond the window (start-up, bursts) or flush != 0 run the window to
-// completion at once.
+// the episode length.  With few envs that would deliver too late, so a settle is also kept shorter than
+// half a mean episode, and the slice grows while envs find their ring nearly empty.  Entries beyond the
+// window (start-up, bursts) or flush != 0 run the window to completion at once.
 __global__ void k_conveyor_ctl(Conveyor cv, const int* __restrict__ slow_count, int slow_block, int wave_blocks,
-                               int block, int nsettle, int s_min, int s_max, int flush) {
+                               int block, int n_envs, int nsettle, int s_min, int s_max, int flush) {
   __shared__ uint32_t first_live;
   const uint32_t head = cv.ctl[CV_HEAD];
   uint32_t tail = cv.ctl[CV_TAIL];
@@ -665,8 +672,21 @@ __global__ void k_conveyor_ctl(Conveyor cv, const int* __restrict__ slow_count, 
     demand += (float(head - cv.ctl[CV_PREV_HEAD]) - demand) * 0.125f;
     cv.ctl[CV_DEMAND] = __float_as_uint(demand);
     const float target = 0.9f * float(lanes);
-    float want = float(nsettle) * demand / target;
+    // dense wave: nsettle * demand / slice entries in flight = target; ring safety: the settle must not take
+    // longer than half a mean episode (n_envs / demand steps, Little's law)
+    float want = float(nsettle) * demand * fmaxf(1.f / target, 2.f / float(n_envs));
     if (float(active) > 0.97f * float(lanes)) want *= 1.5f;  // nearly full: catch up before a backlog forms
+    // ring pressure (smoothed): more than 2 % of the finishing envs one episode from running dry
+    float taken = __uint_as_float(cv.ctl[CV_EMA_TAKEN]), low2 = __uint_as_float(cv.ctl[CV_EMA_LOW2]);
+    float press = fmaxf(__uint_as_float(cv.ctl[CV_PRESS]), 1.f);
+    taken += (float(cv.ctl[CV_TAKEN]) - taken) * 0.125f;
+    low2 += (float(cv.ctl[CV_LOW2]) - low2) * 0.125f;
+    press = low2 > 0.02f * taken + 1e-3f ? fminf(8.f, press * 1.25f) : fmaxf(1.f, press * 0.95f);
+    cv.ctl[CV_EMA_TAKEN] = __float_as_uint(taken);
+    cv.ctl[CV_EMA_LOW2] = __float_as_uint(low2);
+    cv.ctl[CV_PRESS] = __float_as_uint(press);
+    cv.ctl[CV_TAKEN] = 0; cv.ctl[CV_LOW2] = 0;
+    want *= press;
     slice = max(s_min, min(s_max, int(ceilf(want))));
     if (pending > uint32_t(lanes)) slice = nsettle;
   }

@@ -5,7 +5,7 @@ import quadruped_springs_b200 as qs
 from quadruped_springs_b200 import _lib
 W = dict(enable_springs=True, task_env="JUMPING_FORWARD", motor_control_mode="CARTESIAN_PD",
          action_space_mode="SYMMETRIC", observation_space_mode="ARS_BASIC")
-N = 65536
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 env = qs.BatchedQuadrupedGymEnv(num_envs=N, auto_reset=True, **W)
 env.reset()
 L = _lib.lib()

@@ -225,3 +225,46 @@ def test_config5_policy_in_the_loop(qs):
     sys_path.insert(0, __import__("os").path.join(__import__("conftest").ROOT, "examples"))
     import policy_rollout
     policy_rollout.main(2048, 40)
+
+
+def test_settle_conveyor_is_invisible(qs, monkeypatch):
+    """Episodes are settled ahead of time in slices of ticks (csrc/qs_step_kernels.cuh, settle
+    conveyor).  However the 2500 ticks are cut -- tiny slices, whole settles, or so slowly that
+    envs run out of settled slots and take the urgent path -- every env sees bit-identical
+    episodes: the start state depends on (seed, global env id, episode number) only."""
+    import ctypes as C
+    from quadruped_springs_b200 import _lib
+    n, steps = 1024, 520
+    cfg = dict(enable_springs=True, task_env="JUMPING_FORWARD", motor_control_mode="CARTESIAN_PD",
+               observation_space_mode="ARS_BASIC")   # random actions end an episode every ~85 steps
+    g = torch.Generator(device="cuda").manual_seed(11)
+    acts = [torch.rand(n, 6, device="cuda", generator=g) * 2 - 1 for _ in range(steps)]
+
+    def run(slice_min, slice_max):
+        if slice_min is None:
+            monkeypatch.delenv("QS_SETTLE_SLICE_MIN", raising=False)
+            monkeypatch.delenv("QS_SETTLE_SLICE_MAX", raising=False)
+        else:
+            monkeypatch.setenv("QS_SETTLE_SLICE_MIN", str(slice_min))
+            monkeypatch.setenv("QS_SETTLE_SLICE_MAX", str(slice_max))
+        env = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=5, **cfg)
+        out, cnt, urgent, ndone = [env.reset().clone()], (C.c_int32 * 4)(), 0, 0
+        for a in acts:
+            obs, r, d, _ = env.step(a)
+            out.append(torch.cat([obs, r[:, None], d[:, None].float()], dim=1).clone())
+            _lib.check(env._L.qs_debug_counters(env._h, cnt, None))
+            urgent += cnt[1]
+            ndone += int(d.sum())
+        env.close()
+        return out, urgent, ndone
+
+    ref, urgent_ref, ndone = run(None, None)
+    assert ndone > 5 * n and urgent_ref <= ndone // 100   # more episodes per env than ring slots, settled in time
+    for lo, hi in ((100, 100), (2500, 2500), (7, 13)):
+        out, urgent, _ = run(lo, hi)
+        for x, y in zip(ref, out):
+            assert torch.equal(x, y)
+    out, urgent, _ = run(1, 1)                         # 1 tick per step: the ring of 4 runs dry
+    assert urgent > 0
+    for x, y in zip(ref, out):
+        assert torch.equal(x, y)

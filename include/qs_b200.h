@@ -130,6 +130,8 @@ typedef struct qs_state_ptrs {
   float* ep_return;    /* [N] */
   uint8_t* custom_gains; /* [N] set non-zero after writing kp/kd of an env: the kernels then read its gains from
                           * the arrays instead of the config constants; cleared by every reset of that env */
+  uint32_t* work;      /* [3][N] per-env work counters of the step kernels: physics ticks, foot-contact ticks,
+                        * contact x PGS-sweep count (cumulative; bench / diagnostics) */
 } qs_state_ptrs;
 
 void qs_default_config(qs_config* cfg);

@@ -44,7 +44,7 @@ class QsConfig(C.Structure):
 class QsStatePtrs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "state", "tau_motor", "tau_spring", "kp", "kd", "spring", "mu", "foot_force", "contact", "task",
-        "last_action", "sim_steps", "env_steps", "ep_return", "custom_gains")]
+        "last_action", "sim_steps", "env_steps", "ep_return", "custom_gains", "work")]
 
 
 def nvcc_path():

@@ -90,27 +90,32 @@ QS_DEVONLY void load_springs(const DeviceView& D, int env, float* sk, float* sb,
 }
 
 // ApplyAction + stepSimulation for ticks [t0, n_ticks) (quadruped_gym_env.py:207-219).
-// cmd = desired joint angles (PD) or torques (TORQUE).  Returns n_ticks when all
-// ticks ran on the fast path, or the index of the tick that needs the general
-// solver (state untouched by that tick).
+// cmd = desired joint angles (PD) or torques (TORQUE).  Returns n_ticks when all ticks ran,
+// or the index of the tick that needs another solver (state untouched by that tick; *why =
+// TICK_NEEDS_GENERAL / TICK_NEEDS_CONTACT).  kContacts = false is the flight variant: it
+// hands the env over as soon as a foot comes within its contact threshold.
+template <bool kContacts>
 __device__ __forceinline__ int run_ticks(EnvState<float>& st, ContactState<float>& cs, const float* cmd,
                                          bool torque_mode, int t0, int n_ticks, int env, const DeviceView& D,
                                          const EnvCfg& C, const RobotConst& RC, const ModelConstT<float>& M,
                                          const SolverConst& SC, float* tau_m /*12 out*/, float* tau_s /*12 out*/,
-                                         bool detect_invalid_last, const Scratch<float>& scr) {
+                                         bool detect_invalid_last, const Scratch<float>& scr, int* why, bool skip = false) {
   const float mu = D.mu[env];
   const bool custom = D.custom_gains[env] != 0;
   float sk[3], sb[3], sr[3];
   load_springs(D, env, sk, sb, sr);
-  int bail = n_ticks;
+  // skip: this thread only keeps the block's barriers matched (its env is handed over at t0)
+  int bail = skip ? t0 : n_ticks;
+  *why = skip ? TICK_NEEDS_CONTACT : TICK_DONE;
   for (int t = t0; t < n_ticks; t++) {
     // keep the warps of the block in lockstep: the tick is several times larger than the
     // instruction cache, so warps that run it together share every fetched line
-    __syncthreads();
+    if (!__syncthreads_or(bail == n_ticks)) break;  // every env of the block was handed over
     if (bail == n_ticks) {
       float tau[12];
       tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s, custom);
-      if (physics_tick(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1), scr)) bail = t;
+      const int r = physics_tick<float, kContacts>(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1), scr);
+      if (r != TICK_DONE) { bail = t; *why = r; }
     }
   }
   return bail;

@@ -310,8 +310,8 @@ struct qs_env {
   ModelConstT<double> model_d;
   void* pool;       // one allocation backing every SoA array
   size_t pool_bytes;
-  int* lists;          // slow (n + 1) | reset (n + 1) | urgent (2 n) | conveyor fifo, tick, wip, control words
-  int *slow_list, *reset_list;
+  int* lists;          // slow (n + 1) | reset (n + 1) | contact (n + 1) | urgent (2 n) | conveyor fifo, tick, wip, control words
+  int *slow_list, *reset_list, *contact_list;
   Conveyor cv;
   int wave_blocks;     // settle blocks resident at once (SMs x 2)
   int slice_min, slice_max;
@@ -495,13 +495,14 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MIN")) h->slice_min = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MAX")) h->slice_max = std::max(h->slice_min, std::atoi(v));
     const size_t w = size_t(cv.width);
-    const size_t nints = 2 * (n + 1) + 2 * n + 2 * cap + cap + (WIP_ROWS + 1) * w + CV_CTL_WORDS;
+    const size_t nints = 3 * (n + 1) + 2 * n + 2 * cap + cap + (WIP_ROWS + 1) * w + CV_CTL_WORDS;
     e = cudaMalloc(&h->lists, nints * sizeof(int));
     if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(QS_ERR_CUDA, "cudaMalloc lists"); }
     cudaMemset(h->lists, 0, nints * sizeof(int));
     h->slow_list = h->lists;
     h->reset_list = h->slow_list + n + 1;
-    cv.urgent_list = h->reset_list + n + 1;
+    h->contact_list = h->reset_list + n + 1;
+    cv.urgent_list = h->contact_list + n + 1;
     cv.fifo = cv.urgent_list + 2 * n;
     cv.tick = cv.fifo + 2 * cap;
     cv.wip = reinterpret_cast<float*>(cv.tick + cap);
@@ -517,6 +518,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     const int max_smem = int(smem_of(256));
     e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_contact, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_settle_urgent, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_settle_slice, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_debug_ticks<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -610,6 +612,7 @@ int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* o) {
   o->spring = D.spring; o->mu = D.mu; o->foot_force = D.foot_force; o->contact = D.contact; o->task = D.task;
   o->last_action = D.last_action; o->sim_steps = D.sim_steps; o->env_steps = D.env_steps; o->ep_return = D.ep_return;
   o->custom_gains = D.custom_gains;
+  o->work = D.work;
   return QS_OK;
 }
 
@@ -671,6 +674,7 @@ int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_
   CUDA_TRY(cudaSetDevice(h->device));
   const int B = block_of(h);
   CUDA_TRY(cudaMemsetAsync(h->slow_list + h->n, 0, sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(h->contact_list + h->n, 0, sizeof(int), s));
   if (!h->ev_ready) {
     for (int i = 0; i < qs_env::kRing; i++) { CUDA_TRY(cudaEventCreate(&h->ev0[i])); CUDA_TRY(cudaEventCreate(&h->ev1[i])); }
     h->ev_ready = true;
@@ -678,10 +682,13 @@ int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_
   StepIO io;
   io.actions = actions; io.obs = obs; io.reward = reward; io.done = done; io.truncated = truncated;
   io.slow_list = h->slow_list;
+  io.contact_list = h->contact_list;
   io.cv = h->cv;
   const int slot = int(h->n_steps % qs_env::kRing);
   cudaEventRecord(h->ev0[slot], s);
   k_step<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
+  k_step_contact<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
+  g_launches += 1;
   cudaEventRecord(h->ev1[slot], s);
   h->n_steps++;
   if (h->cfg.auto_reset) {

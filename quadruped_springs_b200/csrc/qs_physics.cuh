@@ -438,6 +438,9 @@ template <typename T> struct Scratch {
   QS_DEV T& operator()(int leg, int slot) const { return p[(leg * QS_LEG_SCRATCH + slot) * stride]; }
 };
 enum { SCR_BM = 0, SCR_EV = 18, SCR_MI = 21, SCR_SC = 27, SCR_W = 33, SCR_Q = 42, SCR_QD = 45, SCR_TAU = 48 };
+// Once a foot's contact rows are built, EV / MI / SC / Q of its leg are dead: the 18 floats of the rows'
+// base part Y = L^-1 G^T live there during the PGS sweeps instead of in (spilling) registers.
+QS_DEV constexpr int scr_y(int i) { return i < 15 ? SCR_EV + i : SCR_Q + (i - 15); }
 
 template <typename T> QS_DEV void leg_kin_from_sc(int k, const T* sc, const ModelConstT<T>& M, LegKin<T>& K) {
   K.s1 = sc[0]; K.c1 = sc[1]; K.s2 = sc[2]; K.c2 = sc[3]; K.s23 = sc[4]; K.c23 = sc[5];
@@ -450,10 +453,14 @@ template <typename T> QS_DEV void leg_kin_from_sc(int k, const T* sc, const Mode
   K.r4[0] = K.r3[0] - l * K.s23; K.r4[1] = K.r3[1] + l * K.s1 * K.c23; K.r4[2] = K.r3[2] - l * K.c1 * K.c23;
 }
 
-template <typename T>
-__host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
-                                      const ModelConstT<T>& M, const SolverConst& SC, bool detect_invalid,
-                                      const Scratch<T>& scr) {
+// Returns TICK_DONE, or -- with the state untouched -- TICK_NEEDS_GENERAL (a joint at its limit, a body
+// shape on the ground) or, for the kContacts = false variant (no foot-contact code at all: the flight
+// kernel), TICK_NEEDS_CONTACT when a foot is within its contact threshold.
+enum { TICK_DONE = 0, TICK_NEEDS_GENERAL = 1, TICK_NEEDS_CONTACT = 2 };
+template <typename T, bool kContacts = true>
+__host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
+                                     const ModelConstT<T>& M, const SolverConst& SC, bool detect_invalid,
+                                     const Scratch<T>& scr) {
   const T dt = T(SC.dt);
   const T idt = div_t(T(1), dt);
   const T mcv = T(SC.max_coord_vel);
@@ -530,7 +537,8 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
     invalid += (zt < M.trunk_thresh) + (zi < M.imu_thresh);
     if (SC.body_response && invalid > 0) need_general = true;
   }
-  if (need_general) return true;
+  if (need_general) return TICK_NEEDS_GENERAL;
+  if (!kContacts && active) return TICK_NEEDS_CONTACT;
 
   // ---- base: S = M_bb - sum F^T B, Cholesky, solve
   T Ld[6];
@@ -560,9 +568,11 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
     }
   }
 
-  if (active) {
+  bool in_contact = false;
+  if constexpr (kContacts) in_contact = active != 0;
+  if constexpr (kContacts) if (in_contact) {
     // ---- contact rows of the active feet (rolled loop), results routed into registers
-    T Y[4][18], H[4][6], rhs[4][3], dinv[4][3], lam[4][3];
+    T H[4][6], rhs[4][3], dinv[4][3], lam[4][3];
     T z[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
 #pragma unroll
     for (int k = 0; k < 4; k++) lam[k][0] = lam[k][1] = lam[k][2] = T(0);
@@ -623,10 +633,12 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
 #pragma unroll
         for (int i = 0; i < 6; i++) z[i] += y[i] * l0;
       }
-      // route into the register file (static indices only)
+      // rows' base part to the leg's (now dead) scratch, the small per-foot blocks into the register
+      // file (static indices only)
+#pragma unroll
+      for (int i = 0; i < 18; i++) scr(k, scr_y(i)) = y[i];
 #define QS_ROUTE(KK)                                                                    \
   case KK: {                                                                            \
-    _Pragma("unroll") for (int i = 0; i < 18; i++) Y[KK][i] = y[i];                      \
     _Pragma("unroll") for (int i = 0; i < 6; i++) H[KK][i] = h[i];                       \
     _Pragma("unroll") for (int i = 0; i < 3; i++) { rhs[KK][i] = r3[i]; dinv[KK][i] = di[i]; } \
     lam[KK][0] = l0;                                                                    \
@@ -646,7 +658,9 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         if (!(active & (1 << k))) continue;
-        const T* Yn = Y[k];
+        T Yn[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) Yn[i] = scr(k, scr_y(i));
         T w = H[k][0] * lam[k][0] + H[k][1] * lam[k][1] + H[k][2] * lam[k][2];
 #pragma unroll
         for (int i = 0; i < 6; i++) w += Yn[i] * z[i];
@@ -661,8 +675,9 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         if (!(active & (1 << k))) continue;
-        const T* Ya = Y[k] + 6;
-        const T* Yb = Y[k] + 12;
+        T Ya[6], Yb[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) { Ya[i] = scr(k, scr_y(6 + i)); Yb[i] = scr(k, scr_y(12 + i)); }
         T wa = H[k][1] * lam[k][0] + H[k][3] * lam[k][1] + H[k][4] * lam[k][2];
         T wbb = H[k][2] * lam[k][0] + H[k][4] * lam[k][1] + H[k][5] * lam[k][2];
 #pragma unroll
@@ -710,7 +725,8 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) cs.lam_n[k] = lam[k][0];
-  } else {
+  }
+  if (!in_contact) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       cs.lam_n[k] = T(0);
@@ -721,7 +737,7 @@ __host__ __device__ bool physics_tick(EnvState<T>& st, const T* tau, T mu, Conta
   cs.mask = active;
   cs.invalid = invalid;
   integrate_positions(st, dt);
-  return false;
+  return TICK_DONE;
 }
 
 // ------------------------------------------------------------------------------------------

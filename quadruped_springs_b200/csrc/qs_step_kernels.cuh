@@ -132,6 +132,7 @@ struct StepIO {
   uint8_t* done;
   uint8_t* truncated;
   int* slow_list;    // envs parked for the general solver, slow_list[n] = count
+  int* contact_list; // envs handed from the flight kernel to the contact kernel, contact_list[n] = count
   Conveyor cv;
 };
 
@@ -470,6 +471,23 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   D.ep_return[env] = ep_ret;
 }
 
+// hand an env over to another kernel of the step: state as of the start of tick `t`
+__device__ __forceinline__ void park_env(const KernelArgs& A, const StepIO& io, int env, const EnvState<float>& st,
+                                         const ContactState<float>& cs, const float* cmd, int t, int* list,
+                                         bool store = true) {
+  const DeviceView& D = A.D;
+  const int n = D.n;
+  if (store) {
+    store_state(D, env, st, cs, A.SC.dt);
+    D.work[1 * n + env] += uint32_t(cs.work_contacts);
+    D.work[2 * n + env] += uint32_t(cs.work_row_iters);
+  }
+#pragma unroll
+  for (int i = 0; i < 12; i++) D.cmd[i * n + env] = cmd[i];
+  D.resume_tick[env] = t;
+  list[atomicAdd(list + n, 1)] = env;
+}
+
 // -------------------------------------------------------------------- K1: step
 __global__ void __launch_bounds__(256, 1)
 k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
@@ -525,21 +543,52 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
     torque_mode = C.control_mode == QS_CTRL_TORQUE;
   }
 
-  // ---- action_repeat substeps (:236-237)
+  // ---- action_repeat substeps (:236-237), flight variant of the tick: no foot-contact code.  An env
+  // with a foot on (or reaching) the ground goes to k_step_contact, which runs dense warps of such envs.
   float tau_m[12], tau_s[12];
   extern __shared__ float qs_smem[];
   const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
-  const int t_done = run_ticks(st, cs, cmd, torque_mode, 0, C.action_repeat, env, D, C, A.RC, A.M, A.SC, tau_m, tau_s, true, scr);
+  int why;
+  const bool grounded = (cs.mask & 15) != 0;  // standing / pushing: straight to the contact kernel
+  const int t_done = run_ticks<false>(st, cs, cmd, torque_mode, 0, C.action_repeat, env, D, C, A.RC, A.M, A.SC, tau_m, tau_s,
+                                      true, scr, &why, grounded);
   if (!live) return;
   if (t_done < C.action_repeat) {
-    // park the env (state as of the start of tick t_done) for the general solver
-    store_state(D, env, st, cs, dt);
-    D.work[1 * n + env] += uint32_t(cs.work_contacts);
-    D.work[2 * n + env] += uint32_t(cs.work_row_iters);
+    // (a grounded env is handed over as loaded: nothing to store)
+    park_env(A, io, env, st, cs, cmd, t_done, why == TICK_NEEDS_GENERAL ? io.slow_list : io.contact_list, !grounded);
+    return;
+  }
+  finish_step(A, io, env, st, cs, tau_m, tau_s);
+}
+
+// -------------------------------------------------------------------- K1a: envs with foot contacts
+// Resumes the envs the flight kernel handed over (dense warps: thread i takes contact_list[i]) with
+// the full fast tick; joint limits / body contacts still go on to k_step_slow.
+__global__ void __launch_bounds__(256, 1)
+k_step_contact(const __grid_constant__ KernelArgs A, const StepIO io) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const DeviceView& D = A.D;
+  const EnvCfg& C = A.C;
+  const int n = D.n;
+  const int count = io.contact_list[n];
+  if (blockIdx.x * blockDim.x >= count) return;  // uniform over the block
+  const bool live = tid < count;
+  const int env = io.contact_list[live ? tid : count - 1];
+  EnvState<float> st;
+  ContactState<float> cs;
+  load_state(D, env, st, cs, A.SC.dt);
+  float cmd[12], tau_m[12], tau_s[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) D.cmd[i * n + env] = cmd[i];
-    D.resume_tick[env] = t_done;
-    io.slow_list[atomicAdd(io.slow_list + n, 1)] = env;
+  for (int i = 0; i < 12; i++) cmd[i] = D.cmd[i * n + env];
+  const bool torque_mode = !C.is_rl && C.control_mode == QS_CTRL_TORQUE;
+  extern __shared__ float qs_smem[];
+  const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
+  int why;
+  const int t_done = run_ticks<true>(st, cs, cmd, torque_mode, D.resume_tick[env], C.action_repeat, env, D, C, A.RC, A.M,
+                                     A.SC, tau_m, tau_s, true, scr, &why);
+  if (!live) return;
+  if (t_done < C.action_repeat) {
+    park_env(A, io, env, st, cs, cmd, t_done, io.slow_list);
     return;
   }
   finish_step(A, io, env, st, cs, tau_m, tau_s);

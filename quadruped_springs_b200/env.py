@@ -468,6 +468,7 @@ class BatchedQuadrupedGymEnv:
             "sim_steps": _view(ptrs.sim_steps, (n,), "<i4", dev), "env_steps": _view(ptrs.env_steps, (n,), "<i4", dev),
             "ep_return": _view(ptrs.ep_return, (n,), "<f4", dev),
             "custom_gains": _view(ptrs.custom_gains, (n,), "|u1", dev),
+            "work": _view(ptrs.work, (3, n), "<i4", dev),
         }
         self.robot = BatchedQuadruped(self)
         self.task = _Task(self)

@@ -176,8 +176,9 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    work0 = (C.c_uint64 * 3)()
+    work0, swork0 = (C.c_uint64 * 3)(), (C.c_uint64 * 3)()
     _lib.check(L.qs_work_counters(env._h, work0, None))
+    _lib.check(L.qs_settle_work_counters(env._h, swork0, None))
     launches0 = L.qs_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -195,8 +196,11 @@ def run_ours(args):
     kms = C.c_float()
     _lib.check(L.qs_step_kernel_time(env._h, min(args.steps, 512), C.byref(kms)))
     k_step_ms = kms.value / min(args.steps, 512)
-    work1 = (C.c_uint64 * 3)()
+    _lib.check(L.qs_settle_kernel_time(env._h, min(args.steps, 512), C.byref(kms)))
+    k_settle_ms = kms.value / min(args.steps, 512)
+    work1, swork1 = (C.c_uint64 * 3)(), (C.c_uint64 * 3)()
     _lib.check(L.qs_work_counters(env._h, work1, None))
+    _lib.check(L.qs_settle_work_counters(env._h, swork1, None))
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -236,12 +240,18 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---------------- roofline of the dominant kernel (k_step), FP32 pipe
+    # ---------------- roofline, FP32 pipe: the settle slice (dominant by time) and the step kernels
     fm = json.load(open(os.path.join(ROOT, "quadruped_springs_b200", "flop_model.json")))
-    ticks, cticks, csweeps = (int(work1[i] - work0[i]) for i in range(3))
-    flops = (ticks * fm["W0_flight_tick"] + cticks * (fm["W_per_contact"] + fm["W_any_contact"] / 4.0)
-             + csweeps * fm["W_per_contact_sweep"] + n * args.steps * fm["epilogue_per_control_step_estimate"])
-    flops_per_launch = flops / args.steps
+
+    def tick_flops(w0, w1):
+        ticks, cticks, csweeps = (int(w1[i] - w0[i]) for i in range(3))
+        f = (ticks * fm["W0_flight_tick"] + cticks * (fm["W_per_contact"] + fm["W_any_contact"] / 4.0)
+             + csweeps * fm["W_per_contact_sweep"])
+        return f, ticks, cticks, csweeps
+
+    step_flops, ticks, cticks, csweeps = tick_flops(work0, work1)
+    step_flops += n * args.steps * fm["epilogue_per_control_step_estimate"]
+    settle_flops, sticks, scticks, scsweeps = tick_flops(swork0, swork1)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -249,25 +259,36 @@ def run_ours(args):
         pass
     sm_mhz_max = float(peaks.get("sm_max_mhz", 1965.0))
     fp32_peak = SM_COUNT * FP32_LANES * 2 * sm_mhz_max * 1e6 / 1e12     # TFLOP/s, non-tensor FP32 FMA
-    achieved = flops_per_launch / (k_step_ms * 1e-3) / 1e12
-    state_bytes = n * 4 * (2 * (37 + 12 + 12 + 4 + 1 + 29 + 12 + 3 + 3) + 24 + 9 + 1 + A + O + 2)  # per launch, algorithmic
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    roofline = {
-        "bound": "fp32", "kernel": "k_step", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": achieved / fp32_peak, "traffic": None,
-        "peak_source": f"{SM_COUNT} SMs x {FP32_LANES} FP32 lanes x 2 x {sm_mhz_max:.0f} MHz (clocks.max.sm from "
-                       f"{'MEASURED_PEAKS.json' if peaks else 'nominal'}); no tensor cores: per-env matrices <= 6x6",
-        "kernel_ms": k_step_ms, "kernel_share_of_step": k_step_ms / ms_per_step,
-        "algorithmic_flops_per_env_step": flops_per_launch / n,
+    state_bytes = n * 4 * (2 * (37 + 12 + 12 + 4 + 1 + 29 + 12 + 3 + 3) + 24 + 9 + 1 + A + O + 2)  # per step, algorithmic
+
+    def fp32_line(kernel, flops, ms, extra):
+        ach = flops / args.steps / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        return {"bound": "fp32", "kernel": kernel, "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": ach / fp32_peak, "kernel_ms": ms, "kernel_share_of_step": ms / ms_per_step, **extra}
+
+    settle_line = fp32_line("k_settle_slice", settle_flops, k_settle_ms, {
+        "what": "reset()'s 2500-tick settle of the next episodes, one slice of ticks per control step on a second stream "
+                "(timed there with CUDA events, next to k_step_slow)",
+        "settle_ticks_per_step": sticks / args.steps, "algorithmic_flops_per_settle_tick": settle_flops / max(sticks, 1),
+        "mean_foot_contacts_per_tick": scticks / max(sticks, 1), "mean_pgs_sweeps_per_contact_tick": scsweeps / max(scticks, 1)})
+    step_line = fp32_line("k_step + k_step_contact", step_flops, k_step_ms, {
+        "what": "the action_repeat physics ticks of step(): flight variant, then the envs with foot contacts",
+        "algorithmic_flops_per_env_step": step_flops / args.steps / n,
         "mean_foot_contacts_per_tick": cticks / max(ticks, 1), "mean_pgs_sweeps_per_contact_tick": csweeps / max(cticks, 1),
         "hbm": {"algorithmic_bytes_per_launch": state_bytes, "achieved_GBps": state_bytes / (k_step_ms * 1e-3) / 1e9,
                 "peak_GBps": hbm_peak, "frac": state_bytes / (k_step_ms * 1e-3) / 1e9 / hbm_peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"},
-    }
-    ncu_path = os.path.join(ROOT, "profiles", "k_step_traffic.json")
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s"}})
+    dominant, other = (settle_line, step_line) if k_settle_ms >= k_step_ms else (step_line, settle_line)
+    roofline = dict(dominant)
+    roofline["traffic"] = None
+    roofline["peak_source"] = (f"{SM_COUNT} SMs x {FP32_LANES} FP32 lanes x 2 x {sm_mhz_max:.0f} MHz (clocks.max.sm from "
+                               f"{'MEASURED_PEAKS.json' if peaks else 'nominal'}); no tensor cores: per-env matrices <= 6x6")
+    roofline["other_kernels"] = [other]
+    ncu_path = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(ncu_path):
         try:
-            roofline["traffic"] = json.load(open(ncu_path)).get("dram_bytes_per_launch")
+            roofline["traffic"] = json.load(open(ncu_path)).get(dominant["kernel"], {}).get("dram_bytes_per_launch")
         except Exception:
             pass
 
@@ -290,7 +311,7 @@ def run_ours(args):
                    "parallelism": f"env-sharded x{world}, no per-step collective"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * A * 4, "d2h_bytes_per_step": n * (O * 4 + 4 + 2),
-                "steps": e2e_steps, "path": "qs_step_host: pinned host actions -> H2D -> k_step (+k_reset) -> D2H obs, "
+                "steps": e2e_steps, "path": "qs_step_host: pinned host actions -> H2D -> step kernels + settle slice -> D2H obs, "
                                             "reward, done, truncated -> stream sync"},
         "roofline": roofline, "cpu_baseline": cpu,
         "wall_s_timed_region": t_wall,
@@ -305,8 +326,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=100)  # past the start-up transient (all envs begin in phase)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--seed", type=int, default=0)

@@ -227,6 +227,11 @@ int qs_reduce_stats(qs_handle h, float* out_dev, void* stream);
  * contact x PGS-sweep count} summed over all envs since creation. */
 int qs_step_kernel_time(qs_handle h, int last_k, float* ms_sum);
 int qs_work_counters(qs_handle h, uint64_t* out3, void* stream);
+/* the same two for the settle slices (k_settle_slice, the kernel that pre-computes reset()'s 2500-tick settle,
+ * control_interface/interface_base.py:182-200): device time of the launches of the last `last_k` steps, and
+ * {settle ticks, foot-contact ticks, contact x PGS-sweep count} done so far */
+int qs_settle_kernel_time(qs_handle h, int last_k, float* ms_sum);
+int qs_settle_work_counters(qs_handle h, uint64_t* out3, void* stream);
 /* diagnostics of the last qs_step: out4 = {envs handed to the general solver, envs whose next episode was
  * settled on the spot because no settled slot was ready, entries on the settle conveyor, ticks of its last
  * slice}; synchronises the stream */

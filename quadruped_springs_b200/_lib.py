@@ -109,6 +109,8 @@ EXPORTS = {
     "qs_step_kernel_time": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "qs_work_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "qs_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
+    "qs_settle_kernel_time": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "qs_settle_work_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "qs_launch_count": (C.c_int64, []),
 }
 

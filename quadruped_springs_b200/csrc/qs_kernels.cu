@@ -325,7 +325,8 @@ struct qs_env {
   bool was_reset;
   // CUDA-event ring around k_step launches (roofline timing of the dominant kernel)
   static constexpr int kRing = 512;
-  cudaEvent_t ev0[kRing], ev1[kRing];
+  cudaEvent_t ev0[kRing], ev1[kRing];   // around k_step + k_step_contact, on the caller's stream
+  cudaEvent_t ev2[kRing], ev3[kRing];   // around k_settle_slice, on the second stream
   bool ev_ready;
   int64_t n_steps;
 };
@@ -495,7 +496,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MIN")) h->slice_min = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MAX")) h->slice_max = std::max(h->slice_min, std::atoi(v));
     const size_t w = size_t(cv.width);
-    const size_t nints = 3 * (n + 1) + 2 * n + 2 * cap + cap + (WIP_ROWS + 1) * w + CV_CTL_WORDS;
+    const size_t nints = 3 * (n + 1) + 2 * n + 2 * cap + cap + (WIP_ROWS + 1) * w + CV_CTL_WORDS + 8;
     e = cudaMalloc(&h->lists, nints * sizeof(int));
     if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(QS_ERR_CUDA, "cudaMalloc lists"); }
     cudaMemset(h->lists, 0, nints * sizeof(int));
@@ -508,6 +509,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     cv.wip = reinterpret_cast<float*>(cv.tick + cap);
     cv.wip_contact = reinterpret_cast<int*>(cv.wip + WIP_ROWS * w);
     cv.ctl = reinterpret_cast<uint32_t*>(cv.wip_contact + w);
+    cv.work = reinterpret_cast<unsigned long long*>(h->lists + ((size_t((cv.ctl + CV_CTL_WORDS) - reinterpret_cast<uint32_t*>(h->lists)) + 1) & ~size_t(1)));
     cudaMemset(cv.tick, 0xff, cap * sizeof(int));  // CV_DONE: nothing queued
     e = cudaStreamCreateWithFlags(&h->bg, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
@@ -545,14 +547,16 @@ int qs_destroy(qs_handle h) {
   if (h->dev_reward) cudaFree(h->dev_reward);
   if (h->dev_done) cudaFree(h->dev_done);
   if (h->ev_ready)
-    for (int i = 0; i < qs_env::kRing; i++) { cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); }
+    for (int i = 0; i < qs_env::kRing; i++) {
+      cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); cudaEventDestroy(h->ev2[i]); cudaEventDestroy(h->ev3[i]);
+    }
   delete h;
   return QS_OK;
 }
 
 int qs_step_kernel_time(qs_handle h, int last_k, float* ms_sum) {
   // sum of the device durations of the last `last_k` k_step launches (CUDA events on the
-  // launching stream); the stream must have been synchronised by the caller
+  // launching stream; k_step + k_step_contact); the stream must have been synchronised by the caller
   if (!h || !ms_sum) return fail(QS_ERR_ARG, "NULL argument");
   if (last_k <= 0 || last_k > qs_env::kRing || last_k > h->n_steps) return fail(QS_ERR_ARG, "last_k out of range");
   float tot = 0.f;
@@ -562,6 +566,33 @@ int qs_step_kernel_time(qs_handle h, int last_k, float* ms_sum) {
     tot += ms;
   }
   *ms_sum = tot;
+  return QS_OK;
+}
+
+int qs_settle_kernel_time(qs_handle h, int last_k, float* ms_sum) {
+  // same for the k_settle_slice launches of the last `last_k` steps (events on the library's second stream)
+  if (!h || !ms_sum) return fail(QS_ERR_ARG, "NULL argument");
+  if (!h->cfg.auto_reset) return fail(QS_ERR_STATE, "no settle slices without auto_reset");
+  if (last_k <= 0 || last_k > qs_env::kRing || last_k > h->n_steps) return fail(QS_ERR_ARG, "last_k out of range");
+  float tot = 0.f;
+  for (int64_t i = h->n_steps - last_k; i < h->n_steps; i++) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev2[i % qs_env::kRing], h->ev3[i % qs_env::kRing]));
+    tot += ms;
+  }
+  *ms_sum = tot;
+  return QS_OK;
+}
+
+int qs_settle_work_counters(qs_handle h, uint64_t* out3, void* stream) {
+  // totals of (settle ticks, foot-contact ticks, contact x PGS-sweep count) executed by k_settle_slice so far; synchronises
+  if (!h || !out3) return fail(QS_ERR_ARG, "NULL argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unsigned long long host[3];
+  CUDA_TRY(cudaMemcpyAsync(host, h->cv.work, sizeof(host), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (int r = 0; r < 3; r++) out3[r] = host[r];
   return QS_OK;
 }
 
@@ -676,7 +707,10 @@ int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_
   CUDA_TRY(cudaMemsetAsync(h->slow_list + h->n, 0, sizeof(int), s));
   CUDA_TRY(cudaMemsetAsync(h->contact_list + h->n, 0, sizeof(int), s));
   if (!h->ev_ready) {
-    for (int i = 0; i < qs_env::kRing; i++) { CUDA_TRY(cudaEventCreate(&h->ev0[i])); CUDA_TRY(cudaEventCreate(&h->ev1[i])); }
+    for (int i = 0; i < qs_env::kRing; i++) {
+      CUDA_TRY(cudaEventCreate(&h->ev0[i])); CUDA_TRY(cudaEventCreate(&h->ev1[i]));
+      CUDA_TRY(cudaEventCreate(&h->ev2[i])); CUDA_TRY(cudaEventCreate(&h->ev3[i]));
+    }
     h->ev_ready = true;
   }
   StepIO io;
@@ -702,7 +736,9 @@ int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_
   g_launches += 2;
   if (h->cfg.auto_reset) {
     CUDA_TRY(cudaStreamWaitEvent(h->bg, h->ev_fork, 0));
+    cudaEventRecord(h->ev2[slot], h->bg);
     if (int e = launch_slice(h, h->bg)) return e;
+    cudaEventRecord(h->ev3[slot], h->bg);
     CUDA_TRY(cudaEventRecord(h->ev_join, h->bg));
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
     // envs that finished without a settled slot (rare): settled and started now

@@ -121,6 +121,7 @@ struct Conveyor {
   int* wip_contact;
   uint32_t* ctl;
   int* urgent_list;  // (env, episode) pairs that must be settled and started NOW; count in ctl[CV_URGENT]
+  unsigned long long* work;  // settle ticks, foot-contact ticks, contact x PGS-sweep count done by the slices
   uint32_t cap_mask;
   int width;
 };
@@ -782,6 +783,16 @@ k_settle_slice(const __grid_constant__ KernelArgs A, const Conveyor cv) {
   const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
   settle_ticks(A, st, cs, mu, t0, t1, span, tau_m, tau_s, scr);
   if (!need) return;
+  {  // work counters of the bench's flop model, one atomic per warp
+    const unsigned m = __activemask();
+    const unsigned a = __reduce_add_sync(m, unsigned(t1 - t0)), b = __reduce_add_sync(m, unsigned(cs.work_contacts));
+    const unsigned c = __reduce_add_sync(m, unsigned(cs.work_row_iters));
+    if ((threadIdx.x & 31) == __ffs(m) - 1) {
+      atomicAdd(cv.work + 0, (unsigned long long)a);
+      atomicAdd(cv.work + 1, (unsigned long long)b);
+      atomicAdd(cv.work + 2, (unsigned long long)c);
+    }
+  }
   if (t1 == nsettle) {
     slot_store(D, env, st, cs, tau_m, tau_s, mu, epoch, A.SC.dt);
     cv.tick[pos] = CV_DONE;

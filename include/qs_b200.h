@@ -105,7 +105,11 @@ typedef struct qs_config {
   float contact_erp, limit_erp, linear_slop, warmstart, residual_threshold;
   float max_coord_vel;           /* 30.1 */
   float breaking_threshold;      /* 0.02 */
-  float reserved0;
+  int32_t landing_mode;          /* 0 none; 1 LandingWrapper (env/wrappers/landing_wrapper.py:18-69): after take-off the action is
+                                  * held until the predicted apex, then the landing action with gains 60 / 1.5 until the
+                                  * episode ends; 2 LandingWrapper2 (landing_wrapper_2.py:39-78): default gains, landing until
+                                  * touch-down, once per episode.  The wrappers' inner env.step loops run as a per-env mode
+                                  * machine: one qs_step = one control step, scripted envs ignore the action passed in */
 } qs_config;
 
 typedef struct qs_env* qs_handle;
@@ -130,6 +134,7 @@ typedef struct qs_state_ptrs {
   float* ep_return;    /* [N] */
   uint8_t* custom_gains; /* [N] set non-zero after writing kp/kd of an env: the kernels then read its gains from
                           * the arrays instead of the config constants; cleared by every reset of that env */
+  int32_t* land_mode;  /* [N] landing controller mode: 0 policy, 1 take-off hold, 2 landing, 3 spent (LandingWrapper2) */
   uint32_t* work;      /* [3][N] per-env work counters of the step kernels: physics ticks, foot-contact ticks,
                         * contact x PGS-sweep count (cumulative; bench / diagnostics) */
 } qs_state_ptrs;

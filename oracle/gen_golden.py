@@ -411,6 +411,84 @@ def gen_rollouts_continuous():
         rollout(name, cfg, acts, seed=20 + i)
 
 
+def rollout_landing(name, cfg, wrapper, actions, seed):
+    """Landing wrappers (landing_wrapper.py:18-69, landing_wrapper_2.py:39-78): the reference wrapper drives
+    the env; every INNER env.step it makes is recorded, so the fixture holds the scripted take-off-hold /
+    landing control flow at control-step granularity (which is how the batched env runs it)."""
+    from quadruped_spring.env.wrappers.landing_wrapper import LandingWrapper
+    from quadruped_spring.env.wrappers.landing_wrapper_2 import LandingWrapper2
+    ref_shim.FakeBulletClient.world_params = {}
+    np.random.seed(seed)
+    env = make_env(**cfg)
+    wrapped = {1: LandingWrapper, 2: LandingWrapper2}[wrapper](env)
+    wrapped.reset()
+    mu = env._pybullet_client._mu_ground
+    w = env._pybullet_client.world
+    rec = {k: [] for k in ("pre_state", "state", "applied_action", "policy_action", "obs", "reward", "done", "truncated",
+                           "tau", "kp", "foot_force", "foot_contact", "n_invalid", "wrapper_step")}
+    init_state, init_obs = w.get_state(), flat(env._robot_sensors.get_obs())
+    init_task_height = float(env.task._init_height)
+    inner_step = env.step
+    cur = {"policy": None, "k": 0}
+
+    def recording_step(a):
+        rec["pre_state"].append(w.get_state())
+        out = inner_step(a)
+        _, ninv, ff, fc = env.robot.GetContactInfo()
+        rec["state"].append(w.get_state())
+        rec["applied_action"].append(np.asarray(a, dtype=np.float64))
+        rec["policy_action"].append(cur["policy"])
+        rec["obs"].append(flat(env._robot_sensors.get_obs()))
+        rec["reward"].append(out[1]); rec["done"].append(out[2])
+        rec["truncated"].append(bool(out[3].get("TimeLimit.truncated", False)))
+        rec["tau"].append(np.asarray(env.robot.GetMotorTorques(), dtype=np.float64))
+        rec["kp"].append(np.broadcast_to(np.asarray(env.robot._motor_model._kp, dtype=np.float64), (12,)).copy())
+        rec["foot_force"].append(np.asarray(ff, dtype=np.float64)); rec["foot_contact"].append(np.asarray(fc, dtype=np.float64))
+        rec["n_invalid"].append(ninv); rec["wrapper_step"].append(cur["k"])
+        return out
+
+    env.step = recording_step
+    wrapper_out = []
+    for k, a in enumerate(actions):
+        cur["policy"], cur["k"] = np.asarray(a, dtype=np.float64), k
+        obs, r, d, info = wrapped.step(np.asarray(a, dtype=np.float64))
+        wrapper_out.append([r, float(d)])
+        if d:
+            break
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    out.update(mu=mu, init_state=init_state, init_obs=init_obs, init_task_height=init_task_height,
+               wrapper_out=np.asarray(wrapper_out), cfg=json.dumps(cfg), landing_mode=wrapper)
+    np.savez_compressed(os.path.join(OUT, f"landing_{name}.npz"), **out)
+    ws = out["wrapper_step"]
+    print(f"landing_{name}: {len(ws)} inner steps for {ws[-1] + 1} wrapper steps, done={bool(out['done'][-1])} "
+          f"trunc={bool(out['truncated'][-1])} landing-gain steps={int((out['kp'][:, 0] == 60).sum())} "
+          f"scripted steps={int((np.abs(out['applied_action'] - out['policy_action']).max(axis=1) > 0).sum())}")
+
+
+def cart_hop_actions(n, rng, zc=1.0, zp=-1.0, crouch=25, push=12, period=70):
+    """vertical crouch / push in foot-position space (no fore-aft motion: the robot takes off and lands)"""
+    acts = np.zeros((n, 6))
+    for t in range(n):
+        ph = t % period
+        z = zc if ph < crouch else (zp if ph < crouch + push else -0.1)
+        acts[t] = np.array([0, 0, z, 0, 0, z]) + rng.normal(size=6) * 0.03
+    return acts
+
+
+def gen_landing():
+    rng = np.random.default_rng(77)
+    base = dict(enable_springs=True, task_env="JUMPING_IN_PLACE", motor_control_mode="PD",
+                action_space_mode="SYMMETRIC", observation_space_mode="ARS_BASIC")
+    rollout_landing("w1_jip_pd", base, 1, jump_actions(6, 160, rng), seed=31)
+    rollout_landing("w1_jf_cartesian", dict(base, task_env="JUMPING_FORWARD", motor_control_mode="CARTESIAN_PD"), 1,
+                    cart_hop_actions(160, rng), seed=32)
+    rollout_landing("w2_jip_pd_nosprings", dict(base, enable_springs=False, observation_space_mode="PPO_BASIC"), 2,
+                    jump_actions(6, 400, rng, amp=0.7), seed=33)
+    rollout_landing("w2_jf_cartesian", dict(base, task_env="JUMPING_FORWARD", motor_control_mode="CARTESIAN_PD",
+                                            action_space_mode="DEFAULT"), 2,
+                    np.concatenate([cart_hop_actions(300, rng, zc=0.6)] * 2, axis=1)[:, [0, 1, 2, 6, 7, 8, 3, 4, 5, 9, 10, 11]], seed=34)
+
+
 # ----------------------------------------------------------------------------- CPG
 def gen_hopf():
     from quadruped_spring.hopf_network import HopfNetwork
@@ -462,7 +540,7 @@ def gen_hopf():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "continuous", "rollouts"]
+    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "continuous", "landing", "rollouts"]
     if "urdf" in which:
         gen_urdf()
     # NB: gen_analytic and the last rollout build a BACKFLIP env, which mutates the module-level
@@ -475,6 +553,8 @@ if __name__ == "__main__":
         gen_hopf()
     if "continuous" in which:
         gen_rollouts_continuous()
+    if "landing" in which:
+        gen_landing()
     if "rollouts" in which:
         gen_rollouts()
     print("golden fixtures written to", OUT)

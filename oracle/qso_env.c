@@ -288,7 +288,11 @@ struct QsoEnv {
   TaskState ts;
   /* Butterworth filter (utils/action_filter.py:110-127,191-213) */
   double fb[3], fa[3], xh[2][12], yh[2][12];
+  /* landing controller (landing_wrapper.py, landing_wrapper_2.py; utils/timer.py) */
+  int land_mode, land_gains;
+  double land_timer, land_end, hold_action[12], kp_save[12], kd_save[12];
 };
+enum { LAND_POLICY = 0, LAND_HOLD = 1, LAND_LANDING = 2, LAND_SPENT = 3 };
 
 void qso_env_default_config(QsoEnvConfig* c) {
   c->enable_springs = 0;
@@ -301,6 +305,7 @@ void qso_env_default_config(QsoEnvConfig* c) {
   c->enable_action_interpolation = 0;
   c->enable_action_filter = 0;
   c->settling_steps = 2500;
+  c->landing_mode = 0;
   c->time_step = 0.001;
 }
 
@@ -766,6 +771,13 @@ void qso_env_reset(QsoEnv* e, double mu, double* obs) {
   p.mu_ground = mu; /* env_randomizer.py:287-289 */
   qso_world_set_params(e->w, &p);
   e->sim_steps = e->env_steps = 0;
+  if (e->land_gains) { /* a new Quadruped has the default gains (quadruped_gym_env.py:299-319) */
+    memcpy(e->rc.kp, e->kp_save, sizeof e->kp_save);
+    memcpy(e->rc.kd, e->kd_save, sizeof e->kd_save);
+    e->land_gains = 0;
+  }
+  e->land_mode = LAND_POLICY;
+  e->land_timer = e->land_end = 0;
   memset(e->last_action, 0, sizeof e->last_action);
   memset(e->last_filtered, 0, sizeof e->last_filtered);
   memset(e->tau_motor, 0, sizeof e->tau_motor);
@@ -828,9 +840,49 @@ void qso_env_reset(QsoEnv* e, double mu, double* obs) {
 }
 
 /* ---- step (quadruped_gym_env.py:227-256) ---- */
+/* env.get_landing_action() (quadruped_gym_env.py:375-379): landing pose -> action space */
+static void landing_action(const QsoEnv* e, double* act) {
+  const RobotCfg* c = &e->rc;
+  double a12[12], pose[12];
+  int cart = e->cfg.control_mode == QSO_CTRL_CARTESIAN_PD, sidx = cart ? 1 : 0;
+  if (cart) { /* CARTESIAN_LANDING_POSE: nominal foot position with z = LANDING_Z (configs:67-72) */
+    memcpy(pose, c->nominal_foot, sizeof pose);
+    for (int k = 0; k < 4; k++) pose[3 * k + 2] = -0.29;
+    unscale_command(c->cart_lo, c->cart_hi, pose, a12);
+  } else {    /* ANGLE_LANDING_POSE = INIT_MOTOR_ANGLES (configs:38) */
+    unscale_command(c->ang_lo, c->ang_hi, c->init_angles, a12);
+  }
+  memset(act, 0, 12 * sizeof(double));
+  if (e->cfg.action_mode == QSO_ACT_DEFAULT) memcpy(act, a12, sizeof a12);
+  else if (e->cfg.action_mode == QSO_ACT_SYMMETRIC) { memcpy(act, a12, 3 * sizeof(double)); memcpy(act + 3, a12 + 6, 3 * sizeof(double)); }
+  else {
+    int s = 0;
+    for (int j = 0; j < 3; j++) if (j != sidx) { act[s] = a12[j]; act[2 + s] = a12[6 + j]; s++; }
+  }
+}
+void qso_env_get_landing_state(const QsoEnv* e, double* o) { o[0] = e->land_mode; o[1] = e->land_timer; o[2] = e->land_end; }
+
 void qso_env_step(QsoEnv* e, const double* action, double* obs, double* reward, int* done, int* truncated) {
   int adim = qso_env_action_dim(e);
-  double cur[12];
+  double cur[12], scripted[12];
+  if (e->cfg.landing_mode) {
+    /* take_off_phase (landing_wrapper.py:47-54): repeat the action until the timer is up, then landing_phase */
+    if (e->land_mode == LAND_HOLD) {
+      if (e->land_timer > e->land_end) { /* Timer.time_up, utils/timer.py:39-43 */
+        e->land_mode = LAND_LANDING;
+        if (e->cfg.landing_mode == 1) { /* temporary_switch_motor_control_gain, landing_wrapper.py:18-36 */
+          memcpy(e->kp_save, e->rc.kp, sizeof e->kp_save);
+          memcpy(e->kd_save, e->rc.kd, sizeof e->kd_save);
+          for (int i = 0; i < 12; i++) { e->rc.kp[i] = 60.0; e->rc.kd[i] = 1.5; }
+          e->land_gains = 1;
+        }
+      } else {
+        e->land_timer += e->cfg.action_repeat * e->cfg.time_step; /* step_timer */
+        action = e->hold_action;
+      }
+    }
+    if (e->land_mode == LAND_LANDING) { landing_action(e, scripted); action = scripted; }
+  }
   memset(cur, 0, sizeof cur);
   memcpy(cur, action, adim * sizeof(double));
   memcpy(e->last_action, cur, sizeof cur);
@@ -870,4 +922,17 @@ void qso_env_step(QsoEnv* e, const double* action, double* obs, double* reward, 
   if (d) r += task_reward_end(e);
   if (obs) observe(e, obs);
   *reward = r; *done = d; *truncated = tr;
+  if (e->cfg.landing_mode && !d) {
+    double st[QSO_NSTATE];
+    qso_world_get_state(e->w, st);
+    if (e->land_mode == LAND_POLICY && e->ts.switched) { /* LandingWrapper.step :58-66, start_jumping_timer :56-60 */
+      e->land_mode = LAND_HOLD;
+      memset(e->hold_action, 0, sizeof e->hold_action);
+      memcpy(e->hold_action, e->last_action, adim * sizeof(double));
+      e->land_timer = sim_time(e);
+      e->land_end = e->land_timer + st[9] / 9.81; /* task.compute_time_for_peak_heihgt, task_base.py:157-160 */
+    } else if (e->land_mode == LAND_LANDING && e->cfg.landing_mode == 2 && !is_flying(e)) {
+      e->land_mode = LAND_SPENT; /* LandingWrapper2.landing_phase :39-46, _enable_landing = False :71 */
+    }
+  }
 }

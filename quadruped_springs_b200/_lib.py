@@ -37,14 +37,14 @@ class QsConfig(C.Structure):
         ("gravity_z", C.c_float), ("mu_ground", C.c_float), ("contact_erp", C.c_float),
         ("limit_erp", C.c_float), ("linear_slop", C.c_float), ("warmstart", C.c_float),
         ("residual_threshold", C.c_float), ("max_coord_vel", C.c_float),
-        ("breaking_threshold", C.c_float), ("reserved0", C.c_float),
+        ("breaking_threshold", C.c_float), ("landing_mode", C.c_int32),
     ]
 
 
 class QsStatePtrs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "state", "tau_motor", "tau_spring", "kp", "kd", "spring", "mu", "foot_force", "contact", "task",
-        "last_action", "sim_steps", "env_steps", "ep_return", "custom_gains", "work")]
+        "last_action", "sim_steps", "env_steps", "ep_return", "custom_gains", "land_mode", "work")]
 
 
 def nvcc_path():

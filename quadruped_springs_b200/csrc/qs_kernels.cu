@@ -387,6 +387,9 @@ static int check_config(const qs_config* c) {
   if (c->control_mode < 0 || c->control_mode > 2) return fail(QS_ERR_ARG, "unknown motor control mode");
   if (c->action_mode < 0 || c->action_mode > 2) return fail(QS_ERR_ARG, "unknown action space mode");
   if (c->task < 0 || c->task > QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO) return fail(QS_ERR_ARG, "unknown task");
+  if (c->landing_mode < 0 || c->landing_mode > 2) return fail(QS_ERR_ARG, "unknown landing_mode");
+  if (c->landing_mode && (c->control_mode == QS_CTRL_TORQUE || !c->is_rl_interface))
+    return fail(QS_ERR_ARG, "landing controllers need the RL interface with PD or CARTESIAN_PD control");
   if (c->obs_mode < 0 || c->obs_mode > QS_OBS_PPO_CONTINUOUS_JUMPING_FORWARD) return fail(QS_ERR_ARG, "unknown observation space mode");
   if (c->action_repeat < 1 || c->action_repeat > 1000) return fail(QS_ERR_ARG, "action_repeat out of range");
   if (c->control_mode == QS_CTRL_TORQUE && c->is_rl_interface)  // quadruped_gym_env.py:167-168
@@ -446,12 +449,13 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   C.obs_dim = host::obs_dim_of(cfg->obs_mode);
   C.action_dim = host::action_dim_of(cfg->is_rl_interface, cfg->action_mode);
   C.settling_steps = cfg->settling_steps; C.ground_randomizer = cfg->ground_randomizer; C.auto_reset = cfg->auto_reset;
+  C.landing_mode = cfg->landing_mode;
   C.max_episode_time = float(cfg->max_episode_time); C.mu_ground = cfg->mu_ground;
   C.seed = cfg->seed; C.gid0 = cfg->env_id_offset;
 
   // one pool for all SoA arrays (4-byte elements), 256 B aligned segments
   const size_t n = size_t(n_envs);
-  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1 + 3 + 12 + 1 + 1 + QS_SLOTS * (SLOT_ROWS + 1 + 1);
+  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1 + 3 + 12 + 1 + 1 + 1 + 2 + QS_SLOTS * (SLOT_ROWS + 1 + 1);
   // rows of one array are contiguous with stride n floats; each array starts 256 B aligned
   h->pool_bytes = rows * n * 4 + 64 * 256;
   cudaError_t e = cudaMalloc(&h->pool, h->pool_bytes);
@@ -476,6 +480,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   D.work = (uint32_t*)carve(3);
   D.cmd = (float*)carve(12); D.resume_tick = (int32_t*)carve(1);
   D.custom_gains = (uint8_t*)carve(1);
+  D.land_mode = (int32_t*)carve(1); D.land_timer = (float*)carve(2);
   D.slot = (float*)carve(QS_SLOTS * SLOT_ROWS); D.slot_contact = (int32_t*)carve(QS_SLOTS); D.slot_epoch = (uint32_t*)carve(QS_SLOTS);
   if (size_t(p - static_cast<char*>(h->pool)) > h->pool_bytes) { cudaFree(h->pool); delete h; return fail(QS_ERR_STATE, "pool overflow"); }
   {
@@ -643,6 +648,7 @@ int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* o) {
   o->spring = D.spring; o->mu = D.mu; o->foot_force = D.foot_force; o->contact = D.contact; o->task = D.task;
   o->last_action = D.last_action; o->sim_steps = D.sim_steps; o->env_steps = D.env_steps; o->ep_return = D.ep_return;
   o->custom_gains = D.custom_gains;
+  o->land_mode = D.land_mode;
   o->work = D.work;
   return QS_OK;
 }

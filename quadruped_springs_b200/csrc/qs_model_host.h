@@ -4,6 +4,7 @@
 // Every number restates a reference file:line (paths under
 // /root/reference/quadruped_spring/).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -215,6 +216,26 @@ inline void build_robot(const qs_config& c, RobotConst& R) {
   const double K = std::tan(PI * 3.0 / fs), nrm = 1.0 / (1 + std::sqrt(2.0) * K + K * K);
   R.filt_b[0] = float(K * K * nrm); R.filt_b[1] = float(2 * K * K * nrm); R.filt_b[2] = float(K * K * nrm);
   R.filt_a[0] = 1.f; R.filt_a[1] = float(2 * (K * K - 1) * nrm); R.filt_a[2] = float((1 - std::sqrt(2.0) * K + K * K) * nrm);
+  // ---- env.get_landing_action() (quadruped_gym_env.py:375-379): landing pose -> [-1, 1] -> action space
+  // ANGLE_LANDING_POSE = INIT_MOTOR_ANGLES (configs:38); CARTESIAN_LANDING_POSE = nominal foot, z = -0.29 (configs:67-72)
+  const bool cart = c.control_mode == QS_CTRL_CARTESIAN_PD;
+  double a12[12];
+  for (int i = 0; i < 12; i++) {
+    const double lo = cart ? R.cart_lo[i] : R.ang_lo[i], hi = cart ? R.cart_hi[i] : R.ang_hi[i];
+    double pose = cart ? (i % 3 == 2 ? -0.29 : double(R.nominal_foot[i])) : double(R.init_angles[i]);
+    pose = std::min(std::max(pose, lo), hi);
+    a12[i] = std::min(std::max(-1.0 + 2.0 * (pose - lo) / (hi - lo), -1.0), 1.0);  // interface_base.py:92-100
+  }
+  const int sidx = cart ? 1 : 0;  // _convert_to_actual_action_space (action_interface.py:17-18,41-44,67-74)
+  if (!c.is_rl_interface || c.action_mode == QS_ACT_DEFAULT) {
+    for (int i = 0; i < 12; i++) R.landing_action[i] = float(a12[i]);
+  } else if (c.action_mode == QS_ACT_SYMMETRIC) {
+    for (int j = 0; j < 3; j++) { R.landing_action[j] = float(a12[j]); R.landing_action[3 + j] = float(a12[6 + j]); }
+  } else {
+    int s2 = 0;
+    for (int j = 0; j < 3; j++) if (j != sidx) { R.landing_action[s2] = float(a12[j]); R.landing_action[2 + s2] = float(a12[6 + j]); s2++; }
+  }
+  R.env_dt = float(c.action_repeat * c.time_step);
 }
 
 }  // namespace host

@@ -99,6 +99,7 @@ __device__ __forceinline__ void finish_episode_stats(const DeviceView& D, int en
   s[10 * n] += terminated ? 1.f : 0.f;
 }
 
+enum { LAND_POLICY = 0, LAND_HOLD = 1, LAND_LANDING = 2, LAND_SPENT = 3 };
 constexpr int QS_SLOTS = 4;  // settled episodes kept ahead per env (ring indexed by episode number)
 
 // ---- settle conveyor: the queue of (env, episode) pairs whose settled start state is computed
@@ -358,6 +359,7 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
   D.reset_count[env] = epoch;
   D.mu[env] = mu;
   D.custom_gains[env] = 0;
+  D.land_mode[env] = 0;
 #pragma unroll
   for (int i = 0; i < 12; i++) { D.kp[i * n + env] = A.RC.kp[i]; D.kd[i * n + env] = A.RC.kd[i]; }
 #pragma unroll
@@ -433,6 +435,16 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   D.work[1 * n + env] += uint32_t(cs.work_contacts);
   D.work[2 * n + env] += uint32_t(cs.work_row_iters);
   const uint64_t gid = uint64_t(C.gid0 + env);
+  if (C.landing_mode && !dn) {
+    const int mode = D.land_mode[env];
+    if (mode == LAND_POLICY && ts[TS_SWITCHED] != 0.f) {  // LandingWrapper.step :58-66, start_jumping_timer :56-60
+      D.land_mode[env] = LAND_HOLD;
+      D.land_timer[env] = sim_time;
+      D.land_timer[n + env] = sim_time + st.vlin[2] / 9.81f;  // task.compute_time_for_peak_heihgt, task_base.py:157-160
+    } else if (mode == LAND_LANDING && C.landing_mode == 2 && (cs.mask & 15) != 0) {
+      D.land_mode[env] = LAND_SPENT;  // LandingWrapper2.landing_phase :39-46; _enable_landing = False :71
+    }
+  }
   if (dn) finish_episode_stats(D, env, ts, ep_ret, env_steps, term, C.task);
   if (dn && C.auto_reset) {
     // the finished env starts its next episode inside the same call; its obs row becomes the
@@ -509,6 +521,31 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
   float act[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) act[i] = i < C.action_dim ? io.actions[size_t(env) * C.action_dim + i] : 0.f;
+  if (C.landing_mode) {
+    // landing controllers (landing_wrapper.py:38-66, landing_wrapper_2.py:39-72) as a mode machine: the
+    // wrappers' inner env.step loops, one control step per call; a scripted env ignores the policy's action
+    int mode = D.land_mode[env];
+    if (mode == LAND_HOLD) {  // take_off_phase: repeat the action until the timer is up (utils/timer.py:39-43)
+      const float timer = D.land_timer[env];
+      if (timer > D.land_timer[n + env]) {
+        mode = LAND_LANDING;
+        if (live) D.land_mode[env] = mode;
+        if (C.landing_mode == 1 && live) {  // temporary_switch_motor_control_gain, landing_wrapper.py:18-36
+#pragma unroll
+          for (int i = 0; i < 12; i++) { D.kp[i * n + env] = 60.f; D.kd[i * n + env] = 1.5f; }
+          D.custom_gains[env] = 1;
+        }
+      } else {
+        if (live) D.land_timer[env] = timer + A.RC.env_dt;  // step_timer
+#pragma unroll
+        for (int i = 0; i < 12; i++) act[i] = D.last_action[i * n + env];
+      }
+    }
+    if (mode == LAND_LANDING) {
+#pragma unroll
+      for (int i = 0; i < 12; i++) act[i] = A.RC.landing_action[i];
+    }
+  }
   if (live) {
 #pragma unroll
     for (int i = 0; i < 12; i++) D.last_action[i * n + env] = act[i];

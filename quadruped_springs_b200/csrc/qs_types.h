@@ -18,6 +18,8 @@ struct RobotConst {
   float fallen_height;             // IS_FALLEN_HEIGHT, configs:24
   float obs_noise[QS_MAX_OBS];     // per-element sensor noise std of the selected obs mode
   float filt_b[3], filt_a[3];      // Butterworth(2, 3 Hz) coefficients, action_filter.py:191-213
+  float landing_action[12];        // env.get_landing_action() in the configured action space, quadruped_gym_env.py:375-379
+  float env_dt;                    // action_repeat * time_step
 };
 
 // Merged 13-body dynamics model of go1.urdf: fixed links folded into their
@@ -69,6 +71,8 @@ struct DeviceView {
   uint32_t* work;        // [3][N] k_step work counters: ticks, contact-ticks, contact-sweeps
   float* cmd;            // [12][N] motor command of the current control step (slow-path hand-over)
   int32_t* resume_tick;  // [N] tick at which the fast kernel handed the env to the general solver
+  int32_t* land_mode;    // [N] landing controller: 0 policy, 1 take-off hold, 2 landing, 3 spent
+  float* land_timer;     // [2][N] timer time, timer end (utils/timer.py)
   uint8_t* custom_gains; // [N] non-zero: read kp/kd of this env from the arrays instead of the config constants
   float* slot;           // [slots][66][N] settled states of the next episodes (see qs_step_kernels.cuh)
   int32_t* slot_contact; // [slots][N]

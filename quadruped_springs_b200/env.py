@@ -391,7 +391,12 @@ class BatchedQuadrupedGymEnv:
         enable_noise=True,
         solver=None,
         block_size=0,
+        landing_wrapper=None,
     ):
+        """landing_wrapper: None, "LandingWrapper" (env/wrappers/landing_wrapper.py:18-69) or "LandingWrapper2"
+        (landing_wrapper_2.py:39-78).  The reference wraps the env and loops env.step inside one wrapper step; here
+        the same controller runs per env inside the step kernel: every call is one control step, envs whose
+        controller is scripted (infos["landing_mode"] != 0 and != 3) ignore the action they are given."""
         if render or on_rack:
             raise ValueError("render / on_rack are visual-debug modes of the pybullet GUI and are not provided")
         self._L = _lib.lib()
@@ -439,6 +444,10 @@ class BatchedQuadrupedGymEnv:
         cfg.time_step = float(time_step)
         cfg.max_episode_time = float(EPISODE_LENGTH)
         cfg.block_size = int(block_size)
+        try:
+            cfg.landing_mode = {None: 0, "LandingWrapper": 1, "LandingWrapper2": 2}[landing_wrapper]
+        except KeyError:
+            raise ValueError(f"the landing wrapper {landing_wrapper} is not implemented yet.") from None
         for k, v in (solver or {}).items():
             if not hasattr(cfg, k):
                 raise ValueError(f"unknown solver parameter {k}")
@@ -468,6 +477,7 @@ class BatchedQuadrupedGymEnv:
             "sim_steps": _view(ptrs.sim_steps, (n,), "<i4", dev), "env_steps": _view(ptrs.env_steps, (n,), "<i4", dev),
             "ep_return": _view(ptrs.ep_return, (n,), "<f4", dev),
             "custom_gains": _view(ptrs.custom_gains, (n,), "|u1", dev),
+            "land_mode": _view(ptrs.land_mode, (n,), "<i4", dev),
             "work": _view(ptrs.work, (3, n), "<i4", dev),
         }
         self.robot = BatchedQuadruped(self)
@@ -516,6 +526,8 @@ class BatchedQuadrupedGymEnv:
         _lib.check(self._L.qs_step(self._h, _p(a), _p(self._obs), _p(self._reward), _p(self._done), _p(self._trunc),
                                    _stream_ptr(self.device)))
         infos = {"TimeLimit.truncated": self._trunc.bool()}
+        if self._cfg.landing_mode:
+            infos["landing_mode"] = self._views["land_mode"]
         return self._obs, self._reward, self._done.bool(), infos
 
     def reset_host(self, mask_np=None):

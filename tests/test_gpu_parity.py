@@ -454,3 +454,81 @@ def test_rollout_teacher_forced_matches_reference_env(qs, name):
         p = np.concatenate([fwd, np.zeros(max(0, 3 - len(fwd)))]) / max(fwd.sum(), 1e-30)
         ent = 0.0 if fwd.sum() < 0.05 else float(-(p[p > 0] * np.log2(p[p > 0])).sum() / np.log2(len(p)))
         assert float(env.task.get_entropy_fwd()[0]) == pytest.approx(ent, abs=2e-2)
+
+
+# ------------------------------------------------------------------ 8f rank 1: landing controllers inside the step kernel
+LANDINGS = ["w1_jip_pd", "w1_jf_cartesian", "w2_jip_pd_nosprings", "w2_jf_cartesian"]
+URDF_LO = np.array([-1.0471975512, -0.663225115758, -2.72271363311] * 4)   # go1.urdf joint limits
+URDF_HI = np.array([1.0471975512, 2.96705972839, -0.837758040957] * 4)
+
+
+@pytest.mark.parametrize("name", LANDINGS)
+def test_landing_controller_teacher_forced_matches_reference_wrapper(qs, name):
+    """every INNER env.step the reference's LandingWrapper / LandingWrapper2 made (fixture from the unmodified
+    wrappers, oracle/gen_golden.py::rollout_landing): the kernel is given the policy's action at every control
+    step and must itself hold it after take-off, switch to the landing action (and the 60 / 1.5 gains for
+    LandingWrapper) when the apex timer is up, and hand control back (LandingWrapper2) at touch-down."""
+    g = load_golden(f"landing_{name}.npz")
+    cfg = json.loads(str(g["cfg"]))
+    wrapper = {1: "LandingWrapper", 2: "LandingWrapper2"}[int(g["landing_mode"])]
+    env = qs.BatchedQuadrupedGymEnv(num_envs=2, enable_noise=False, auto_reset=False, env_randomizer_mode="NO_RANDOMIZER",
+                                    solver=dict(mu_ground=float(g["mu"])), landing_wrapper=wrapper, **cfg)
+    env.reset()
+    env._views["task"][6] = float(g["init_task_height"])
+    modes = []
+    for t in range(len(g["reward"])):
+        env.set_state(cuda(np.stack([g["pre_state"][t]] * 2)))
+        if t > 0:
+            env._views["foot_force"][:] = cuda(g["foot_force"][t - 1])[:, None]
+            env._views["contact"][:] = int(sum(int(b) << k for k, b in enumerate(g["foot_contact"][t - 1])))
+        else:
+            env._views["contact"][:] = 15
+            env._views["foot_force"][:] = 12.01301 * 9.8 / 4
+        obs, r, d, info = env.step(cuda(g["policy_action"][t]).expand(2, -1))
+        A = env.action_dim
+        np.testing.assert_allclose(env.get_last_action()[0, :A].cpu().numpy(), g["applied_action"][t][:A], atol=2e-6,
+                                   err_msg=f"applied action {t}")
+        got, ref = env.get_state()[0].cpu().numpy(), g["state"][t]
+        # hard-constraint steps get the looser bound of the crash steps: a body shape on the ground, or a joint riding
+        # its URDF limit (the fully extended calf in flight): limit rows switching one tick apart change qd by O(0.1)
+        margin = min(np.minimum(q - URDF_LO, URDF_HI - q).min() for q in (g["pre_state"][t][13:25], ref[13:25]))
+        crashing = int(g["n_invalid"][t]) > 0 or margin < 1e-3
+        err_q = max(np.abs(got[:7] - ref[:7]).max(), np.abs(got[13:25] - ref[13:25]).max())
+        # one control step, fp32 vs fp64: positions 5e-4 (touch-down impacts under the landing gains), 2e-3 on hard steps
+        assert err_q < (2e-3 if crashing else 5e-4), (t, err_q)
+        same_contacts = (env._views["contact"][0].item() & 15) == int(sum(int(b) << k for k, b in enumerate(g["foot_contact"][t])))
+        if not crashing and same_contacts:   # a foot touching down one tick earlier / later changes qd, hence kd * qd
+            np.testing.assert_allclose(env.robot.GetMotorTorques()[0].cpu().numpy(), g["tau"][t], rtol=1e-3, atol=1e-1)
+        if not crashing:
+            assert float(r[0]) == pytest.approx(float(g["reward"][t]), rel=1e-4, abs=3e-5), t
+        assert bool(d[0]) == bool(g["done"][t]), t
+        assert float(env._views["kp"][0, 0]) == pytest.approx(float(g["kp"][t][0])), t   # landing gains
+        modes.append(int(info["landing_mode"][0]))
+    assert 1 in modes and 2 in modes
+    assert (3 in modes) == (wrapper == "LandingWrapper2")
+
+
+def test_landing_controller_batched_free_running(qs):
+    """4096 envs with LandingWrapper semantics and auto-reset: scripted envs ignore the policy, every episode that
+    takes off goes hold -> landing -> done, gains are back to the defaults after the reset."""
+    n = 4096
+    env = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=2, enable_springs=True, task_env="JUMPING_IN_PLACE",
+                                    observation_space_mode="ARS_BASIC", landing_wrapper="LandingWrapper")
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    seen = torch.zeros(4, dtype=torch.long)
+    prev = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for t in range(250):
+        a = torch.rand(n, 6, device="cuda", generator=g) * 2 - 1
+        obs, r, d, info = env.step(a)
+        mode = info["landing_mode"].clone()
+        assert torch.isfinite(obs).all()
+        seen += torch.bincount(mode, minlength=4).cpu()
+        # legal transitions only: 0->0/1, 1->1/2, 2->2, anything -> 0 through a reset
+        ok = (mode == prev) | ((prev == 0) & (mode == 1)) | ((prev == 1) & (mode == 2)) | (d & (mode == 0))
+        assert ok.all()
+        landing = mode == 2
+        assert (env._views["kp"][0][landing] == 60).all() and (env._views["kd"][0][landing] == 1.5).all()
+        assert (env._views["kp"][0][mode == 0] == 75).all()
+        prev = mode
+    assert seen[1] > 0 and seen[2] > 0 and seen[3] == 0

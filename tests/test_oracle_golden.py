@@ -137,3 +137,39 @@ def test_rollout_matches_reference_env(name):
         fwd, perf, _ = env.jump_arrays()
         np.testing.assert_allclose(fwd, g["jumps"][0], rtol=1e-8, atol=1e-10)
         np.testing.assert_allclose(perf, g["jumps"][1], rtol=1e-8, atol=1e-10)
+
+
+LANDINGS = ["w1_jip_pd", "w1_jf_cartesian", "w2_jip_pd_nosprings", "w2_jf_cartesian"]
+
+
+@pytest.mark.parametrize("name", LANDINGS)
+def test_landing_controller_matches_reference_wrapper(name):
+    """The reference's LandingWrapper / LandingWrapper2 loop env.step inside one wrapper step
+    (landing_wrapper.py:38-66, landing_wrapper_2.py:39-72).  The oracle runs the same control flow
+    as a mode machine, one qso_env_step per inner step: fed with the policy's action at every
+    control step, it must apply the action the wrapper applied (hold, then landing action, with the
+    landing gains) and reproduce every inner state, reward and done."""
+    g = load_golden(f"landing_{name}.npz")
+    cfg = json.loads(str(g["cfg"]))
+    env = O.Env(enable_springs=cfg["enable_springs"], motor_control_mode=cfg["motor_control_mode"],
+                action_space_mode=cfg["action_space_mode"], task_env=cfg["task_env"],
+                observation_space_mode=cfg["observation_space_mode"], landing_mode=int(g["landing_mode"]))
+    obs = env.reset(mu=float(g["mu"]))
+    np.testing.assert_allclose(env.world.get_state(), g["init_state"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(obs, g["init_obs"], rtol=1e-9, atol=1e-10)
+    modes = []
+    for t in range(len(g["reward"])):
+        obs, r, d, tr = env.step(g["policy_action"][t])      # ignored while the controller is scripted
+        np.testing.assert_allclose(env.last_action(), g["applied_action"][t], rtol=1e-9, atol=1e-12, err_msg=f"action {t}")
+        np.testing.assert_allclose(env.world.get_state(), g["state"][t], rtol=1e-8, atol=1e-9, err_msg=f"step {t}")
+        np.testing.assert_allclose(obs, g["obs"][t], rtol=1e-8, atol=1e-9, err_msg=f"obs {t}")
+        np.testing.assert_allclose(r, g["reward"][t], rtol=1e-8, atol=1e-10, err_msg=f"reward {t}")
+        assert d == bool(g["done"][t]) and tr == bool(g["truncated"][t]), t
+        np.testing.assert_allclose(env.torques()[0], g["tau"][t], rtol=1e-8, atol=1e-9)
+        modes.append(env.landing_state()[0])
+    # the wrapper returns the reward / done of its LAST inner step
+    last = np.flatnonzero(np.diff(np.append(g["wrapper_step"], -1)) != 0)
+    np.testing.assert_allclose(g["reward"][last], g["wrapper_out"][:, 0], rtol=0, atol=0)
+    assert 1 in modes and 2 in modes                         # take-off hold and landing both happened
+    if int(g["landing_mode"]) == 2:
+        assert 3 in modes                                    # LandingWrapper2 hands control back to the policy

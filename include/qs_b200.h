@@ -110,6 +110,10 @@ typedef struct qs_config {
                                   * episode ends; 2 LandingWrapper2 (landing_wrapper_2.py:39-78): default gains, landing until
                                   * touch-down, once per episode.  The wrappers' inner env.step loops run as a per-env mode
                                   * machine: one qs_step = one control step, scripted envs ignore the action passed in */
+  int32_t spring_randomizer;     /* EnvRandomizerSprings (env_randomizers/env_randomizer.py:86-122): every reset draws the
+                                  * spring stiffness and damping of hip / thigh / calf within +-10 % of the nominal values;
+                                  * the settle of that episode already runs on them.  No effect without springs */
+  int32_t reserved1;
 } qs_config;
 
 typedef struct qs_env* qs_handle;

@@ -294,6 +294,8 @@ def rollout(name, cfg, actions, seed, world_params=None):
     out = {k: np.asarray(v) for k, v in rec.items()}
     if hasattr(T, "fwd_array"):
         out["jumps"] = jumps
+    if cfg.get("env_randomizer_mode") == "SPRING_RANDOMIZER":  # the episode's draw (env_randomizer.py:101-122)
+        out["springs"] = np.concatenate([np.asarray(x, dtype=np.float64) for x in env.robot.get_spring_nominal_params()])
     out.update(actions=np.asarray(actions)[: len(out["reward"])], mu=mu, init_state=init_state, init_obs=init_obs,
                init_last_action=init_last_action, init_task=init_task,
                cfg=json.dumps(cfg), world_params=json.dumps(world_params or {}))
@@ -475,6 +477,13 @@ def cart_hop_actions(n, rng, zc=1.0, zp=-1.0, crouch=25, push=12, period=70):
     return acts
 
 
+def gen_spring_randomizer():
+    """EnvRandomizerSprings (env_randomizer.py:86-122): stiffness / damping drawn before the settle"""
+    base = dict(enable_springs=True, task_env="JUMPING_IN_PLACE", motor_control_mode="PD", action_space_mode="SYMMETRIC",
+                observation_space_mode="ARS_BASIC", env_randomizer_mode="SPRING_RANDOMIZER")
+    rollout("spring_randomizer", base, jump_actions(6, 160, np.random.default_rng(91)), seed=41)
+
+
 def gen_landing():
     rng = np.random.default_rng(77)
     base = dict(enable_springs=True, task_env="JUMPING_IN_PLACE", motor_control_mode="PD",
@@ -540,7 +549,7 @@ def gen_hopf():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "continuous", "landing", "rollouts"]
+    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "continuous", "landing", "springs", "rollouts"]
     if "urdf" in which:
         gen_urdf()
     # NB: gen_analytic and the last rollout build a BACKFLIP env, which mutates the module-level
@@ -555,6 +564,8 @@ if __name__ == "__main__":
         gen_rollouts_continuous()
     if "landing" in which:
         gen_landing()
+    if "springs" in which:
+        gen_spring_randomizer()
     if "rollouts" in which:
         gen_rollouts()
     print("golden fixtures written to", OUT)

@@ -310,6 +310,13 @@ class Env:
         self.L.qso_env_get_torques(self.h, ap, bp)
         return a, b
 
+    def set_springs(self, k3, b3, rest3):
+        """nominal spring stiffness / damping / rest angle of hip, thigh, calf (env/springs.py:28-52)"""
+        a, ap = _d(k3)
+        b, bp = _d(b3)
+        c, cp = _d(rest3)
+        self.L.qso_env_set_springs(self.h, ap, bp, cp)
+
     def set_gains(self, kp, kd):
         a, ap = _d(np.broadcast_to(kp, (12,)).copy())
         b, bp = _d(np.broadcast_to(kd, (12,)).copy())

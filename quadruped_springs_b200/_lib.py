@@ -38,6 +38,7 @@ class QsConfig(C.Structure):
         ("limit_erp", C.c_float), ("linear_slop", C.c_float), ("warmstart", C.c_float),
         ("residual_threshold", C.c_float), ("max_coord_vel", C.c_float),
         ("breaking_threshold", C.c_float), ("landing_mode", C.c_int32),
+        ("spring_randomizer", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 

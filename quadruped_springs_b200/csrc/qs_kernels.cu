@@ -449,7 +449,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   C.obs_dim = host::obs_dim_of(cfg->obs_mode);
   C.action_dim = host::action_dim_of(cfg->is_rl_interface, cfg->action_mode);
   C.settling_steps = cfg->settling_steps; C.ground_randomizer = cfg->ground_randomizer; C.auto_reset = cfg->auto_reset;
-  C.landing_mode = cfg->landing_mode;
+  C.landing_mode = cfg->landing_mode; C.spring_randomizer = cfg->spring_randomizer && cfg->enable_springs;
   C.max_episode_time = float(cfg->max_episode_time); C.mu_ground = cfg->mu_ground;
   C.seed = cfg->seed; C.gid0 = cfg->env_id_offset;
 

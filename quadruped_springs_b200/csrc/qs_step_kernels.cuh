@@ -287,13 +287,26 @@ __device__ __forceinline__ float episode_mu(const EnvCfg& C, uint64_t gid, uint3
   return C.ground_randomizer ? 0.5f + 0.5f * uniform1(C.seed, gid, epoch, 100) : C.mu_ground;
 }
 __device__ __forceinline__ int settle_length(const EnvCfg& C) { return C.is_rl ? C.settling_steps : 1500; }
+// spring stiffness / damping / rest angle (hip, thigh, calf) of an episode: nominal, or EnvRandomizerSprings'
+// U[(1 - 0.1) x, (1 + 0.1) x] draw (env_randomizer.py:101-122), taken before the settle like randomize_env()
+__device__ __forceinline__ void episode_springs(const EnvCfg& C, const RobotConst& RC, uint64_t gid, uint32_t epoch,
+                                                float* sk, float* sb, float* sr) {
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    sk[j] = RC.spring_k[j]; sb[j] = RC.spring_b[j]; sr[j] = RC.spring_rest[j];
+    if (C.spring_randomizer) {
+      sk[j] *= 0.9f + 0.2f * uniform1(C.seed, gid, epoch, 101 + j);
+      sb[j] *= 0.9f + 0.2f * uniform1(C.seed, gid, epoch, 104 + j);
+    }
+  }
+}
 
 // Settle ticks [t0, t1) of the reset (control_interface/interface_base.py:182-200), at most `span` of them.
 // Every thread of the block runs the same `span` iterations (one barrier each, see run_ticks);
 // a thread works while t < t1.
-__device__ __forceinline__ void settle_ticks(const KernelArgs& A, EnvState<float>& st, ContactState<float>& cs, float mu,
-                                             int t0, int t1, int span, float* tau_m, float* tau_s,
-                                             const Scratch<float>& scr) {
+__device__ __forceinline__ void settle_ticks(const KernelArgs& A, uint64_t gid, uint32_t epoch, EnvState<float>& st,
+                                             ContactState<float>& cs, float mu, int t0, int t1, int span, float* tau_m,
+                                             float* tau_s, const Scratch<float>& scr) {
   const EnvCfg& C = A.C;
   float cmd[12], act12[12];
   settle_command(C, A.RC, cmd, act12);
@@ -304,8 +317,7 @@ __device__ __forceinline__ void settle_ticks(const KernelArgs& A, EnvState<float
   SCs.body_response = 0;
   const int nsettle = settle_length(C);
   float sk[3], sb[3], sr[3];
-#pragma unroll
-  for (int j = 0; j < 3; j++) { sk[j] = A.RC.spring_k[j]; sb[j] = A.RC.spring_b[j]; sr[j] = A.RC.spring_rest[j]; }
+  episode_springs(C, A.RC, gid, epoch, sk, sb, sr);
   for (int i = 0; i < span; i++) {
     __syncthreads();  // lockstep across the block (see run_ticks)
     const int t = t0 + i;
@@ -343,7 +355,7 @@ __device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint6
 #pragma unroll
   for (int i = 0; i < 12; i++) { tau_m[i] = 0.f; tau_s[i] = 0.f; }
   const int nsettle = settle_length(A.C);
-  settle_ticks(A, st, cs, mu, 0, need ? nsettle : 0, nsettle, tau_m, tau_s, scr);
+  settle_ticks(A, gid, epoch, st, cs, mu, 0, need ? nsettle : 0, nsettle, tau_m, tau_s, scr);
   if (!need) { st = st_keep; cs = cs_keep; }
 }
 
@@ -362,11 +374,13 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
   D.land_mode[env] = 0;
 #pragma unroll
   for (int i = 0; i < 12; i++) { D.kp[i * n + env] = A.RC.kp[i]; D.kd[i * n + env] = A.RC.kd[i]; }
+  float sk[3], sb[3], sr[3];
+  episode_springs(C, A.RC, uint64_t(C.gid0 + env), epoch, sk, sb, sr);
 #pragma unroll
   for (int j = 0; j < 3; j++) {
-    D.spring[(0 + j) * n + env] = A.RC.spring_k[j];
-    D.spring[(3 + j) * n + env] = A.RC.spring_b[j];
-    D.spring[(6 + j) * n + env] = A.RC.spring_rest[j];
+    D.spring[(0 + j) * n + env] = sk[j];
+    D.spring[(3 + j) * n + env] = sb[j];
+    D.spring[(6 + j) * n + env] = sr[j];
   }
   float cmd[12], act12[12];
   settle_command(C, A.RC, cmd, act12);
@@ -818,7 +832,7 @@ k_settle_slice(const __grid_constant__ KernelArgs A, const Conveyor cv) {
   const int t1 = need ? min(t0 + span, nsettle) : 0;
   extern __shared__ float qs_smem[];
   const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
-  settle_ticks(A, st, cs, mu, t0, t1, span, tau_m, tau_s, scr);
+  settle_ticks(A, uint64_t(A.C.gid0 + env), epoch, st, cs, mu, t0, t1, span, tau_m, tau_s, scr);
   if (!need) return;
   {  // work counters of the bench's flop model, one atomic per warp
     const unsigned m = __activemask();

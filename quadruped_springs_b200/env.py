@@ -48,8 +48,8 @@ TaskCollection = lambda: _Collection("task", [
     "CONTINUOUS_JUMPING_FORWARD2", "CONTINUOUS_JUMPING_FORWARD3", "CONTINUOUS_JUMPING_FORWARD_PPO"])
 # sensors/sensor_collection.py:92-105
 SensorCollection = lambda: _Collection("sensor package", list(SENSOR_SETS))
-# env_randomizers/env_randomizer_collection.py:15-21 (mass/spring randomizers: SURVEY.md 8f "next")
-EnvRandomizerCollection = lambda: _Collection("env randomizer", ["GROUND_RANDOMIZER", "NO_RANDOMIZER"])
+# env_randomizers/env_randomizer_collection.py:15-21 (mass / curriculum randomizers: SURVEY.md 8f "next")
+EnvRandomizerCollection = lambda: _Collection("env randomizer", ["GROUND_RANDOMIZER", "NO_RANDOMIZER", "SPRING_RANDOMIZER"])
 
 
 class Box:
@@ -432,7 +432,9 @@ class BatchedQuadrupedGymEnv:
         cfg.action_mode = ActionInterfaceCollection().get_el(action_space_mode)
         cfg.task = TaskCollection().get_el(task_env)
         cfg.obs_mode = SensorCollection().get_el(observation_space_mode)
-        cfg.ground_randomizer = int(EnvRandomizerCollection().get_el(env_randomizer_mode) == 0)
+        rnd = EnvRandomizerCollection().get_el(env_randomizer_mode)
+        cfg.ground_randomizer = int(rnd in (0, 2))     # SPRING_RANDOMIZER = [ground, springs] (collection :18)
+        cfg.spring_randomizer = int(rnd == 2)
         cfg.action_repeat = self._action_repeat
         cfg.is_rl_interface = int(isRLGymInterface)
         cfg.enable_action_filter = int(enable_action_filter)

@@ -354,6 +354,7 @@ def test_reset_settle_matches_oracle(qs, cfg):
 # ------------------------------------------------------------------ a1/a17-a20 whole step against the reference env
 def _make_env_for(qs, g, n=2):
     cfg = json.loads(str(g["cfg"]))
+    cfg.pop("env_randomizer_mode", None)   # the fixture's draws (mu, springs) are imposed below
     return qs.BatchedQuadrupedGymEnv(num_envs=n, enable_noise=False, auto_reset=False,
                                      env_randomizer_mode="NO_RANDOMIZER", solver=dict(mu_ground=float(g["mu"])), **cfg), cfg
 
@@ -364,6 +365,8 @@ def test_rollout_free_running_tracks_reference_env(qs, name):
     QuadrupedGymEnv; fp32 vs fp64 physics drift apart slowly, so the first 30
     control steps (300 ticks) are held to a stated tolerance."""
     g = load_golden(f"rollout_{name}.npz")
+    if "springs" in g.files:
+        pytest.skip("randomized springs enter the settle: covered by test_spring_randomizer_* and the teacher-forced replay")
     env, cfg = _make_env_for(qs, g)
     obs = env.reset()
     np.testing.assert_allclose(env.get_state()[0].cpu().numpy(), g["init_state"], atol=1e-3)
@@ -392,6 +395,8 @@ def test_rollout_teacher_forced_matches_reference_env(qs, name):
     g = load_golden(f"rollout_{name}.npz")
     env, cfg = _make_env_for(qs, g)
     env.reset()
+    if "springs" in g.files:          # the fixture's spring draw (per-env arrays stay until the next reset)
+        env._views["spring"][:] = cuda(g["springs"])[:, None]
     if cfg["task_env"] != "NO_TASK":  # the task remembers the settled height of ITS reset; take the fixture's
         env._views["task"][6] = float(g["init_task"][3])
     n_steps = len(g["reward"])
@@ -532,3 +537,49 @@ def test_landing_controller_batched_free_running(qs):
         assert (env._views["kp"][0][mode == 0] == 75).all()
         prev = mode
     assert seen[1] > 0 and seen[2] > 0 and seen[3] == 0
+
+
+# ------------------------------------------------------------------ 8f rank 2 (springs): EnvRandomizerSprings inside reset
+def test_spring_randomizer_draws_and_settles_on_them(qs):
+    """SPRING_RANDOMIZER = [ground, springs] (env_randomizer_collection.py:18): stiffness / damping of hip, thigh, calf
+    are drawn per episode within +-10 % of nominal (env_randomizer.py:101-122) BEFORE the settle, so the settled pose
+    depends on them: an oracle env given the same draw and friction settles to the same state and steps alike."""
+    from oracle import oracle as O
+    n = 256
+    cfg = dict(enable_springs=True, task_env="JUMPING_IN_PLACE", observation_space_mode="ARS_BASIC")
+    env = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=9, enable_noise=False, auto_reset=False,
+                                    env_randomizer_mode="SPRING_RANDOMIZER", **cfg)
+    obs = env.reset()
+    sp = env._views["spring"].cpu().numpy()           # [k3 | b3 | rest3][n]
+    nominal = np.array([20, 20, 30, 0.3, 0.3, 0.3])
+    ratio = sp[:6] / nominal[:, None]
+    assert (ratio > 0.9 - 1e-6).all() and (ratio < 1.1 + 1e-6).all()
+    assert ratio.std(axis=1).min() > 0.04             # U[0.9, 1.1] has std 0.0577
+    assert np.abs(np.corrcoef(ratio)[np.triu_indices(6, 1)]).max() < 0.25   # six independent streams
+    np.testing.assert_allclose(sp[6:], np.array([0, np.pi / 4, -np.pi / 2 + 0.3])[:, None] * np.ones((1, n)), atol=1e-6)
+    mu = env._views["mu"].cpu().numpy()
+    S = env.get_state().cpu().numpy()
+    a = np.random.default_rng(0).uniform(-1, 1, size=(5, 6))
+    refs = []
+    for i in (0, 7):
+        o = O.Env(**cfg)
+        o.set_springs(sp[:3, i], sp[3:6, i], sp[6:, i])
+        ref_obs = o.reset(mu=float(mu[i]))
+        np.testing.assert_allclose(S[i], o.world.get_state(), atol=1e-3)
+        np.testing.assert_allclose(obs[i].cpu().numpy(), ref_obs, atol=1e-3)
+        refs.append(o)
+    assert np.abs(S[0, 13:25] - S[7, 13:25]).max() > 1e-4           # different draws, different settled poses
+    for t in range(5):
+        ob, r, d, _ = env.step(cuda(a[t]).expand(n, -1))
+        for i, o in zip((0, 7), refs):
+            ro, rr, rd, _ = o.step(a[t])
+            np.testing.assert_allclose(ob[i].cpu().numpy(), ro, atol=5e-2)
+            np.testing.assert_allclose(env.robot.GetMotorAngles()[i].cpu().numpy(), o.world.get_state()[13:25], atol=2e-3)
+    # a new episode draws again; the same (seed, env, episode) draws the same
+    env.reset()
+    sp2 = env._views["spring"].cpu().numpy()
+    assert np.abs(sp2[:6] - sp[:6]).max() > 0.1
+    env_b = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=9, enable_noise=False, auto_reset=False,
+                                      env_randomizer_mode="SPRING_RANDOMIZER", **cfg)
+    env_b.reset()
+    assert torch.equal(env_b._views["spring"], torch.as_tensor(sp, device="cuda"))

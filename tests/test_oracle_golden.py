@@ -109,6 +109,8 @@ def test_rollout_matches_reference_env(name):
                 action_space_mode=cfg["action_space_mode"], task_env=cfg["task_env"],
                 observation_space_mode=cfg["observation_space_mode"],
                 enable_action_filter=cfg.get("enable_action_filter", False))
+    if "springs" in g.files:   # SPRING_RANDOMIZER: the episode's draw, used by the settle too (env_randomizer.py:101-122)
+        env.set_springs(g["springs"][:3], g["springs"][3:6], g["springs"][6:])
     obs = env.reset(mu=float(g["mu"]))
     np.testing.assert_allclose(env.world.get_state(), g["init_state"], rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(obs, g["init_obs"], rtol=1e-9, atol=1e-10)

@@ -316,6 +316,9 @@ struct qs_env {
   int wave_blocks;     // settle blocks resident at once (SMs x 2)
   int slice_min, slice_max;
   cudaStream_t bg;     // the conveyor's slices run here, next to k_step_slow on the caller's stream
+  cudaStream_t copy;   // qs_step_host: results go to the host while the slice is still running
+  cudaEvent_t ev_results, ev_copied;
+  uint32_t* host_urgent;  // pinned: urgent settles of the last step (their obs rows are written after the early copy)
   cudaEvent_t ev_fork, ev_join;
   float* dev_actions;  // staging for qs_step_host
   float* dev_obs;
@@ -517,6 +520,10 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     cv.work = reinterpret_cast<unsigned long long*>(h->lists + ((size_t((cv.ctl + CV_CTL_WORDS) - reinterpret_cast<uint32_t*>(h->lists)) + 1) & ~size_t(1)));
     cudaMemset(cv.tick, 0xff, cap * sizeof(int));  // CV_DONE: nothing queued
     e = cudaStreamCreateWithFlags(&h->bg, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_results, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMallocHost(&h->host_urgent, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) { cudaFree(h->pool); cudaFree(h->lists); delete h; return fail(QS_ERR_CUDA, "stream / event creation"); }
@@ -545,6 +552,10 @@ int qs_destroy(qs_handle h) {
   cudaFree(h->pool);
   cudaFree(h->lists);
   cudaStreamDestroy(h->bg);
+  cudaStreamDestroy(h->copy);
+  cudaEventDestroy(h->ev_results);
+  cudaEventDestroy(h->ev_copied);
+  cudaFreeHost(h->host_urgent);
   cudaEventDestroy(h->ev_fork);
   cudaEventDestroy(h->ev_join);
   if (h->dev_actions) cudaFree(h->dev_actions);
@@ -702,8 +713,16 @@ int qs_reset(qs_handle h, const uint8_t* mask, float* obs, void* stream) {
   return QS_OK;
 }
 
-int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_t* done, uint8_t* truncated,
-            void* stream) {
+// host destinations of qs_step_host: copied as soon as the last step kernel has written them
+struct HostOut {
+  float* obs;
+  float* reward;
+  uint8_t* done;
+  uint8_t* truncated;
+};
+
+static int step_impl(qs_handle h, const float* actions, float* obs, float* reward, uint8_t* done, uint8_t* truncated,
+                     void* stream, const HostOut* host) {
   if (!h) return fail(QS_ERR_ARG, "handle is NULL");
   if (!actions || !obs || !reward || !done || !truncated) return fail(QS_ERR_ARG, "NULL buffer");
   if (!h->was_reset) return fail(QS_ERR_STATE, "qs_step before qs_reset");
@@ -740,6 +759,18 @@ int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_
   // that its few blocks are placed first
   k_step_slow<<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io);
   g_launches += 2;
+  if (host) {
+    // the step's outputs are final here (only an urgent settle, below, rewrites obs rows: the caller checks
+    // host_urgent and repeats the obs copy in that case); the copies overlap the settle slice
+    const size_t n = size_t(h->n), O = size_t(h->args.C.obs_dim);
+    CUDA_TRY(cudaEventRecord(h->ev_results, s));
+    CUDA_TRY(cudaStreamWaitEvent(h->copy, h->ev_results, 0));
+    CUDA_TRY(cudaMemcpyAsync(host->obs, obs, n * O * sizeof(float), cudaMemcpyDeviceToHost, h->copy));
+    CUDA_TRY(cudaMemcpyAsync(host->reward, reward, n * sizeof(float), cudaMemcpyDeviceToHost, h->copy));
+    CUDA_TRY(cudaMemcpyAsync(host->done, done, n, cudaMemcpyDeviceToHost, h->copy));
+    CUDA_TRY(cudaMemcpyAsync(host->truncated, truncated, n, cudaMemcpyDeviceToHost, h->copy));
+    CUDA_TRY(cudaEventRecord(h->ev_copied, h->copy));
+  }
   if (h->cfg.auto_reset) {
     CUDA_TRY(cudaStreamWaitEvent(h->bg, h->ev_fork, 0));
     cudaEventRecord(h->ev2[slot], h->bg);
@@ -754,6 +785,11 @@ int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_
   }
   CUDA_TRY(cudaGetLastError());
   return QS_OK;
+}
+
+int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_t* done, uint8_t* truncated,
+            void* stream) {
+  return step_impl(h, actions, obs, reward, done, truncated, stream, nullptr);
 }
 
 static int ensure_staging(qs_handle h) {
@@ -791,12 +827,17 @@ int qs_step_host(qs_handle h, const float* actions, float* obs, float* reward, u
   const size_t n = size_t(h->n), A = size_t(h->args.C.action_dim), O = size_t(h->args.C.obs_dim);
   if (int e0 = ensure_staging(h)) return e0;
   CUDA_TRY(cudaMemcpyAsync(h->dev_actions, actions, n * A * sizeof(float), cudaMemcpyHostToDevice, s));
-  if (int e = qs_step(h, h->dev_actions, h->dev_obs, h->dev_reward, h->dev_done, h->dev_trunc, stream)) return e;
-  CUDA_TRY(cudaMemcpyAsync(obs, h->dev_obs, n * O * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(reward, h->dev_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(done, h->dev_done, n, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(truncated, h->dev_trunc, n, cudaMemcpyDeviceToHost, s));
+  const HostOut host{obs, reward, done, truncated};
+  *h->host_urgent = 0;
+  if (int e = step_impl(h, h->dev_actions, h->dev_obs, h->dev_reward, h->dev_done, h->dev_trunc, stream, &host)) return e;
+  if (h->cfg.auto_reset)
+    CUDA_TRY(cudaMemcpyAsync(h->host_urgent, h->cv.ctl + CV_URGENT_LAST, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamWaitEvent(s, h->ev_copied, 0));
   CUDA_TRY(cudaStreamSynchronize(s));
+  if (*h->host_urgent > 0) {  // some episodes were settled and started after the early copy: fetch their first obs
+    CUDA_TRY(cudaMemcpyAsync(obs, h->dev_obs, n * O * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+  }
   return QS_OK;
 }
 

@@ -268,3 +268,32 @@ def test_settle_conveyor_is_invisible(qs, monkeypatch):
     assert urgent > 0
     for x, y in zip(ref, out):
         assert torch.equal(x, y)
+
+
+def test_step_host_fetches_urgent_first_observations(qs, monkeypatch):
+    """qs_step_host copies the results to the host while the settle slice is still running; an episode that
+    had to be settled on the spot writes its first observation after that copy, so the call repeats the
+    observation copy.  Starve the conveyor (1 tick per step) and compare with the device-buffer step."""
+    monkeypatch.setenv("QS_SETTLE_SLICE_MIN", "1")
+    monkeypatch.setenv("QS_SETTLE_SLICE_MAX", "1")
+    n, steps = 256, 460
+    cfg = dict(enable_springs=True, task_env="JUMPING_FORWARD", motor_control_mode="CARTESIAN_PD",
+               observation_space_mode="ARS_BASIC")
+    a_dev = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=3, **cfg)
+    a_host = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=3, **cfg)
+    a_dev.reset()
+    a_host.reset()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    out = (np.empty((n, a_host.obs_dim), np.float32), np.empty(n, np.float32), np.empty(n, np.uint8), np.empty(n, np.uint8))
+    import ctypes as C
+    from quadruped_springs_b200 import _lib
+    cnt, urgent = (C.c_int32 * 4)(), 0
+    for t in range(steps):
+        a = torch.rand(n, 6, device="cuda", generator=g) * 2 - 1
+        obs, r, d, info = a_dev.step(a)
+        a_host.step_host(a.cpu().numpy(), out)
+        _lib.check(a_host._L.qs_debug_counters(a_host._h, cnt, None))
+        urgent += cnt[1]
+        assert np.array_equal(out[0], obs.cpu().numpy()), t
+        assert np.array_equal(out[1], r.cpu().numpy()) and np.array_equal(out[2].astype(bool), d.cpu().numpy()), t
+    assert urgent > 0

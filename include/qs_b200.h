@@ -95,7 +95,7 @@ typedef struct qs_config {
   int32_t num_iterations;        /* int(300/action_repeat) unless overridden (>0) */
   int32_t enable_limits;         /* joint-limit constraint rows */
   int32_t body_contact_response; /* non-foot shapes touching the ground are constrained too (general solver) */
-  int32_t block_size;            /* CUDA block size for the step kernel (0 = default) */
+  int32_t block_size;            /* CUDA block size of the step kernels: 0 or 128 (compiled in) */
   uint64_t seed;                 /* Philox key; streams are indexed by GLOBAL env id */
   int64_t env_id_offset;         /* global id of local env 0 (multi-GPU sharding) */
   double time_step;              /* 0.001; double so that sim_time > 10 s fires on control step 1001 like the reference */

@@ -94,12 +94,17 @@ QS_DEVONLY void load_springs(const DeviceView& D, int env, float* sk, float* sb,
 // or the index of the tick that needs another solver (state untouched by that tick; *why =
 // TICK_NEEDS_GENERAL / TICK_NEEDS_CONTACT).  kContacts = false is the flight variant: it
 // hands the env over as soon as a foot comes within its contact threshold.
+// block size of the step / reset / settle kernels: a compile-time constant so that the per-leg scratch is addressed
+// with immediate offsets (qs_physics.cuh Scratch)
+constexpr int QS_BLOCK = 128;
+using StepScratch = Scratch<float, QS_BLOCK>;
+
 template <bool kContacts>
 __device__ __forceinline__ int run_ticks(EnvState<float>& st, ContactState<float>& cs, const float* cmd,
                                          bool torque_mode, int t0, int n_ticks, int env, const DeviceView& D,
                                          const EnvCfg& C, const RobotConst& RC, const ModelConstT<float>& M,
                                          const SolverConst& SC, float* tau_m /*12 out*/, float* tau_s /*12 out*/,
-                                         bool detect_invalid_last, const Scratch<float>& scr, int* why, bool skip = false) {
+                                         bool detect_invalid_last, const StepScratch& scr, int* why, bool skip = false) {
   const float mu = D.mu[env];
   const bool custom = D.custom_gains[env] != 0;
   float sk[3], sb[3], sr[3];
@@ -114,7 +119,7 @@ __device__ __forceinline__ int run_ticks(EnvState<float>& st, ContactState<float
     if (bail == n_ticks) {
       float tau[12];
       tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s, custom);
-      const int r = physics_tick<float, kContacts>(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1), scr);
+      const int r = physics_tick<float, kContacts, QS_BLOCK>(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1), scr);
       if (r != TICK_DONE) { bail = t; *why = r; }
     }
   }

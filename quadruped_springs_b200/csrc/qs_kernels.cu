@@ -335,7 +335,7 @@ struct qs_env {
 };
 
 static inline unsigned grid_for(int n, int block) { return unsigned((n + block - 1) / block); }
-static int block_of(qs_handle h) { return h->cfg.block_size > 0 ? std::min(h->cfg.block_size, 256) : 128; }
+static int block_of(qs_handle) { return QS_BLOCK; }
 static size_t smem_of(int block) { return size_t(block) * QS_TICK_SCRATCH * sizeof(float); }
 
 extern "C" {
@@ -390,6 +390,7 @@ static int check_config(const qs_config* c) {
   if (c->control_mode < 0 || c->control_mode > 2) return fail(QS_ERR_ARG, "unknown motor control mode");
   if (c->action_mode < 0 || c->action_mode > 2) return fail(QS_ERR_ARG, "unknown action space mode");
   if (c->task < 0 || c->task > QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO) return fail(QS_ERR_ARG, "unknown task");
+  if (c->block_size != 0 && c->block_size != QS_BLOCK) return fail(QS_ERR_ARG, "block_size is fixed at 128 (0 = default)");
   if (c->landing_mode < 0 || c->landing_mode > 2) return fail(QS_ERR_ARG, "unknown landing_mode");
   if (c->landing_mode && (c->control_mode == QS_CTRL_TORQUE || !c->is_rl_interface))
     return fail(QS_ERR_ARG, "landing controllers need the RL interface with PD or CARTESIAN_PD control");

@@ -432,10 +432,14 @@ template <typename T> QS_DEV void integrate_positions(EnvState<T>& st, T dt) {
 constexpr int QS_LEG_SCRATCH = 18 + 3 + 6 + 6 + 9 + 9;      // Bm, ev, Mi, sincos, W, (q, qd, tau)
 constexpr int QS_TICK_SCRATCH = 4 * QS_LEG_SCRATCH;          // floats per thread
 
-template <typename T> struct Scratch {
+// kStride > 0: the stride is a compile-time constant (the block size of the step / settle kernels), so every
+// slot of a leg is an immediate offset from one per-leg base address; kStride = 0 reads it at run time.
+template <typename T, int kStride = 0> struct Scratch {
   T* p;        // this thread's first element
-  int stride;  // elements between consecutive slots of one thread
-  QS_DEV T& operator()(int leg, int slot) const { return p[(leg * QS_LEG_SCRATCH + slot) * stride]; }
+  int stride;  // elements between consecutive slots of one thread (ignored when kStride > 0)
+  QS_DEV T& operator()(int leg, int slot) const {
+    return p[(leg * QS_LEG_SCRATCH + slot) * (kStride > 0 ? kStride : stride)];
+  }
 };
 enum { SCR_BM = 0, SCR_EV = 18, SCR_MI = 21, SCR_SC = 27, SCR_W = 33, SCR_Q = 42, SCR_QD = 45, SCR_TAU = 48 };
 // Once a foot's contact rows are built, EV / MI / SC / Q of its leg are dead: the 18 floats of the rows'
@@ -457,10 +461,10 @@ template <typename T> QS_DEV void leg_kin_from_sc(int k, const T* sc, const Mode
 // shape on the ground) or, for the kContacts = false variant (no foot-contact code at all: the flight
 // kernel), TICK_NEEDS_CONTACT when a foot is within its contact threshold.
 enum { TICK_DONE = 0, TICK_NEEDS_GENERAL = 1, TICK_NEEDS_CONTACT = 2 };
-template <typename T, bool kContacts = true>
+template <typename T, bool kContacts = true, int kStride = 0>
 __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
                                      const ModelConstT<T>& M, const SolverConst& SC, bool detect_invalid,
-                                     const Scratch<T>& scr) {
+                                     const Scratch<T, kStride>& scr) {
   const T dt = T(SC.dt);
   const T idt = div_t(T(1), dt);
   const T mcv = T(SC.max_coord_vel);

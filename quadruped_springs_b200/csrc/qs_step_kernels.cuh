@@ -306,7 +306,7 @@ __device__ __forceinline__ void episode_springs(const EnvCfg& C, const RobotCons
 // a thread works while t < t1.
 __device__ __forceinline__ void settle_ticks(const KernelArgs& A, uint64_t gid, uint32_t epoch, EnvState<float>& st,
                                              ContactState<float>& cs, float mu, int t0, int t1, int span, float* tau_m,
-                                             float* tau_s, const Scratch<float>& scr) {
+                                             float* tau_s, const StepScratch& scr) {
   const EnvCfg& C = A.C;
   float cmd[12], act12[12];
   settle_command(C, A.RC, cmd, act12);
@@ -336,14 +336,14 @@ __device__ __forceinline__ void settle_ticks(const KernelArgs& A, uint64_t gid, 
         for (int j = 0; j < 3; j++) tau[3 * k + j] += tau_s[3 * k + j];
       }
     }
-    physics_tick(st, tau, mu, cs, A.M, SCs, t == nsettle - 1, scr);
+    physics_tick<float, true, QS_BLOCK>(st, tau, mu, cs, A.M, SCs, t == nsettle - 1, scr);
   }
 }
 
 // A fresh robot settled for episode `epoch` of global env `gid`, start to end.
 __device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint64_t gid, uint32_t epoch,
                                              EnvState<float>& st, ContactState<float>& cs, float* tau_m, float* tau_s,
-                                             float* mu_out, const Scratch<float>& scr, bool need) {
+                                             float* mu_out, const StepScratch& scr, bool need) {
   // `need` = this thread really settles; the others only keep the block's barriers matched.
   // Must be called by every thread of the block.
   if (!__syncthreads_or(need)) return;
@@ -599,7 +599,7 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
   // with a foot on (or reaching) the ground goes to k_step_contact, which runs dense warps of such envs.
   float tau_m[12], tau_s[12];
   extern __shared__ float qs_smem[];
-  const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
+  const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
   int why;
   const bool grounded = (cs.mask & 15) != 0;  // standing / pushing: straight to the contact kernel
   const int t_done = run_ticks<false>(st, cs, cmd, torque_mode, 0, C.action_repeat, env, D, C, A.RC, A.M, A.SC, tau_m, tau_s,
@@ -634,7 +634,7 @@ k_step_contact(const __grid_constant__ KernelArgs A, const StepIO io) {
   for (int i = 0; i < 12; i++) cmd[i] = D.cmd[i * n + env];
   const bool torque_mode = !C.is_rl && C.control_mode == QS_CTRL_TORQUE;
   extern __shared__ float qs_smem[];
-  const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
+  const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
   int why;
   const int t_done = run_ticks<true>(st, cs, cmd, torque_mode, D.resume_tick[env], C.action_repeat, env, D, C, A.RC, A.M,
                                      A.SC, tau_m, tau_s, true, scr, &why);
@@ -688,7 +688,7 @@ k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, cons
   float tau_m[12], tau_s[12], mu;
   const bool have = slot_ready(D, env, epoch);
   extern __shared__ float qs_smem[];
-  const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
+  const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
   float tm2[12], ts2[12];
   settle_fresh(A, env, gid, epoch, st, cs, tm2, ts2, &mu, scr, !have);
   if (have) {
@@ -725,7 +725,7 @@ k_settle_urgent(const __grid_constant__ KernelArgs A, const Conveyor cv, float* 
   ContactState<float> cs;
   float tau_m[12], tau_s[12], mu = 0.f;
   extern __shared__ float qs_smem[];
-  const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
+  const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
   settle_fresh(A, env, uint64_t(A.C.gid0 + env), epoch, st, cs, tau_m, tau_s, &mu, scr, live);
   if (!live) return;
   // its ring: the slot of this episode never became ready, the others may be missing too
@@ -831,7 +831,7 @@ k_settle_slice(const __grid_constant__ KernelArgs A, const Conveyor cv) {
   const float mu = episode_mu(A.C, uint64_t(A.C.gid0 + env), epoch);
   const int t1 = need ? min(t0 + span, nsettle) : 0;
   extern __shared__ float qs_smem[];
-  const Scratch<float> scr{qs_smem + threadIdx.x, int(blockDim.x)};
+  const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
   settle_ticks(A, uint64_t(A.C.gid0 + env), epoch, st, cs, mu, t0, t1, span, tau_m, tau_s, scr);
   if (!need) return;
   {  // work counters of the bench's flop model, one atomic per warp

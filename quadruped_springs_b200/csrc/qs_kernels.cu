@@ -314,7 +314,7 @@ struct qs_env {
   int *slow_list, *reset_list, *contact_list;
   Conveyor cv;
   int wave_blocks;     // settle blocks resident at once (SMs x 2)
-  int slice_min, slice_max;
+  int slice_min, slice_max, slice_early;
   cudaStream_t bg;     // the conveyor's slices run here, next to k_step_slow on the caller's stream
   cudaStream_t copy;   // qs_step_host: results go to the host while the slice is still running
   cudaEvent_t ev_results, ev_copied;
@@ -329,7 +329,9 @@ struct qs_env {
   // CUDA-event ring around k_step launches (roofline timing of the dominant kernel)
   static constexpr int kRing = 512;
   cudaEvent_t ev0[kRing], ev1[kRing];   // around k_step + k_step_contact, on the caller's stream
-  cudaEvent_t ev2[kRing], ev3[kRing];   // around k_settle_slice, on the second stream
+  cudaEvent_t ev2[kRing], ev3[kRing];   // around the late k_settle_slice, on the second stream
+  cudaEvent_t ev4[kRing], ev5[kRing];   // around the early one
+  cudaEvent_t ev_fork0;
   bool ev_ready;
   int64_t n_steps;
 };
@@ -502,6 +504,8 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     cv.cap_mask = uint32_t(cap - 1);
     h->slice_min = 4;
     h->slice_max = 1 << 20;  // no cap: the slice follows the demand
+    h->slice_early = 10;  // ticks of the early slice (measured optimum 6-12: longer and it slows k_step_contact down)
+    if (const char* v = std::getenv("QS_SETTLE_SLICE_EARLY")) h->slice_early = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MIN")) h->slice_min = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MAX")) h->slice_max = std::max(h->slice_min, std::atoi(v));
     const size_t w = size_t(cv.width);
@@ -526,6 +530,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost(&h->host_urgent, sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork0, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (e != cudaSuccess) { cudaFree(h->pool); cudaFree(h->lists); delete h; return fail(QS_ERR_CUDA, "stream / event creation"); }
   }
@@ -558,6 +563,7 @@ int qs_destroy(qs_handle h) {
   cudaEventDestroy(h->ev_copied);
   cudaFreeHost(h->host_urgent);
   cudaEventDestroy(h->ev_fork);
+  cudaEventDestroy(h->ev_fork0);
   cudaEventDestroy(h->ev_join);
   if (h->dev_actions) cudaFree(h->dev_actions);
   if (h->dev_obs) cudaFree(h->dev_obs);
@@ -566,6 +572,7 @@ int qs_destroy(qs_handle h) {
   if (h->ev_ready)
     for (int i = 0; i < qs_env::kRing; i++) {
       cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); cudaEventDestroy(h->ev2[i]); cudaEventDestroy(h->ev3[i]);
+      cudaEventDestroy(h->ev4[i]); cudaEventDestroy(h->ev5[i]);
     }
   delete h;
   return QS_OK;
@@ -595,6 +602,8 @@ int qs_settle_kernel_time(qs_handle h, int last_k, float* ms_sum) {
   for (int64_t i = h->n_steps - last_k; i < h->n_steps; i++) {
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev2[i % qs_env::kRing], h->ev3[i % qs_env::kRing]));
+    tot += ms;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev4[i % qs_env::kRing], h->ev5[i % qs_env::kRing]));
     tot += ms;
   }
   *ms_sum = tot;
@@ -669,18 +678,20 @@ int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* o) {
 // One turn of the settle conveyor.  In qs_step it runs on the second stream, forked after k_step and
 // joined before the urgent pass, so that the slice shares the GPU with k_step_slow (a few latency-bound
 // blocks); `flush` runs the whole window to completion in stream order (reset-time prefill).
-static int launch_conveyor(qs_handle h, cudaStream_t s, int flush) {
+static int launch_conveyor(qs_handle h, cudaStream_t s, int phase, int flush) {
   const int B = block_of(h);
   const int nsettle = h->cfg.is_rl_interface ? h->cfg.settling_steps : 1500;
-  k_conveyor_ctl<<<1, 1024, 0, s>>>(h->cv, flush ? nullptr : h->slow_list + h->n, 64, h->wave_blocks, B, h->n, nsettle,
-                                    h->slice_min, h->slice_max, flush);
+  // the latency-bound kernel the slice of this phase runs next to, and its block size
+  const int* busy = phase == 0 ? h->contact_list + h->n : h->slow_list + h->n;
+  k_conveyor_ctl<<<1, 1024, 0, s>>>(h->cv, phase, busy, phase == 0 ? B : 64, h->wave_blocks, B, h->n, nsettle,
+                                    h->slice_min, h->slice_max, h->slice_early, flush);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return QS_OK;
 }
-static int launch_slice(qs_handle h, cudaStream_t s) {
+static int launch_slice(qs_handle h, cudaStream_t s, int early) {
   const int B = block_of(h);
-  k_settle_slice<<<h->wave_blocks, B, smem_of(B), s>>>(h->args, h->cv);
+  k_settle_slice<<<h->wave_blocks, B, smem_of(B), s>>>(h->args, h->cv, early);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return QS_OK;
@@ -706,8 +717,8 @@ int qs_reset(qs_handle h, const uint8_t* mask, float* obs, void* stream) {
     const size_t entries = size_t(QS_SLOTS) * size_t(h->n);
     const int rounds = int((entries + size_t(h->cv.width) - 1) / size_t(h->cv.width));
     for (int r = 0; r < rounds; r++) {
-      if (int e = launch_conveyor(h, s, 1)) return e;
-      if (int e = launch_slice(h, s)) return e;
+      if (int e = launch_conveyor(h, s, 1, 1)) return e;
+      if (int e = launch_slice(h, s, 0)) return e;
     }
   }
   h->was_reset = true;
@@ -736,6 +747,7 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
     for (int i = 0; i < qs_env::kRing; i++) {
       CUDA_TRY(cudaEventCreate(&h->ev0[i])); CUDA_TRY(cudaEventCreate(&h->ev1[i]));
       CUDA_TRY(cudaEventCreate(&h->ev2[i])); CUDA_TRY(cudaEventCreate(&h->ev3[i]));
+      CUDA_TRY(cudaEventCreate(&h->ev4[i])); CUDA_TRY(cudaEventCreate(&h->ev5[i]));
     }
     h->ev_ready = true;
   }
@@ -747,13 +759,22 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   const int slot = int(h->n_steps % qs_env::kRing);
   cudaEventRecord(h->ev0[slot], s);
   k_step<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
+  if (h->cfg.auto_reset) {
+    // conveyor, early slice: on the second stream, next to k_step_contact (about half a wave of blocks)
+    if (int e = launch_conveyor(h, s, 0, 0)) return e;
+    CUDA_TRY(cudaEventRecord(h->ev_fork0, s));
+  }
   k_step_contact<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
   g_launches += 1;
   cudaEventRecord(h->ev1[slot], s);
   h->n_steps++;
   if (h->cfg.auto_reset) {
-    // conveyor turn: bookkeeping in stream order, then the slice on the second stream next to k_step_slow
-    if (int e = launch_conveyor(h, s, 0)) return e;
+    CUDA_TRY(cudaStreamWaitEvent(h->bg, h->ev_fork0, 0));
+    cudaEventRecord(h->ev4[slot], h->bg);
+    if (int e = launch_slice(h, h->bg, 1)) return e;
+    cudaEventRecord(h->ev5[slot], h->bg);
+    // late slice: bookkeeping in stream order, then the slice on the second stream next to k_step_slow
+    if (int e = launch_conveyor(h, s, 1, 0)) return e;
     CUDA_TRY(cudaEventRecord(h->ev_fork, s));
   }
   // envs parked for the general solver (joint limits / body contacts); launched before the slice so
@@ -775,7 +796,7 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   if (h->cfg.auto_reset) {
     CUDA_TRY(cudaStreamWaitEvent(h->bg, h->ev_fork, 0));
     cudaEventRecord(h->ev2[slot], h->bg);
-    if (int e = launch_slice(h, h->bg)) return e;
+    if (int e = launch_slice(h, h->bg, 0)) return e;
     cudaEventRecord(h->ev3[slot], h->bg);
     CUDA_TRY(cudaEventRecord(h->ev_join, h->bg));
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));

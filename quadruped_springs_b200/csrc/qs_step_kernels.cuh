@@ -15,9 +15,9 @@
 // reference's 2500 settle ticks.  Each env owns a ring of QS_SLOTS slots holding its next
 // episodes' settled states; a finished env copies its slot inside k_step and queues the
 // slot's next tenant on the conveyor.  Every control step the conveyor advances all its
-// entries by a slice of ticks (k_settle_slice, on a second stream, next to the few
-// latency-bound blocks of k_step_slow), saving the unfinished ones bit-exactly in between, so
-// the settles run as one dense wave and their cost hides behind the step's serial tail.
+// entries by a slice of ticks (k_settle_slice, on a second stream, next to the latency-bound
+// blocks of k_step_contact and k_step_slow), saving the unfinished ones bit-exactly in between,
+// so the settles run as dense waves and their cost hides behind the step's serial chain.
 // If a slot is not ready in time the episode is settled start to end at the end of the step
 // (k_settle_urgent) -- same numbers either way, so results never depend on scheduling,
 // slicing or sharding.
@@ -111,7 +111,9 @@ constexpr int QS_SLOTS = 4;  // settled episodes kept ahead per env (ring indexe
 enum {
   CV_HEAD = 0, CV_TAIL, CV_ACTIVE, CV_SLICE, CV_URGENT, CV_URGENT_LAST, CV_PREV_HEAD, CV_DEMAND,
   // ring pressure: slots consumed this step, and how many of those envs found their next slot missing
-  CV_TAKEN, CV_LOW2, CV_EMA_TAKEN, CV_EMA_LOW2, CV_PRESS, CV_CTL_WORDS = 16
+  CV_TAKEN, CV_LOW2, CV_EMA_TAKEN, CV_EMA_LOW2, CV_PRESS,
+  // the early slice (next to k_step_contact): entries, ticks; ticks per entry wanted from this step in total
+  CV_ACTIVE_EARLY, CV_SLICE_EARLY, CV_WANT, CV_CTL_WORDS = 16
 };
 constexpr int CV_DONE = -1;
 constexpr int WIP_ROWS = 37 + 4;  // state | normal impulses (warm start); + contact mask (int row)
@@ -739,44 +741,53 @@ __global__ void k_urgent_clear(Conveyor cv) {
   cv.ctl[CV_URGENT] = 0;
 }
 
-// Conveyor bookkeeping, once per step between k_step and the slice: retire the finished entries at
-// the tail, then choose how many entries run (`lanes` = what fits next to this step's k_step_slow
-// blocks) and for how many ticks.  The slice length follows the demand (entries pushed per step,
-// smoothed): with d episodes ending per step, nsettle * d / slice entries are in flight, and the slice
-// is chosen so that they fill ~90 % of one wave -- the settles then run as a dense launch whatever
-// the episode length.  With few envs that would deliver too late, so a settle is also kept shorter than
-// half a mean episode, and the slice grows while envs find their ring nearly empty.  Entries beyond the
-// window (start-up, bursts) or flush != 0 run the window to completion at once.
-__global__ void k_conveyor_ctl(Conveyor cv, const int* __restrict__ slow_count, int slow_block, int wave_blocks,
-                               int block, int n_envs, int nsettle, int s_min, int s_max, int flush) {
+// Conveyor bookkeeping.  The slice length follows the demand (entries pushed per step, smoothed): with d
+// episodes ending per step, nsettle * d / slice entries are in flight, and the slice is chosen so that they
+// fill ~90 % of one wave -- the settles then run as a dense launch whatever the episode length.  With few
+// envs that would deliver too late, so a settle is also kept shorter than half a mean episode, and the
+// slice grows while envs find their ring nearly empty.  Entries beyond the window (start-up, bursts) or
+// flush != 0 run the window to completion at once.
+//
+// A step runs two slices, each next to a latency-bound kernel that leaves SMs idle:
+//   phase 0 (after k_step):         retire the finished entries at the tail, update demand and pressure, and give
+//                                   the oldest entries that fit next to k_step_contact's blocks `early` ticks;
+//   phase 1 (after k_step_contact): the entries that fit next to k_step_slow's blocks get the rest of the ticks.
+__global__ void k_conveyor_ctl(Conveyor cv, int phase, const int* __restrict__ busy_count, int busy_block, int wave_blocks,
+                               int block, int n_envs, int nsettle, int s_min, int s_max, int early, int flush) {
   __shared__ uint32_t first_live;
   const uint32_t head = cv.ctl[CV_HEAD];
   uint32_t tail = cv.ctl[CV_TAIL];
-  const uint32_t span = min(head - tail, uint32_t(cv.width));
-  if (threadIdx.x == 0) first_live = span;
-  __syncthreads();
-  for (uint32_t j = threadIdx.x; j < span; j += blockDim.x)
-    if (cv.tick[(tail + j) & cv.cap_mask] != CV_DONE) { atomicMin(&first_live, j); break; }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  tail += first_live;
-  const uint32_t pending = head - tail;
-  int lanes = cv.width;
-  if (slow_count && !flush) {
-    const int reserve = (*slow_count + slow_block - 1) / slow_block;  // one settle block displaced per slow block
-    lanes = max(block, min(cv.width, (wave_blocks - reserve) * block));
+  if (phase == 0 || flush) {
+    const uint32_t span = min(head - tail, uint32_t(cv.width));
+    if (threadIdx.x == 0) first_live = span;
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < span; j += blockDim.x)
+      if (cv.tick[(tail + j) & cv.cap_mask] != CV_DONE) { atomicMin(&first_live, j); break; }
+    __syncthreads();
+    tail += first_live;
   }
-  const uint32_t active = min(pending, uint32_t(lanes));
-  int slice = nsettle;
-  if (!flush) {
+  if (threadIdx.x != 0) return;
+  cv.ctl[CV_TAIL] = tail;
+  const uint32_t pending = head - tail;
+  if (flush) {
+    cv.ctl[CV_ACTIVE] = min(pending, uint32_t(cv.width));
+    cv.ctl[CV_SLICE] = uint32_t(nsettle);
+    cv.ctl[CV_PREV_HEAD] = head;
+    return;
+  }
+  // room next to the other kernel of this phase: one settle block displaced per block of it
+  const int lanes = max(0, min(cv.width, (wave_blocks - (*busy_count + busy_block - 1) / busy_block) * block));
+  const bool backlog = pending > uint32_t(cv.width);
+  if (phase == 0) {
     float demand = __uint_as_float(cv.ctl[CV_DEMAND]);
     demand += (float(head - cv.ctl[CV_PREV_HEAD]) - demand) * 0.125f;
     cv.ctl[CV_DEMAND] = __float_as_uint(demand);
-    const float target = 0.9f * float(lanes);
+    cv.ctl[CV_PREV_HEAD] = head;
     // dense wave: nsettle * demand / slice entries in flight = target; ring safety: the settle must not take
     // longer than half a mean episode (n_envs / demand steps, Little's law)
+    const float target = 0.9f * float(cv.width);
     float want = float(nsettle) * demand * fmaxf(1.f / target, 2.f / float(n_envs));
-    if (float(active) > 0.97f * float(lanes)) want *= 1.5f;  // nearly full: catch up before a backlog forms
+    if (float(pending) > 0.97f * float(cv.width)) want *= 1.5f;  // nearly full: catch up before a backlog forms
     // ring pressure (smoothed): more than 2 % of the finishing envs one episode from running dry
     float taken = __uint_as_float(cv.ctl[CV_EMA_TAKEN]), low2 = __uint_as_float(cv.ctl[CV_EMA_LOW2]);
     float press = fmaxf(__uint_as_float(cv.ctl[CV_PRESS]), 1.f);
@@ -787,12 +798,21 @@ __global__ void k_conveyor_ctl(Conveyor cv, const int* __restrict__ slow_count, 
     cv.ctl[CV_EMA_LOW2] = __float_as_uint(low2);
     cv.ctl[CV_PRESS] = __float_as_uint(press);
     cv.ctl[CV_TAKEN] = 0; cv.ctl[CV_LOW2] = 0;
-    want *= press;
-    slice = max(s_min, min(s_max, int(ceilf(want))));
-    if (pending > uint32_t(lanes)) slice = nsettle;
+    want = fmaxf(float(s_min), fminf(float(s_max), ceilf(want * press)));
+    cv.ctl[CV_WANT] = __float_as_uint(want);
+    const int s0 = backlog ? 0 : min(early, int(want) / 2);
+    cv.ctl[CV_ACTIVE_EARLY] = s0 > 0 ? min(pending, uint32_t(lanes)) : 0u;
+    cv.ctl[CV_SLICE_EARLY] = uint32_t(s0);
+    return;
   }
-  cv.ctl[CV_PREV_HEAD] = head;
-  cv.ctl[CV_TAIL] = tail;
+  // phase 1: what is left of this step's ticks, spread over the entries that run now
+  const uint32_t active = min(pending, uint32_t(max(lanes, block)));
+  const float want = __uint_as_float(cv.ctl[CV_WANT]);
+  const float done0 = float(cv.ctl[CV_ACTIVE_EARLY]) * float(cv.ctl[CV_SLICE_EARLY]);
+  const float all = float(min(pending, uint32_t(cv.width)));  // the entries `want` was computed for
+  int slice = int(ceilf((want * all - done0) / fmaxf(float(active), 1.f)));
+  slice = max(s_min, min(s_max, slice));
+  if (backlog) slice = nsettle;
   cv.ctl[CV_ACTIVE] = active;
   cv.ctl[CV_SLICE] = uint32_t(slice);
 }
@@ -800,16 +820,16 @@ __global__ void k_conveyor_ctl(Conveyor cv, const int* __restrict__ slow_count, 
 // One slice of the conveyor: entry tail + j advances by ctl[CV_SLICE] settle ticks; an entry that
 // reaches the end of its settle stores the episode's slot and retires.
 __global__ void __launch_bounds__(256, 1)
-k_settle_slice(const __grid_constant__ KernelArgs A, const Conveyor cv) {
+k_settle_slice(const __grid_constant__ KernelArgs A, const Conveyor cv, int early) {
   const DeviceView& D = A.D;
   const int n = D.n;
-  const int active = int(cv.ctl[CV_ACTIVE]);
+  const int active = int(cv.ctl[early ? CV_ACTIVE_EARLY : CV_ACTIVE]);
   if (blockIdx.x * blockDim.x >= active) return;  // uniform over the block
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = j < active;
   const uint32_t idx = cv.ctl[CV_TAIL] + uint32_t(live ? j : active - 1);
   const uint32_t pos = idx & cv.cap_mask;
-  const int span = int(cv.ctl[CV_SLICE]);
+  const int span = int(cv.ctl[early ? CV_SLICE_EARLY : CV_SLICE]);
   const int env = cv.fifo[2 * pos];
   const uint32_t epoch = uint32_t(cv.fifo[2 * pos + 1]);
   const int t0 = cv.tick[pos];

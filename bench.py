@@ -268,8 +268,10 @@ def run_ours(args):
                 "frac": ach / fp32_peak, "kernel_ms": ms, "kernel_share_of_step": ms / ms_per_step, **extra}
 
     settle_line = fp32_line("k_settle_slice", settle_flops, k_settle_ms, {
-        "what": "reset()'s 2500-tick settle of the next episodes, one slice of ticks per control step on a second stream "
-                "(timed there with CUDA events, next to k_step_slow)",
+        "what": "reset()'s 2500-tick settle of the next episodes: two slices of ticks per control step on a second stream "
+                "(timed there with CUDA events; the early one runs next to k_step_contact, the late one next to "
+                "k_step_slow); achieved = flops of both launches / their summed duration",
+        "launches_per_step": 2,
         "settle_ticks_per_step": sticks / args.steps, "algorithmic_flops_per_settle_tick": settle_flops / max(sticks, 1),
         "mean_foot_contacts_per_tick": scticks / max(sticks, 1), "mean_pgs_sweeps_per_contact_tick": scsweeps / max(scticks, 1)})
     step_line = fp32_line("k_step + k_step_contact", step_flops, k_step_ms, {

@@ -108,7 +108,11 @@ typedef struct qs_config {
   int32_t landing_mode;          /* 0 none; 1 LandingWrapper (env/wrappers/landing_wrapper.py:18-69): after take-off the action is
                                   * held until the predicted apex, then the landing action with gains 60 / 1.5 until the
                                   * episode ends; 2 LandingWrapper2 (landing_wrapper_2.py:39-78): default gains, landing until
-                                  * touch-down, once per episode.  The wrappers' inner env.step loops run as a per-env mode
+                                  * touch-down, once per episode; 3 LandingWrapperContinuous (landing_wrapper_continuous.py:38-70):
+                                  * triggered by every detected jump, landing until the jump is over; 4 / 5
+                                  * LandingWrapperBackflip / Backflip2 (landing_wrapper_backflip*.py:47-80): scripted take-off
+                                  * action until the backflip pitch reaches 5 pi / 8, then landing until the episode ends /
+                                  * until touch-down.  The wrappers' inner env.step loops run as a per-env mode
                                   * machine: one qs_step = one control step, scripted envs ignore the action passed in */
   int32_t spring_randomizer;     /* EnvRandomizerSprings (env_randomizers/env_randomizer.py:86-122): every reset draws the
                                   * spring stiffness and damping of hip / thigh / calf within +-10 % of the nominal values;
@@ -138,7 +142,7 @@ typedef struct qs_state_ptrs {
   float* ep_return;    /* [N] */
   uint8_t* custom_gains; /* [N] set non-zero after writing kp/kd of an env: the kernels then read its gains from
                           * the arrays instead of the config constants; cleared by every reset of that env */
-  int32_t* land_mode;  /* [N] landing controller mode: 0 policy, 1 take-off hold, 2 landing, 3 spent (LandingWrapper2) */
+  int32_t* land_mode;  /* [N] landing controller mode: 0 policy, 1 take-off hold, 2 landing, 3 spent, 4 backflip take-off */
   uint32_t* work;      /* [3][N] per-env work counters of the step kernels: physics ticks, foot-contact ticks,
                         * contact x PGS-sweep count (cumulative; bench / diagnostics) */
 } qs_state_ptrs;

@@ -419,10 +419,14 @@ def rollout_landing(name, cfg, wrapper, actions, seed):
     landing control flow at control-step granularity (which is how the batched env runs it)."""
     from quadruped_spring.env.wrappers.landing_wrapper import LandingWrapper
     from quadruped_spring.env.wrappers.landing_wrapper_2 import LandingWrapper2
+    from quadruped_spring.env.wrappers.landing_wrapper_backflip import LandingWrapperBackflip
+    from quadruped_spring.env.wrappers.landing_wrapper_backflip2 import LandingWrapperBackflip2
+    from quadruped_spring.env.wrappers.landing_wrapper_continuous import LandingWrapperContinuous
     ref_shim.FakeBulletClient.world_params = {}
     np.random.seed(seed)
     env = make_env(**cfg)
-    wrapped = {1: LandingWrapper, 2: LandingWrapper2}[wrapper](env)
+    wrapped = {1: LandingWrapper, 2: LandingWrapper2, 3: LandingWrapperContinuous, 4: LandingWrapperBackflip,
+               5: LandingWrapperBackflip2}[wrapper](env)
     wrapped.reset()
     mu = env._pybullet_client._mu_ground
     w = env._pybullet_client.world
@@ -484,6 +488,16 @@ def gen_spring_randomizer():
     rollout("spring_randomizer", base, jump_actions(6, 160, np.random.default_rng(91)), seed=41)
 
 
+def backflip_actions(n, rng, delay_rear):
+    """crouch, then front and (delayed) rear push: pitches the trunk up at take-off"""
+    acts = np.zeros((n, 6))
+    for t in range(n):
+        f = (0.9, -0.9) if t < 25 else ((-0.6, 1.0) if t < 33 else (0.0, 0.0))
+        r = (0.9, -0.9) if t < 25 + delay_rear else ((-0.6, 1.0) if t < 33 + delay_rear else (0.0, 0.0))
+        acts[t] = np.array([0, f[0], f[1], 0, r[0], r[1]]) + rng.normal(size=6) * 0.02
+    return acts
+
+
 def gen_landing():
     rng = np.random.default_rng(77)
     base = dict(enable_springs=True, task_env="JUMPING_IN_PLACE", motor_control_mode="PD",
@@ -496,6 +510,15 @@ def gen_landing():
     rollout_landing("w2_jf_cartesian", dict(base, task_env="JUMPING_FORWARD", motor_control_mode="CARTESIAN_PD",
                                             action_space_mode="DEFAULT"), 2,
                     np.concatenate([cart_hop_actions(300, rng, zc=0.6)] * 2, axis=1)[:, [0, 1, 2, 6, 7, 8, 3, 4, 5, 9, 10, 11]], seed=34)
+    rng = np.random.default_rng(78)   # (the four fixtures above keep their draws)
+    rollout_landing("w3_continuous", dict(base, task_env="CONTINUOUS_JUMPING_FORWARD3",
+                                          observation_space_mode="PPO_CONTINUOUS_JUMPING_FORWARD"), 3,
+                    jump_actions(6, 400, rng, amp=0.8), seed=35)
+    # BACKFLIP mutates RL_UPPER_ANGLE_JOINT for the rest of the process (App. D.7): keep these last
+    bf = dict(base, task_env="BACKFLIP", observation_space_mode="ARS_BACKFLIP")
+    rollout_landing("w4_backflip", bf, 4, backflip_actions(200, rng, 6), seed=36)
+    rollout_landing("w5_backflip2", bf, 5, backflip_actions(200, rng, 3), seed=37)
+    rollout_landing("w5_backflip2_late", bf, 5, backflip_actions(200, rng, 6), seed=38)
 
 
 # ----------------------------------------------------------------------------- CPG

@@ -292,7 +292,7 @@ struct QsoEnv {
   int land_mode, land_gains;
   double land_timer, land_end, hold_action[12], kp_save[12], kd_save[12];
 };
-enum { LAND_POLICY = 0, LAND_HOLD = 1, LAND_LANDING = 2, LAND_SPENT = 3 };
+enum { LAND_POLICY = 0, LAND_HOLD = 1, LAND_LANDING = 2, LAND_SPENT = 3, LAND_TAKEOFF_BF = 4 };
 
 void qso_env_default_config(QsoEnvConfig* c) {
   c->enable_springs = 0;
@@ -881,6 +881,11 @@ void qso_env_step(QsoEnv* e, const double* action, double* obs, double* reward, 
         action = e->hold_action;
       }
     }
+    if (e->land_mode == LAND_TAKEOFF_BF) { /* take_off_action, landing_wrapper_backflip.py:21 */
+      static const double bf[12] = {0, 1, -1, 0, 1, -1, 0, 0, 0, 0, 0, 0};
+      memcpy(scripted, bf, sizeof bf);
+      action = scripted;
+    }
     if (e->land_mode == LAND_LANDING) { landing_action(e, scripted); action = scripted; }
   }
   memset(cur, 0, sizeof cur);
@@ -925,14 +930,26 @@ void qso_env_step(QsoEnv* e, const double* action, double* obs, double* reward, 
   if (e->cfg.landing_mode && !d) {
     double st[QSO_NSTATE];
     qso_world_get_state(e->w, st);
-    if (e->land_mode == LAND_POLICY && e->ts.switched) { /* LandingWrapper.step :58-66, start_jumping_timer :56-60 */
-      e->land_mode = LAND_HOLD;
-      memset(e->hold_action, 0, sizeof e->hold_action);
-      memcpy(e->hold_action, e->last_action, adim * sizeof(double));
-      e->land_timer = sim_time(e);
-      e->land_end = e->land_timer + st[9] / 9.81; /* task.compute_time_for_peak_heihgt, task_base.py:157-160 */
-    } else if (e->land_mode == LAND_LANDING && e->cfg.landing_mode == 2 && !is_flying(e)) {
-      e->land_mode = LAND_SPENT; /* LandingWrapper2.landing_phase :39-46, _enable_landing = False :71 */
+    const int lm = e->cfg.landing_mode, flying = is_flying(e);
+    /* what starts the scripted phase: the take-off switch (:58-66), or -- continuous variant -- a detected jump */
+    const int trigger = lm == 3 ? e->ts.is_jumping : e->ts.switched;
+    if (e->land_mode == LAND_POLICY && trigger) {
+      if (lm == 4 || lm == 5) {
+        e->land_mode = LAND_TAKEOFF_BF; /* landing_wrapper_backflip.py:54-60,72-73 */
+      } else { /* take_off_phase with the apex timer, start_jumping_timer (landing_wrapper.py:47-60) */
+        e->land_mode = LAND_HOLD;
+        memset(e->hold_action, 0, sizeof e->hold_action);
+        memcpy(e->hold_action, e->last_action, adim * sizeof(double));
+        e->land_timer = sim_time(e);
+        e->land_end = e->land_timer + st[9] / 9.81; /* task.compute_time_for_peak_heihgt, task_base.py:157-160 */
+      }
+    } else if (e->land_mode == LAND_TAKEOFF_BF) {
+      /* until PitchBackFlip._get_pitch >= 5 pi / 8 (landing_wrapper_backflip.py:22-23,57-60) */
+      if (qso_backflip_pitch(st + 3, e->ts.switched) >= 5.0 * PI / 8.0)
+        e->land_mode = (lm == 5 && !flying) ? LAND_SPENT : LAND_LANDING; /* backflip2: `while ... and is_flying` :50 */
+    } else if (e->land_mode == LAND_LANDING) {
+      if ((lm == 2 || lm == 5) && !flying) e->land_mode = LAND_SPENT;      /* landing_wrapper_2.py:39-46,71 */
+      else if (lm == 3 && !e->ts.is_jumping) e->land_mode = LAND_POLICY;    /* landing_wrapper_continuous.py:39-46 */
     }
   }
 }

@@ -393,7 +393,11 @@ static int check_config(const qs_config* c) {
   if (c->action_mode < 0 || c->action_mode > 2) return fail(QS_ERR_ARG, "unknown action space mode");
   if (c->task < 0 || c->task > QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO) return fail(QS_ERR_ARG, "unknown task");
   if (c->block_size != 0 && c->block_size != QS_BLOCK) return fail(QS_ERR_ARG, "block_size is fixed at 128 (0 = default)");
-  if (c->landing_mode < 0 || c->landing_mode > 2) return fail(QS_ERR_ARG, "unknown landing_mode");
+  if (c->landing_mode < 0 || c->landing_mode > 5) return fail(QS_ERR_ARG, "unknown landing_mode");
+  if (c->landing_mode >= 4 && c->action_mode != QS_ACT_SYMMETRIC)
+    return fail(QS_ERR_ARG, "the backflip landing controllers script a SYMMETRIC action (landing_wrapper_backflip.py:21)");
+  if (c->landing_mode == 3 && !(c->task >= QS_TASK_CONTINUOUS_JUMPING_FORWARD && c->task <= QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO))
+    return fail(QS_ERR_ARG, "LandingWrapperContinuous needs a continuous-jumping task (task.get_jumping)");
   if (c->landing_mode && (c->control_mode == QS_CTRL_TORQUE || !c->is_rl_interface))
     return fail(QS_ERR_ARG, "landing controllers need the RL interface with PD or CARTESIAN_PD control");
   if (c->obs_mode < 0 || c->obs_mode > QS_OBS_PPO_CONTINUOUS_JUMPING_FORWARD) return fail(QS_ERR_ARG, "unknown observation space mode");

@@ -99,7 +99,7 @@ __device__ __forceinline__ void finish_episode_stats(const DeviceView& D, int en
   s[10 * n] += terminated ? 1.f : 0.f;
 }
 
-enum { LAND_POLICY = 0, LAND_HOLD = 1, LAND_LANDING = 2, LAND_SPENT = 3 };
+enum { LAND_POLICY = 0, LAND_HOLD = 1, LAND_LANDING = 2, LAND_SPENT = 3, LAND_TAKEOFF_BF = 4 };
 constexpr int QS_SLOTS = 4;  // settled episodes kept ahead per env (ring indexed by episode number)
 
 // ---- settle conveyor: the queue of (env, episode) pairs whose settled start state is computed
@@ -452,13 +452,25 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   D.work[2 * n + env] += uint32_t(cs.work_row_iters);
   const uint64_t gid = uint64_t(C.gid0 + env);
   if (C.landing_mode && !dn) {
-    const int mode = D.land_mode[env];
-    if (mode == LAND_POLICY && ts[TS_SWITCHED] != 0.f) {  // LandingWrapper.step :58-66, start_jumping_timer :56-60
-      D.land_mode[env] = LAND_HOLD;
-      D.land_timer[env] = sim_time;
-      D.land_timer[n + env] = sim_time + st.vlin[2] / 9.81f;  // task.compute_time_for_peak_heihgt, task_base.py:157-160
-    } else if (mode == LAND_LANDING && C.landing_mode == 2 && (cs.mask & 15) != 0) {
-      D.land_mode[env] = LAND_SPENT;  // LandingWrapper2.landing_phase :39-46; _enable_landing = False :71
+    const int mode = D.land_mode[env], lm = C.landing_mode;
+    const bool flying = (cs.mask & 15) == 0;
+    // what starts the scripted phase: the take-off switch (landing_wrapper.py:58-66) or, continuous variant, a detected jump
+    const bool trigger = lm == 3 ? ts[TS_IS_JUMPING] != 0.f : ts[TS_SWITCHED] != 0.f;
+    if (mode == LAND_POLICY && trigger) {
+      if (lm >= 4) {
+        D.land_mode[env] = LAND_TAKEOFF_BF;  // landing_wrapper_backflip.py:54-60,72-73
+      } else {                               // take_off_phase with the apex timer, start_jumping_timer :47-60
+        D.land_mode[env] = LAND_HOLD;
+        D.land_timer[env] = sim_time;
+        D.land_timer[n + env] = sim_time + st.vlin[2] / 9.81f;  // task.compute_time_for_peak_heihgt, task_base.py:157-160
+      }
+    } else if (mode == LAND_TAKEOFF_BF) {
+      // until PitchBackFlip._get_pitch >= 5 pi / 8 (landing_wrapper_backflip.py:22-23,57-60)
+      if (backflip_pitch(Rb, ts[TS_SWITCHED] != 0.f) >= 5.f * float(QS_PI) / 8.f)
+        D.land_mode[env] = (lm == 5 && !flying) ? LAND_SPENT : LAND_LANDING;  // backflip2: `while ... and is_flying` :50
+    } else if (mode == LAND_LANDING) {
+      if ((lm == 2 || lm == 5) && !flying) D.land_mode[env] = LAND_SPENT;             // landing_wrapper_2.py:39-46,71
+      else if (lm == 3 && ts[TS_IS_JUMPING] == 0.f) D.land_mode[env] = LAND_POLICY;  // landing_wrapper_continuous.py:39-46
     }
   }
   if (dn) finish_episode_stats(D, env, ts, ep_ret, env_steps, term, C.task);
@@ -556,6 +568,10 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
 #pragma unroll
         for (int i = 0; i < 12; i++) act[i] = D.last_action[i * n + env];
       }
+    }
+    if (mode == LAND_TAKEOFF_BF) {  // take_off_action (0, 1, -1) per leg pair, landing_wrapper_backflip.py:21
+#pragma unroll
+      for (int i = 0; i < 12; i++) act[i] = i >= 6 ? 0.f : (i % 3 == 0 ? 0.f : (i % 3 == 1 ? 1.f : -1.f));
     }
     if (mode == LAND_LANDING) {
 #pragma unroll

@@ -393,8 +393,9 @@ class BatchedQuadrupedGymEnv:
         block_size=0,
         landing_wrapper=None,
     ):
-        """landing_wrapper: None, "LandingWrapper" (env/wrappers/landing_wrapper.py:18-69) or "LandingWrapper2"
-        (landing_wrapper_2.py:39-78).  The reference wraps the env and loops env.step inside one wrapper step; here
+        """landing_wrapper: None, "LandingWrapper" (env/wrappers/landing_wrapper.py:18-69), "LandingWrapper2"
+        (landing_wrapper_2.py:39-78), "LandingWrapperContinuous" (landing_wrapper_continuous.py:38-70),
+        "LandingWrapperBackflip" or "LandingWrapperBackflip2" (landing_wrapper_backflip*.py:47-80).  The reference wraps the env and loops env.step inside one wrapper step; here
         the same controller runs per env inside the step kernel: every call is one control step, envs whose
         controller is scripted (infos["landing_mode"] != 0 and != 3) ignore the action they are given."""
         if render or on_rack:
@@ -447,7 +448,8 @@ class BatchedQuadrupedGymEnv:
         cfg.max_episode_time = float(EPISODE_LENGTH)
         cfg.block_size = int(block_size)
         try:
-            cfg.landing_mode = {None: 0, "LandingWrapper": 1, "LandingWrapper2": 2}[landing_wrapper]
+            cfg.landing_mode = {None: 0, "LandingWrapper": 1, "LandingWrapper2": 2, "LandingWrapperContinuous": 3,
+                                "LandingWrapperBackflip": 4, "LandingWrapperBackflip2": 5}[landing_wrapper]
         except KeyError:
             raise ValueError(f"the landing wrapper {landing_wrapper} is not implemented yet.") from None
         for k, v in (solver or {}).items():

@@ -462,7 +462,8 @@ def test_rollout_teacher_forced_matches_reference_env(qs, name):
 
 
 # ------------------------------------------------------------------ 8f rank 1: landing controllers inside the step kernel
-LANDINGS = ["w1_jip_pd", "w1_jf_cartesian", "w2_jip_pd_nosprings", "w2_jf_cartesian"]
+LANDINGS = ["w1_jip_pd", "w1_jf_cartesian", "w2_jip_pd_nosprings", "w2_jf_cartesian", "w3_continuous", "w4_backflip",
+            "w5_backflip2", "w5_backflip2_late"]
 URDF_LO = np.array([-1.0471975512, -0.663225115758, -2.72271363311] * 4)   # go1.urdf joint limits
 URDF_HI = np.array([1.0471975512, 2.96705972839, -0.837758040957] * 4)
 
@@ -475,7 +476,8 @@ def test_landing_controller_teacher_forced_matches_reference_wrapper(qs, name):
     LandingWrapper) when the apex timer is up, and hand control back (LandingWrapper2) at touch-down."""
     g = load_golden(f"landing_{name}.npz")
     cfg = json.loads(str(g["cfg"]))
-    wrapper = {1: "LandingWrapper", 2: "LandingWrapper2"}[int(g["landing_mode"])]
+    wrapper = {1: "LandingWrapper", 2: "LandingWrapper2", 3: "LandingWrapperContinuous", 4: "LandingWrapperBackflip",
+               5: "LandingWrapperBackflip2"}[int(g["landing_mode"])]
     env = qs.BatchedQuadrupedGymEnv(num_envs=2, enable_noise=False, auto_reset=False, env_randomizer_mode="NO_RANDOMIZER",
                                     solver=dict(mu_ground=float(g["mu"])), landing_wrapper=wrapper, **cfg)
     env.reset()
@@ -509,8 +511,11 @@ def test_landing_controller_teacher_forced_matches_reference_wrapper(qs, name):
         assert bool(d[0]) == bool(g["done"][t]), t
         assert float(env._views["kp"][0, 0]) == pytest.approx(float(g["kp"][t][0])), t   # landing gains
         modes.append(int(info["landing_mode"][0]))
-    assert 1 in modes and 2 in modes
-    assert (3 in modes) == (wrapper == "LandingWrapper2")
+    assert (4 if "Backflip" in wrapper else 1) in modes and 2 in modes
+    if wrapper == "LandingWrapper2":
+        assert 3 in modes
+    if wrapper == "LandingWrapperContinuous":
+        assert any(a == 2 and b == 0 for a, b in zip(modes, modes[1:]))   # re-armed after the jump
 
 
 def test_landing_controller_batched_free_running(qs):

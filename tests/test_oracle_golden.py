@@ -141,7 +141,8 @@ def test_rollout_matches_reference_env(name):
         np.testing.assert_allclose(perf, g["jumps"][1], rtol=1e-8, atol=1e-10)
 
 
-LANDINGS = ["w1_jip_pd", "w1_jf_cartesian", "w2_jip_pd_nosprings", "w2_jf_cartesian"]
+LANDINGS = ["w1_jip_pd", "w1_jf_cartesian", "w2_jip_pd_nosprings", "w2_jf_cartesian", "w3_continuous", "w4_backflip",
+            "w5_backflip2", "w5_backflip2_late"]
 
 
 @pytest.mark.parametrize("name", LANDINGS)
@@ -172,6 +173,9 @@ def test_landing_controller_matches_reference_wrapper(name):
     # the wrapper returns the reward / done of its LAST inner step
     last = np.flatnonzero(np.diff(np.append(g["wrapper_step"], -1)) != 0)
     np.testing.assert_allclose(g["reward"][last], g["wrapper_out"][:, 0], rtol=0, atol=0)
-    assert 1 in modes and 2 in modes                         # take-off hold and landing both happened
-    if int(g["landing_mode"]) == 2:
+    lm = int(g["landing_mode"])
+    assert (4 if lm >= 4 else 1) in modes and 2 in modes     # take-off phase and landing both happened
+    if lm == 2:
         assert 3 in modes                                    # LandingWrapper2 hands control back to the policy
+    if lm == 3:                                              # the continuous variant re-arms after every jump
+        assert any(a == 2 and b == 0 for a, b in zip(modes, modes[1:]))

@@ -413,7 +413,7 @@ def gen_rollouts_continuous():
         rollout(name, cfg, acts, seed=20 + i)
 
 
-def rollout_landing(name, cfg, wrapper, actions, seed):
+def rollout_landing(name, cfg, wrapper, actions, seed, rest=False):
     """Landing wrappers (landing_wrapper.py:18-69, landing_wrapper_2.py:39-78): the reference wrapper drives
     the env; every INNER env.step it makes is recorded, so the fixture holds the scripted take-off-hold /
     landing control flow at control-step granularity (which is how the batched env runs it)."""
@@ -425,8 +425,13 @@ def rollout_landing(name, cfg, wrapper, actions, seed):
     ref_shim.FakeBulletClient.world_params = {}
     np.random.seed(seed)
     env = make_env(**cfg)
-    wrapped = {1: LandingWrapper, 2: LandingWrapper2, 3: LandingWrapperContinuous, 4: LandingWrapperBackflip,
-               5: LandingWrapperBackflip2}[wrapper](env)
+    if rest:
+        env.reset()   # GoToRestWrapper.__init__ asks the interface for the init action, which needs a robot (:13)
+    wrapped = {0: lambda e: e, 1: LandingWrapper, 2: LandingWrapper2, 3: LandingWrapperContinuous,
+               4: LandingWrapperBackflip, 5: LandingWrapperBackflip2}[wrapper](env)
+    if rest:   # GoToRestWrapper goes outside the landing wrapper (go_to_rest_wrapper.py:8-52)
+        from quadruped_spring.env.wrappers.go_to_rest_wrapper import GoToRestWrapper
+        wrapped = GoToRestWrapper(wrapped)
     wrapped.reset()
     mu = env._pybullet_client._mu_ground
     w = env._pybullet_client.world
@@ -463,7 +468,7 @@ def rollout_landing(name, cfg, wrapper, actions, seed):
             break
     out = {k: np.asarray(v) for k, v in rec.items()}
     out.update(mu=mu, init_state=init_state, init_obs=init_obs, init_task_height=init_task_height,
-               wrapper_out=np.asarray(wrapper_out), cfg=json.dumps(cfg), landing_mode=wrapper)
+               wrapper_out=np.asarray(wrapper_out), cfg=json.dumps(cfg), landing_mode=wrapper, rest_mode=int(rest))
     np.savez_compressed(os.path.join(OUT, f"landing_{name}.npz"), **out)
     ws = out["wrapper_step"]
     print(f"landing_{name}: {len(ws)} inner steps for {ws[-1] + 1} wrapper steps, done={bool(out['done'][-1])} "
@@ -514,8 +519,31 @@ def gen_landing():
     rollout_landing("w3_continuous", dict(base, task_env="CONTINUOUS_JUMPING_FORWARD3",
                                           observation_space_mode="PPO_CONTINUOUS_JUMPING_FORWARD"), 3,
                     jump_actions(6, 400, rng, amp=0.8), seed=35)
+    rollout_landing("rest_w2_jip_pd", base, 2, jump_actions(6, 1100, rng, amp=0.8), seed=39, rest=True)
+    rollout_landing("rest_w2_jf_cartesian", dict(base, task_env="JUMPING_FORWARD", motor_control_mode="CARTESIAN_PD"), 2,
+                    cart_hop_actions(1100, rng, zc=0.6), seed=40, rest=True)
+    # a run in which the robot comes to rest and the episode ends on the 10 s time limit: first seed whose friction
+    # draw lets the (oracle-predicted) landing succeed
+    from oracle import oracle as O
+    acts = jump_actions(6, 1100, rng, amp=0.8)
+    for seed in range(50, 90):
+        np.random.seed(seed)
+        probe = make_env(**base)
+        probe.reset(); probe.reset()
+        e = O.Env(landing_mode=0, rest_mode=1, **base)
+        e.reset(mu=float(probe._pybullet_client._mu_ground))
+        out = None
+        for a in acts:
+            out = e.step(a)
+            if out[2]:
+                break
+        if out[3]:   # truncated
+            rollout_landing("rest_only_jip_pd_full", base, 0, acts, seed=seed, rest=True)
+            break
     # BACKFLIP mutates RL_UPPER_ANGLE_JOINT for the rest of the process (App. D.7): keep these last
     bf = dict(base, task_env="BACKFLIP", observation_space_mode="ARS_BACKFLIP")
+    rng = np.random.default_rng(78)
+    rng.normal(size=6 * 400)          # (the draws w3_continuous took when these fixtures were first made)
     rollout_landing("w4_backflip", bf, 4, backflip_actions(200, rng, 6), seed=36)
     rollout_landing("w5_backflip2", bf, 5, backflip_actions(200, rng, 3), seed=37)
     rollout_landing("w5_backflip2_late", bf, 5, backflip_actions(200, rng, 6), seed=38)

@@ -44,6 +44,7 @@ class EnvConfig(C.Structure):
         ("task", C.c_int), ("obs_mode", C.c_int), ("action_repeat", C.c_int),
         ("is_rl_interface", C.c_int), ("enable_action_interpolation", C.c_int),
         ("enable_action_filter", C.c_int), ("settling_steps", C.c_int), ("landing_mode", C.c_int),
+        ("rest_mode", C.c_int),
         ("time_step", C.c_double),
     ]
 
@@ -96,6 +97,7 @@ def lib():
         "qso_env_get_task_state": (None, [vp, dp]),
         "qso_env_get_jump_arrays": (None, [vp, dp]),
         "qso_env_get_landing_state": (None, [vp, dp]),
+        "qso_env_get_rest_state": (None, [vp, dp]),
         "qso_env_get_torques": (None, [vp, dp, dp]),
         "qso_env_get_last_action": (None, [vp, dp]),
         "qso_env_set_gains": (None, [vp, dp, dp]),
@@ -238,7 +240,7 @@ class Env:
     def __init__(self, enable_springs=False, motor_control_mode="PD", action_space_mode="SYMMETRIC",
                  task_env="NO_TASK", observation_space_mode="ENCODER", action_repeat=10,
                  isRLGymInterface=True, enable_action_filter=False, enable_action_interpolation=False,
-                 time_step=0.001, settling_steps=2500, landing_mode=0, **world_params):
+                 time_step=0.001, settling_steps=2500, landing_mode=0, rest_mode=0, **world_params):
         self.L = lib()
         c = EnvConfig()
         self.L.qso_env_default_config(C.byref(c))
@@ -254,6 +256,7 @@ class Env:
         c.time_step = time_step
         c.settling_steps = settling_steps
         c.landing_mode = int(landing_mode)
+        c.rest_mode = int(rest_mode)
         self.h = self.L.qso_env_create(C.byref(c))
         self.world = World(handle=self.L.qso_env_world(self.h))
         if world_params:
@@ -290,6 +293,12 @@ class Env:
         """(mode, timer, end) of the landing controller (0 policy, 1 take-off hold, 2 landing, 3 spent)."""
         o, op = _out(3)
         self.L.qso_env_get_landing_state(self.h, op)
+        return int(o[0]), o[1], o[2]
+
+    def rest_state(self):
+        """(active, h_actual, t_start) of the go-to-rest controller"""
+        o, op = _out(3)
+        self.L.qso_env_get_rest_state(self.h, op)
         return int(o[0]), o[1], o[2]
 
     def jump_arrays(self):

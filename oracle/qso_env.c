@@ -291,6 +291,9 @@ struct QsoEnv {
   /* landing controller (landing_wrapper.py, landing_wrapper_2.py; utils/timer.py) */
   int land_mode, land_gains;
   double land_timer, land_end, hold_action[12], kp_save[12], kd_save[12];
+  /* go-to-rest controller (go_to_rest_wrapper.py) */
+  int rest_active;
+  double rest_h, rest_t0, rest_start[12], init_action[12];
 };
 enum { LAND_POLICY = 0, LAND_HOLD = 1, LAND_LANDING = 2, LAND_SPENT = 3, LAND_TAKEOFF_BF = 4 };
 
@@ -306,6 +309,7 @@ void qso_env_default_config(QsoEnvConfig* c) {
   c->enable_action_filter = 0;
   c->settling_steps = 2500;
   c->landing_mode = 0;
+  c->rest_mode = 0;
   c->time_step = 0.001;
 }
 
@@ -778,6 +782,7 @@ void qso_env_reset(QsoEnv* e, double mu, double* obs) {
   }
   e->land_mode = LAND_POLICY;
   e->land_timer = e->land_end = 0;
+  e->rest_active = 0;
   memset(e->last_action, 0, sizeof e->last_action);
   memset(e->last_filtered, 0, sizeof e->last_filtered);
   memset(e->tau_motor, 0, sizeof e->tau_motor);
@@ -820,6 +825,7 @@ void qso_env_reset(QsoEnv* e, double mu, double* obs) {
     }
     memset(e->last_action, 0, sizeof e->last_action);
     memcpy(e->last_action, sact, adim * sizeof(double));
+    memcpy(e->init_action, e->last_action, sizeof e->init_action); /* ac_interface.get_init_action(), interface_base.py:74-78 */
   } else {
     /* settle_robot_by_pd (control_interface/utils.py:22-30): PD, DEFAULT space, 1500 ticks */
     double a12[12], cmd[12];
@@ -835,6 +841,11 @@ void qso_env_reset(QsoEnv* e, double mu, double* obs) {
   if (e->cfg.enable_action_filter) {
     for (int h = 0; h < 2; h++)
       for (int i = 0; i < 12; i++) { e->xh[h][i] = e->last_action[i]; e->yh[h][i] = e->last_action[i]; }
+  }
+  {
+    double st[QSO_NSTATE];
+    qso_world_get_state(e->w, st);
+    e->rest_h = st[2]; /* GoToRestWrapper.reset: h_old = h_actual = z (go_to_rest_wrapper.py:83-87) */
   }
   if (obs) observe(e, obs);
 }
@@ -861,10 +872,37 @@ static void landing_action(const QsoEnv* e, double* act) {
   }
 }
 void qso_env_get_landing_state(const QsoEnv* e, double* o) { o[0] = e->land_mode; o[1] = e->land_timer; o[2] = e->land_end; }
+void qso_env_get_rest_state(const QsoEnv* e, double* o) { o[0] = e->rest_active; o[1] = e->rest_h; o[2] = e->rest_t0; }
+/* ActionWrapper._transform_motor_command_to_action (action_interface.py): a 12-vector scaled with the interface's
+ * limits (joint angles, or -- CARTESIAN_PD -- foot positions), reduced to the action space */
+static void command_to_action_space(const QsoEnv* e, const double* cmd12, double* act) {
+  const RobotCfg* c = &e->rc;
+  double a12[12];
+  int cart = e->cfg.control_mode == QSO_CTRL_CARTESIAN_PD, sidx = cart ? 1 : 0;
+  if (cart) unscale_command(c->cart_lo, c->cart_hi, cmd12, a12);
+  else unscale_command(c->ang_lo, c->ang_hi, cmd12, a12);
+  memset(act, 0, 12 * sizeof(double));
+  if (e->cfg.action_mode == QSO_ACT_DEFAULT) memcpy(act, a12, sizeof a12);
+  else if (e->cfg.action_mode == QSO_ACT_SYMMETRIC) { memcpy(act, a12, 3 * sizeof(double)); memcpy(act + 3, a12 + 6, 3 * sizeof(double)); }
+  else {
+    int s = 0;
+    for (int j = 0; j < 3; j++) if (j != sidx) { act[s] = a12[j]; act[2 + s] = a12[6 + j]; s++; }
+  }
+}
 
 void qso_env_step(QsoEnv* e, const double* action, double* obs, double* reward, int* done, int* truncated) {
   int adim = qso_env_action_dim(e);
-  double cur[12], scripted[12];
+  double cur[12], scripted[12], ramp[12];
+  if (e->cfg.rest_mode && e->rest_active) {
+    /* go_to_rest (go_to_rest_wrapper.py:58-81): ramp from the pose at activation to the init action */
+    const double T = e->cfg.enable_springs ? 1.0 : 0.3, t = sim_time(e), t0 = e->rest_t0, t1 = t0 + T;
+    for (int i = 0; i < 12; i++) { /* generate_ramp, interface_base.py:112-119 */
+      if (t < t0) ramp[i] = e->rest_start[i];
+      else if (t > t1) ramp[i] = e->init_action[i];
+      else ramp[i] = e->rest_start[i] + (e->init_action[i] - e->rest_start[i]) * (t - t0) / (t1 - t0);
+    }
+    action = ramp;
+  }
   if (e->cfg.landing_mode) {
     /* take_off_phase (landing_wrapper.py:47-54): repeat the action until the timer is up, then landing_phase */
     if (e->land_mode == LAND_HOLD) {
@@ -950,6 +988,26 @@ void qso_env_step(QsoEnv* e, const double* action, double* obs, double* reward, 
     } else if (e->land_mode == LAND_LANDING) {
       if ((lm == 2 || lm == 5) && !flying) e->land_mode = LAND_SPENT;      /* landing_wrapper_2.py:39-46,71 */
       else if (lm == 3 && !e->ts.is_jumping) e->land_mode = LAND_POLICY;    /* landing_wrapper_continuous.py:39-46 */
+    }
+  }
+  /* GoToRestWrapper.step (:43-52) runs where the wrapper below it returns: after a step that leaves the landing
+   * controller unscripted */
+  if (e->cfg.rest_mode && !e->rest_active && (e->land_mode == LAND_POLICY || e->land_mode == LAND_SPENT)) {
+    double st[QSO_NSTATE];
+    qso_world_get_state(e->w, st);
+    const double h_old = e->rest_h;
+    e->rest_h = st[2];
+    const int ground = e->foot_contact[0] && e->foot_contact[1] && e->foot_contact[2] && e->foot_contact[3];
+    if (!d && e->ts.switched && ground && e->rest_h - h_old > 0) { /* rest_condition :89-95 */
+      e->rest_active = 1;
+      e->rest_t0 = sim_time(e);
+      command_to_action_space(e, st + 13, e->rest_start); /* get_start_action :54-56 */
+      if (!e->land_gains) {
+        memcpy(e->kp_save, e->rc.kp, sizeof e->kp_save);
+        memcpy(e->kd_save, e->rc.kd, sizeof e->kd_save);
+        e->land_gains = 1;
+      }
+      for (int i = 0; i < 12; i++) { e->rc.kp[i] = 60.0; e->rc.kd[i] = e->cfg.enable_springs ? 0.8 : 1.5; } /* :21-41 */
     }
   }
 }

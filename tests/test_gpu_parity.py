@@ -463,7 +463,7 @@ def test_rollout_teacher_forced_matches_reference_env(qs, name):
 
 # ------------------------------------------------------------------ 8f rank 1: landing controllers inside the step kernel
 LANDINGS = ["w1_jip_pd", "w1_jf_cartesian", "w2_jip_pd_nosprings", "w2_jf_cartesian", "w3_continuous", "w4_backflip",
-            "w5_backflip2", "w5_backflip2_late"]
+            "w5_backflip2", "w5_backflip2_late", "rest_w2_jip_pd", "rest_w2_jf_cartesian", "rest_only_jip_pd_full"]
 URDF_LO = np.array([-1.0471975512, -0.663225115758, -2.72271363311] * 4)   # go1.urdf joint limits
 URDF_HI = np.array([1.0471975512, 2.96705972839, -0.837758040957] * 4)
 

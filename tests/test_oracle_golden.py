@@ -142,7 +142,7 @@ def test_rollout_matches_reference_env(name):
 
 
 LANDINGS = ["w1_jip_pd", "w1_jf_cartesian", "w2_jip_pd_nosprings", "w2_jf_cartesian", "w3_continuous", "w4_backflip",
-            "w5_backflip2", "w5_backflip2_late"]
+            "w5_backflip2", "w5_backflip2_late", "rest_w2_jip_pd", "rest_w2_jf_cartesian", "rest_only_jip_pd_full"]
 
 
 @pytest.mark.parametrize("name", LANDINGS)
@@ -156,13 +156,15 @@ def test_landing_controller_matches_reference_wrapper(name):
     cfg = json.loads(str(g["cfg"]))
     env = O.Env(enable_springs=cfg["enable_springs"], motor_control_mode=cfg["motor_control_mode"],
                 action_space_mode=cfg["action_space_mode"], task_env=cfg["task_env"],
-                observation_space_mode=cfg["observation_space_mode"], landing_mode=int(g["landing_mode"]))
+                observation_space_mode=cfg["observation_space_mode"], landing_mode=int(g["landing_mode"]),
+                rest_mode=int(g["rest_mode"]) if "rest_mode" in g.files else 0)
     obs = env.reset(mu=float(g["mu"]))
     np.testing.assert_allclose(env.world.get_state(), g["init_state"], rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(obs, g["init_obs"], rtol=1e-9, atol=1e-10)
-    modes = []
+    modes, rest = [], 0
     for t in range(len(g["reward"])):
         obs, r, d, tr = env.step(g["policy_action"][t])      # ignored while the controller is scripted
+        rest += env.rest_state()[0]
         np.testing.assert_allclose(env.last_action(), g["applied_action"][t], rtol=1e-9, atol=1e-12, err_msg=f"action {t}")
         np.testing.assert_allclose(env.world.get_state(), g["state"][t], rtol=1e-8, atol=1e-9, err_msg=f"step {t}")
         np.testing.assert_allclose(obs, g["obs"][t], rtol=1e-8, atol=1e-9, err_msg=f"obs {t}")
@@ -174,6 +176,11 @@ def test_landing_controller_matches_reference_wrapper(name):
     last = np.flatnonzero(np.diff(np.append(g["wrapper_step"], -1)) != 0)
     np.testing.assert_allclose(g["reward"][last], g["wrapper_out"][:, 0], rtol=0, atol=0)
     lm = int(g["landing_mode"])
+    if "rest_mode" in g.files and int(g["rest_mode"]):
+        assert rest > 5                                      # GoToRestWrapper took over (go_to_rest_wrapper.py:58-81)
+        np.testing.assert_allclose(g["kp"][-1], 60.0)        # and ran on its own gains until the episode ended
+    if lm == 0:
+        return
     assert (4 if lm >= 4 else 1) in modes and 2 in modes     # take-off phase and landing both happened
     if lm == 2:
         assert 3 in modes                                    # LandingWrapper2 hands control back to the policy

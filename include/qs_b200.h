@@ -117,7 +117,10 @@ typedef struct qs_config {
   int32_t spring_randomizer;     /* EnvRandomizerSprings (env_randomizers/env_randomizer.py:86-122): every reset draws the
                                   * spring stiffness and damping of hip / thigh / calf within +-10 % of the nominal values;
                                   * the settle of that episode already runs on them.  No effect without springs */
-  int32_t reserved1;
+  int32_t rest_mode;             /* 1: GoToRestWrapper (env/wrappers/go_to_rest_wrapper.py:43-95) outside the landing controller:
+                                  * once the robot has jumped, stands on four feet and its base rises again, the env ramps from
+                                  * its pose to the init action (1 s with springs, 0.3 s without) on gains 60 / 0.8 (60 / 1.5
+                                  * without springs) and holds it until the episode ends; the action passed in is ignored */
 } qs_config;
 
 typedef struct qs_env* qs_handle;
@@ -143,6 +146,8 @@ typedef struct qs_state_ptrs {
   uint8_t* custom_gains; /* [N] set non-zero after writing kp/kd of an env: the kernels then read its gains from
                           * the arrays instead of the config constants; cleared by every reset of that env */
   int32_t* land_mode;  /* [N] landing controller mode: 0 policy, 1 take-off hold, 2 landing, 3 spent, 4 backflip take-off */
+  int32_t* rest_active; /* [N] go-to-rest controller engaged (go_to_rest_wrapper.py:58-81) */
+  float* rest;         /* [14][N] go-to-rest: h_actual, sim step of activation, start action[12] */
   uint32_t* work;      /* [3][N] per-env work counters of the step kernels: physics ticks, foot-contact ticks,
                         * contact x PGS-sweep count (cumulative; bench / diagnostics) */
 } qs_state_ptrs;
@@ -176,6 +181,12 @@ int qs_reset(qs_handle h, const uint8_t* mask_dev, float* obs_dev, void* stream)
  * (infos["TimeLimit.truncated"]). */
 int qs_step(qs_handle h, const float* actions_dev, float* obs_dev, float* reward_dev,
             uint8_t* done_dev, uint8_t* truncated_dev, void* stream);
+
+/* Optional device buffer [N, O] (caller-owned; NULL detaches it): with auto_reset, qs_step writes there the LAST
+ * observation of every env whose episode ended in that step -- infos[i]["terminal_observation"] of the
+ * stable-baselines3 VecEnv the reference is trained through (load_model.py:109-113 make_vec_env -> DummyVecEnv);
+ * rows of envs that did not finish are left untouched. */
+int qs_set_terminal_obs(qs_handle h, float* term_obs_dev);
 
 /* qs_reset with HOST buffers: mask_host [N] bytes or NULL (all), obs_host [N, O] or NULL;
  * synchronises the stream. */

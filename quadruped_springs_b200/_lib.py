@@ -38,14 +38,14 @@ class QsConfig(C.Structure):
         ("limit_erp", C.c_float), ("linear_slop", C.c_float), ("warmstart", C.c_float),
         ("residual_threshold", C.c_float), ("max_coord_vel", C.c_float),
         ("breaking_threshold", C.c_float), ("landing_mode", C.c_int32),
-        ("spring_randomizer", C.c_int32), ("reserved1", C.c_int32),
+        ("spring_randomizer", C.c_int32), ("rest_mode", C.c_int32),
     ]
 
 
 class QsStatePtrs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "state", "tau_motor", "tau_spring", "kp", "kd", "spring", "mu", "foot_force", "contact", "task",
-        "last_action", "sim_steps", "env_steps", "ep_return", "custom_gains", "land_mode", "work")]
+        "last_action", "sim_steps", "env_steps", "ep_return", "custom_gains", "land_mode", "rest_active", "rest", "work")]
 
 
 def nvcc_path():
@@ -93,6 +93,7 @@ EXPORTS = {
     "qs_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qs_step": (C.c_int, [C.c_void_p] * 7),
     "qs_step_host": (C.c_int, [C.c_void_p] * 7),
+    "qs_set_terminal_obs": (C.c_int, [C.c_void_p, C.c_void_p]),
     "qs_reset_host": (C.c_int, [C.c_void_p] * 4),
     "qs_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "qs_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

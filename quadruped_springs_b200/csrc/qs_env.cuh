@@ -42,7 +42,7 @@ QS_DEVONLY float uniform1(uint64_t seed, uint64_t gid, uint32_t epoch, uint32_t 
 // ---------------------------------------------------------------- substeps
 struct EnvCfg {
   int enable_springs, control_mode, action_mode, task, obs_mode, action_repeat, is_rl, enable_filter;
-  int enable_noise, obs_dim, action_dim, settling_steps, ground_randomizer, auto_reset, landing_mode, spring_randomizer;
+  int enable_noise, obs_dim, action_dim, settling_steps, ground_randomizer, auto_reset, landing_mode, spring_randomizer, rest_mode;
   float max_episode_time, mu_ground;
   uint64_t seed;
   int64_t gid0;

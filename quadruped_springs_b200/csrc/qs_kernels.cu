@@ -325,6 +325,7 @@ struct qs_env {
   float* dev_reward;
   uint8_t* dev_done;
   uint8_t* dev_trunc;
+  float* term_obs;     // caller-owned, optional (qs_set_terminal_obs)
   bool was_reset;
   // CUDA-event ring around k_step launches (roofline timing of the dominant kernel)
   static constexpr int kRing = 512;
@@ -400,6 +401,8 @@ static int check_config(const qs_config* c) {
     return fail(QS_ERR_ARG, "LandingWrapperContinuous needs a continuous-jumping task (task.get_jumping)");
   if (c->landing_mode && (c->control_mode == QS_CTRL_TORQUE || !c->is_rl_interface))
     return fail(QS_ERR_ARG, "landing controllers need the RL interface with PD or CARTESIAN_PD control");
+  if (c->rest_mode && (c->control_mode == QS_CTRL_TORQUE || !c->is_rl_interface))
+    return fail(QS_ERR_ARG, "the go-to-rest controller needs the RL interface with PD or CARTESIAN_PD control");
   if (c->obs_mode < 0 || c->obs_mode > QS_OBS_PPO_CONTINUOUS_JUMPING_FORWARD) return fail(QS_ERR_ARG, "unknown observation space mode");
   if (c->action_repeat < 1 || c->action_repeat > 1000) return fail(QS_ERR_ARG, "action_repeat out of range");
   if (c->control_mode == QS_CTRL_TORQUE && c->is_rl_interface)  // quadruped_gym_env.py:167-168
@@ -460,12 +463,13 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   C.action_dim = host::action_dim_of(cfg->is_rl_interface, cfg->action_mode);
   C.settling_steps = cfg->settling_steps; C.ground_randomizer = cfg->ground_randomizer; C.auto_reset = cfg->auto_reset;
   C.landing_mode = cfg->landing_mode; C.spring_randomizer = cfg->spring_randomizer && cfg->enable_springs;
+  C.rest_mode = cfg->rest_mode != 0;
   C.max_episode_time = float(cfg->max_episode_time); C.mu_ground = cfg->mu_ground;
   C.seed = cfg->seed; C.gid0 = cfg->env_id_offset;
 
   // one pool for all SoA arrays (4-byte elements), 256 B aligned segments
   const size_t n = size_t(n_envs);
-  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1 + 3 + 12 + 1 + 1 + 1 + 2 + QS_SLOTS * (SLOT_ROWS + 1 + 1);
+  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1 + 3 + 12 + 1 + 1 + 1 + 2 + 1 + 14 + QS_SLOTS * (SLOT_ROWS + 1 + 1);
   // rows of one array are contiguous with stride n floats; each array starts 256 B aligned
   h->pool_bytes = rows * n * 4 + 64 * 256;
   cudaError_t e = cudaMalloc(&h->pool, h->pool_bytes);
@@ -491,6 +495,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   D.cmd = (float*)carve(12); D.resume_tick = (int32_t*)carve(1);
   D.custom_gains = (uint8_t*)carve(1);
   D.land_mode = (int32_t*)carve(1); D.land_timer = (float*)carve(2);
+  D.rest_active = (int32_t*)carve(1); D.rest = (float*)carve(14);
   D.slot = (float*)carve(QS_SLOTS * SLOT_ROWS); D.slot_contact = (int32_t*)carve(QS_SLOTS); D.slot_epoch = (uint32_t*)carve(QS_SLOTS);
   if (size_t(p - static_cast<char*>(h->pool)) > h->pool_bytes) { cudaFree(h->pool); delete h; return fail(QS_ERR_STATE, "pool overflow"); }
   {
@@ -674,6 +679,7 @@ int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* o) {
   o->last_action = D.last_action; o->sim_steps = D.sim_steps; o->env_steps = D.env_steps; o->ep_return = D.ep_return;
   o->custom_gains = D.custom_gains;
   o->land_mode = D.land_mode;
+  o->rest_active = D.rest_active; o->rest = D.rest;
   o->work = D.work;
   return QS_OK;
 }
@@ -757,6 +763,7 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   }
   StepIO io;
   io.actions = actions; io.obs = obs; io.reward = reward; io.done = done; io.truncated = truncated;
+  io.term_obs = h->term_obs;
   io.slow_list = h->slow_list;
   io.contact_list = h->contact_list;
   io.cv = h->cv;
@@ -810,6 +817,12 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
     g_launches += 2;
   }
   CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_set_terminal_obs(qs_handle h, float* term_obs) {
+  if (!h) return fail(QS_ERR_ARG, "handle is NULL");
+  h->term_obs = term_obs;
   return QS_OK;
 }
 

@@ -135,6 +135,7 @@ struct StepIO {
   float* reward;
   uint8_t* done;
   uint8_t* truncated;
+  float* term_obs;   // optional [N][O]: last observation of the episodes that finished in this step (qs_set_terminal_obs)
   int* slow_list;    // envs parked for the general solver, slow_list[n] = count
   int* contact_list; // envs handed from the flight kernel to the contact kernel, contact_list[n] = count
   Conveyor cv;
@@ -342,6 +343,26 @@ __device__ __forceinline__ void settle_ticks(const KernelArgs& A, uint64_t gid, 
   }
 }
 
+// ActionWrapper._transform_motor_command_to_action (action_interface.py:17-18,41-44,67-74 after
+// interface_base.py:92-100): a 12-vector scaled with the interface's limits, reduced to the action space.
+__device__ __forceinline__ void command_to_action_space(const EnvCfg& C, const RobotConst& RC, const float* cmd12, float* act12) {
+  const bool cart = C.control_mode == QS_CTRL_CARTESIAN_PD;
+  float a12[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    a12[i] = cart ? command_to_action1(cmd12[i], RC.cart_lo[i], RC.cart_hi[i]) : command_to_action1(cmd12[i], RC.ang_lo[i], RC.ang_hi[i]);
+    act12[i] = 0.f;
+  }
+  if (C.action_mode == QS_ACT_DEFAULT) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) act12[i] = a12[i];
+  } else if (C.action_mode == QS_ACT_SYMMETRIC) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) { act12[j] = a12[j]; act12[3 + j] = a12[6 + j]; }
+  } else if (!cart) { act12[0] = a12[1]; act12[1] = a12[2]; act12[2] = a12[7]; act12[3] = a12[8]; }
+  else { act12[0] = a12[0]; act12[1] = a12[2]; act12[2] = a12[6]; act12[3] = a12[8]; }
+}
+
 // A fresh robot settled for episode `epoch` of global env `gid`, start to end.
 __device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint64_t gid, uint32_t epoch,
                                              EnvState<float>& st, ContactState<float>& cs, float* tau_m, float* tau_s,
@@ -374,6 +395,10 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
   D.mu[env] = mu;
   D.custom_gains[env] = 0;
   D.land_mode[env] = 0;
+  if (C.rest_mode) {  // GoToRestWrapper.reset: h_old = h_actual = z (go_to_rest_wrapper.py:83-87)
+    D.rest_active[env] = 0;
+    D.rest[env] = st.pos[2];
+  }
 #pragma unroll
   for (int i = 0; i < 12; i++) { D.kp[i * n + env] = A.RC.kp[i]; D.kd[i * n + env] = A.RC.kd[i]; }
   float sk[3], sb[3], sr[3];
@@ -451,30 +476,59 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   D.work[1 * n + env] += uint32_t(cs.work_contacts);
   D.work[2 * n + env] += uint32_t(cs.work_row_iters);
   const uint64_t gid = uint64_t(C.gid0 + env);
+  int land_now = C.landing_mode ? D.land_mode[env] : LAND_POLICY;
   if (C.landing_mode && !dn) {
-    const int mode = D.land_mode[env], lm = C.landing_mode;
+    const int mode = land_now, lm = C.landing_mode;
     const bool flying = (cs.mask & 15) == 0;
     // what starts the scripted phase: the take-off switch (landing_wrapper.py:58-66) or, continuous variant, a detected jump
     const bool trigger = lm == 3 ? ts[TS_IS_JUMPING] != 0.f : ts[TS_SWITCHED] != 0.f;
     if (mode == LAND_POLICY && trigger) {
       if (lm >= 4) {
-        D.land_mode[env] = LAND_TAKEOFF_BF;  // landing_wrapper_backflip.py:54-60,72-73
+        land_now = LAND_TAKEOFF_BF;  // landing_wrapper_backflip.py:54-60,72-73
       } else {                               // take_off_phase with the apex timer, start_jumping_timer :47-60
-        D.land_mode[env] = LAND_HOLD;
+        land_now = LAND_HOLD;
         D.land_timer[env] = sim_time;
         D.land_timer[n + env] = sim_time + st.vlin[2] / 9.81f;  // task.compute_time_for_peak_heihgt, task_base.py:157-160
       }
     } else if (mode == LAND_TAKEOFF_BF) {
       // until PitchBackFlip._get_pitch >= 5 pi / 8 (landing_wrapper_backflip.py:22-23,57-60)
       if (backflip_pitch(Rb, ts[TS_SWITCHED] != 0.f) >= 5.f * float(QS_PI) / 8.f)
-        D.land_mode[env] = (lm == 5 && !flying) ? LAND_SPENT : LAND_LANDING;  // backflip2: `while ... and is_flying` :50
+        land_now = (lm == 5 && !flying) ? LAND_SPENT : LAND_LANDING;  // backflip2: `while ... and is_flying` :50
     } else if (mode == LAND_LANDING) {
-      if ((lm == 2 || lm == 5) && !flying) D.land_mode[env] = LAND_SPENT;             // landing_wrapper_2.py:39-46,71
-      else if (lm == 3 && ts[TS_IS_JUMPING] == 0.f) D.land_mode[env] = LAND_POLICY;  // landing_wrapper_continuous.py:39-46
+      if ((lm == 2 || lm == 5) && !flying) land_now = LAND_SPENT;             // landing_wrapper_2.py:39-46,71
+      else if (lm == 3 && ts[TS_IS_JUMPING] == 0.f) land_now = LAND_POLICY;  // landing_wrapper_continuous.py:39-46
+    }
+    D.land_mode[env] = land_now;
+  }
+  if (C.rest_mode && !dn && (land_now == LAND_POLICY || land_now == LAND_SPENT) && D.rest_active[env] == 0) {
+    // GoToRestWrapper.step (go_to_rest_wrapper.py:43-52) runs where the wrapper below it returns, i.e. after a
+    // step that leaves the landing controller unscripted; rest_condition :89-95
+    const float h_old = D.rest[env];
+    D.rest[env] = st.pos[2];
+    if (ts[TS_SWITCHED] != 0.f && (cs.mask & 15) == 15 && st.pos[2] - h_old > 0.f) {
+      D.rest_active[env] = 1;
+      D.rest[1 * n + env] = float(sim_steps);  // t_start as a tick count: exact
+      float start[12];
+      command_to_action_space(C, A.RC, st.q, start);  // get_start_action :54-56
+#pragma unroll
+      for (int i = 0; i < 12; i++) {
+        D.rest[(2 + i) * n + env] = start[i];
+        D.kp[i * n + env] = 60.f;  // temporary_switch_motor_control_gain :21-41, until the episode ends
+        D.kd[i * n + env] = C.enable_springs ? 0.8f : 1.5f;
+      }
+      D.custom_gains[env] = 1;
     }
   }
   if (dn) finish_episode_stats(D, env, ts, ep_ret, env_steps, term, C.task);
+  // ---- sensors (:253-254)
+  float o[QS_MAX_OBS];
+#pragma unroll
+  for (int i = 0; i < QS_MAX_OBS; i++) o[i] = 0.f;
+  observe(st, cs, ts, rpy, Rb, C.obs_mode, C.task, o);
   if (dn && C.auto_reset) {
+    // SB3's VecEnv contract: infos["terminal_observation"] of an env that is reset inside step_wait
+    if (io.term_obs)
+      store_obs(io.term_obs + size_t(env) * C.obs_dim, o, C, A.RC, gid, D.reset_count[env], uint32_t(env_steps), C.enable_noise);
     // the finished env starts its next episode inside the same call; its obs row becomes the
     // first observation of that episode (SB3 VecEnv convention)
 #pragma unroll
@@ -496,11 +550,7 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
     }
     return;
   }
-  // ---- sensors (:253-254) and write-back
-  float o[QS_MAX_OBS];
-#pragma unroll
-  for (int i = 0; i < QS_MAX_OBS; i++) o[i] = 0.f;
-  observe(st, cs, ts, rpy, Rb, C.obs_mode, C.task, o);
+  // ---- write-back
   store_obs(io.obs + size_t(env) * C.obs_dim, o, C, A.RC, gid, D.reset_count[env], uint32_t(env_steps), C.enable_noise);
   store_state(D, env, st, cs, dt);
 #pragma unroll
@@ -549,6 +599,19 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
   float act[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) act[i] = i < C.action_dim ? io.actions[size_t(env) * C.action_dim + i] : 0.f;
+  if (C.rest_mode && D.rest_active[env]) {
+    // go_to_rest (go_to_rest_wrapper.py:58-81): ramp from the pose at activation to the init action
+    // (generate_ramp, interface_base.py:112-119), then hold it; the policy's action is ignored
+    float cmd0[12], init12[12];
+    settle_command(C, A.RC, cmd0, init12);  // ac_interface.get_init_action(), interface_base.py:74-78
+    const float T = C.enable_springs ? 1.0f : 0.3f;
+    const float el = float(double(D.sim_steps[env] - int(D.rest[1 * n + env])) * A.time_step_d);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const float s0 = D.rest[(2 + i) * n + env];
+      act[i] = el < 0.f ? s0 : (el > T ? init12[i] : s0 + (init12[i] - s0) * el / T);
+    }
+  }
   if (C.landing_mode) {
     // landing controllers (landing_wrapper.py:38-66, landing_wrapper_2.py:39-72) as a mode machine: the
     // wrappers' inner env.step loops, one control step per call; a scripted env ignores the policy's action

@@ -73,6 +73,8 @@ struct DeviceView {
   int32_t* resume_tick;  // [N] tick at which the fast kernel handed the env to the general solver
   int32_t* land_mode;    // [N] landing controller: 0 policy, 1 take-off hold, 2 landing, 3 spent
   float* land_timer;     // [2][N] timer time, timer end (utils/timer.py)
+  int32_t* rest_active;  // [N] go-to-rest controller engaged (go_to_rest_wrapper.py:58-81)
+  float* rest;           // [14][N] h_actual, sim step of activation, start action[12]
   uint8_t* custom_gains; // [N] non-zero: read kp/kd of this env from the arrays instead of the config constants
   float* slot;           // [slots][66][N] settled states of the next episodes (see qs_step_kernels.cuh)
   int32_t* slot_contact; // [slots][N]

@@ -392,12 +392,16 @@ class BatchedQuadrupedGymEnv:
         solver=None,
         block_size=0,
         landing_wrapper=None,
+        go_to_rest_wrapper=False,
     ):
         """landing_wrapper: None, "LandingWrapper" (env/wrappers/landing_wrapper.py:18-69), "LandingWrapper2"
         (landing_wrapper_2.py:39-78), "LandingWrapperContinuous" (landing_wrapper_continuous.py:38-70),
         "LandingWrapperBackflip" or "LandingWrapperBackflip2" (landing_wrapper_backflip*.py:47-80).  The reference wraps the env and loops env.step inside one wrapper step; here
         the same controller runs per env inside the step kernel: every call is one control step, envs whose
-        controller is scripted (infos["landing_mode"] != 0 and != 3) ignore the action they are given."""
+        controller is scripted (infos["landing_mode"] != 0 and != 3) ignore the action they are given.
+        go_to_rest_wrapper: GoToRestWrapper (env/wrappers/go_to_rest_wrapper.py:8-95) around that: once the robot has
+        jumped, stands on its four feet and its base rises again, the env ramps to the init action on gains 60 / 0.8
+        (60 / 1.5 without springs) until the episode ends (infos["rest_active"])."""
         if render or on_rack:
             raise ValueError("render / on_rack are visual-debug modes of the pybullet GUI and are not provided")
         self._L = _lib.lib()
@@ -452,6 +456,7 @@ class BatchedQuadrupedGymEnv:
                                 "LandingWrapperBackflip": 4, "LandingWrapperBackflip2": 5}[landing_wrapper]
         except KeyError:
             raise ValueError(f"the landing wrapper {landing_wrapper} is not implemented yet.") from None
+        cfg.rest_mode = int(bool(go_to_rest_wrapper))
         for k, v in (solver or {}).items():
             if not hasattr(cfg, k):
                 raise ValueError(f"unknown solver parameter {k}")
@@ -482,6 +487,7 @@ class BatchedQuadrupedGymEnv:
             "ep_return": _view(ptrs.ep_return, (n,), "<f4", dev),
             "custom_gains": _view(ptrs.custom_gains, (n,), "|u1", dev),
             "land_mode": _view(ptrs.land_mode, (n,), "<i4", dev),
+            "rest_active": _view(ptrs.rest_active, (n,), "<i4", dev), "rest": _view(ptrs.rest, (14, n), "<f4", dev),
             "work": _view(ptrs.work, (3, n), "<i4", dev),
         }
         self.robot = BatchedQuadruped(self)
@@ -532,7 +538,19 @@ class BatchedQuadrupedGymEnv:
         infos = {"TimeLimit.truncated": self._trunc.bool()}
         if self._cfg.landing_mode:
             infos["landing_mode"] = self._views["land_mode"]
+        if self._cfg.rest_mode:
+            infos["rest_active"] = self._views["rest_active"]
         return self._obs, self._reward, self._done.bool(), infos
+
+    def set_terminal_obs_buffer(self, buf):
+        """device tensor [N, O] (or None) that receives the last observation of every env whose episode ends inside
+        step() under auto_reset: SB3's infos["terminal_observation"] (qs_set_terminal_obs)"""
+        if buf is not None:
+            if buf.shape != (self.num_envs, self.obs_dim) or buf.dtype != torch.float32 or not buf.is_contiguous() \
+                    or buf.device.type != "cuda":
+                raise ValueError(f"terminal-obs buffer must be a contiguous float32 cuda tensor {(self.num_envs, self.obs_dim)}")
+        self._term_obs = buf        # keep it alive
+        _lib.check(self._L.qs_set_terminal_obs(self._h, _p(buf)))
 
     def reset_host(self, mask_np=None):
         """numpy twin of reset(): returns the host observation array [N, O]"""

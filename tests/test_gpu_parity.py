@@ -476,13 +476,14 @@ def test_landing_controller_teacher_forced_matches_reference_wrapper(qs, name):
     LandingWrapper) when the apex timer is up, and hand control back (LandingWrapper2) at touch-down."""
     g = load_golden(f"landing_{name}.npz")
     cfg = json.loads(str(g["cfg"]))
-    wrapper = {1: "LandingWrapper", 2: "LandingWrapper2", 3: "LandingWrapperContinuous", 4: "LandingWrapperBackflip",
+    rest = bool(int(g["rest_mode"])) if "rest_mode" in g.files else False
+    wrapper = {0: None, 1: "LandingWrapper", 2: "LandingWrapper2", 3: "LandingWrapperContinuous", 4: "LandingWrapperBackflip",
                5: "LandingWrapperBackflip2"}[int(g["landing_mode"])]
     env = qs.BatchedQuadrupedGymEnv(num_envs=2, enable_noise=False, auto_reset=False, env_randomizer_mode="NO_RANDOMIZER",
-                                    solver=dict(mu_ground=float(g["mu"])), landing_wrapper=wrapper, **cfg)
+                                    solver=dict(mu_ground=float(g["mu"])), landing_wrapper=wrapper, go_to_rest_wrapper=rest, **cfg)
     env.reset()
     env._views["task"][6] = float(g["init_task_height"])
-    modes = []
+    modes, resting = [], 0
     for t in range(len(g["reward"])):
         env.set_state(cuda(np.stack([g["pre_state"][t]] * 2)))
         if t > 0:
@@ -492,6 +493,12 @@ def test_landing_controller_teacher_forced_matches_reference_wrapper(qs, name):
             env._views["contact"][:] = 15
             env._views["foot_force"][:] = 12.01301 * 9.8 / 4
         obs, r, d, info = env.step(cuda(g["policy_action"][t]).expand(2, -1))
+        if rest:
+            resting += int(info["rest_active"][0])
+            # the controller's h_actual is teacher-forced like the rest of the state: it is taken on the steps the
+            # outer wrapper sees (landing controller unscripted, go_to_rest_wrapper.py:43-52)
+            if not int(info["rest_active"][0]) and (wrapper is None or int(info["landing_mode"][0]) in (0, 3)):
+                env._views["rest"][0] = float(g["state"][t][2])
         A = env.action_dim
         np.testing.assert_allclose(env.get_last_action()[0, :A].cpu().numpy(), g["applied_action"][t][:A], atol=2e-6,
                                    err_msg=f"applied action {t}")
@@ -509,8 +516,15 @@ def test_landing_controller_teacher_forced_matches_reference_wrapper(qs, name):
         if not crashing:
             assert float(r[0]) == pytest.approx(float(g["reward"][t]), rel=1e-4, abs=3e-5), t
         assert bool(d[0]) == bool(g["done"][t]), t
-        assert float(env._views["kp"][0, 0]) == pytest.approx(float(g["kp"][t][0])), t   # landing gains
-        modes.append(int(info["landing_mode"][0]))
+        # landing gains; the rest controller switches its gains at the end of the step that engages it, the reference
+        # wrapper right after that inner step returned (same physics, the fixture's sample is one step older)
+        kp_ref = float(g["kp"][min(t + 1, len(g["kp"]) - 1)][0]) if rest and int(info["rest_active"][0]) else float(g["kp"][t][0])
+        assert float(env._views["kp"][0, 0]) == pytest.approx(kp_ref), t
+        modes.append(int(info["landing_mode"][0]) if wrapper else 0)
+    if rest:
+        assert resting > 5 and float(env._views["kp"][0, 0]) == 60.0    # GoToRestWrapper took over until the episode ended
+    if wrapper is None:
+        return
     assert (4 if "Backflip" in wrapper else 1) in modes and 2 in modes
     if wrapper == "LandingWrapper2":
         assert 3 in modes

@@ -296,6 +296,10 @@ def rollout(name, cfg, actions, seed, world_params=None):
         out["jumps"] = jumps
     if cfg.get("env_randomizer_mode") == "SPRING_RANDOMIZER":  # the episode's draw (env_randomizer.py:101-122)
         out["springs"] = np.concatenate([np.asarray(x, dtype=np.float64) for x in env.robot.get_spring_nominal_params()])
+    if cfg.get("env_randomizer_mode") == "MASS_RANDOMIZER":   # the episode's draw (env_randomizer.py:56-84)
+        bc, rb = env._pybullet_client, env.robot
+        out["masses"] = np.array([bc.getDynamicsInfo(rb.quadruped, i)[0] for i in (2, 3, 4, 0)] + [rb.get_offset_mass_value()]
+                                 + list(bc._block_delta), dtype=np.float64)   # hip, thigh, calf, trunk, block, block pos
     out.update(actions=np.asarray(actions)[: len(out["reward"])], mu=mu, init_state=init_state, init_obs=init_obs,
                init_last_action=init_last_action, init_task=init_task,
                cfg=json.dumps(cfg), world_params=json.dumps(world_params or {}))
@@ -493,6 +497,15 @@ def gen_spring_randomizer():
     rollout("spring_randomizer", base, jump_actions(6, 160, np.random.default_rng(91)), seed=41)
 
 
+def gen_mass_randomizer():
+    """EnvRandomizerMasses (env_randomizer.py:19-84): leg masses, payload block and trunk mass drawn before the settle"""
+    base = dict(enable_springs=True, task_env="JUMPING_IN_PLACE", motor_control_mode="PD", action_space_mode="SYMMETRIC",
+                observation_space_mode="ARS_BASIC", env_randomizer_mode="MASS_RANDOMIZER")
+    rollout("mass_randomizer", base, jump_actions(6, 160, np.random.default_rng(92)), seed=43)
+    rollout("mass_randomizer_jf_cartesian", dict(base, task_env="JUMPING_FORWARD", motor_control_mode="CARTESIAN_PD"),
+            cart_jump_actions(160, np.random.default_rng(93)), seed=44)
+
+
 def backflip_actions(n, rng, delay_rear):
     """crouch, then front and (delayed) rear push: pitches the trunk up at take-off"""
     acts = np.zeros((n, 6))
@@ -600,7 +613,7 @@ def gen_hopf():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "continuous", "landing", "springs", "rollouts"]
+    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "continuous", "landing", "springs", "masses", "rollouts"]
     if "urdf" in which:
         gen_urdf()
     # NB: gen_analytic and the last rollout build a BACKFLIP env, which mutates the module-level
@@ -617,6 +630,8 @@ if __name__ == "__main__":
         gen_landing()
     if "springs" in which:
         gen_spring_randomizer()
+    if "masses" in which:
+        gen_mass_randomizer()
     if "rollouts" in which:
         gen_rollouts()
     print("golden fixtures written to", OUT)

@@ -79,6 +79,7 @@ def lib():
         "qso_world_get_contact": (None, [vp, C.c_int, ip, dp, dp, dp]),
         "qso_world_get_dynamics": (None, [vp, C.c_int, dp, dp, dp]),
         "qso_world_set_mass": (None, [vp, C.c_int, C.c_double]),
+        "qso_world_set_payload": (None, [vp, C.c_double, dp]),
         "qso_world_last_iterations": (C.c_int, [vp]),
         "qso_world_cone_clamped": (C.c_int, [vp]),
         "qso_world_last_rows": (C.c_int, [vp, ip, ip]),
@@ -187,6 +188,15 @@ class World:
             self.L.qso_world_get_contact(self.h, i, C.byref(link), C.byref(nf), C.byref(dist), pp)
             out.append((link.value, nf.value, dist.value, pos))
         return out
+
+    def set_mass(self, pyb_link, mass):
+        """changeDynamics(robot, link, mass=) (quadruped.py:744-776)"""
+        self.L.qso_world_set_mass(self.h, int(pyb_link), float(mass))
+
+    def set_payload(self, mass, pos):
+        """Quadruped._add_base_mass_offset (quadruped.py:778-819): block welded to the trunk at pos (base frame)"""
+        p = np.ascontiguousarray(pos, dtype=np.float64)
+        self.L.qso_world_set_payload(self.h, float(mass), p.ctypes.data_as(C.POINTER(C.c_double)))
 
     def dynamics(self, pyb_link):
         m = C.c_double()

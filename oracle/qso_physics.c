@@ -72,6 +72,7 @@ typedef struct {
 struct QsoWorld {
   Link L[NL];
   QsoWorldParams P;
+  double payload_m, payload_pos[3]; /* block rigidly attached to the trunk (quadruped.py:778-819) */
   /* state */
   double pos[3], quat[4], vlin[3], vang[3], q[12], qd[12];
   double tau[12];
@@ -377,6 +378,11 @@ void qso_world_set_mass(QsoWorld* w, int pyb, double mass) {
   w->L[pyb + 1].mass = mass;
   w->factored = 0;
 }
+void qso_world_set_payload(QsoWorld* w, double mass, const double* pos3) {
+  w->payload_m = mass;
+  memcpy(w->payload_pos, pos3, sizeof w->payload_pos);
+  w->factored = 0;
+}
 int qso_world_last_iterations(const QsoWorld* w) { return w->last_iters; }
 int qso_world_cone_clamped(const QsoWorld* w) { return w->cone_clamped; }
 double qso_world_max_fric_ratio(QsoWorld* w, int reset) { double r = w->max_fric_ratio; if (reset) w->max_fric_ratio = 0; return r; }
@@ -404,6 +410,23 @@ static void kinematics(QsoWorld* w) {
         I[6 * (a + 3) + b] = l->mass * cxT[3 * a + b];
       }
     for (int a = 0; a < 3; a++) I[6 * (a + 3) + a + 3] = l->mass;
+    if (i == 1 && w->payload_m > 0) {
+      /* _add_base_mass_offset (quadruped.py:778-819): a 0.1 m cube of mass m held to the trunk by a JOINT_FIXED
+       * constraint at `pos` in the base frame.  Bullet solves that constraint with the contacts (a stiff but not
+       * rigid link between two bodies); here the block is welded on: its spatial inertia is added to the trunk's. */
+      const double mp = w->payload_m, ib = mp * (0.1 * 0.1) / 6.0;
+      skew(w->payload_pos, cx);
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) cxT[3 * a + b] = cx[3 * b + a];
+      m3_mul(cx, cxT, cxcxT);
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) {
+          I[6 * a + b] += (a == b ? ib : 0.0) + mp * cxcxT[3 * a + b];
+          I[6 * a + b + 3] += mp * cx[3 * a + b];
+          I[6 * (a + 3) + b] += mp * cxT[3 * a + b];
+        }
+      for (int a = 0; a < 3; a++) I[6 * (a + 3) + a + 3] += mp;
+    }
     if (i == 0) continue;
     double Rj[9], E[9];
     if (l->jtype == JT_REVOLUTE) {

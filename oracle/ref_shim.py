@@ -162,6 +162,8 @@ class FakeBulletClient:
         return (i, _JOINT_NAMES[i].encode("UTF-8"))
 
     def getDynamicsInfo(self, body, link):
+        if body == self._block:
+            return (self._block_mass, 0.5, (0.0,) * 3, (0.0,) * 3)
         m, I, c = self.world.dynamics(link)
         return (m, self._mu_link, tuple(I), tuple(c))
 
@@ -178,6 +180,30 @@ class FakeBulletClient:
         if mass is not None and body == self._robot:
             self.world.L.qso_world_set_mass(self.world.h, link, float(mass))
         # linear/angular damping: the oracle world has none (quadruped.py:663-668 zeroes them)
+
+    # payload block of the mass randomizer (quadruped.py:778-819): a second body held by a JOINT_FIXED constraint
+    GEOM_BOX = 3
+    JOINT_FIXED = 4
+    _block = 2
+
+    def createCollisionShape(self, shapeType, halfExtents=None, collisionFramePosition=None, **kw):
+        return 0
+
+    def createMultiBody(self, baseMass=0, baseCollisionShapeIndex=-1, basePosition=(0, 0, 0), baseOrientation=(0, 0, 0, 1), **kw):
+        self._block_mass = float(baseMass)
+        return self._block
+
+    def createConstraint(self, parentBodyUniqueId, parentLinkIndex, childBodyUniqueId, childLinkIndex, jointType, jointAxis,
+                         parentFramePosition, childFramePosition, **kw):
+        assert parentBodyUniqueId == self._robot and parentLinkIndex == -1 and childBodyUniqueId == self._block
+        assert jointType == self.JOINT_FIXED and not np.any(np.asarray(parentFramePosition))
+        # the block's point childFramePosition sits on the base origin: block centre = base origin - childFramePosition
+        self._block_delta = -np.asarray(childFramePosition, dtype=float)
+        self.world.set_payload(self._block_mass, self._block_delta)
+        return 0
+
+    def setCollisionFilterPair(self, *a, **k):
+        pass
 
     # state
     def resetBasePositionAndOrientation(self, body, pos, orn):
@@ -208,6 +234,9 @@ class FakeBulletClient:
     def getBasePositionAndOrientation(self, body):
         self.calls["getBasePositionAndOrientation"] += 1
         s = self.world.get_state()
+        if body == self._block:
+            d, _ = _quat_rot(tuple(s[3:7]), tuple(self._block_delta))
+            return tuple(np.asarray(s[0:3]) + d), tuple(s[3:7])
         return tuple(s[0:3]), tuple(s[3:7])
 
     def getBaseVelocity(self, body):

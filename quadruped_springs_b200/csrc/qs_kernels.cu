@@ -315,6 +315,7 @@ struct qs_env {
   Conveyor cv;
   int wave_blocks;     // settle blocks resident at once (SMs x 2)
   int slice_min, slice_max, slice_early;
+  int slow_spread;     // envs per warp in k_step_slow (power of two)
   cudaStream_t bg;     // the conveyor's slices run here, next to k_step_slow on the caller's stream
   cudaStream_t copy;   // qs_step_host: results go to the host while the slice is still running
   cudaEvent_t ev_results, ev_copied;
@@ -514,6 +515,11 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     h->slice_min = 4;
     h->slice_max = 1 << 20;  // no cap: the slice follows the demand
     h->slice_early = 10;  // ticks of the early slice (measured optimum 6-12: longer and it slows k_step_contact down)
+    h->slow_spread = 32;
+    if (const char* v = std::getenv("QS_SLOW_SPREAD")) {
+      const int k = std::atoi(v);
+      if (k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32) h->slow_spread = k;
+    }
     if (const char* v = std::getenv("QS_SETTLE_SLICE_EARLY")) h->slice_early = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MIN")) h->slice_min = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MAX")) h->slice_max = std::max(h->slice_min, std::atoi(v));
@@ -693,7 +699,7 @@ static int launch_conveyor(qs_handle h, cudaStream_t s, int phase, int flush) {
   const int nsettle = h->cfg.is_rl_interface ? h->cfg.settling_steps : 1500;
   // the latency-bound kernel the slice of this phase runs next to, and its block size
   const int* busy = phase == 0 ? h->contact_list + h->n : h->slow_list + h->n;
-  k_conveyor_ctl<<<1, 1024, 0, s>>>(h->cv, phase, busy, phase == 0 ? B : 64, h->wave_blocks, B, h->n, nsettle,
+  k_conveyor_ctl<<<1, 1024, 0, s>>>(h->cv, phase, busy, phase == 0 ? B : 2 * h->slow_spread, h->wave_blocks, B, h->n, nsettle,
                                     h->slice_min, h->slice_max, h->slice_early, flush);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
@@ -790,7 +796,7 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   }
   // envs parked for the general solver (joint limits / body contacts); launched before the slice so
   // that its few blocks are placed first
-  k_step_slow<<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io);
+  k_step_slow<<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread);
   g_launches += 2;
   if (host) {
     // the step's outputs are final here (only an urgent settle, below, rewrites obs rows: the caller checks

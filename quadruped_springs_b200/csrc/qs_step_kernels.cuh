@@ -729,12 +729,22 @@ k_step_contact(const __grid_constant__ KernelArgs A, const StepIO io) {
 
 // -------------------------------------------------------------------- K1b: general-solver continuation
 __global__ void __launch_bounds__(64)
-k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io) {
+k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io, int spread) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const DeviceView& D = A.D;
   const int n = D.n;
-  if (tid >= io.slow_list[n]) return;
-  const int env = io.slow_list[tid];
+  // `spread` envs per warp: these envs take different paths through the general solver (which shapes touch, which
+  // limits are active), so a full warp runs the union of 32 paths; the kernel is a few hundred envs, latency-bound,
+  // on an otherwise idle part of the GPU, so fewer envs per warp shorten the step's serial chain.
+  const int count = io.slow_list[n];
+  const int warps = int(gridDim.x * blockDim.x) >> 5;
+  int K = spread;
+  while (K < 32 && (count + K - 1) / K > warps) K <<= 1;  // a list too long for the grid packs denser
+  const int lane = tid & 31;
+  if (lane >= K) return;
+  const int idx = (tid >> 5) * K + lane;
+  if (idx >= count) return;
+  const int env = io.slow_list[idx];
   EnvState<float> st;
   ContactState<float> cs;
   load_state(D, env, st, cs, A.SC.dt);

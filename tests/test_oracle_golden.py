@@ -111,6 +111,14 @@ def test_rollout_matches_reference_env(name):
                 enable_action_filter=cfg.get("enable_action_filter", False))
     if "springs" in g.files:   # SPRING_RANDOMIZER: the episode's draw, used by the settle too (env_randomizer.py:101-122)
         env.set_springs(g["springs"][:3], g["springs"][3:6], g["springs"][6:])
+    if "masses" in g.files:    # MASS_RANDOMIZER: link masses and payload block of the episode (env_randomizer.py:56-84)
+        m = g["masses"]
+        for leg in range(4):
+            for j in range(3):
+                env.world.set_mass(2 + 4 * leg + j, m[j])
+        env.world.set_mass(0, m[3])
+        env.world.set_payload(m[4], m[5:8])
+        assert 0 < m[4] < 1 and abs(m[3] + m[4] + 4 * m[:3].sum() + 0.24 - 12.01301) < 1e-9   # total mass is kept (:56-60)
     obs = env.reset(mu=float(g["mu"]))
     np.testing.assert_allclose(env.world.get_state(), g["init_state"], rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(obs, g["init_obs"], rtol=1e-9, atol=1e-10)

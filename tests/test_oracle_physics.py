@@ -138,3 +138,25 @@ def test_joint_limit_row_stops_the_joint():
     st = w.get_state()
     assert st[13 + 2] < -0.8378 + 2e-3
     assert abs(st[25 + 2]) < 0.5
+
+
+def test_payload_block_adds_a_welded_rigid_body_to_the_trunk():
+    """Quadruped._add_base_mass_offset (quadruped.py:778-819) restated as a welded block: the generalized mass matrix
+    gains exactly the block's mass, first moment and inertia about the base origin (0.1 m cube)."""
+    w0, w1 = O.World(), O.World()
+    mp, p = 0.73, np.array([0.08, 0.0, -0.06])
+    w1.set_payload(mp, p)
+    s = w0.get_state()
+    s[13:25] += np.random.default_rng(0).normal(size=12) * 0.2
+    w0.set_state(s); w1.set_state(s)
+    dM = w1.mass_matrix() - w0.mass_matrix()
+    px = np.array([[0, -p[2], p[1]], [p[2], 0, -p[0]], [-p[1], p[0], 0]])
+    np.testing.assert_allclose(dM[3:6, 3:6], mp * np.eye(3), atol=1e-12)
+    np.testing.assert_allclose(dM[0:3, 0:3], mp * 0.01 / 6 * np.eye(3) + mp * (p @ p * np.eye(3) - np.outer(p, p)), atol=1e-12)
+    np.testing.assert_allclose(dM[0:3, 3:6], mp * px, atol=1e-12)
+    np.testing.assert_allclose(dM[6:, :], 0, atol=1e-12)     # the legs do not see it
+    # free fall is unchanged, and the robot still falls at g
+    for w in (w0, w1):
+        s2 = s.copy(); s2[2] = 1.0
+        w.set_state(s2); w.step()
+        assert w.get_state()[9] == pytest.approx(-9.8e-3, rel=1e-6)

@@ -121,6 +121,16 @@ typedef struct qs_config {
                                   * once the robot has jumped, stands on four feet and its base rises again, the env ramps from
                                   * its pose to the init action (1 s with springs, 0.3 s without) on gains 60 / 0.8 (60 / 1.5
                                   * without springs) and holds it until the episode ends; the action passed in is ignored */
+  int32_t mass_randomizer;       /* EnvRandomizerMasses (env_randomizers/env_randomizer.py:19-84): every reset draws the hip /
+                                  * thigh / calf link masses (the same for the four legs) within +-rand_leg_mass_err of nominal,
+                                  * welds a block of U[0, rand_payload_max) kg to the trunk at U[-rand_payload_pos, +rand_payload_pos]
+                                  * (base frame) and sets the trunk mass so that the total stays 12.01301 kg; the settle of that
+                                  * episode already runs on them.  The reference's block is a second body on a JOINT_FIXED
+                                  * constraint (quadruped.py:778-819); here it is welded on (folded into the trunk's inertia) */
+  float rand_leg_mass_err;       /* 0.1; the *_CURRICULUM modes interpolate towards 0.2 (env_randomizer.py:148-169) */
+  float rand_payload_max;        /* 1 kg -> 4 kg */
+  float rand_payload_pos[3];     /* (0.1, 0, 0.1) m -> (0.2, 0, 0.2) */
+  float rand_spring_err;         /* relative range of the spring stiffness / damping draws: 0.1 -> 0.3 (:242-262) */
 } qs_config;
 
 typedef struct qs_env* qs_handle;
@@ -148,6 +158,8 @@ typedef struct qs_state_ptrs {
   int32_t* land_mode;  /* [N] landing controller mode: 0 policy, 1 take-off hold, 2 landing, 3 spent, 4 backflip take-off */
   int32_t* rest_active; /* [N] go-to-rest controller engaged (go_to_rest_wrapper.py:58-81) */
   float* rest;         /* [14][N] go-to-rest: h_actual, sim step of activation, start action[12] */
+  float* mass_draw;    /* [8][N] mass randomizer, current episode: hip, thigh, calf link mass, trunk mass, block mass, block
+                        * position[3] (Quadruped.GetLegMasses / get_offset_mass_value / get_offset_mass_position) */
   uint32_t* work;      /* [3][N] per-env work counters of the step kernels: physics ticks, foot-contact ticks,
                         * contact x PGS-sweep count (cumulative; bench / diagnostics) */
 } qs_state_ptrs;
@@ -181,6 +193,11 @@ int qs_reset(qs_handle h, const uint8_t* mask_dev, float* obs_dev, void* stream)
  * (infos["TimeLimit.truncated"]). */
 int qs_step(qs_handle h, const float* actions_dev, float* obs_dev, float* reward_dev,
             uint8_t* done_dev, uint8_t* truncated_dev, void* stream);
+
+/* Quadruped.SetLegMasses / SetBaseMass / _add_base_mass_offset (quadruped.py:744-819) on the batch: after the caller
+ * wrote qs_state_ptrs.mass_draw, recompute the per-env mass properties the physics reads.  Needs
+ * qs_config.mass_randomizer (the next reset of an env draws again). */
+int qs_apply_masses(qs_handle h, void* stream);
 
 /* Optional device buffer [N, O] (caller-owned; NULL detaches it): with auto_reset, qs_step writes there the LAST
  * observation of every env whose episode ended in that step -- infos[i]["terminal_observation"] of the

@@ -38,14 +38,15 @@ class QsConfig(C.Structure):
         ("limit_erp", C.c_float), ("linear_slop", C.c_float), ("warmstart", C.c_float),
         ("residual_threshold", C.c_float), ("max_coord_vel", C.c_float),
         ("breaking_threshold", C.c_float), ("landing_mode", C.c_int32),
-        ("spring_randomizer", C.c_int32), ("rest_mode", C.c_int32),
+        ("spring_randomizer", C.c_int32), ("rest_mode", C.c_int32), ("mass_randomizer", C.c_int32), ("rand_leg_mass_err", C.c_float),
+        ("rand_payload_max", C.c_float), ("rand_payload_pos", C.c_float * 3), ("rand_spring_err", C.c_float),
     ]
 
 
 class QsStatePtrs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "state", "tau_motor", "tau_spring", "kp", "kd", "spring", "mu", "foot_force", "contact", "task",
-        "last_action", "sim_steps", "env_steps", "ep_return", "custom_gains", "land_mode", "rest_active", "rest", "work")]
+        "last_action", "sim_steps", "env_steps", "ep_return", "custom_gains", "land_mode", "rest_active", "rest", "mass_draw", "work")]
 
 
 def nvcc_path():
@@ -94,6 +95,7 @@ EXPORTS = {
     "qs_step": (C.c_int, [C.c_void_p] * 7),
     "qs_step_host": (C.c_int, [C.c_void_p] * 7),
     "qs_set_terminal_obs": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "qs_apply_masses": (C.c_int, [C.c_void_p, C.c_void_p]),
     "qs_reset_host": (C.c_int, [C.c_void_p] * 4),
     "qs_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "qs_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

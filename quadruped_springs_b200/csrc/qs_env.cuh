@@ -42,8 +42,8 @@ QS_DEVONLY float uniform1(uint64_t seed, uint64_t gid, uint32_t epoch, uint32_t 
 // ---------------------------------------------------------------- substeps
 struct EnvCfg {
   int enable_springs, control_mode, action_mode, task, obs_mode, action_repeat, is_rl, enable_filter;
-  int enable_noise, obs_dim, action_dim, settling_steps, ground_randomizer, auto_reset, landing_mode, spring_randomizer, rest_mode;
-  float max_episode_time, mu_ground;
+  int enable_noise, obs_dim, action_dim, settling_steps, ground_randomizer, auto_reset, landing_mode, spring_randomizer, rest_mode, mass_randomizer;
+  float max_episode_time, mu_ground, leg_mass_err, payload_max, payload_pos[3], spring_err;
   uint64_t seed;
   int64_t gid0;
 };
@@ -119,7 +119,8 @@ __device__ __forceinline__ int run_ticks(EnvState<float>& st, ContactState<float
     if (bail == n_ticks) {
       float tau[12];
       tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s, custom);
-      const int r = physics_tick<float, kContacts, QS_BLOCK>(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1), scr);
+      const int r = physics_tick<float, kContacts, QS_BLOCK>(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1), scr,
+                                                             EnvModelRef{C.mass_randomizer ? D.model : nullptr, D.n, env});
       if (r != TICK_DONE) { bail = t; *why = r; }
     }
   }
@@ -138,7 +139,7 @@ __device__ __noinline__ void run_ticks_general(EnvState<float>& st, ContactState
   for (int t = t0; t < n_ticks; t++) {
     float tau[12];
     tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s, custom);
-    physics_tick_general(st, tau, mu, cs, M, SC);
+    physics_tick_general(st, tau, mu, cs, M, SC, EnvModelRef{C.mass_randomizer ? D.model : nullptr, D.n, env});
   }
 }
 

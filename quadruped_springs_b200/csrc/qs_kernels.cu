@@ -83,11 +83,22 @@ __global__ void k_get_state(DeviceView D, float* __restrict__ dst) {
   dst[i] = D.state[c * D.n + env];
 }
 
+// -------------------------------------------------------------------- per-env masses written by the caller
+__global__ void k_apply_masses(DeviceView D) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= D.n) return;
+  float raw[8], em[EM_ROWS];
+  for (int i = 0; i < 8; i++) raw[i] = D.mass_draw[size_t(i) * D.n + env];
+  model_from_masses(raw, em);
+  for (int i = 0; i < EM_ROWS; i++) D.model[size_t(i) * D.n + env] = em[i];
+}
+
 // -------------------------------------------------------------------- debug ticks (fp32 product / fp64 check)
 template <typename T> struct DebugArgs {
   DeviceView D;
   ModelConstT<T> M;
   SolverConst SC;
+  int mass_randomizer;
 };
 template <typename T>
 __global__ void __launch_bounds__(64)
@@ -114,7 +125,10 @@ k_debug_ticks(const __grid_constant__ DebugArgs<T> A, const float* __restrict__ 
   extern __shared__ unsigned char qs_smem_raw[];
   const Scratch<T> scr{reinterpret_cast<T*>(qs_smem_raw) + threadIdx.x, int(blockDim.x)};
   for (int t = 0; t < n_ticks; t++)
-    if (physics_tick<T>(st, t12, mu, cs, A.M, A.SC, true, scr)) physics_tick_general<T>(st, t12, mu, cs, A.M, A.SC);
+    {
+    const EnvModelRef em{A.mass_randomizer ? D.model : nullptr, D.n, env};
+    if (physics_tick<T>(st, t12, mu, cs, A.M, A.SC, true, scr, em)) physics_tick_general<T>(st, t12, mu, cs, A.M, A.SC, em);
+  }
 #pragma unroll
   for (int i = 0; i < 3; i++) { sf.pos[i] = float(st.pos[i]); sf.vlin[i] = float(st.vlin[i]); sf.vang[i] = float(st.vang[i]); }
 #pragma unroll
@@ -387,6 +401,10 @@ void qs_default_config(qs_config* c) {
   c->residual_threshold = 1e-7f;
   c->max_coord_vel = 30.1f;                    // quadruped.py:678-683
   c->breaking_threshold = 0.02f;
+  c->rand_leg_mass_err = 0.1f;                 // env_randomizer.py:5-14
+  c->rand_payload_max = 1.0f;
+  c->rand_payload_pos[0] = 0.1f; c->rand_payload_pos[1] = 0.0f; c->rand_payload_pos[2] = 0.1f;
+  c->rand_spring_err = 0.1f;
 }
 
 static int check_config(const qs_config* c) {
@@ -404,6 +422,10 @@ static int check_config(const qs_config* c) {
     return fail(QS_ERR_ARG, "landing controllers need the RL interface with PD or CARTESIAN_PD control");
   if (c->rest_mode && (c->control_mode == QS_CTRL_TORQUE || !c->is_rl_interface))
     return fail(QS_ERR_ARG, "the go-to-rest controller needs the RL interface with PD or CARTESIAN_PD control");
+  if (c->mass_randomizer && (!(c->rand_leg_mass_err >= 0.f && c->rand_leg_mass_err < 1.f) || !(c->rand_payload_max >= 0.f) ||
+                             c->rand_payload_max > 5.f))
+    return fail(QS_ERR_ARG, "mass randomizer ranges out of bounds");
+  if (!(c->rand_spring_err >= 0.f && c->rand_spring_err < 1.f)) return fail(QS_ERR_ARG, "rand_spring_err out of range");
   if (c->obs_mode < 0 || c->obs_mode > QS_OBS_PPO_CONTINUOUS_JUMPING_FORWARD) return fail(QS_ERR_ARG, "unknown observation space mode");
   if (c->action_repeat < 1 || c->action_repeat > 1000) return fail(QS_ERR_ARG, "action_repeat out of range");
   if (c->control_mode == QS_CTRL_TORQUE && c->is_rl_interface)  // quadruped_gym_env.py:167-168
@@ -465,12 +487,15 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   C.settling_steps = cfg->settling_steps; C.ground_randomizer = cfg->ground_randomizer; C.auto_reset = cfg->auto_reset;
   C.landing_mode = cfg->landing_mode; C.spring_randomizer = cfg->spring_randomizer && cfg->enable_springs;
   C.rest_mode = cfg->rest_mode != 0;
+  C.mass_randomizer = cfg->mass_randomizer != 0;
+  C.leg_mass_err = cfg->rand_leg_mass_err; C.payload_max = cfg->rand_payload_max; C.spring_err = cfg->rand_spring_err;
+  for (int i = 0; i < 3; i++) C.payload_pos[i] = cfg->rand_payload_pos[i];
   C.max_episode_time = float(cfg->max_episode_time); C.mu_ground = cfg->mu_ground;
   C.seed = cfg->seed; C.gid0 = cfg->env_id_offset;
 
   // one pool for all SoA arrays (4-byte elements), 256 B aligned segments
   const size_t n = size_t(n_envs);
-  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1 + 3 + 12 + 1 + 1 + 1 + 2 + 1 + 14 + QS_SLOTS * (SLOT_ROWS + 1 + 1);
+  const size_t rows = 37 + 12 + 12 + 12 + 12 + 9 + 1 + 4 + 1 + QS_TASK_DIM + 12 + 48 + 1 + 1 + 1 + QS_STATS_DIM + 1 + 3 + 12 + 1 + 1 + 1 + 2 + 1 + 14 + EM_ROWS + 8 + QS_SLOTS * (SLOT_ROWS + 1 + 1);
   // rows of one array are contiguous with stride n floats; each array starts 256 B aligned
   h->pool_bytes = rows * n * 4 + 64 * 256;
   cudaError_t e = cudaMalloc(&h->pool, h->pool_bytes);
@@ -497,6 +522,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   D.custom_gains = (uint8_t*)carve(1);
   D.land_mode = (int32_t*)carve(1); D.land_timer = (float*)carve(2);
   D.rest_active = (int32_t*)carve(1); D.rest = (float*)carve(14);
+  D.model = (float*)carve(EM_ROWS); D.mass_draw = (float*)carve(8);
   D.slot = (float*)carve(QS_SLOTS * SLOT_ROWS); D.slot_contact = (int32_t*)carve(QS_SLOTS); D.slot_epoch = (uint32_t*)carve(QS_SLOTS);
   if (size_t(p - static_cast<char*>(h->pool)) > h->pool_bytes) { cudaFree(h->pool); delete h; return fail(QS_ERR_STATE, "pool overflow"); }
   {
@@ -524,7 +550,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MIN")) h->slice_min = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MAX")) h->slice_max = std::max(h->slice_min, std::atoi(v));
     const size_t w = size_t(cv.width);
-    const size_t nints = 3 * (n + 1) + 2 * n + 2 * cap + cap + (WIP_ROWS + 1) * w + CV_CTL_WORDS + 8;
+    const size_t nints = 3 * (n + 1) + 2 * n + 2 * cap + cap + (WIP_ROWS + 1 + EM_ROWS) * w + CV_CTL_WORDS + 8;
     e = cudaMalloc(&h->lists, nints * sizeof(int));
     if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(QS_ERR_CUDA, "cudaMalloc lists"); }
     cudaMemset(h->lists, 0, nints * sizeof(int));
@@ -536,7 +562,8 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     cv.tick = cv.fifo + 2 * cap;
     cv.wip = reinterpret_cast<float*>(cv.tick + cap);
     cv.wip_contact = reinterpret_cast<int*>(cv.wip + WIP_ROWS * w);
-    cv.ctl = reinterpret_cast<uint32_t*>(cv.wip_contact + w);
+    cv.model = reinterpret_cast<float*>(cv.wip_contact + w);
+    cv.ctl = reinterpret_cast<uint32_t*>(cv.model + EM_ROWS * w);
     cv.work = reinterpret_cast<unsigned long long*>(h->lists + ((size_t((cv.ctl + CV_CTL_WORDS) - reinterpret_cast<uint32_t*>(h->lists)) + 1) & ~size_t(1)));
     cudaMemset(cv.tick, 0xff, cap * sizeof(int));  // CV_DONE: nothing queued
     e = cudaStreamCreateWithFlags(&h->bg, cudaStreamNonBlocking);
@@ -686,6 +713,7 @@ int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* o) {
   o->custom_gains = D.custom_gains;
   o->land_mode = D.land_mode;
   o->rest_active = D.rest_active; o->rest = D.rest;
+  o->mass_draw = D.mass_draw;
   o->work = D.work;
   return QS_OK;
 }
@@ -826,6 +854,17 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   return QS_OK;
 }
 
+int qs_apply_masses(qs_handle h, void* stream) {
+  if (!h) return fail(QS_ERR_ARG, "handle is NULL");
+  if (!h->args.C.mass_randomizer)
+    return fail(QS_ERR_STATE, "per-env masses need an env built with a mass randomizer mode (qs_config.mass_randomizer)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  k_apply_masses<<<grid_for(h->n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(h->args.D);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
 int qs_set_terminal_obs(qs_handle h, float* term_obs) {
   if (!h) return fail(QS_ERR_ARG, "handle is NULL");
   h->term_obs = term_obs;
@@ -918,11 +957,11 @@ int qs_debug_ticks(qs_handle h, const float* tau, int n_ticks, int use_f64, void
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (use_f64) {
     DebugArgs<double> a;
-    a.D = h->args.D; a.M = h->model_d; a.SC = h->args.SC;
+    a.D = h->args.D; a.M = h->model_d; a.SC = h->args.SC; a.mass_randomizer = h->args.C.mass_randomizer;
     k_debug_ticks<double><<<grid_for(h->n, 64), 64, 64 * QS_TICK_SCRATCH * sizeof(double), s>>>(a, tau, n_ticks);
   } else {
     DebugArgs<float> a;
-    a.D = h->args.D; a.M = h->args.M; a.SC = h->args.SC;
+    a.D = h->args.D; a.M = h->args.M; a.SC = h->args.SC; a.mass_randomizer = h->args.C.mass_randomizer;
     k_debug_ticks<float><<<grid_for(h->n, 64), 64, 64 * QS_TICK_SCRATCH * sizeof(float), s>>>(a, tau, n_ticks);
   }
   g_launches += 1;

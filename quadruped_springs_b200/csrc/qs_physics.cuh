@@ -104,6 +104,19 @@ template <typename T> struct ContactState {
   int work_row_iters;  // sum over ticks of contacts x PGS sweeps run   } (bench.py roofline)
 };
 
+// Per-env mass properties (EnvRandomizerMasses, env_randomizers/env_randomizer.py:19-84): column `idx` of a
+// [EM_ROWS][stride] float array holding what differs from the nominal model M -- the three leg-link masses
+// (the same for the four legs, :62-71), the calf+foot body re-merged for that calf mass, and body 0 (base + trunk +
+// imu + payload block, :73-84 and :56-60) about the base origin.  base == nullptr: the nominal model.  The pointer
+// and the stride are uniform (kernel parameters); only `idx` is per thread.
+struct EnvModelRef {
+  const float* base;
+  int stride, idx;
+};
+enum { EM_HIP_M = 0, EM_THIGH_M = 1, EM_CALF_M = 2, EM_CALF_COM = 3, EM_CALF_IC = 6, EM_TRUNK_M = 12, EM_TRUNK_H = 13,
+       EM_TRUNK_I = 16, EM_ROWS = 22 };
+template <typename T> QS_DEV T em_get(const EnvModelRef& em, int row) { return T(em.base[size_t(row) * em.stride + em.idx]); }
+
 template <typename T> struct LegKin {
   T s1, c1, s2, c2, s23, c23;
   T a2[3];                     // thigh/calf joint axis (base coords); hip axis is x
@@ -193,6 +206,23 @@ template <typename T> QS_DEV void link_rotations(const LegKin<T>& K, T* RH, T* R
   RC[6] = -K.c1 * K.s23; RC[7] = K.s1; RC[8] = K.c1 * K.c23;
 }
 
+// body 0 (base + trunk + imu, plus the payload block when the masses are randomized) about the base origin
+template <typename T> QS_DEV void trunk_spi(const ModelConstT<T>& M, const EnvModelRef& em, SpI<T>& tot) {
+  if (em.base) {
+    tot.m = em_get<T>(em, EM_TRUNK_M);
+#pragma unroll
+    for (int i = 0; i < 3; i++) tot.h[i] = em_get<T>(em, EM_TRUNK_H + i);
+#pragma unroll
+    for (int i = 0; i < 6; i++) tot.I[i] = em_get<T>(em, EM_TRUNK_I + i);
+  } else {
+    tot.m = M.trunk_m;
+#pragma unroll
+    for (int i = 0; i < 3; i++) tot.h[i] = M.trunk_h[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) tot.I[i] = M.trunk_I[i];
+  }
+}
+
 // Per-leg dynamics: joint-space inertia inverse Mi (sym 3x3: 00 01 02 11 12 22),
 // Bm = M_kk^-1 F_k (3x6), ev = M_kk^-1 (tau - h) + B_lin (w x v); accumulates the
 // Schur complement S6 -= F^T B, the base force fb += f_leg + F^T d and the
@@ -200,13 +230,24 @@ template <typename T> QS_DEV void link_rotations(const LegKin<T>& K, T* RH, T* R
 template <typename T>
 QS_DEV void leg_dynamics(int k, const T* q, const T* qd, const T* tau3, const TickCtx<T>& X, const ModelConstT<T>& M,
                          const LegKin<T>& K, const T* RH, const T* RT, const T* RC, T* Mi, T* Bm, T* ev, T* S6, T* fb,
-                         SpI<T>& tot) {
+                         SpI<T>& tot, const EnvModelRef& em) {
   const T* wb = X.wb;
   const T* vb = X.vb;
   SpI<T> Ih, It, Ic;
-  body_spi(M.body_m[k][0], M.body_com[k][0], M.body_Ic[k][0], RH, K.r1, Ih);
-  body_spi(M.body_m[k][1], M.body_com[k][1], M.body_Ic[k][1], RT, K.r2, It);
-  body_spi(M.body_m[k][2], M.body_com[k][2], M.body_Ic[k][2], RC, K.r3, Ic);
+  if (em.base) {  // randomized masses: changeDynamics(mass=) keeps each link's inertia diagonal and inertial frame
+    T cc[3], ci[6];
+#pragma unroll
+    for (int i = 0; i < 3; i++) cc[i] = em_get<T>(em, EM_CALF_COM + i);
+#pragma unroll
+    for (int i = 0; i < 6; i++) ci[i] = em_get<T>(em, EM_CALF_IC + i);
+    body_spi(em_get<T>(em, EM_HIP_M), M.body_com[k][0], M.body_Ic[k][0], RH, K.r1, Ih);
+    body_spi(em_get<T>(em, EM_THIGH_M), M.body_com[k][1], M.body_Ic[k][1], RT, K.r2, It);
+    body_spi(em_get<T>(em, EM_CALF_M), cc, ci, RC, K.r3, Ic);
+  } else {
+    body_spi(M.body_m[k][0], M.body_com[k][0], M.body_Ic[k][0], RH, K.r1, Ih);
+    body_spi(M.body_m[k][1], M.body_com[k][1], M.body_Ic[k][1], RT, K.r2, It);
+    body_spi(M.body_m[k][2], M.body_com[k][2], M.body_Ic[k][2], RC, K.r3, Ic);
+  }
 
   // motion subspaces S_j = (a_j, r_j x a_j)
   const T a1[3] = {T(1), T(0), T(0)};
@@ -464,7 +505,7 @@ enum { TICK_DONE = 0, TICK_NEEDS_GENERAL = 1, TICK_NEEDS_CONTACT = 2 };
 template <typename T, bool kContacts = true, int kStride = 0>
 __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
                                      const ModelConstT<T>& M, const SolverConst& SC, bool detect_invalid,
-                                     const Scratch<T, kStride>& scr) {
+                                     const Scratch<T, kStride>& scr, const EnvModelRef em = EnvModelRef{nullptr, 0, 0}) {
   const T dt = T(SC.dt);
   const T idt = div_t(T(1), dt);
   const T mcv = T(SC.max_coord_vel);
@@ -475,11 +516,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
 
   // composite inertia of the whole robot and Newton-Euler base force, trunk first
   SpI<T> tot;
-  tot.m = M.trunk_m;
-#pragma unroll
-  for (int i = 0; i < 3; i++) tot.h[i] = M.trunk_h[i];
-#pragma unroll
-  for (int i = 0; i < 6; i++) tot.I[i] = M.trunk_I[i];
+  trunk_spi(M, em, tot);
   T fb[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
   body_force(tot, X.wb, X.vb, zero3, X.A0, fb, fb + 3);
   T S6[21];
@@ -511,7 +548,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
     leg_kin(k, q, M, K);
     T RH[9], RT[9], RC[9], Mi[6], Bm[18], ev[3];
     link_rotations(K, RH, RT, RC);
-    leg_dynamics(k, q, qd, tk, X, M, K, RH, RT, RC, Mi, Bm, ev, S6, fb, tot);
+    leg_dynamics(k, q, qd, tk, X, M, K, RH, RT, RC, Mi, Bm, ev, S6, fb, tot, em);
 #pragma unroll
     for (int i = 0; i < 18; i++) scr(k, SCR_BM + i) = Bm[i];
 #pragma unroll
@@ -816,7 +853,8 @@ QS_DEV void body_point_jac(const LegKin<T>& K, int level, const T* pc, const T* 
 
 template <typename T>
 __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
-                                              const ModelConstT<T>& M, const SolverConst& SC) {
+                                              const ModelConstT<T>& M, const SolverConst& SC,
+                                              const EnvModelRef em = EnvModelRef{nullptr, 0, 0}) {
   const T dt = T(SC.dt);
   const T mcv = T(SC.max_coord_vel);
   TickCtx<T> X;
@@ -824,9 +862,7 @@ __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T m
   const T* nb = X.nb;
   const T zero3[3] = {T(0), T(0), T(0)};
   SpI<T> tot;
-  tot.m = M.trunk_m;
-  for (int i = 0; i < 3; i++) tot.h[i] = M.trunk_h[i];
-  for (int i = 0; i < 6; i++) tot.I[i] = M.trunk_I[i];
+  trunk_spi(M, em, tot);
   T fb[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
   body_force(tot, X.wb, X.vb, zero3, X.A0, fb, fb + 3);
   T S6[21];
@@ -858,7 +894,7 @@ __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T m
     leg_kin(k, st.q + 3 * k, M, K[k]);
     T RH[9], RT[9], RC[9];
     link_rotations(K[k], RH, RT, RC);
-    leg_dynamics(k, st.q + 3 * k, st.qd + 3 * k, tau + 3 * k, X, M, K[k], RH, RT, RC, Mi[k], Bm[k], ev[k], S6, fb, tot);
+    leg_dynamics(k, st.q + 3 * k, st.qd + 3 * k, tau + 3 * k, X, M, K[k], RH, RT, RC, Mi[k], Bm[k], ev[k], S6, fb, tot, em);
     T zh, zt, zc;
     leg_shape_gaps(st, X, M, K[k], RT, RC, &zh, &zt, &zc);
     if (zh < M.hip_thresh) {  // lowest point of the lower rim of the hip cylinder (axis a2)

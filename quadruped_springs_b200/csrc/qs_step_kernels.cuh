@@ -122,6 +122,7 @@ struct Conveyor {
   int* tick;
   float* wip;
   int* wip_contact;
+  float* model;      // [EM_ROWS][width] mass properties of the episodes in flight (mass randomizer)
   uint32_t* ctl;
   int* urgent_list;  // (env, episode) pairs that must be settled and started NOW; count in ctl[CV_URGENT]
   unsigned long long* work;  // settle ticks, foot-contact ticks, contact x PGS-sweep count done by the slices
@@ -298,10 +299,82 @@ __device__ __forceinline__ void episode_springs(const EnvCfg& C, const RobotCons
   for (int j = 0; j < 3; j++) {
     sk[j] = RC.spring_k[j]; sb[j] = RC.spring_b[j]; sr[j] = RC.spring_rest[j];
     if (C.spring_randomizer) {
-      sk[j] *= 0.9f + 0.2f * uniform1(C.seed, gid, epoch, 101 + j);
-      sb[j] *= 0.9f + 0.2f * uniform1(C.seed, gid, epoch, 104 + j);
+      sk[j] *= 1.f - C.spring_err + 2.f * C.spring_err * uniform1(C.seed, gid, epoch, 101 + j);
+      sb[j] *= 1.f - C.spring_err + 2.f * C.spring_err * uniform1(C.seed, gid, epoch, 104 + j);
     }
   }
+}
+
+// EnvRandomizerMasses.randomize_env (env_randomizer.py:56-84) for episode `epoch` of global env `gid`:
+// raw = hip, thigh, calf link mass | trunk mass | block mass | block position (base frame)
+__device__ __forceinline__ void episode_masses(const EnvCfg& C, uint64_t gid, uint32_t epoch, float* raw) {
+  const float nominal[3] = {0.591f, 0.92f, 0.131f};  // go1.urdf hip / thigh / calf
+  float legs = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {  // _randomize_leg_masses :62-71: each leg in the same way
+    raw[j] = nominal[j] * (1.f - C.leg_mass_err + 2.f * C.leg_mass_err * uniform1(C.seed, gid, epoch, 110 + j));
+    legs += raw[j];
+  }
+  raw[4] = C.payload_max * uniform1(C.seed, gid, epoch, 113);  // _add_mass_offset :73-84
+#pragma unroll
+  for (int j = 0; j < 3; j++) raw[5 + j] = C.payload_pos[j] * (2.f * uniform1(C.seed, gid, epoch, 114 + j) - 1.f);
+  // _change_base_mass :56-60: total (all 19 URDF links, 12.01301 kg) - block - leg links - feet
+  raw[3] = 12.01301f - raw[4] - 4.f * legs - 4.f * 0.06f;
+}
+// The mass properties the tick reads (EnvModelRef rows) for those draws.  changeDynamics(mass=) leaves every link's
+// inertia diagonal and inertial frame as loaded (collision-geometry inertias of the NOMINAL masses),
+// so only masses, first moments and parallel-axis terms move.  Same constants as qs_model_host.h build_model.
+__device__ __noinline__ void model_from_masses(const float* raw, float* em) {
+  em[EM_HIP_M] = raw[0];
+  em[EM_THIGH_M] = raw[1];
+  {  // calf + foot (fixed joint), in the calf frame
+    const double mc = raw[2], mf = 0.06, m = mc + mf;
+    const double cc[3] = {0.006286, 0.001307, -0.122269}, cf[3] = {0.0, 0.0, -0.213};
+    const double Ic[3] = {0.131 / 12.0 * (0.016 * 0.016 + 0.213 * 0.213), 0.131 / 12.0 * (0.016 * 0.016 + 0.213 * 0.213),
+                          0.131 / 12.0 * (0.016 * 0.016 + 0.016 * 0.016)};
+    const double If = 0.4 * 0.06 * 0.02 * 0.02;
+    double c[3], I[6] = {Ic[0] + If, 0, 0, Ic[1] + If, 0, Ic[2] + If};
+    for (int i = 0; i < 3; i++) c[i] = (mc * cc[i] + mf * cf[i]) / m;
+    for (int b = 0; b < 2; b++) {
+      const double mm = b ? mf : mc;
+      const double d[3] = {(b ? cf[0] : cc[0]) - c[0], (b ? cf[1] : cc[1]) - c[1], (b ? cf[2] : cc[2]) - c[2]};
+      const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+      I[0] += mm * (dd - d[0] * d[0]); I[1] -= mm * d[0] * d[1]; I[2] -= mm * d[0] * d[2];
+      I[3] += mm * (dd - d[1] * d[1]); I[4] -= mm * d[1] * d[2]; I[5] += mm * (dd - d[2] * d[2]);
+    }
+    em[EM_CALF_M] = float(m);
+    for (int i = 0; i < 3; i++) em[EM_CALF_COM + i] = float(c[i]);
+    for (int i = 0; i < 6; i++) em[EM_CALF_IC + i] = float(I[i]);
+  }
+  {  // body 0 about the base origin: base (1e-5 kg, no inertia) + trunk + imu_link + block (0.1 m cube)
+    const double mt = raw[3], mp = raw[4];
+    const double ct[3] = {0.0223, 0.0, -0.0005}, ci[3] = {-0.01592, -0.06659, -0.00617}, cp[3] = {raw[5], raw[6], raw[7]};
+    const double It[3] = {5.204 / 12.0 * (0.0935 * 0.0935 + 0.114 * 0.114), 5.204 / 12.0 * (0.3762 * 0.3762 + 0.114 * 0.114),
+                          5.204 / 12.0 * (0.3762 * 0.3762 + 0.0935 * 0.0935)};
+    const double Ii = 0.001 / 12.0 * (2e-6), Ip = mp * 0.01 / 6.0;
+    double I[6] = {It[0] + Ii + Ip, 0, 0, It[1] + Ii + Ip, 0, It[2] + Ii + Ip}, hh[3] = {0, 0, 0};
+    const double ms[3] = {mt, 0.001, mp};
+    for (int b = 0; b < 3; b++) {
+      const double* c = b == 0 ? ct : (b == 1 ? ci : cp);
+      const double mm = ms[b], dd = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+      for (int i = 0; i < 3; i++) hh[i] += mm * c[i];
+      I[0] += mm * (dd - c[0] * c[0]); I[1] -= mm * c[0] * c[1]; I[2] -= mm * c[0] * c[2];
+      I[3] += mm * (dd - c[1] * c[1]); I[4] -= mm * c[1] * c[2]; I[5] += mm * (dd - c[2] * c[2]);
+    }
+    em[EM_TRUNK_M] = float(0.00001 + mt + 0.001 + mp);
+    for (int i = 0; i < 3; i++) em[EM_TRUNK_H + i] = float(hh[i]);
+    for (int i = 0; i < 6; i++) em[EM_TRUNK_I + i] = float(I[i]);
+  }
+}
+// draws of (gid, epoch) -> the rows of column idx
+__device__ __forceinline__ void episode_model_store(const EnvCfg& C, uint64_t gid, uint32_t epoch, float* base, int stride, int idx,
+                                                    float* draw_base /* [8][stride] or nullptr */) {
+  float raw[8], em[EM_ROWS];
+  episode_masses(C, gid, epoch, raw);
+  model_from_masses(raw, em);
+  for (int i = 0; i < EM_ROWS; i++) base[size_t(i) * stride + idx] = em[i];
+  if (draw_base)
+    for (int i = 0; i < 8; i++) draw_base[size_t(i) * stride + idx] = raw[i];
 }
 
 // Settle ticks [t0, t1) of the reset (control_interface/interface_base.py:182-200), at most `span` of them.
@@ -309,8 +382,12 @@ __device__ __forceinline__ void episode_springs(const EnvCfg& C, const RobotCons
 // a thread works while t < t1.
 __device__ __forceinline__ void settle_ticks(const KernelArgs& A, uint64_t gid, uint32_t epoch, EnvState<float>& st,
                                              ContactState<float>& cs, float mu, int t0, int t1, int span, float* tau_m,
-                                             float* tau_s, const StepScratch& scr) {
+                                             float* tau_s, const StepScratch& scr, float* em_base, int em_stride, int em_idx) {
   const EnvCfg& C = A.C;
+  // randomize_env() comes before the settle (quadruped_gym_env.py:286-289): the episode's masses, in the column
+  // (em_base, em_stride, em_idx) -- the env's own rows, or the conveyor's for an episode settled ahead
+  if (C.mass_randomizer && t1 > t0) episode_model_store(C, gid, epoch, em_base, em_stride, em_idx, nullptr);
+  const EnvModelRef em{C.mass_randomizer ? em_base : nullptr, em_stride, em_idx};
   float cmd[12], act12[12];
   settle_command(C, A.RC, cmd, act12);
   // a fresh Quadruped has the default gains / springs (quadruped_gym_env.py:299-319); the settle
@@ -339,7 +416,7 @@ __device__ __forceinline__ void settle_ticks(const KernelArgs& A, uint64_t gid, 
         for (int j = 0; j < 3; j++) tau[3 * k + j] += tau_s[3 * k + j];
       }
     }
-    physics_tick<float, true, QS_BLOCK>(st, tau, mu, cs, A.M, SCs, t == nsettle - 1, scr);
+    physics_tick<float, true, QS_BLOCK>(st, tau, mu, cs, A.M, SCs, t == nsettle - 1, scr, em);
   }
 }
 
@@ -378,7 +455,7 @@ __device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint6
 #pragma unroll
   for (int i = 0; i < 12; i++) { tau_m[i] = 0.f; tau_s[i] = 0.f; }
   const int nsettle = settle_length(A.C);
-  settle_ticks(A, gid, epoch, st, cs, mu, 0, need ? nsettle : 0, nsettle, tau_m, tau_s, scr);
+  settle_ticks(A, gid, epoch, st, cs, mu, 0, need ? nsettle : 0, nsettle, tau_m, tau_s, scr, A.D.model, A.D.n, env);
   if (!need) { st = st_keep; cs = cs_keep; }
 }
 
@@ -401,6 +478,7 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
   }
 #pragma unroll
   for (int i = 0; i < 12; i++) { D.kp[i * n + env] = A.RC.kp[i]; D.kd[i * n + env] = A.RC.kd[i]; }
+  if (C.mass_randomizer) episode_model_store(C, uint64_t(C.gid0 + env), epoch, D.model, n, env, D.mass_draw);
   float sk[3], sb[3], sr[3];
   episode_springs(C, A.RC, uint64_t(C.gid0 + env), epoch, sk, sb, sr);
 #pragma unroll
@@ -941,7 +1019,7 @@ k_settle_slice(const __grid_constant__ KernelArgs A, const Conveyor cv, int earl
   const int t1 = need ? min(t0 + span, nsettle) : 0;
   extern __shared__ float qs_smem[];
   const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
-  settle_ticks(A, uint64_t(A.C.gid0 + env), epoch, st, cs, mu, t0, t1, span, tau_m, tau_s, scr);
+  settle_ticks(A, uint64_t(A.C.gid0 + env), epoch, st, cs, mu, t0, t1, span, tau_m, tau_s, scr, cv.model, cv.width, col);
   if (!need) return;
   {  // work counters of the bench's flop model, one atomic per warp
     const unsigned m = __activemask();

@@ -75,6 +75,8 @@ struct DeviceView {
   float* land_timer;     // [2][N] timer time, timer end (utils/timer.py)
   int32_t* rest_active;  // [N] go-to-rest controller engaged (go_to_rest_wrapper.py:58-81)
   float* rest;           // [14][N] h_actual, sim step of activation, start action[12]
+  float* model;          // [EM_ROWS][N] mass randomizer: per-env mass properties of the current episode (qs_physics.cuh EnvModelRef)
+  float* mass_draw;      // [8][N] the draws they come from: hip, thigh, calf, trunk mass, block mass, block position
   uint8_t* custom_gains; // [N] non-zero: read kp/kd of this env from the arrays instead of the config constants
   float* slot;           // [slots][66][N] settled states of the next episodes (see qs_step_kernels.cuh)
   int32_t* slot_contact; // [slots][N]

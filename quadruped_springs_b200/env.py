@@ -49,7 +49,9 @@ TaskCollection = lambda: _Collection("task", [
 # sensors/sensor_collection.py:92-105
 SensorCollection = lambda: _Collection("sensor package", list(SENSOR_SETS))
 # env_randomizers/env_randomizer_collection.py:15-21 (mass / curriculum randomizers: SURVEY.md 8f "next")
-EnvRandomizerCollection = lambda: _Collection("env randomizer", ["GROUND_RANDOMIZER", "NO_RANDOMIZER", "SPRING_RANDOMIZER"])
+EnvRandomizerCollection = lambda: _Collection("env randomizer", [
+    "GROUND_RANDOMIZER", "NO_RANDOMIZER", "SPRING_RANDOMIZER", "MASS_RANDOMIZER", "TEST_RANDOMIZER",
+    "TEST_RANDOMIZER_CURRICULUM"])
 
 
 class Box:
@@ -212,6 +214,35 @@ class BatchedQuadruped:
     def get_spring_nominal_params(self):
         sp = self._env._views["spring"]
         return sp[0:3].t(), sp[3:6].t(), sp[6:9].t()
+
+    # --- mass randomizer read-outs (quadruped.py:685-718): the current episode's draw, zero-copy views
+    def GetLegMasses(self):
+        """[N, 3] hip, thigh, calf link mass (the same for the four legs, env_randomizer.py:62-71)"""
+        return self._env._views["mass_draw"][0:3].t()
+
+    def GetBaseMass(self):
+        return self._env._views["mass_draw"][3]
+
+    def get_offset_mass_value(self):
+        return self._env._views["mass_draw"][4]
+
+    def get_offset_mass_position(self):
+        return self._env._views["mass_draw"][5:8].t()
+
+    def set_masses(self, leg_masses=None, base_mass=None, offset_mass=None, offset_position=None):
+        """SetLegMasses ([N, 3] or [3]: hip, thigh, calf), SetBaseMass, _add_base_mass_offset (quadruped.py:744-819) for
+        the current episode; needs a mass randomizer mode (the next reset draws again)."""
+        v, dev = self._env._views["mass_draw"], self._env.device
+        f = lambda x: torch.as_tensor(x, dtype=torch.float32, device=dev)
+        if leg_masses is not None:
+            v[0:3] = f(leg_masses).reshape(-1, 3).t().expand(3, self._env.num_envs)
+        if base_mass is not None:
+            v[3] = f(base_mass)
+        if offset_mass is not None:
+            v[4] = f(offset_mass)
+        if offset_position is not None:
+            v[5:8] = f(offset_position).reshape(-1, 3).t().expand(3, self._env.num_envs)
+        _lib.check(self._env._L.qs_apply_masses(self._env._h, _stream_ptr(dev)))
 
     def set_spring_stiffness(self, stiffness):
         self._env._views["spring"][0:3] = torch.as_tensor(stiffness, dtype=torch.float32, device=self._env.device).view(3, -1)
@@ -438,8 +469,20 @@ class BatchedQuadrupedGymEnv:
         cfg.task = TaskCollection().get_el(task_env)
         cfg.obs_mode = SensorCollection().get_el(observation_space_mode)
         rnd = EnvRandomizerCollection().get_el(env_randomizer_mode)
-        cfg.ground_randomizer = int(rnd in (0, 2))     # SPRING_RANDOMIZER = [ground, springs] (collection :18)
-        cfg.spring_randomizer = int(rnd == 2)
+        # env_randomizer_collection.py:15-21: every mode but NO_RANDOMIZER starts with the ground randomizer
+        cfg.ground_randomizer = int(rnd != 1)
+        cfg.spring_randomizer = int(rnd in (2, 4, 5))
+        cfg.mass_randomizer = int(rnd in (3, 4, 5))
+        if rnd == 5:
+            # *Curriculum randomizers (env_randomizer.py:125-262): ranges interpolated by the level, which the env
+            # raises once at construction (quadruped_gym_env.py:147-150)
+            lvl = float(np.clip(curriculum_level, 0.0, 1.0))
+            self.curriculum_level = lvl
+            mix = lambda lo, hi: (1.0 - lvl) * lo + lvl * hi
+            cfg.rand_leg_mass_err = mix(0.1, 0.2)
+            cfg.rand_payload_max = mix(1.0, 4.0)
+            cfg.rand_payload_pos = (C.c_float * 3)(mix(0.1, 0.2), 0.0, mix(0.1, 0.2))
+            cfg.rand_spring_err = mix(0.1, 0.3)
         cfg.action_repeat = self._action_repeat
         cfg.is_rl_interface = int(isRLGymInterface)
         cfg.enable_action_filter = int(enable_action_filter)
@@ -488,6 +531,7 @@ class BatchedQuadrupedGymEnv:
             "custom_gains": _view(ptrs.custom_gains, (n,), "|u1", dev),
             "land_mode": _view(ptrs.land_mode, (n,), "<i4", dev),
             "rest_active": _view(ptrs.rest_active, (n,), "<i4", dev), "rest": _view(ptrs.rest, (14, n), "<f4", dev),
+            "mass_draw": _view(ptrs.mass_draw, (8, n), "<f4", dev),
             "work": _view(ptrs.work, (3, n), "<i4", dev),
         }
         self.robot = BatchedQuadruped(self)

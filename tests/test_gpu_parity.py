@@ -354,9 +354,10 @@ def test_reset_settle_matches_oracle(qs, cfg):
 # ------------------------------------------------------------------ a1/a17-a20 whole step against the reference env
 def _make_env_for(qs, g, n=2):
     cfg = json.loads(str(g["cfg"]))
-    cfg.pop("env_randomizer_mode", None)   # the fixture's draws (mu, springs) are imposed below
+    cfg.pop("env_randomizer_mode", None)   # the fixture's draws (mu, springs, masses) are imposed below
+    mode = "MASS_RANDOMIZER" if "masses" in g.files else "NO_RANDOMIZER"   # per-env mass properties need the mode
     return qs.BatchedQuadrupedGymEnv(num_envs=n, enable_noise=False, auto_reset=False,
-                                     env_randomizer_mode="NO_RANDOMIZER", solver=dict(mu_ground=float(g["mu"])), **cfg), cfg
+                                     env_randomizer_mode=mode, solver=dict(mu_ground=float(g["mu"])), **cfg), cfg
 
 
 @pytest.mark.parametrize("name", ROLLOUTS)
@@ -365,8 +366,8 @@ def test_rollout_free_running_tracks_reference_env(qs, name):
     QuadrupedGymEnv; fp32 vs fp64 physics drift apart slowly, so the first 30
     control steps (300 ticks) are held to a stated tolerance."""
     g = load_golden(f"rollout_{name}.npz")
-    if "springs" in g.files:
-        pytest.skip("randomized springs enter the settle: covered by test_spring_randomizer_* and the teacher-forced replay")
+    if "springs" in g.files or "masses" in g.files:
+        pytest.skip("randomized springs / masses enter the settle: covered by test_*_randomizer_* and the teacher-forced replay")
     env, cfg = _make_env_for(qs, g)
     obs = env.reset()
     np.testing.assert_allclose(env.get_state()[0].cpu().numpy(), g["init_state"], atol=1e-3)
@@ -397,6 +398,10 @@ def test_rollout_teacher_forced_matches_reference_env(qs, name):
     env.reset()
     if "springs" in g.files:          # the fixture's spring draw (per-env arrays stay until the next reset)
         env._views["spring"][:] = cuda(g["springs"])[:, None]
+    if "masses" in g.files:           # the fixture's mass draw and friction
+        m = g["masses"]
+        env.robot.set_masses(leg_masses=m[:3], base_mass=m[3], offset_mass=m[4], offset_position=m[5:8])
+        env._views["mu"][:] = float(g["mu"])
     if cfg["task_env"] != "NO_TASK":  # the task remembers the settled height of ITS reset; take the fixture's
         env._views["task"][6] = float(g["init_task"][3])
     n_steps = len(g["reward"])
@@ -602,3 +607,108 @@ def test_spring_randomizer_draws_and_settles_on_them(qs):
                                       env_randomizer_mode="SPRING_RANDOMIZER", **cfg)
     env_b.reset()
     assert torch.equal(env_b._views["spring"], torch.as_tensor(sp, device="cuda"))
+
+
+# ------------------------------------------------------------------ 8f rank 2 (masses): EnvRandomizerMasses inside reset
+def test_mass_randomizer_draws_and_settles_on_them(qs):
+    """MASS_RANDOMIZER = [ground, masses] (env_randomizer_collection.py:17): hip / thigh / calf link masses within +-10 %
+    (the same for the four legs), a block of U[0, 1) kg at U[+-(0.1, 0, 0.1)] m on the trunk, trunk mass such that the
+    total stays 12.01301 kg (env_randomizer.py:56-84), all BEFORE the settle: an oracle env given the same masses and
+    friction settles to the same state and steps alike; the feet carry the total weight."""
+    from oracle import oracle as O
+    n = 256
+    cfg = dict(enable_springs=True, task_env="JUMPING_IN_PLACE", observation_space_mode="ARS_BASIC")
+    env = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=11, enable_noise=False, auto_reset=False,
+                                    env_randomizer_mode="MASS_RANDOMIZER", **cfg)
+    obs = env.reset()
+    md = env._views["mass_draw"].cpu().numpy().astype(np.float64)     # hip, thigh, calf, trunk, block, pos3
+    ratio = md[:3] / np.array([0.591, 0.92, 0.131])[:, None]
+    assert (ratio > 0.9 - 1e-6).all() and (ratio < 1.1 + 1e-6).all() and ratio.std(axis=1).min() > 0.04
+    assert (md[4] >= 0).all() and (md[4] < 1).all() and md[4].std() > 0.2
+    assert (np.abs(md[5]) <= 0.1 + 1e-7).all() and (md[6] == 0).all() and (np.abs(md[7]) <= 0.1 + 1e-7).all()
+    assert md[5].std() > 0.04 and md[7].std() > 0.04
+    assert np.abs(np.corrcoef(np.vstack([ratio, md[4:6], md[7:8]]))[np.triu_indices(6, 1)]).max() < 0.25
+    np.testing.assert_allclose(md[3] + md[4] + 4 * md[:3].sum(0) + 0.24, 12.01301, atol=2e-5)   # _change_base_mass :56-60
+    np.testing.assert_allclose(env.robot.get_offset_mass_value().cpu().numpy(), md[4], atol=0)
+    total = env._views["foot_force"].sum(0).cpu().numpy()
+    np.testing.assert_allclose(total, 12.01301 * 9.8, rtol=5e-3)      # the settled feet carry the (unchanged) total weight
+    mu = env._views["mu"].cpu().numpy()
+    S = env.get_state().cpu().numpy()
+    a = np.random.default_rng(0).uniform(-1, 1, size=(5, 6))
+
+    def oracle_env(i):
+        o = O.Env(**cfg)
+        for leg in range(4):
+            for j in range(3):
+                o.world.set_mass(2 + 4 * leg + j, md[j, i])
+        o.world.set_mass(0, md[3, i])
+        o.world.set_payload(md[4, i], md[5:8, i])
+        return o
+
+    heavy = int(np.argmax(md[4] * np.abs(md[5])))      # the most lopsided payload of the batch
+    refs = []
+    for i in (0, heavy):
+        o = oracle_env(i)
+        ref_obs = o.reset(mu=float(mu[i]))
+        np.testing.assert_allclose(S[i], o.world.get_state(), atol=1e-3)
+        np.testing.assert_allclose(obs[i].cpu().numpy(), ref_obs, atol=1e-3)
+        refs.append(o)
+    nominal = O.Env(**cfg)
+    nominal.reset(mu=float(mu[heavy]))
+    assert np.abs(S[heavy, :7] - nominal.world.get_state()[:7]).max() > 5e-4     # the payload shows in the settled pose
+    for t in range(5):
+        ob, r, d, _ = env.step(cuda(a[t]).expand(n, -1))
+        for i, o in zip((0, heavy), refs):
+            ro, rr, rd, _ = o.step(a[t])
+            np.testing.assert_allclose(ob[i].cpu().numpy(), ro, atol=5e-2)
+            np.testing.assert_allclose(env.robot.GetMotorAngles()[i].cpu().numpy(), o.world.get_state()[13:25], atol=2e-3)
+    # a new episode draws again; the same (seed, env, episode) draws the same
+    env.reset()
+    md2 = env._views["mass_draw"].cpu().numpy()
+    assert np.abs(md2[4] - md[4]).max() > 0.3
+    env_b = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=11, enable_noise=False, auto_reset=False,
+                                      env_randomizer_mode="MASS_RANDOMIZER", **cfg)
+    env_b.reset()
+    np.testing.assert_array_equal(env_b._views["mass_draw"].cpu().numpy(), md.astype(np.float32))
+
+
+def test_mass_randomizer_single_tick_matches_oracle_fp64(qs):
+    """the per-env mass properties in the tick itself: fp64 instantiation of the kernels' formulation against the oracle
+    (un-merged 19-link ABA with the welded block) from a random airborne and a standing state, same masses."""
+    from oracle import oracle as O
+    n = 64
+    env = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=3, enable_noise=False, auto_reset=False, env_randomizer_mode="MASS_RANDOMIZER",
+                                    enable_springs=True, task_env="JUMPING_IN_PLACE", observation_space_mode="ARS_BASIC")
+    env.reset()
+    md = env._views["mass_draw"].cpu().numpy().astype(np.float64)
+    rng = np.random.default_rng(5)
+    S = env.get_state().cpu().numpy().astype(np.float64)
+    S[: n // 2, 2] += 0.3                                   # first half airborne
+    S[:, 13:25] += rng.normal(size=(n, 12)) * 0.1
+    S[:, 7:13] = rng.normal(size=(n, 6)) * 0.3
+    S[:, 25:] = rng.normal(size=(n, 12)) * 1.0
+    tau = rng.uniform(-8, 8, size=(n, 12))
+    mu = env._views["mu"].cpu().numpy()
+    sl = (slice(0, 3), slice(3, 7), slice(7, 10), slice(10, 13), slice(13, 25), slice(25, 37))
+    for use64, tol in ((True, TOL_F64), (False, TOL_F32)):
+        env.set_state(cuda(S))
+        env._views["contact"][:] = 0
+        env._views["foot_force"][:] = 0
+        env.debug_ticks(cuda(tau), n_ticks=1, use_f64=use64)
+        got = env.get_state().cpu().numpy()
+        for i in (0, 1, n // 2, n - 1):
+            w = O.World(mu_ground=float(mu[i]))
+            for leg in range(4):
+                for j in range(3):
+                    w.set_mass(2 + 4 * leg + j, md[j, i])
+            w.set_mass(0, md[3, i])
+            w.set_payload(md[4, i], md[5:8, i])
+            w.set_state(S[i].astype(np.float32).astype(np.float64))
+            w.step(tau[i].astype(np.float32).astype(np.float64))
+            ref = w.get_state()
+            for s, t in zip(sl, tol):      # 3x: the mass properties themselves are stored in fp32
+                assert np.abs(got[i][s] - ref[s]).max() < 3 * t, (i, use64, s, np.abs(got[i][s] - ref[s]).max())
+            wn = O.World(mu_ground=float(mu[i]))
+            wn.set_state(S[i].astype(np.float32).astype(np.float64))
+            wn.step(tau[i].astype(np.float32).astype(np.float64))
+            assert np.abs(wn.get_state()[25:] - ref[25:]).max() > 1e-3      # the nominal model gives a different answer

@@ -99,7 +99,7 @@ QS_DEVONLY void load_springs(const DeviceView& D, int env, float* sk, float* sb,
 constexpr int QS_BLOCK = 128;
 using StepScratch = Scratch<float, QS_BLOCK>;
 
-template <bool kContacts>
+template <bool kContacts, bool kEM>
 __device__ __forceinline__ int run_ticks(EnvState<float>& st, ContactState<float>& cs, const float* cmd,
                                          bool torque_mode, int t0, int n_ticks, int env, const DeviceView& D,
                                          const EnvCfg& C, const RobotConst& RC, const ModelConstT<float>& M,
@@ -119,8 +119,8 @@ __device__ __forceinline__ int run_ticks(EnvState<float>& st, ContactState<float
     if (bail == n_ticks) {
       float tau[12];
       tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s, custom);
-      const int r = physics_tick<float, kContacts, QS_BLOCK>(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1), scr,
-                                                             EnvModelRef{C.mass_randomizer ? D.model : nullptr, D.n, env});
+      const int r = physics_tick<float, kContacts, QS_BLOCK, kEM>(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1), scr,
+                                                             EnvModelRef{D.model, D.n, env});
       if (r != TICK_DONE) { bail = t; *why = r; }
     }
   }
@@ -128,6 +128,7 @@ __device__ __forceinline__ int run_ticks(EnvState<float>& st, ContactState<float
 }
 
 // same loop on the general solver (joint limits, every collision shape); rare path
+template <bool kEM>
 __device__ __noinline__ void run_ticks_general(EnvState<float>& st, ContactState<float>& cs, const float* cmd,
                                                bool torque_mode, int t0, int n_ticks, int env, const DeviceView& D,
                                                const EnvCfg& C, const RobotConst& RC, const ModelConstT<float>& M,
@@ -139,7 +140,7 @@ __device__ __noinline__ void run_ticks_general(EnvState<float>& st, ContactState
   for (int t = t0; t < n_ticks; t++) {
     float tau[12];
     tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s, custom);
-    physics_tick_general(st, tau, mu, cs, M, SC, EnvModelRef{C.mass_randomizer ? D.model : nullptr, D.n, env});
+    physics_tick_general<float, kEM>(st, tau, mu, cs, M, SC, EnvModelRef{D.model, D.n, env});
   }
 }
 

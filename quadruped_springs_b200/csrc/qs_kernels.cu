@@ -127,7 +127,7 @@ k_debug_ticks(const __grid_constant__ DebugArgs<T> A, const float* __restrict__ 
   for (int t = 0; t < n_ticks; t++)
     {
     const EnvModelRef em{A.mass_randomizer ? D.model : nullptr, D.n, env};
-    if (physics_tick<T>(st, t12, mu, cs, A.M, A.SC, true, scr, em)) physics_tick_general<T>(st, t12, mu, cs, A.M, A.SC, em);
+    if (physics_tick<T, true, 0, true>(st, t12, mu, cs, A.M, A.SC, true, scr, em)) physics_tick_general<T, true>(st, t12, mu, cs, A.M, A.SC, em);
   }
 #pragma unroll
   for (int i = 0; i < 3; i++) { sf.pos[i] = float(st.pos[i]); sf.vlin[i] = float(st.vlin[i]); sf.vang[i] = float(st.vang[i]); }
@@ -578,11 +578,16 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   }
   {
     const int max_smem = int(smem_of(256));
-    e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_contact, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_settle_urgent, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_settle_slice, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    e = cudaFuncSetAttribute(k_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_reset<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_contact<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_step_contact<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_settle_urgent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_settle_urgent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_settle_slice<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_settle_slice<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_debug_ticks<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    int(64 * QS_TICK_SCRATCH * sizeof(double)));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_debug_ticks<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -735,7 +740,7 @@ static int launch_conveyor(qs_handle h, cudaStream_t s, int phase, int flush) {
 }
 static int launch_slice(qs_handle h, cudaStream_t s, int early) {
   const int B = block_of(h);
-  k_settle_slice<<<h->wave_blocks, B, smem_of(B), s>>>(h->args, h->cv, early);
+  if (h->args.C.mass_randomizer) k_settle_slice<true><<<h->wave_blocks, B, smem_of(B), s>>>(h->args, h->cv, early); else k_settle_slice<false><<<h->wave_blocks, B, smem_of(B), s>>>(h->args, h->cv, early);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return QS_OK;
@@ -749,10 +754,10 @@ int qs_reset(qs_handle h, const uint8_t* mask, float* obs, void* stream) {
   if (mask) {
     CUDA_TRY(cudaMemsetAsync(h->reset_list + h->n, 0, sizeof(int), s));
     k_compact<<<grid_for(h->n, 256), 256, 0, s>>>(mask, h->n, h->reset_list);
-    k_reset<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, h->reset_list, h->cv, obs);
+    if (h->args.C.mass_randomizer) k_reset<true><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, h->reset_list, h->cv, obs); else k_reset<false><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, h->reset_list, h->cv, obs);
     g_launches += 2;
   } else {
-    k_reset<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, nullptr, h->cv, obs);
+    if (h->args.C.mass_randomizer) k_reset<true><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, nullptr, h->cv, obs); else k_reset<false><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, nullptr, h->cv, obs);
     g_launches += 1;
   }
   CUDA_TRY(cudaGetLastError());
@@ -803,13 +808,13 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   io.cv = h->cv;
   const int slot = int(h->n_steps % qs_env::kRing);
   cudaEventRecord(h->ev0[slot], s);
-  k_step<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
+  if (h->args.C.mass_randomizer) k_step<true><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io); else k_step<false><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
   if (h->cfg.auto_reset) {
     // conveyor, early slice: on the second stream, next to k_step_contact (about half a wave of blocks)
     if (int e = launch_conveyor(h, s, 0, 0)) return e;
     CUDA_TRY(cudaEventRecord(h->ev_fork0, s));
   }
-  k_step_contact<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
+  if (h->args.C.mass_randomizer) k_step_contact<true><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io); else k_step_contact<false><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
   g_launches += 1;
   cudaEventRecord(h->ev1[slot], s);
   h->n_steps++;
@@ -824,7 +829,7 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   }
   // envs parked for the general solver (joint limits / body contacts); launched before the slice so
   // that its few blocks are placed first
-  k_step_slow<<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread);
+  if (h->args.C.mass_randomizer) k_step_slow<true><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread); else k_step_slow<false><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread);
   g_launches += 2;
   if (host) {
     // the step's outputs are final here (only an urgent settle, below, rewrites obs rows: the caller checks
@@ -846,7 +851,7 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
     CUDA_TRY(cudaEventRecord(h->ev_join, h->bg));
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
     // envs that finished without a settled slot (rare): settled and started now
-    k_settle_urgent<<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, h->cv, obs);
+    if (h->args.C.mass_randomizer) k_settle_urgent<true><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, h->cv, obs); else k_settle_urgent<false><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, h->cv, obs);
     k_urgent_clear<<<1, 1, 0, s>>>(h->cv);
     g_launches += 2;
   }

@@ -207,8 +207,8 @@ template <typename T> QS_DEV void link_rotations(const LegKin<T>& K, T* RH, T* R
 }
 
 // body 0 (base + trunk + imu, plus the payload block when the masses are randomized) about the base origin
-template <typename T> QS_DEV void trunk_spi(const ModelConstT<T>& M, const EnvModelRef& em, SpI<T>& tot) {
-  if (em.base) {
+template <typename T, bool kEM> QS_DEV void trunk_spi(const ModelConstT<T>& M, const EnvModelRef& em, SpI<T>& tot) {
+  if (kEM && em.base) {
     tot.m = em_get<T>(em, EM_TRUNK_M);
 #pragma unroll
     for (int i = 0; i < 3; i++) tot.h[i] = em_get<T>(em, EM_TRUNK_H + i);
@@ -227,14 +227,14 @@ template <typename T> QS_DEV void trunk_spi(const ModelConstT<T>& M, const EnvMo
 // Bm = M_kk^-1 F_k (3x6), ev = M_kk^-1 (tau - h) + B_lin (w x v); accumulates the
 // Schur complement S6 -= F^T B, the base force fb += f_leg + F^T d and the
 // composite inertia tot += I_leg.
-template <typename T>
+template <typename T, bool kEM>
 QS_DEV void leg_dynamics(int k, const T* q, const T* qd, const T* tau3, const TickCtx<T>& X, const ModelConstT<T>& M,
                          const LegKin<T>& K, const T* RH, const T* RT, const T* RC, T* Mi, T* Bm, T* ev, T* S6, T* fb,
                          SpI<T>& tot, const EnvModelRef& em) {
   const T* wb = X.wb;
   const T* vb = X.vb;
   SpI<T> Ih, It, Ic;
-  if (em.base) {  // randomized masses: changeDynamics(mass=) keeps each link's inertia diagonal and inertial frame
+  if (kEM && em.base) {  // randomized masses: changeDynamics(mass=) keeps each link's inertia diagonal and inertial frame
     T cc[3], ci[6];
 #pragma unroll
     for (int i = 0; i < 3; i++) cc[i] = em_get<T>(em, EM_CALF_COM + i);
@@ -502,7 +502,8 @@ template <typename T> QS_DEV void leg_kin_from_sc(int k, const T* sc, const Mode
 // shape on the ground) or, for the kContacts = false variant (no foot-contact code at all: the flight
 // kernel), TICK_NEEDS_CONTACT when a foot is within its contact threshold.
 enum { TICK_DONE = 0, TICK_NEEDS_GENERAL = 1, TICK_NEEDS_CONTACT = 2 };
-template <typename T, bool kContacts = true, int kStride = 0>
+// kEM: read the per-env mass properties `em` (compiled out of the default kernels)
+template <typename T, bool kContacts = true, int kStride = 0, bool kEM = false>
 __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
                                      const ModelConstT<T>& M, const SolverConst& SC, bool detect_invalid,
                                      const Scratch<T, kStride>& scr, const EnvModelRef em = EnvModelRef{nullptr, 0, 0}) {
@@ -516,7 +517,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
 
   // composite inertia of the whole robot and Newton-Euler base force, trunk first
   SpI<T> tot;
-  trunk_spi(M, em, tot);
+  trunk_spi<T, kEM>(M, em, tot);
   T fb[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
   body_force(tot, X.wb, X.vb, zero3, X.A0, fb, fb + 3);
   T S6[21];
@@ -548,7 +549,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
     leg_kin(k, q, M, K);
     T RH[9], RT[9], RC[9], Mi[6], Bm[18], ev[3];
     link_rotations(K, RH, RT, RC);
-    leg_dynamics(k, q, qd, tk, X, M, K, RH, RT, RC, Mi, Bm, ev, S6, fb, tot, em);
+    leg_dynamics<T, kEM>(k, q, qd, tk, X, M, K, RH, RT, RC, Mi, Bm, ev, S6, fb, tot, em);
 #pragma unroll
     for (int i = 0; i < 18; i++) scr(k, SCR_BM + i) = Bm[i];
 #pragma unroll
@@ -851,7 +852,7 @@ QS_DEV void body_point_jac(const LegKin<T>& K, int level, const T* pc, const T* 
   if (level < 1) Jk[1] = T(0);
 }
 
-template <typename T>
+template <typename T, bool kEM = false>
 __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
                                               const ModelConstT<T>& M, const SolverConst& SC,
                                               const EnvModelRef em = EnvModelRef{nullptr, 0, 0}) {
@@ -862,7 +863,7 @@ __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T m
   const T* nb = X.nb;
   const T zero3[3] = {T(0), T(0), T(0)};
   SpI<T> tot;
-  trunk_spi(M, em, tot);
+  trunk_spi<T, kEM>(M, em, tot);
   T fb[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
   body_force(tot, X.wb, X.vb, zero3, X.A0, fb, fb + 3);
   T S6[21];
@@ -894,7 +895,7 @@ __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T m
     leg_kin(k, st.q + 3 * k, M, K[k]);
     T RH[9], RT[9], RC[9];
     link_rotations(K[k], RH, RT, RC);
-    leg_dynamics(k, st.q + 3 * k, st.qd + 3 * k, tau + 3 * k, X, M, K[k], RH, RT, RC, Mi[k], Bm[k], ev[k], S6, fb, tot, em);
+    leg_dynamics<T, kEM>(k, st.q + 3 * k, st.qd + 3 * k, tau + 3 * k, X, M, K[k], RH, RT, RC, Mi[k], Bm[k], ev[k], S6, fb, tot, em);
     T zh, zt, zc;
     leg_shape_gaps(st, X, M, K[k], RT, RC, &zh, &zt, &zc);
     if (zh < M.hip_thresh) {  // lowest point of the lower rim of the hip cylinder (axis a2)

@@ -380,14 +380,15 @@ __device__ __forceinline__ void episode_model_store(const EnvCfg& C, uint64_t gi
 // Settle ticks [t0, t1) of the reset (control_interface/interface_base.py:182-200), at most `span` of them.
 // Every thread of the block runs the same `span` iterations (one barrier each, see run_ticks);
 // a thread works while t < t1.
+template <bool kEM>
 __device__ __forceinline__ void settle_ticks(const KernelArgs& A, uint64_t gid, uint32_t epoch, EnvState<float>& st,
                                              ContactState<float>& cs, float mu, int t0, int t1, int span, float* tau_m,
                                              float* tau_s, const StepScratch& scr, float* em_base, int em_stride, int em_idx) {
   const EnvCfg& C = A.C;
   // randomize_env() comes before the settle (quadruped_gym_env.py:286-289): the episode's masses, in the column
   // (em_base, em_stride, em_idx) -- the env's own rows, or the conveyor's for an episode settled ahead
-  if (C.mass_randomizer && t1 > t0) episode_model_store(C, gid, epoch, em_base, em_stride, em_idx, nullptr);
-  const EnvModelRef em{C.mass_randomizer ? em_base : nullptr, em_stride, em_idx};
+  if (kEM && t1 > t0) episode_model_store(C, gid, epoch, em_base, em_stride, em_idx, nullptr);
+  const EnvModelRef em{em_base, em_stride, em_idx};
   float cmd[12], act12[12];
   settle_command(C, A.RC, cmd, act12);
   // a fresh Quadruped has the default gains / springs (quadruped_gym_env.py:299-319); the settle
@@ -416,7 +417,7 @@ __device__ __forceinline__ void settle_ticks(const KernelArgs& A, uint64_t gid, 
         for (int j = 0; j < 3; j++) tau[3 * k + j] += tau_s[3 * k + j];
       }
     }
-    physics_tick<float, true, QS_BLOCK>(st, tau, mu, cs, A.M, SCs, t == nsettle - 1, scr, em);
+    physics_tick<float, true, QS_BLOCK, kEM>(st, tau, mu, cs, A.M, SCs, t == nsettle - 1, scr, em);
   }
 }
 
@@ -441,6 +442,7 @@ __device__ __forceinline__ void command_to_action_space(const EnvCfg& C, const R
 }
 
 // A fresh robot settled for episode `epoch` of global env `gid`, start to end.
+template <bool kEM>
 __device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint64_t gid, uint32_t epoch,
                                              EnvState<float>& st, ContactState<float>& cs, float* tau_m, float* tau_s,
                                              float* mu_out, const StepScratch& scr, bool need) {
@@ -455,12 +457,13 @@ __device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint6
 #pragma unroll
   for (int i = 0; i < 12; i++) { tau_m[i] = 0.f; tau_s[i] = 0.f; }
   const int nsettle = settle_length(A.C);
-  settle_ticks(A, gid, epoch, st, cs, mu, 0, need ? nsettle : 0, nsettle, tau_m, tau_s, scr, A.D.model, A.D.n, env);
+  settle_ticks<kEM>(A, gid, epoch, st, cs, mu, 0, need ? nsettle : 0, nsettle, tau_m, tau_s, scr, A.D.model, A.D.n, env);
   if (!need) { st = st_keep; cs = cs_keep; }
 }
 
 // Everything QuadrupedGymEnv.reset does after the settle (quadruped_gym_env.py:282-297),
 // from a settled state: counters, task._reset, sensors, filter history; writes the env back.
+template <bool kEM>
 __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint32_t epoch, float mu,
                                               const EnvState<float>& st, const ContactState<float>& cs,
                                               const float* tau_m, const float* tau_s, float* obs) {
@@ -478,7 +481,7 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
   }
 #pragma unroll
   for (int i = 0; i < 12; i++) { D.kp[i * n + env] = A.RC.kp[i]; D.kd[i * n + env] = A.RC.kd[i]; }
-  if (C.mass_randomizer) episode_model_store(C, uint64_t(C.gid0 + env), epoch, D.model, n, env, D.mass_draw);
+  if (kEM) episode_model_store(C, uint64_t(C.gid0 + env), epoch, D.model, n, env, D.mass_draw);
   float sk[3], sb[3], sr[3];
   episode_springs(C, A.RC, uint64_t(C.gid0 + env), epoch, sk, sb, sr);
 #pragma unroll
@@ -521,6 +524,7 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
 }
 
 // Epilogue of a control step (quadruped_gym_env.py:239-256) + write-back + auto-reset.
+template <bool kEM>
 __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& io, int env, EnvState<float>& st,
                                             ContactState<float>& cs, const float* tau_m, const float* tau_s) {
   const DeviceView& D = A.D;
@@ -619,7 +623,7 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
       conveyor_push(io.cv, env, epoch + QS_SLOTS);  // the freed slot's next tenant
       atomicAdd(io.cv.ctl + CV_TAKEN, 1u);           // feedback for the slice length (k_conveyor_ctl)
       if (!slot_ready(D, env, epoch + 1)) atomicAdd(io.cv.ctl + CV_LOW2, 1u);
-      begin_episode(A, env, epoch, mu, st, cs, tm, tsp, io.obs);
+      begin_episode<kEM>(A, env, epoch, mu, st, cs, tm, tsp, io.obs);
     } else {
       // no spare slot ready: an urgent entry makes k_settle_urgent (launched at the end of this step)
       // settle this episode now and start it; same numbers as the prefetched path
@@ -658,6 +662,7 @@ __device__ __forceinline__ void park_env(const KernelArgs& A, const StepIO& io, 
 }
 
 // -------------------------------------------------------------------- K1: step
+template <bool kEM>
 __global__ void __launch_bounds__(256, 1)
 k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -761,7 +766,7 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
   const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
   int why;
   const bool grounded = (cs.mask & 15) != 0;  // standing / pushing: straight to the contact kernel
-  const int t_done = run_ticks<false>(st, cs, cmd, torque_mode, 0, C.action_repeat, env, D, C, A.RC, A.M, A.SC, tau_m, tau_s,
+  const int t_done = run_ticks<false, kEM>(st, cs, cmd, torque_mode, 0, C.action_repeat, env, D, C, A.RC, A.M, A.SC, tau_m, tau_s,
                                       true, scr, &why, grounded);
   if (!live) return;
   if (t_done < C.action_repeat) {
@@ -769,12 +774,13 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
     park_env(A, io, env, st, cs, cmd, t_done, why == TICK_NEEDS_GENERAL ? io.slow_list : io.contact_list, !grounded);
     return;
   }
-  finish_step(A, io, env, st, cs, tau_m, tau_s);
+  finish_step<kEM>(A, io, env, st, cs, tau_m, tau_s);
 }
 
 // -------------------------------------------------------------------- K1a: envs with foot contacts
 // Resumes the envs the flight kernel handed over (dense warps: thread i takes contact_list[i]) with
 // the full fast tick; joint limits / body contacts still go on to k_step_slow.
+template <bool kEM>
 __global__ void __launch_bounds__(256, 1)
 k_step_contact(const __grid_constant__ KernelArgs A, const StepIO io) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -795,17 +801,18 @@ k_step_contact(const __grid_constant__ KernelArgs A, const StepIO io) {
   extern __shared__ float qs_smem[];
   const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
   int why;
-  const int t_done = run_ticks<true>(st, cs, cmd, torque_mode, D.resume_tick[env], C.action_repeat, env, D, C, A.RC, A.M,
+  const int t_done = run_ticks<true, kEM>(st, cs, cmd, torque_mode, D.resume_tick[env], C.action_repeat, env, D, C, A.RC, A.M,
                                      A.SC, tau_m, tau_s, true, scr, &why);
   if (!live) return;
   if (t_done < C.action_repeat) {
     park_env(A, io, env, st, cs, cmd, t_done, io.slow_list);
     return;
   }
-  finish_step(A, io, env, st, cs, tau_m, tau_s);
+  finish_step<kEM>(A, io, env, st, cs, tau_m, tau_s);
 }
 
 // -------------------------------------------------------------------- K1b: general-solver continuation
+template <bool kEM>
 __global__ void __launch_bounds__(64)
 k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io, int spread) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -830,14 +837,15 @@ k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io, int spread) {
 #pragma unroll
   for (int i = 0; i < 12; i++) cmd[i] = D.cmd[i * n + env];
   const bool torque_mode = !A.C.is_rl && A.C.control_mode == QS_CTRL_TORQUE;
-  run_ticks_general(st, cs, cmd, torque_mode, D.resume_tick[env], A.C.action_repeat, env, D, A.C, A.RC, A.M, A.SC,
+  run_ticks_general<kEM>(st, cs, cmd, torque_mode, D.resume_tick[env], A.C.action_repeat, env, D, A.C, A.RC, A.M, A.SC,
                     tau_m, tau_s);
-  finish_step(A, io, env, st, cs, tau_m, tau_s);
+  finish_step<kEM>(A, io, env, st, cs, tau_m, tau_s);
 }
 
 // -------------------------------------------------------------------- K2: reset + settle
 // list == nullptr: thread i resets env i (all envs).  Otherwise thread i resets env list[i]
 // for i < list[n] (dense warps whatever the done pattern).
+template <bool kEM>
 __global__ void __launch_bounds__(256, 1)
 k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, const Conveyor cv,
         float* __restrict__ obs) {
@@ -859,7 +867,7 @@ k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, cons
   extern __shared__ float qs_smem[];
   const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
   float tm2[12], ts2[12];
-  settle_fresh(A, env, gid, epoch, st, cs, tm2, ts2, &mu, scr, !have);
+  settle_fresh<kEM>(A, env, gid, epoch, st, cs, tm2, ts2, &mu, scr, !have);
   if (have) {
     slot_load(D, env, epoch, st, cs, tau_m, tau_s, &mu, A.SC.dt);
   } else {
@@ -875,11 +883,12 @@ k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, cons
     for (int d = 1; d <= QS_SLOTS; d++)
       if (!slot_ready(D, env, epoch + d)) conveyor_push(cv, env, epoch + d);
   }
-  begin_episode(A, env, epoch, mu, st, cs, tau_m, tau_s, obs);
+  begin_episode<kEM>(A, env, epoch, mu, st, cs, tau_m, tau_s, obs);
 }
 
 // Episodes of envs that finished without a ready slot: settled start to end and started, in stream
 // order at the end of the step.  Exits at once when there is none (the usual case).
+template <bool kEM>
 __global__ void __launch_bounds__(256, 1)
 k_settle_urgent(const __grid_constant__ KernelArgs A, const Conveyor cv, float* __restrict__ obs) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -895,13 +904,13 @@ k_settle_urgent(const __grid_constant__ KernelArgs A, const Conveyor cv, float* 
   float tau_m[12], tau_s[12], mu = 0.f;
   extern __shared__ float qs_smem[];
   const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
-  settle_fresh(A, env, uint64_t(A.C.gid0 + env), epoch, st, cs, tau_m, tau_s, &mu, scr, live);
+  settle_fresh<kEM>(A, env, uint64_t(A.C.gid0 + env), epoch, st, cs, tau_m, tau_s, &mu, scr, live);
   if (!live) return;
   // its ring: the slot of this episode never became ready, the others may be missing too
 #pragma unroll
   for (int d = 1; d <= QS_SLOTS; d++)
     if (!slot_ready(D, env, epoch + d)) conveyor_push(cv, env, epoch + d);
-  begin_episode(A, env, epoch, mu, st, cs, tau_m, tau_s, obs);
+  begin_episode<kEM>(A, env, epoch, mu, st, cs, tau_m, tau_s, obs);
 }
 __global__ void k_urgent_clear(Conveyor cv) {
   cv.ctl[CV_URGENT_LAST] = cv.ctl[CV_URGENT];
@@ -986,6 +995,7 @@ __global__ void k_conveyor_ctl(Conveyor cv, int phase, const int* __restrict__ b
 
 // One slice of the conveyor: entry tail + j advances by ctl[CV_SLICE] settle ticks; an entry that
 // reaches the end of its settle stores the episode's slot and retires.
+template <bool kEM>
 __global__ void __launch_bounds__(256, 1)
 k_settle_slice(const __grid_constant__ KernelArgs A, const Conveyor cv, int early) {
   const DeviceView& D = A.D;
@@ -1019,7 +1029,7 @@ k_settle_slice(const __grid_constant__ KernelArgs A, const Conveyor cv, int earl
   const int t1 = need ? min(t0 + span, nsettle) : 0;
   extern __shared__ float qs_smem[];
   const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
-  settle_ticks(A, uint64_t(A.C.gid0 + env), epoch, st, cs, mu, t0, t1, span, tau_m, tau_s, scr, cv.model, cv.width, col);
+  settle_ticks<kEM>(A, uint64_t(A.C.gid0 + env), epoch, st, cs, mu, t0, t1, span, tau_m, tau_s, scr, cv.model, cv.width, col);
   if (!need) return;
   {  // work counters of the bench's flop model, one atomic per warp
     const unsigned m = __activemask();

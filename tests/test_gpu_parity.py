@@ -712,3 +712,28 @@ def test_mass_randomizer_single_tick_matches_oracle_fp64(qs):
             wn.set_state(S[i].astype(np.float32).astype(np.float64))
             wn.step(tau[i].astype(np.float32).astype(np.float64))
             assert np.abs(wn.get_state()[25:] - ref[25:]).max() > 1e-3      # the nominal model gives a different answer
+
+
+def test_curriculum_randomizer_ranges(qs):
+    """TEST_RANDOMIZER_CURRICULUM = [ground, masses-curriculum, springs-curriculum] (env_randomizer_collection.py:20): the
+    draw ranges are interpolated by the curriculum level (env_randomizer.py:148-169,242-262): leg masses +-10 % -> +-20 %,
+    block 1 kg -> 4 kg at +-0.1 m -> +-0.2 m, springs +-10 % -> +-30 %; TEST_RANDOMIZER is level 0 of the same."""
+    cfg = dict(enable_springs=True, task_env="JUMPING_IN_PLACE", observation_space_mode="ARS_BASIC", enable_noise=False,
+               auto_reset=False, num_envs=2048, seed=4)
+    nominal_m, nominal_s = np.array([0.591, 0.92, 0.131])[:, None], np.array([20, 20, 30, 0.3, 0.3, 0.3])[:, None]
+    for mode, lvl, leg, pay, pos, spr in (("TEST_RANDOMIZER", 0.0, 0.1, 1.0, 0.1, 0.1),
+                                          ("TEST_RANDOMIZER_CURRICULUM", 0.5, 0.15, 2.5, 0.15, 0.2),
+                                          ("TEST_RANDOMIZER_CURRICULUM", 1.0, 0.2, 4.0, 0.2, 0.3)):
+        env = qs.BatchedQuadrupedGymEnv(env_randomizer_mode=mode, curriculum_level=lvl, **cfg)
+        obs = env.reset()
+        assert torch.isfinite(obs).all() and env.get_curriculum_level() == lvl
+        md = env._views["mass_draw"].cpu().numpy().astype(np.float64)
+        sp = env._views["spring"].cpu().numpy().astype(np.float64)
+        for x, rng_ in ((md[:3] / nominal_m - 1, leg), (sp[:6] / nominal_s - 1, spr), (md[5:6] , pos), (md[7:8], pos)):
+            assert np.abs(x).max() <= rng_ * (1 + 1e-5) and np.abs(x).max() > 0.9 * rng_ and abs(x.mean()) < 0.1 * rng_
+        assert 0 <= md[4].min() and 0.9 * pay < md[4].max() < pay
+        np.testing.assert_allclose(md[3] + md[4] + 4 * md[:3].sum(0) + 0.24, 12.01301, atol=2e-5)
+        total = env._views["foot_force"].sum(0).cpu().numpy()
+        np.testing.assert_allclose(total, 12.01301 * 9.8, rtol=1e-2)       # every robot settled standing on its feet
+        mu = env._views["mu"].cpu().numpy()
+        assert mu.min() >= 0.5 and mu.max() < 1.0 and mu.std() > 0.1      # the ground randomizer comes first (:17-20)

@@ -160,6 +160,8 @@ typedef struct qs_state_ptrs {
   float* rest;         /* [14][N] go-to-rest: h_actual, sim step of activation, start action[12] */
   float* mass_draw;    /* [8][N] mass randomizer, current episode: hip, thigh, calf link mass, trunk mass, block mass, block
                         * position[3] (Quadruped.GetLegMasses / get_offset_mass_value / get_offset_mass_position) */
+  float* filt;         /* [4][12][N] action-filter history x[t-1], x[t-2], y[t-1], y[t-2] (utils/action_filter.py:110-127);
+                        * y[t-1] is env.get_last_filtered_action() when the filter is on */
   uint32_t* work;      /* [3][N] per-env work counters of the step kernels: physics ticks, foot-contact ticks,
                         * contact x PGS-sweep count (cumulative; bench / diagnostics) */
 } qs_state_ptrs;
@@ -204,6 +206,12 @@ int qs_apply_masses(qs_handle h, void* stream);
  * stable-baselines3 VecEnv the reference is trained through (load_model.py:109-113 make_vec_env -> DummyVecEnv);
  * rows of envs that did not finish are left untouched. */
 int qs_set_terminal_obs(qs_handle h, float* term_obs_dev);
+
+/* QuadrupedGymEnv.reset with env.set_robot_desired_state(...) (quadruped_gym_env.py:288-289,401; quadruped.py:470-471,
+ * 521-525; ReferenceStateInitializationWrapper): the masked envs (all when mask == NULL) start a new episode from the
+ * given physical state, rows of states_dev [N, 37] = pos3 quat4(xyzw) lin_vel3 ang_vel3 q12 qd12, WITHOUT the settle;
+ * _last_action is zero, the task is reset on that state.  obs_dev [N, O] (optional) gets their first observation. */
+int qs_reset_to_state(qs_handle h, const uint8_t* mask_dev, const float* states_dev, float* obs_dev, void* stream);
 
 /* qs_reset with HOST buffers: mask_host [N] bytes or NULL (all), obs_host [N, O] or NULL;
  * synchronises the stream. */

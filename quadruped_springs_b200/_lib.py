@@ -46,7 +46,7 @@ class QsConfig(C.Structure):
 class QsStatePtrs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "state", "tau_motor", "tau_spring", "kp", "kd", "spring", "mu", "foot_force", "contact", "task",
-        "last_action", "sim_steps", "env_steps", "ep_return", "custom_gains", "land_mode", "rest_active", "rest", "mass_draw", "work")]
+        "last_action", "sim_steps", "env_steps", "ep_return", "custom_gains", "land_mode", "rest_active", "rest", "mass_draw", "filt", "work")]
 
 
 def nvcc_path():
@@ -96,6 +96,7 @@ EXPORTS = {
     "qs_step_host": (C.c_int, [C.c_void_p] * 7),
     "qs_set_terminal_obs": (C.c_int, [C.c_void_p, C.c_void_p]),
     "qs_apply_masses": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "qs_reset_to_state": (C.c_int, [C.c_void_p] * 5),
     "qs_reset_host": (C.c_int, [C.c_void_p] * 4),
     "qs_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "qs_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

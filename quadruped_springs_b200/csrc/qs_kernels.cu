@@ -719,6 +719,7 @@ int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* o) {
   o->land_mode = D.land_mode;
   o->rest_active = D.rest_active; o->rest = D.rest;
   o->mass_draw = D.mass_draw;
+  o->filt = D.filt;
   o->work = D.work;
   return QS_OK;
 }
@@ -856,6 +857,26 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
     g_launches += 2;
   }
   CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_reset_to_state(qs_handle h, const uint8_t* mask, const float* states, float* obs, void* stream) {
+  if (!h) return fail(QS_ERR_ARG, "handle is NULL");
+  if (!states) return fail(QS_ERR_ARG, "states is NULL");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int* list = nullptr;
+  if (mask) {
+    CUDA_TRY(cudaMemsetAsync(h->reset_list + h->n, 0, sizeof(int), s));
+    k_compact<<<grid_for(h->n, 256), 256, 0, s>>>(mask, h->n, h->reset_list);
+    g_launches += 1;
+    list = h->reset_list;
+  }
+  if (h->args.C.mass_randomizer) k_reset_state<true><<<grid_for(h->n, 128), 128, 0, s>>>(h->args, list, states, h->cv, obs);
+  else k_reset_state<false><<<grid_for(h->n, 128), 128, 0, s>>>(h->args, list, states, h->cv, obs);
+  g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  if (!mask) h->was_reset = true;
   return QS_OK;
 }
 

@@ -466,7 +466,7 @@ __device__ __forceinline__ void settle_fresh(const KernelArgs& A, int env, uint6
 template <bool kEM>
 __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint32_t epoch, float mu,
                                               const EnvState<float>& st, const ContactState<float>& cs,
-                                              const float* tau_m, const float* tau_s, float* obs) {
+                                              const float* tau_m, const float* tau_s, float* obs, bool settled = true) {
   const DeviceView& D = A.D;
   const EnvCfg& C = A.C;
   const int n = D.n;
@@ -492,6 +492,10 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
   }
   float cmd[12], act12[12];
   settle_command(C, A.RC, cmd, act12);
+  if (!settled) {  // robot_desired_state: no settle, _last_action stays zero (quadruped_gym_env.py:284,288-289)
+#pragma unroll
+    for (int i = 0; i < 12; i++) act12[i] = 0.f;
+  }
   float Rb[9], rpy[3];
   quat_to_R(st.quat, Rb);
   rpy_from_quat(st.quat, rpy);
@@ -884,6 +888,42 @@ k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, cons
       if (!slot_ready(D, env, epoch + d)) conveyor_push(cv, env, epoch + d);
   }
   begin_episode<kEM>(A, env, epoch, mu, st, cs, tau_m, tau_s, obs);
+}
+
+// QuadrupedGymEnv.reset with robot_desired_state set (quadruped_gym_env.py:288-289, quadruped.py:470-471,521-525;
+// ReferenceStateInitializationWrapper): the robot is placed in the given state [N][37] and NOT settled.
+template <bool kEM>
+__global__ void __launch_bounds__(128)
+k_reset_state(const __grid_constant__ KernelArgs A, const int* __restrict__ list, const float* __restrict__ states,
+              const Conveyor cv, float* __restrict__ obs) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const DeviceView& D = A.D;
+  const int n = D.n;
+  const int count = list ? list[n] : n;
+  if (tid >= count) return;
+  const int env = list ? list[tid] : tid;
+  const uint32_t epoch = D.reset_count[env] + 1;
+  EnvState<float> st;
+  ContactState<float> cs;
+  fresh_state(A, st, cs);  // no contact points until the first stepSimulation
+  const float* s = states + size_t(env) * QS_STATE_DIM;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { st.pos[i] = s[i]; st.vlin[i] = s[7 + i]; st.vang[i] = s[10 + i]; }
+#pragma unroll
+  for (int i = 0; i < 4; i++) st.quat[i] = s[3 + i];
+#pragma unroll
+  for (int i = 0; i < 12; i++) { st.q[i] = s[13 + i]; st.qd[i] = s[25 + i]; }
+  float zero12[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) zero12[i] = 0.f;
+  if (A.C.auto_reset) {
+    // this episode's prefetched slot (if any) is skipped; the ring keeps the episodes after it
+    if (slot_ready(D, env, epoch)) D.slot_epoch[int(epoch % QS_SLOTS) * n + env] = 0;
+#pragma unroll
+    for (int d = 1; d <= QS_SLOTS; d++)
+      if (!slot_ready(D, env, epoch + d)) conveyor_push(cv, env, epoch + d);
+  }
+  begin_episode<kEM>(A, env, epoch, episode_mu(A.C, uint64_t(A.C.gid0 + env), epoch), st, cs, zero12, zero12, obs, false);
 }
 
 // Episodes of envs that finished without a ready slot: settled start to end and started, in stream

@@ -531,7 +531,7 @@ class BatchedQuadrupedGymEnv:
             "custom_gains": _view(ptrs.custom_gains, (n,), "|u1", dev),
             "land_mode": _view(ptrs.land_mode, (n,), "<i4", dev),
             "rest_active": _view(ptrs.rest_active, (n,), "<i4", dev), "rest": _view(ptrs.rest, (14, n), "<f4", dev),
-            "mass_draw": _view(ptrs.mass_draw, (8, n), "<f4", dev),
+            "mass_draw": _view(ptrs.mass_draw, (8, n), "<f4", dev), "filt": _view(ptrs.filt, (4, 12, n), "<f4", dev),
             "work": _view(ptrs.work, (3, n), "<i4", dev),
         }
         self.robot = BatchedQuadruped(self)
@@ -585,6 +585,25 @@ class BatchedQuadrupedGymEnv:
         if self._cfg.rest_mode:
             infos["rest_active"] = self._views["rest_active"]
         return self._obs, self._reward, self._done.bool(), infos
+
+    def reset_to_state(self, states, mask=None):
+        """reset() with `set_robot_desired_state(states)` (quadruped_gym_env.py:288-289,401): the selected envs start a new
+        episode from rows of states [N, 37] (pos3 quat4 lin_vel3 ang_vel3 q12 qd12), without the settle."""
+        s = torch.as_tensor(states, dtype=torch.float32, device=self.device).contiguous()
+        if s.shape != (self.num_envs, 37):
+            raise ValueError(f"states must have shape {(self.num_envs, 37)}")
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        _lib.check(self._L.qs_reset_to_state(self._h, _p(m), _p(s), _p(self._obs), _stream_ptr(self.device)))
+        return self._obs
+
+    def get_last_filtered_action(self):
+        """quadruped_gym_env.py:385-387: the filter's last output; zeros when the filter is off (the reference only
+        assigns it inside `if self._enable_action_filter`, :232-234)"""
+        if self._enable_action_filter:
+            return self._views["filt"][2].t()[:, :self.action_dim]
+        return torch.zeros(self.num_envs, self.action_dim, device=self.device)
 
     def set_terminal_obs_buffer(self, buf):
         """device tensor [N, O] (or None) that receives the last observation of every env whose episode ends inside

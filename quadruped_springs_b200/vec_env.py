@@ -305,3 +305,35 @@ class MlpPolicyTorch(torch.nn.Module):
         own = pol.state_dict()
         pol.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
         return pol.to(device)
+
+
+class EvaluationWrapper:
+    """env/wrappers/evaluation_wrapper.py:6-61 on the batch: `infos["feet_forces"]` (mean normal force over the four feet),
+    `infos["max_height"]` and `infos["max_fwd"]` (running maxima of the base height and of the task's jumping distance;
+    the height maximum restarts at reset, the distance maximum never does, as upstream :18-20,57-59).  The reference
+    samples them at every substep through `set_sub_step_callback`; here they are sampled once per control step, from
+    the state the step kernel leaves (a fused kernel cannot call back into Python between substeps)."""
+
+    def __init__(self, env):
+        self.env = env
+        n, dev = env.num_envs, env.device
+        self.max_h = torch.zeros(n, device=dev)
+        self.max_fwd = torch.zeros(n, device=dev)
+
+    def __getattr__(self, k):
+        return getattr(self.env, k)
+
+    def reset(self, *a, **k):
+        self.max_h.zero_()
+        return self.env.reset(*a, **k)
+
+    def step(self, action):
+        obs, reward, done, infos = self.env.step(action)
+        infos = dict(infos)
+        _, _, feet_forces, _ = self.env.robot.GetContactInfo()
+        self.max_fwd = torch.maximum(self.max_fwd, self.env.task.compute_jumping_distance())
+        self.max_h = torch.maximum(self.max_h, self.env.robot.GetBasePosition()[:, 2])
+        infos["feet_forces"] = feet_forces.sum(-1) / 4
+        infos["max_height"] = self.max_h
+        infos["max_fwd"] = self.max_fwd
+        return obs, reward, done, infos

@@ -205,3 +205,31 @@ def test_policy_in_the_loop_with_vecnormalize_on_device():
     torch.testing.assert_close(vn.obs_rms.mean, allobs.mean(0), rtol=1e-3, atol=1e-4)
     torch.testing.assert_close(vn.obs_rms.var, allobs.var(0, unbiased=False), rtol=1e-3, atol=1e-4)
     assert ep_done > 0 and vn.ret_rms.count > n
+
+
+@pytest.mark.gpu
+def test_evaluation_wrapper_infos():
+    """env/wrappers/evaluation_wrapper.py:43-53: feet_forces = sum(F_n) / 4, running max height (restarts at reset) and
+    running max jumping distance"""
+    import quadruped_springs_b200 as qs
+    from quadruped_springs_b200.vec_env import EvaluationWrapper
+    n = 256
+    env = EvaluationWrapper(qs.BatchedQuadrupedGymEnv(num_envs=n, seed=3, auto_reset=False, enable_noise=False,
+                                                      task_env="JUMPING_FORWARD", enable_springs=True,
+                                                      observation_space_mode="ARS_BASIC"))
+    env.reset()
+    a = torch.zeros(n, 6, device="cuda")
+    obs, r, d, info = env.step(a)
+    np.testing.assert_allclose(info["feet_forces"].cpu().numpy() * 4, 12.01301 * 9.8, rtol=2e-2)   # standing
+    hs = []
+    for t in range(40):
+        a[:, [1, 4]] = 0.9 if t < 12 else -0.7
+        a[:, [2, 5]] = -0.9 if t < 12 else 1.0
+        obs, r, d, info = env.step(a)
+        hs.append(env.robot.GetBasePosition()[:, 2].clone())
+    np.testing.assert_allclose(info["max_height"].cpu().numpy(), torch.stack(hs).max(0).values.cpu().numpy(), rtol=1e-6)
+    assert (info["max_height"] > 0.4).float().mean() > 0.9 and (info["max_fwd"] >= 0).all()
+    flying = env.robot._is_flying()
+    assert (info["feet_forces"][flying] == 0).all()
+    env.reset()
+    assert (env.max_h == 0).all()

@@ -218,9 +218,10 @@ def test_evaluation_wrapper_infos():
                                                       task_env="JUMPING_FORWARD", enable_springs=True,
                                                       observation_space_mode="ARS_BASIC"))
     env.reset()
-    a = torch.zeros(n, 6, device="cuda")
+    a = env.get_last_action().clone()            # the settling action: the robot keeps standing
     obs, r, d, info = env.step(a)
     np.testing.assert_allclose(info["feet_forces"].cpu().numpy() * 4, 12.01301 * 9.8, rtol=2e-2)   # standing
+    a = torch.zeros(n, 6, device="cuda")
     hs = []
     for t in range(40):
         a[:, [1, 4]] = 0.9 if t < 12 else -0.7

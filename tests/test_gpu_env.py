@@ -227,7 +227,9 @@ def test_config5_policy_in_the_loop(qs):
     policy_rollout.main(2048, 40)
 
 
-def test_settle_conveyor_is_invisible(qs, monkeypatch):
+@pytest.mark.parametrize("mode,variants", [("GROUND_RANDOMIZER", ((100, 100), (2500, 2500), (7, 13))),
+                                           ("TEST_RANDOMIZER", ((37, 37),))])   # masses + springs ride the conveyor too
+def test_settle_conveyor_is_invisible(qs, monkeypatch, mode, variants):
     """Episodes are settled ahead of time in slices of ticks (csrc/qs_step_kernels.cuh, settle
     conveyor).  However the 2500 ticks are cut -- tiny slices, whole settles, or so slowly that
     envs run out of settled slots and take the urgent path -- every env sees bit-identical
@@ -236,7 +238,7 @@ def test_settle_conveyor_is_invisible(qs, monkeypatch):
     from quadruped_springs_b200 import _lib
     n, steps = 1024, 520
     cfg = dict(enable_springs=True, task_env="JUMPING_FORWARD", motor_control_mode="CARTESIAN_PD",
-               observation_space_mode="ARS_BASIC")   # random actions end an episode every ~85 steps
+               observation_space_mode="ARS_BASIC", env_randomizer_mode=mode)   # random actions end an episode every ~85 steps
     g = torch.Generator(device="cuda").manual_seed(11)
     acts = [torch.rand(n, 6, device="cuda", generator=g) * 2 - 1 for _ in range(steps)]
 
@@ -260,7 +262,7 @@ def test_settle_conveyor_is_invisible(qs, monkeypatch):
 
     ref, urgent_ref, ndone = run(None, None)
     assert ndone > 5 * n and urgent_ref <= ndone // 100   # more episodes per env than ring slots, settled in time
-    for lo, hi in ((100, 100), (2500, 2500), (7, 13)):
+    for lo, hi in variants:
         out, urgent, _ = run(lo, hi)
         for x, y in zip(ref, out):
             assert torch.equal(x, y)

@@ -58,7 +58,12 @@ enum qs_task {
   QS_TASK_CONTINUOUS_JUMPING_FORWARD = 9,      /* robot_tasks.py:102-131 */
   QS_TASK_CONTINUOUS_JUMPING_FORWARD2 = 10,    /* robot_tasks.py:134-166 */
   QS_TASK_CONTINUOUS_JUMPING_FORWARD3 = 11,    /* robot_tasks.py:169-212 */
-  QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO = 12  /* robot_tasks.py:553-698 */
+  QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO = 12, /* robot_tasks.py:553-698 */
+  /* imitation tasks (tasks/task_base.py:169-220, robot_tasks.py:222-241): per-step reward exp(-0.35 |a_demo - a|) / (rows
+   * left at reset), episode ends with the demonstration; the demonstration is given with qs_set_demo */
+  QS_TASK_JUMPING_IN_PLACE_DEMO = 13,
+  QS_TASK_JUMPING_FORWARD_DEMO = 14,
+  QS_TASK_BACKFLIP_DEMO = 15
 };
 enum qs_obs_mode {
   QS_OBS_ENCODER = 0,
@@ -195,6 +200,13 @@ int qs_reset(qs_handle h, const uint8_t* mask_dev, float* obs_dev, void* stream)
  * (infos["TimeLimit.truncated"]). */
 int qs_step(qs_handle h, const float* actions_dev, float* obs_dev, float* reward_dev,
             uint8_t* done_dev, uint8_t* truncated_dev, void* stream);
+
+/* TaskJumpingDemo.demo_list (tasks/task_base.py:169-176): the demonstration of the *_DEMO tasks, `length` rows of
+ * action_dim actions in HOST memory (the action block of the rows GetDemonstrationWrapper records,
+ * env/wrappers/get_demonstration_wrapper.py:35-57); copied to the device.  Must be set before qs_reset for those tasks.
+ * The per-env position in it is task-state row QS_TS_DEMO_COUNTER (set_demo_counter, task_base.py:218-219). */
+int qs_set_demo(qs_handle h, const float* actions_host, int length);
+#define QS_TS_DEMO_COUNTER 29
 
 /* Quadruped.SetLegMasses / SetBaseMass / _add_base_mass_offset (quadruped.py:744-819) on the batch: after the caller
  * wrote qs_state_ptrs.mass_draw, recompute the per-env mass properties the physics reads.  Needs

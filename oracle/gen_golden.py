@@ -248,11 +248,12 @@ def cart_jump_actions(n, rng, period=70):
     return acts
 
 
-def rollout(name, cfg, actions, seed, world_params=None):
+def rollout(name, cfg, actions, seed, world_params=None, wrap=None, extra=None):
     ref_shim.FakeBulletClient.world_params = dict(world_params or {})
     np.random.seed(seed)
     env = make_env(**cfg)
-    env.reset()
+    wrapped = wrap(env) if wrap else env
+    wrapped.reset()
     mu = env._pybullet_client._mu_ground
     w = env._pybullet_client.world
     rec = {k: [] for k in ("state", "obs", "reward", "done", "truncated", "tau", "n_invalid", "foot_force",
@@ -300,6 +301,8 @@ def rollout(name, cfg, actions, seed, world_params=None):
         bc, rb = env._pybullet_client, env.robot
         out["masses"] = np.array([bc.getDynamicsInfo(rb.quadruped, i)[0] for i in (2, 3, 4, 0)] + [rb.get_offset_mass_value()]
                                  + list(bc._block_delta), dtype=np.float64)   # hip, thigh, calf, trunk, block, block pos
+    if extra:
+        out.update(extra(env, wrapped))
     out.update(actions=np.asarray(actions)[: len(out["reward"])], mu=mu, init_state=init_state, init_obs=init_obs,
                init_last_action=init_last_action, init_task=init_task,
                cfg=json.dumps(cfg), world_params=json.dumps(world_params or {}))
@@ -506,6 +509,44 @@ def gen_mass_randomizer():
             cart_jump_actions(160, np.random.default_rng(93)), seed=44)
 
 
+def gen_demo():
+    """Imitation tasks (task_base.py:169-220, robot_tasks.py:222-241) and reference-state initialisation
+    (reference_state_initialization_wrapper.py:10-43).  The reference ships no demonstration files, so one is recorded
+    first with its own GetDemonstrationWrapper (get_demonstration_wrapper.py:7-57) and handed to the task by redirecting
+    the `np.load` of its demo path."""
+    import tempfile
+    from quadruped_spring.env.wrappers.get_demonstration_wrapper import GetDemonstrationWrapper
+    from quadruped_spring.env.wrappers.reference_state_initialization_wrapper import ReferenceStateInitializationWrapper
+    base = dict(enable_springs=True, task_env="JUMPING_IN_PLACE", motor_control_mode="PD", action_space_mode="SYMMETRIC",
+                observation_space_mode="ARS_BASIC", enable_action_filter=True)
+    tmp = tempfile.mkdtemp()
+    np.random.seed(45)
+    env = GetDemonstrationWrapper(make_env(**base), path=tmp)
+    env.reset()
+    for a in jump_actions(6, 70, np.random.default_rng(94)):
+        _, _, d, _ = env.step(a)
+        if d:
+            break
+    env.save_demo()
+    demo = np.load(os.path.join(tmp, "demo_list.npy"))
+    np_load = np.load
+    np.load = lambda p, *a, **k: np_load(os.path.join(tmp, "demo_list.npy") if "demonstrations" in str(p) else p, *a, **k)
+    try:
+        rng = np.random.default_rng(95)
+        for task, name in (("JUMPING_IN_PLACE_DEMO", "demo_jip"), ("BACKFLIP_DEMO", "demo_backflip")):
+            cfg = dict(base, task_env=task, enable_action_filter=False)
+            # imitate the demonstration's (filtered) actions with a little noise: the episode ends when the demo does
+            acts = demo[:, :6] + rng.normal(size=(len(demo), 6)) * 0.05
+            rollout(name, cfg, np.concatenate([acts, acts[-5:]]), seed=46,
+                    extra=lambda e, w: dict(demo=demo, demo_counter_end=e.task.demo_counter, demo_start=0))
+        cfg = dict(base, task_env="JUMPING_FORWARD_DEMO", enable_action_filter=False)
+        for i in range(2):   # episodes started from a random element of the demonstration, unsettled
+            rollout(f"demo_rsi{i}", cfg, demo[:, :6] * 0.9, seed=47 + i, wrap=ReferenceStateInitializationWrapper,
+                    extra=lambda e, w: dict(demo=demo, demo_counter_end=e.task.demo_counter, demo_start=w.random_el))
+    finally:
+        np.load = np_load
+
+
 def backflip_actions(n, rng, delay_rear):
     """crouch, then front and (delayed) rear push: pitches the trunk up at take-off"""
     acts = np.zeros((n, 6))
@@ -613,7 +654,7 @@ def gen_hopf():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "continuous", "landing", "springs", "masses", "rollouts"]
+    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "continuous", "landing", "springs", "masses", "demo", "rollouts"]
     if "urdf" in which:
         gen_urdf()
     # NB: gen_analytic and the last rollout build a BACKFLIP env, which mutates the module-level
@@ -632,6 +673,8 @@ if __name__ == "__main__":
         gen_spring_randomizer()
     if "masses" in which:
         gen_mass_randomizer()
+    if "demo" in which:
+        gen_demo()
     if "rollouts" in which:
         gen_rollouts()
     print("golden fixtures written to", OUT)

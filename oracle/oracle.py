@@ -17,6 +17,7 @@ TASKS = {
     "JUMPING_IN_PLACE_PPO": 4, "JUMPING_FORWARD_PPO": 5, "BACKFLIP_PPO": 6,
     "JUMPING_IN_PLACE_PPO_HP": 7, "JUMPING_FORWARD_PPO_HP": 8, "CONTINUOUS_JUMPING_FORWARD": 9,
     "CONTINUOUS_JUMPING_FORWARD2": 10, "CONTINUOUS_JUMPING_FORWARD3": 11, "CONTINUOUS_JUMPING_FORWARD_PPO": 12,
+    "JUMPING_IN_PLACE_DEMO": 13, "JUMPING_FORWARD_DEMO": 14, "BACKFLIP_DEMO": 15,
 }
 CONTROL = {"PD": 0, "CARTESIAN_PD": 1, "TORQUE": 2}
 ACTION = {"DEFAULT": 0, "SYMMETRIC": 1, "SYMMETRIC_NO_HIP": 2}
@@ -94,6 +95,10 @@ def lib():
         "qso_env_action_dim": (C.c_int, [vp]),
         "qso_env_obs_dim": (C.c_int, [vp]),
         "qso_env_reset": (None, [vp, C.c_double, dp]),
+        "qso_env_reset_to_state": (None, [vp, C.c_double, dp, dp]),
+        "qso_env_set_demo": (None, [vp, dp, C.c_int]),
+        "qso_env_set_demo_counter": (None, [vp, C.c_int]),
+        "qso_env_get_demo_counter": (C.c_int, [vp]),
         "qso_env_step": (None, [vp, dp, dp, dp, ip, ip]),
         "qso_env_get_task_state": (None, [vp, dp]),
         "qso_env_get_jump_arrays": (None, [vp, dp]),
@@ -283,6 +288,26 @@ class Env:
         o, op = _out(self.obs_dim)
         self.L.qso_env_reset(self.h, float(mu), op)
         return o
+
+    def reset_to_state(self, state37, mu=1.0):
+        """reset() after set_robot_desired_state (quadruped_gym_env.py:288-289): no settle"""
+        s, sp = _d(state37)
+        assert s.shape == (37,)
+        o, op = _out(self.obs_dim)
+        self.L.qso_env_reset_to_state(self.h, float(mu), sp, op)
+        return o
+
+    def set_demo(self, actions):
+        """demonstration actions [L, A] of the *_DEMO tasks (task_base.py:169-176)"""
+        a = np.ascontiguousarray(actions, dtype=np.float64)
+        assert a.ndim == 2 and a.shape[1] == self.action_dim
+        self.L.qso_env_set_demo(self.h, a.ctypes.data_as(C.POINTER(C.c_double)), a.shape[0])
+
+    def set_demo_counter(self, value):
+        self.L.qso_env_set_demo_counter(self.h, int(value))
+
+    def demo_counter(self):
+        return int(self.L.qso_env_get_demo_counter(self.h))
 
     def step(self, action):
         a, ap = _d(action)

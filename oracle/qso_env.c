@@ -291,6 +291,9 @@ struct QsoEnv {
   /* landing controller (landing_wrapper.py, landing_wrapper_2.py; utils/timer.py) */
   int land_mode, land_gains;
   double land_timer, land_end, hold_action[12], kp_save[12], kd_save[12];
+  /* imitation tasks (task_base.py:169-220) */
+  double* demo;
+  int demo_len, demo_counter, delta_demo, desired_reset;
   /* go-to-rest controller (go_to_rest_wrapper.py) */
   int rest_active;
   double rest_h, rest_t0, rest_start[12], init_action[12];
@@ -338,7 +341,7 @@ QsoEnv* qso_env_create(const QsoEnvConfig* c) {
   e->fa[0] = 1; e->fa[1] = 2 * (K * K - 1) * nrm; e->fa[2] = (1 - sqrt(2.0) * K + K * K) * nrm;
   return e;
 }
-void qso_env_destroy(QsoEnv* e) { qso_world_destroy(e->w); free(e); }
+void qso_env_destroy(QsoEnv* e) { qso_world_destroy(e->w); free(e->demo); free(e); }
 QsoWorld* qso_env_world(QsoEnv* e) { return e->w; }
 void qso_env_set_gains(QsoEnv* e, const double* kp, const double* kd) {
   memcpy(e->rc.kp, kp, sizeof e->rc.kp);
@@ -539,9 +542,15 @@ static void task_on_step(QsoEnv* e) { /* task_base.py:61-107 */
   }
 }
 
+static int is_demo_task(int t) { return t >= QSO_TASK_JUMPING_IN_PLACE_DEMO && t <= QSO_TASK_BACKFLIP_DEMO; }
+
 static void task_reset(QsoEnv* e) { /* task_base.py:40-59 */
   TaskState* t = &e->ts;
   if (!is_jump_task(e->cfg.task)) return;
+  if (is_demo_task(e->cfg.task)) { /* TaskJumpingDemo._reset, task_base.py:178-183 */
+    if (!e->desired_reset) e->demo_counter = 0;
+    e->delta_demo = e->demo_len - e->demo_counter;
+  }
   double st[QSO_NSTATE];
   qso_world_get_state(e->w, st);
   double keep_bf = t->max_pitch_bf;
@@ -566,6 +575,9 @@ static int task_terminated(QsoEnv* e) {
   int fallen_ground = e->ts.pos[2] < e->rc.fallen_height; /* task_base.py:123-124 */
   int fallen_orient = R[8] < 0.85;                        /* task_base.py:126-130 */
   if (task == QSO_TASK_BACKFLIP) return fallen_ground || e->n_invalid > 0; /* robot_tasks.py:532-533 */
+  if (task == QSO_TASK_BACKFLIP_DEMO) return fallen_ground || e->n_invalid > 0 || e->demo_len == e->demo_counter; /* :239-241 */
+  if (is_demo_task(task)) /* task_base.py:211-212 */
+    return (fallen_orient && fallen_ground) || e->n_invalid > 0 || e->demo_counter == e->demo_len;
   return (fallen_orient && fallen_ground) || e->n_invalid > 0;          /* task_base.py:146-147 */
 }
 
@@ -579,6 +591,14 @@ static double task_reward(QsoEnv* e) {
   const TaskState* t = &e->ts;
   int task = e->cfg.task;
   double max_h_task, k_h;
+  if (is_demo_task(task)) { /* TaskJumpingDemo._reward, task_base.py:194-209 */
+    const int A = qso_env_action_dim(e);
+    const double* da = e->demo + (size_t)e->demo_counter * A;
+    double s = 0;
+    for (int i = 0; i < A; i++) s += (da[i] - e->last_action[i]) * (da[i] - e->last_action[i]);
+    e->demo_counter += 1;
+    return exp(-0.35 * sqrt(s)) / e->delta_demo;
+  }
   switch (task) {
     case QSO_TASK_JUMPING_IN_PLACE_PPO: max_h_task = 1.0; k_h = 0.023; break;   /* robot_tasks.py:259,268 */
     case QSO_TASK_JUMPING_IN_PLACE_PPO_HP: max_h_task = 1.25; k_h = 0.023; break; /* :493 */
@@ -763,12 +783,29 @@ static void observe(QsoEnv* e, double* obs) {
 #undef PUTN
 }
 
+void qso_env_set_demo(QsoEnv* e, const double* actions, int length) {
+  const int A = qso_env_action_dim(e);
+  free(e->demo);
+  e->demo = (double*)malloc(sizeof(double) * (size_t)length * A);
+  memcpy(e->demo, actions, sizeof(double) * (size_t)length * A);
+  e->demo_len = length;
+  e->demo_counter = 0;
+}
+void qso_env_set_demo_counter(QsoEnv* e, int value) { e->demo_counter = value; }
+int qso_env_get_demo_counter(const QsoEnv* e) { return e->demo_counter; }
+
+static void reset_impl(QsoEnv* e, double mu, const double* desired, double* obs);
+void qso_env_reset(QsoEnv* e, double mu, double* obs) { reset_impl(e, mu, NULL, obs); }
+void qso_env_reset_to_state(QsoEnv* e, double mu, const double* state37, double* obs) { reset_impl(e, mu, state37, obs); }
+
 /* ---- reset (quadruped_gym_env.py:278-329, interface_base.py:182-200) ---- */
-void qso_env_reset(QsoEnv* e, double mu, double* obs) {
+static void reset_impl(QsoEnv* e, double mu, const double* desired, double* obs) {
   double st[QSO_NSTATE];
   memset(st, 0, sizeof st);
   st[2] = 0.32; st[6] = 1.0; /* configs:23,26 */
   memcpy(st + 13, e->rc.init_angles, 12 * sizeof(double));
+  if (desired) memcpy(st, desired, sizeof st); /* Quadruped.reset_desired_state, quadruped.py:521-525 */
+  e->desired_reset = desired != NULL;
   qso_world_set_state(e->w, st);
   QsoWorldParams p;
   qso_world_get_params(e->w, &p);
@@ -788,7 +825,9 @@ void qso_env_reset(QsoEnv* e, double mu, double* obs) {
   memset(e->tau_motor, 0, sizeof e->tau_motor);
   memset(e->tau_spring, 0, sizeof e->tau_spring);
   int adim = qso_env_action_dim(e);
-  if (e->cfg.is_rl_interface) {
+  if (desired) {
+    /* robot_desired_state is set: no settle, _last_action stays zero (quadruped_gym_env.py:284,288-289) */
+  } else if (e->cfg.is_rl_interface) {
     /* _settle_robot_by_reference(get_init_pose(), 2500) */
     const RobotCfg* c = &e->rc;
     double a12[12], act[12], cmd[12];

@@ -96,6 +96,7 @@ EXPORTS = {
     "qs_step_host": (C.c_int, [C.c_void_p] * 7),
     "qs_set_terminal_obs": (C.c_int, [C.c_void_p, C.c_void_p]),
     "qs_apply_masses": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "qs_set_demo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "qs_reset_to_state": (C.c_int, [C.c_void_p] * 5),
     "qs_reset_host": (C.c_int, [C.c_void_p] * 4),
     "qs_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -44,6 +44,8 @@ struct EnvCfg {
   int enable_springs, control_mode, action_mode, task, obs_mode, action_repeat, is_rl, enable_filter;
   int enable_noise, obs_dim, action_dim, settling_steps, ground_randomizer, auto_reset, landing_mode, spring_randomizer, rest_mode, mass_randomizer;
   float max_episode_time, mu_ground, leg_mass_err, payload_max, payload_pos[3], spring_err;
+  const float* demo;  // [demo_len][action_dim] demonstration actions of the *_DEMO tasks (device)
+  int demo_len;
   uint64_t seed;
   int64_t gid0;
 };
@@ -153,7 +155,8 @@ QS_DEV int task_family(int task) {
   return 0;
 }
 // rows of DeviceView::task this task reads and writes
-QS_DEV int task_slots(int task) { return task_family(task) ? int(TS_END) : int(TS_END_BASIC); }
+QS_DEV bool is_demo_task(int task) { return task >= QS_TASK_JUMPING_IN_PLACE_DEMO && task <= QS_TASK_BACKFLIP_DEMO; }
+QS_DEV int task_slots(int task) { return task_family(task) ? int(TS_END) : (is_demo_task(task) ? int(TS_END_DEMO) : int(TS_END_BASIC)); }
 
 QS_DEVONLY float jumping_distance(const float* ts, const float* pos) {  // task_base.py:109-116
   float s, c;
@@ -251,7 +254,7 @@ QS_DEVONLY bool task_terminated(const float* ts, const EnvState<float>& st, cons
   if (!is_jump_task(task)) return false;
   const bool fallen_ground = st.pos[2] < fallen_height;  // task_base.py:123-124
   const bool fallen_orient = Rb[8] < 0.85f;              // task_base.py:126-130
-  if (task == QS_TASK_BACKFLIP) return fallen_ground || cs.invalid > 0;  // robot_tasks.py:532-533
+  if (task == QS_TASK_BACKFLIP || task == QS_TASK_BACKFLIP_DEMO) return fallen_ground || cs.invalid > 0;  // robot_tasks.py:532-533,239-241
   return (fallen_orient && fallen_ground) || cs.invalid > 0;            // task_base.py:146-147
 }
 

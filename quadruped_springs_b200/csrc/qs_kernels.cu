@@ -341,6 +341,7 @@ struct qs_env {
   uint8_t* dev_done;
   uint8_t* dev_trunc;
   float* term_obs;     // caller-owned, optional (qs_set_terminal_obs)
+  float* dev_demo;     // demonstration actions of the *_DEMO tasks (qs_set_demo)
   bool was_reset;
   // CUDA-event ring around k_step launches (roofline timing of the dominant kernel)
   static constexpr int kRing = 512;
@@ -411,7 +412,7 @@ static int check_config(const qs_config* c) {
   if (!c) return fail(QS_ERR_ARG, "config is NULL");
   if (c->control_mode < 0 || c->control_mode > 2) return fail(QS_ERR_ARG, "unknown motor control mode");
   if (c->action_mode < 0 || c->action_mode > 2) return fail(QS_ERR_ARG, "unknown action space mode");
-  if (c->task < 0 || c->task > QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO) return fail(QS_ERR_ARG, "unknown task");
+  if (c->task < 0 || c->task > QS_TASK_BACKFLIP_DEMO) return fail(QS_ERR_ARG, "unknown task");
   if (c->block_size != 0 && c->block_size != QS_BLOCK) return fail(QS_ERR_ARG, "block_size is fixed at 128 (0 = default)");
   if (c->landing_mode < 0 || c->landing_mode > 5) return fail(QS_ERR_ARG, "unknown landing_mode");
   if (c->landing_mode >= 4 && c->action_mode != QS_ACT_SYMMETRIC)
@@ -604,6 +605,7 @@ int qs_destroy(qs_handle h) {
   cudaDeviceSynchronize();
   cudaFree(h->pool);
   cudaFree(h->lists);
+  if (h->dev_demo) cudaFree(h->dev_demo);
   cudaStreamDestroy(h->bg);
   cudaStreamDestroy(h->copy);
   cudaEventDestroy(h->ev_results);
@@ -747,8 +749,15 @@ static int launch_slice(qs_handle h, cudaStream_t s, int early) {
   return QS_OK;
 }
 
+static int need_demo(qs_handle h) {
+  if (is_demo_task(h->args.C.task) && !h->args.C.demo)
+    return fail(QS_ERR_STATE, "the *_DEMO tasks need a demonstration: call qs_set_demo first (tasks/task_base.py:169-176)");
+  return QS_OK;
+}
+
 int qs_reset(qs_handle h, const uint8_t* mask, float* obs, void* stream) {
   if (!h) return fail(QS_ERR_ARG, "handle is NULL");
+  if (int e = need_demo(h)) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(h->device));
   const int B = block_of(h);
@@ -788,6 +797,7 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   if (!h) return fail(QS_ERR_ARG, "handle is NULL");
   if (!actions || !obs || !reward || !done || !truncated) return fail(QS_ERR_ARG, "NULL buffer");
   if (!h->was_reset) return fail(QS_ERR_STATE, "qs_step before qs_reset");
+  if (int e = need_demo(h)) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(h->device));
   const int B = block_of(h);
@@ -863,6 +873,7 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
 int qs_reset_to_state(qs_handle h, const uint8_t* mask, const float* states, float* obs, void* stream) {
   if (!h) return fail(QS_ERR_ARG, "handle is NULL");
   if (!states) return fail(QS_ERR_ARG, "states is NULL");
+  if (int e = need_demo(h)) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaSetDevice(h->device));
   const int* list = nullptr;
@@ -877,6 +888,21 @@ int qs_reset_to_state(qs_handle h, const uint8_t* mask, const float* states, flo
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   if (!mask) h->was_reset = true;
+  return QS_OK;
+}
+
+int qs_set_demo(qs_handle h, const float* actions, int length) {
+  if (!h || !actions) return fail(QS_ERR_ARG, "NULL argument");
+  if (length < 1) return fail(QS_ERR_ARG, "a demonstration needs at least one row");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());  // no step may still be reading the old one
+  if (h->dev_demo) CUDA_TRY(cudaFree(h->dev_demo));
+  h->dev_demo = nullptr;
+  const size_t bytes = size_t(length) * size_t(h->args.C.action_dim) * sizeof(float);
+  CUDA_TRY(cudaMalloc(&h->dev_demo, bytes));
+  CUDA_TRY(cudaMemcpy(h->dev_demo, actions, bytes, cudaMemcpyHostToDevice));
+  h->args.C.demo = h->dev_demo;
+  h->args.C.demo_len = length;
   return QS_OK;
 }
 

@@ -502,7 +502,12 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
   float ts[QS_TASK_DIM];
 #pragma unroll
   for (int i = 0; i < TS_END; i++) ts[i] = i < task_slots(C.task) ? D.task[i * n + env] : 0.f;
+  const float demo_at = ts[TS_DEMO_COUNTER];
   task_reset(ts, st, cs, tau_m, rpy, Rb, 0.f, C.task);
+  if (is_demo_task(C.task)) {  // TaskJumpingDemo._reset (task_base.py:178-183): the counter survives a desired-state reset
+    ts[TS_DEMO_COUNTER] = settled ? 0.f : demo_at;
+    ts[TS_DELTA_DEMO] = float(C.demo_len) - ts[TS_DEMO_COUNTER];
+  }
 #pragma unroll
   for (int i = 0; i < TS_END; i++) if (i < task_slots(C.task)) D.task[i * n + env] = ts[i];
 #pragma unroll
@@ -549,7 +554,19 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   for (int k = 0; k < 4; k++) foot_force[k] = (cs.mask >> k) & 1 ? cs.lam_n[k] / dt : 0.f;
   task_on_step(ts, st, cs, tau_m, rpy, Rb, sim_time, C.task);
   float r = task_reward(ts, st, foot_force, ts + TS_OLD_TAU0, tau_m, rpy, Rb, C.task);
-  const bool term = task_terminated(ts, st, cs, Rb, A.RC.fallen_height, C.task);
+  bool term = task_terminated(ts, st, cs, Rb, A.RC.fallen_height, C.task);
+  if (is_demo_task(C.task)) {
+    // TaskJumpingDemo._reward / _terminated (task_base.py:194-212): distance of this step's action to the demonstration's
+    const int row = min(int(ts[TS_DEMO_COUNTER]), C.demo_len - 1);
+    float s = 0.f;
+    for (int i = 0; i < C.action_dim; i++) {
+      const float d = C.demo[row * C.action_dim + i] - D.last_action[i * n + env];
+      s += d * d;
+    }
+    r = expf(-0.35f * sqrtf(s)) / ts[TS_DELTA_DEMO];
+    ts[TS_DEMO_COUNTER] += 1.f;
+    term = term || int(ts[TS_DEMO_COUNTER]) == C.demo_len;
+  }
   const bool dn = term || (double(sim_steps) * A.time_step_d > A.max_time_d);
   if (dn) r += task_reward_end(ts, term, C.task, sim_time, C.max_episode_time);
 #pragma unroll

@@ -91,8 +91,12 @@ enum TaskSlot {
   // continuous-jumping tasks only (task_base.py:222-400).  The reference keeps per-jump arrays; the
   // end-of-episode reward needs only their count, sum, max and the entropy sums S = sum f, Q = sum f log2 f.
   TS_IS_JUMPING = TS_END_BASIC, TS_CUM_FWD, TS_CUM_FLIGHT, TS_FIRST_JUMP, TS_JUMP_COUNT, TS_GOOD_JUMPS, TS_MAX_JUMP_H,
-  TS_SUM_FWD, TS_SUM_FLOG, TS_SUM_PERF, TS_MAX_PERF, TS_LAST_PERF, TS_END_JUMP, TS_END
+  TS_SUM_FWD, TS_SUM_FLOG, TS_SUM_PERF, TS_MAX_PERF, TS_LAST_PERF, TS_END_JUMP, TS_END,
+  // imitation tasks only (task_base.py:169-220): position in the demonstration, rows left at reset (they share the
+  // continuous-jumping rows: a task is one or the other)
+  TS_DEMO_COUNTER = TS_END_BASIC, TS_DELTA_DEMO, TS_END_DEMO
 };
+static_assert(TS_DEMO_COUNTER == QS_TS_DEMO_COUNTER, "header constant out of date");
 static_assert(TS_END <= QS_TASK_DIM, "task state too large");
 
 }  // namespace qs

@@ -2,10 +2,10 @@
 
 Reference: `env/wrappers/get_demonstration_wrapper.py:7-70` (row layout, `read_demo`, `save_demo`),
 `env/wrappers/save_demo_wrapper.py:7-19`, `env/wrappers/reference_state_initialization_wrapper.py:10-43`.
-The reference ships no demonstration files and its `*_DEMO` tasks load them at import (`tasks/task_base.py:169-176`),
-so the imitation tasks themselves are not rebuilt; what is here lets a user record demonstrations from the batched env in
-the reference's `.npy` layout and start episodes from demonstration rows.  Host-side glue over the C ABI
-(`qs_reset_to_state`), not part of the measured path.
+The reference ships no demonstration files (its `*_DEMO` tasks load one at construction, `tasks/task_base.py:169-176`):
+here a user records demonstrations from the batched env in the reference's `.npy` layout, hands one to the imitation
+tasks (`env.set_demo`, kernels: `QS_TASK_*_DEMO`) and starts episodes from demonstration rows.  Host-side glue over the
+C ABI (`qs_set_demo`, `qs_reset_to_state`), not part of the measured path.
 """
 import os
 import random
@@ -111,6 +111,8 @@ class ReferenceStateInitialization:
         idx = m.nonzero().flatten().tolist()
         els = torch.as_tensor([self.compute_random_el() for _ in idx], dtype=torch.long, device=self.env.device)
         self.random_el[m] = els
+        if self.env.task_env.endswith("_DEMO"):      # env.task.set_demo_counter(value=self.random_el), :31
+            self.env.task.set_demo_counter(els.to(torch.float32), m)
         states = self.env.get_state()
         states[m] = demo_rows_to_states(self.demo_list[els], self.env.action_dim)
         return self.env.reset_to_state(states, mask=m)

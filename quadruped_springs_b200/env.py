@@ -45,7 +45,8 @@ ActionInterfaceCollection = lambda: _Collection("action space mode", ["DEFAULT",
 TaskCollection = lambda: _Collection("task", [
     "NO_TASK", "JUMPING_IN_PLACE", "JUMPING_FORWARD", "BACKFLIP", "JUMPING_IN_PLACE_PPO", "JUMPING_FORWARD_PPO",
     "BACKFLIP_PPO", "JUMPING_IN_PLACE_PPO_HP", "JUMPING_FORWARD_PPO_HP", "CONTINUOUS_JUMPING_FORWARD",
-    "CONTINUOUS_JUMPING_FORWARD2", "CONTINUOUS_JUMPING_FORWARD3", "CONTINUOUS_JUMPING_FORWARD_PPO"])
+    "CONTINUOUS_JUMPING_FORWARD2", "CONTINUOUS_JUMPING_FORWARD3", "CONTINUOUS_JUMPING_FORWARD_PPO",
+    "JUMPING_IN_PLACE_DEMO", "JUMPING_FORWARD_DEMO", "BACKFLIP_DEMO"])
 # sensors/sensor_collection.py:92-105
 SensorCollection = lambda: _Collection("sensor package", list(SENSOR_SETS))
 # env_randomizers/env_randomizer_collection.py:15-21 (mass / curriculum randomizers: SURVEY.md 8f "next")
@@ -345,6 +346,7 @@ _TASK_FIELDS = {  # reference attribute name -> task-state slot (csrc/qs_types.h
     "is_jumping": 29, "cumulative_fwd": 30, "cumulative_flight_time": 31, "first_jump": 32, "jump_counter": 33,
     "good_jump_counter": 34, "max_jump_height": 35, "end_jump": 41,
 }
+_DEMO_TASK_FIELDS = {"demo_counter": 29, "delta_demo": 30}   # imitation tasks (task_base.py:169-220) reuse those rows
 
 
 class _Task:
@@ -355,9 +357,19 @@ class _Task:
         self._env = env
 
     def __getattr__(self, name):
+        if name in _DEMO_TASK_FIELDS and self._env.task_env.endswith("_DEMO"):
+            return self._env._views["task"][_DEMO_TASK_FIELDS[name]]
         if name in _TASK_FIELDS:
             return self._env._views["task"][_TASK_FIELDS[name]]
         raise AttributeError(name)
+
+    def set_demo_counter(self, value, mask=None):    # task_base.py:218-219
+        row = self._env._views["task"][_DEMO_TASK_FIELDS["demo_counter"]]
+        v = torch.as_tensor(value, dtype=torch.float32, device=self._env.device)
+        if mask is None:
+            row[:] = v
+        else:
+            row[mask] = v
 
     @property
     def _robot_pose_take_off(self):
@@ -604,6 +616,16 @@ class BatchedQuadrupedGymEnv:
         if self._enable_action_filter:
             return self._views["filt"][2].t()[:, :self.action_dim]
         return torch.zeros(self.num_envs, self.action_dim, device=self.device)
+
+    def set_demo(self, demo, rows_are_actions=False):
+        """the demonstration of the *_DEMO tasks (TaskJumpingDemo.demo_list, tasks/task_base.py:169-176): an array of
+        GetDemonstrationWrapper rows [L, A + 38] (or of bare actions [L, A])"""
+        d = np.asarray(demo, dtype=np.float32)
+        a = np.ascontiguousarray(d if rows_are_actions else d[:, :self.action_dim])
+        if a.ndim != 2 or a.shape[1] != self.action_dim:
+            raise ValueError(f"demonstration rows must start with {self.action_dim} action values")
+        self.demo_list, self.demo_length = d, int(a.shape[0])
+        _lib.check(self._L.qs_set_demo(self._h, a.ctypes.data_as(C.c_void_p), int(a.shape[0])))
 
     def set_terminal_obs_buffer(self, buf):
         """device tensor [N, O] (or None) that receives the last observation of every env whose episode ends inside

@@ -356,8 +356,11 @@ def _make_env_for(qs, g, n=2):
     cfg = json.loads(str(g["cfg"]))
     cfg.pop("env_randomizer_mode", None)   # the fixture's draws (mu, springs, masses) are imposed below
     mode = "MASS_RANDOMIZER" if "masses" in g.files else "NO_RANDOMIZER"   # per-env mass properties need the mode
-    return qs.BatchedQuadrupedGymEnv(num_envs=n, enable_noise=False, auto_reset=False,
-                                     env_randomizer_mode=mode, solver=dict(mu_ground=float(g["mu"])), **cfg), cfg
+    env = qs.BatchedQuadrupedGymEnv(num_envs=n, enable_noise=False, auto_reset=False,
+                                    env_randomizer_mode=mode, solver=dict(mu_ground=float(g["mu"])), **cfg)
+    if "demo" in g.files:      # *_DEMO tasks: the demonstration the reference task loaded (task_base.py:169-176)
+        env.set_demo(g["demo"])
+    return env, cfg
 
 
 @pytest.mark.parametrize("name", ROLLOUTS)
@@ -369,7 +372,15 @@ def test_rollout_free_running_tracks_reference_env(qs, name):
     if "springs" in g.files or "masses" in g.files:
         pytest.skip("randomized springs / masses enter the settle: covered by test_*_randomizer_* and the teacher-forced replay")
     env, cfg = _make_env_for(qs, g)
-    obs = env.reset()
+    if "rsi" in name:   # ReferenceStateInitializationWrapper: the episode starts on a demonstration row, unsettled
+        from quadruped_springs_b200.demo import demo_rows_to_states
+        el = int(g["demo_start"])
+        env.reset()
+        env.task.set_demo_counter(float(el))
+        obs = env.reset_to_state(cuda(np.stack([demo_rows_to_states(g["demo"][el], 6)] * 2)))
+        assert float(env.task.delta_demo[0]) == len(g["demo"]) - el
+    else:
+        obs = env.reset()
     np.testing.assert_allclose(env.get_state()[0].cpu().numpy(), g["init_state"], atol=1e-3)
     np.testing.assert_allclose(obs[0].cpu().numpy(), g["init_obs"], atol=1e-3)
     np.testing.assert_allclose(env.get_last_action()[0].cpu().numpy(), g["init_last_action"], atol=1e-5)
@@ -385,6 +396,8 @@ def test_rollout_free_running_tracks_reference_env(qs, name):
         assert float(r[0]) == pytest.approx(float(g["reward"][t]), abs=2e-5)
         assert bool(d[0]) == bool(g["done"][t])
         assert torch.equal(obs[0], obs[1])   # identical envs stay bit-identical
+        if "demo" in g.files:
+            assert int(env.task.demo_counter[0]) == int(g["demo_start"]) + t + 1
 
 
 @pytest.mark.parametrize("name", ROLLOUTS)
@@ -396,6 +409,9 @@ def test_rollout_teacher_forced_matches_reference_env(qs, name):
     g = load_golden(f"rollout_{name}.npz")
     env, cfg = _make_env_for(qs, g)
     env.reset()
+    if "rsi" in name:                 # the episode the fixture recorded started at row `demo_start` of the demonstration
+        env.task.set_demo_counter(float(int(g["demo_start"])))
+        env.reset_to_state(cuda(np.stack([g["init_state"]] * 2)))
     if "springs" in g.files:          # the fixture's spring draw (per-env arrays stay until the next reset)
         env._views["spring"][:] = cuda(g["springs"])[:, None]
     if "masses" in g.files:           # the fixture's mass draw and friction
@@ -456,6 +472,8 @@ def test_rollout_teacher_forced_matches_reference_env(qs, name):
                 assert [float(T.jump_counter[0]), float(T.good_jump_counter[0]), float(T.first_jump[0])] == list(gt[16:19]), t
                 assert float(T.max_jump_height[0]) == pytest.approx(gt[19], abs=1e-3), t
     assert bool(g["done"][-1]) == bool(d[0])
+    if "demo" in g.files:
+        assert int(env.task.demo_counter[0]) == int(g["demo_counter_end"])
     if "jumps" in g.files and len(g["jumps"][0]):
         # the kernels keep sums instead of the reference's per-jump arrays (csrc/qs_types.h TaskSlot)
         fwd, perf = g["jumps"]

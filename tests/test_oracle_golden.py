@@ -119,7 +119,16 @@ def test_rollout_matches_reference_env(name):
         env.world.set_mass(0, m[3])
         env.world.set_payload(m[4], m[5:8])
         assert 0 < m[4] < 1 and abs(m[3] + m[4] + 4 * m[:3].sum() + 0.24 - 12.01301) < 1e-9   # total mass is kept (:56-60)
-    obs = env.reset(mu=float(g["mu"]))
+    if "demo" in g.files:      # *_DEMO tasks: the demonstration the reference task loaded (task_base.py:169-176)
+        env.set_demo(g["demo"][:, :env.action_dim])
+    if "rsi" in name:          # ReferenceStateInitializationWrapper: start on a demonstration row, unsettled (:24-32)
+        from quadruped_springs_b200.demo import demo_rows_to_states
+        el = int(g["demo_start"])
+        env.set_demo_counter(el)
+        obs = env.reset_to_state(demo_rows_to_states(g["demo"][el], env.action_dim), mu=float(g["mu"]))
+        assert np.abs(g["init_last_action"]).max() == 0 and env.demo_counter() == el
+    else:
+        obs = env.reset(mu=float(g["mu"]))
     np.testing.assert_allclose(env.world.get_state(), g["init_state"], rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(obs, g["init_obs"], rtol=1e-9, atol=1e-10)
     for t in range(len(g["reward"])):
@@ -143,6 +152,8 @@ def test_rollout_matches_reference_env(name):
                 np.testing.assert_allclose(ts[29:32], gt[13:16], rtol=1e-8, atol=1e-10, err_msg=f"continuous step {t}")
                 if cfg["task_env"] in ("CONTINUOUS_JUMPING_FORWARD3", "CONTINUOUS_JUMPING_FORWARD_PPO"):
                     np.testing.assert_allclose(cnt, gt[16:21], rtol=1e-8, atol=1e-10, err_msg=f"jump counters step {t}")
+    if "demo" in g.files:
+        assert env.demo_counter() == int(g["demo_counter_end"])
     if "jumps" in g.files:
         fwd, perf, _ = env.jump_arrays()
         np.testing.assert_allclose(fwd, g["jumps"][0], rtol=1e-8, atol=1e-10)

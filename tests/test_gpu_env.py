@@ -299,3 +299,52 @@ def test_step_host_fetches_urgent_first_observations(qs, monkeypatch):
         assert np.array_equal(out[0], obs.cpu().numpy()), t
         assert np.array_equal(out[1], r.cpu().numpy()) and np.array_equal(out[2].astype(bool), d.cpu().numpy()), t
     assert urgent > 0
+
+
+def test_everything_on_is_shard_invariant_and_consistent(qs):
+    """all the widened pieces at once -- curriculum randomizers (ground, masses + payload, springs), LandingWrapper2,
+    GoToRestWrapper, action filter, sensor noise, auto-reset with the settle conveyor -- for 400 steps: finite, legal
+    controller transitions, controller gains where they belong, and the second shard of a two-GPU run (global env ids
+    2048..4095) reproduces the second half of the full run bit for bit, resets included."""
+    n, steps = 4096, 400
+    cfg = dict(enable_springs=True, task_env="JUMPING_FORWARD", motor_control_mode="CARTESIAN_PD", observation_space_mode="ARS_BASIC",
+               env_randomizer_mode="TEST_RANDOMIZER_CURRICULUM", curriculum_level=0.5, landing_wrapper="LandingWrapper2",
+               go_to_rest_wrapper=True, enable_action_filter=True, seed=13)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    # mostly hops (the scripted controllers need take-offs), some random steps
+    acts = []
+    for t in range(steps):
+        ph = t % 70
+        z, x = (1.0, 0.3) if ph < 25 else ((-1.0, -0.5) if ph < 37 else (-0.1, 0.0))
+        a = torch.tensor([x, 0, z, x, 0, z], device="cuda").expand(n, -1) + 0.15 * torch.randn(n, 6, device="cuda", generator=g)
+        acts.append(a.clamp(-1, 1).contiguous())
+
+    def run(offset, count, sl, check):
+        env = qs.BatchedQuadrupedGymEnv(num_envs=count, env_id_offset=offset, **cfg)
+        out = [env.reset().clone()]
+        prev_land = torch.zeros(count, dtype=torch.int32, device="cuda")
+        seen_rest = seen_land = episodes = 0
+        for a in acts:
+            obs, r, d, info = env.step(a[sl].contiguous())
+            out.append(torch.cat([obs, r[:, None], d[:, None].float()], dim=1).clone())
+            if check:
+                land, rest = info["landing_mode"].clone(), info["rest_active"].clone()
+                assert torch.isfinite(obs).all() and torch.isfinite(r).all()
+                ok = (land == prev_land) | ((prev_land == 0) & (land == 1)) | ((prev_land == 1) & (land == 2)) | \
+                     ((prev_land == 2) & (land == 3)) | (d & (land == 0))
+                assert ok.all()
+                kp = env._views["kp"][0]
+                assert (kp[rest != 0] == 60).all() and (kp[(rest == 0)] == 75).all()     # LandingWrapper2 keeps the default gains
+                assert (rest[d] == 0).all()                                                # a new episode starts unscripted
+                seen_rest += int((rest != 0).sum()); seen_land += int((land == 2).sum()); episodes += int(d.sum())
+                prev_land = land
+        if check:
+            assert seen_rest > 0 and seen_land > 0 and episodes > n
+            md = env._views["mass_draw"]
+            assert float(md[4].max()) > 1.5 and float(md[4].max()) < 2.5                 # curriculum level 0.5: block up to 2.5 kg
+        return out
+
+    full = run(0, n, slice(0, n), True)
+    half = run(n // 2, n // 2, slice(n // 2, n), False)
+    for x, y in zip(full, half):
+        assert torch.equal(x[n // 2:], y)

@@ -34,6 +34,27 @@ def test_config_struct_layout_matches_c():
     assert cfg.time_step == 0.001 and cfg.max_episode_time == 10.0
     assert cfg.gravity_z == pytest.approx(-9.8) and cfg.max_coord_vel == pytest.approx(30.1)
     assert cfg.breaking_threshold == pytest.approx(0.02) and cfg.warmstart == pytest.approx(0.1)
+    # the fields after the solver block (wrappers, randomizers): a layout drift would scramble these
+    assert cfg.landing_mode == 0 and cfg.spring_randomizer == 0 and cfg.rest_mode == 0 and cfg.mass_randomizer == 0
+    assert cfg.rand_leg_mass_err == pytest.approx(0.1) and cfg.rand_payload_max == pytest.approx(1.0)
+    assert list(cfg.rand_payload_pos) == pytest.approx([0.1, 0.0, 0.1]) and cfg.rand_spring_err == pytest.approx(0.1)
+
+
+def test_integration_md_binding_matches_the_header_struct():
+    """the ctypes QsConfig shown to reference maintainers in INTEGRATION.md has the fields of include/qs_b200.h, in order"""
+    header = open(os.path.join(ROOT, "include", "qs_b200.h")).read()
+    body = header[header.index("typedef struct qs_config {"):header.index("} qs_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split("{", 1)[1].split(";"):
+        m = re.match(r"\s*(?:int32_t|uint64_t|int64_t|double|float)\s+(.*)", decl, flags=re.S)
+        if m:
+            fields += [re.match(r"[a-z_0-9]+", x.strip()).group(0) for x in m.group(1).split(",")]
+    assert fields == [f[0] for f in _lib.QsConfig._fields_]
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = doc[doc.index("class QsConfig(C.Structure)"):doc.index("CONTROL = {")]
+    names = re.findall(r'"([a-z_0-9]+)"', block)
+    assert names == fields
 
 
 def test_no_gpu_means_loud_failure():

@@ -324,8 +324,8 @@ struct qs_env {
   ModelConstT<double> model_d;
   void* pool;       // one allocation backing every SoA array
   size_t pool_bytes;
-  int* lists;          // slow (n + 1) | reset (n + 1) | contact (n + 1) | urgent (2 n) | conveyor fifo, tick, wip, control words
-  int *slow_list, *reset_list, *contact_list;
+  int* lists;          // slow (n + 1) | reset (n + 1) | contact (n + 1) | flight (n + 1) | urgent (2 n) | conveyor fifo, tick, wip, control words
+  int *slow_list, *reset_list, *contact_list, *flight_list;
   Conveyor cv;
   int wave_blocks;     // settle blocks resident at once (SMs x 2)
   int slice_min, slice_max, slice_early;
@@ -551,14 +551,15 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MIN")) h->slice_min = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MAX")) h->slice_max = std::max(h->slice_min, std::atoi(v));
     const size_t w = size_t(cv.width);
-    const size_t nints = 3 * (n + 1) + 2 * n + 2 * cap + cap + (WIP_ROWS + 1 + EM_ROWS) * w + CV_CTL_WORDS + 8;
+    const size_t nints = 4 * (n + 1) + 2 * n + 2 * cap + cap + (WIP_ROWS + 1 + EM_ROWS) * w + CV_CTL_WORDS + 8;
     e = cudaMalloc(&h->lists, nints * sizeof(int));
     if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(QS_ERR_CUDA, "cudaMalloc lists"); }
     cudaMemset(h->lists, 0, nints * sizeof(int));
     h->slow_list = h->lists;
     h->reset_list = h->slow_list + n + 1;
     h->contact_list = h->reset_list + n + 1;
-    cv.urgent_list = h->contact_list + n + 1;
+    h->flight_list = h->contact_list + n + 1;
+    cv.urgent_list = h->flight_list + n + 1;
     cv.fifo = cv.urgent_list + 2 * n;
     cv.tick = cv.fifo + 2 * cap;
     cv.wip = reinterpret_cast<float*>(cv.tick + cap);
@@ -803,6 +804,7 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   const int B = block_of(h);
   CUDA_TRY(cudaMemsetAsync(h->slow_list + h->n, 0, sizeof(int), s));
   CUDA_TRY(cudaMemsetAsync(h->contact_list + h->n, 0, sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(h->flight_list + h->n, 0, sizeof(int), s));
   if (!h->ev_ready) {
     for (int i = 0; i < qs_env::kRing; i++) {
       CUDA_TRY(cudaEventCreate(&h->ev0[i])); CUDA_TRY(cudaEventCreate(&h->ev1[i]));
@@ -816,9 +818,12 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   io.term_obs = h->term_obs;
   io.slow_list = h->slow_list;
   io.contact_list = h->contact_list;
+  io.flight_list = h->flight_list;
   io.cv = h->cv;
   const int slot = int(h->n_steps % qs_env::kRing);
   cudaEventRecord(h->ev0[slot], s);
+  k_pre<<<grid_for(h->n, 256), 256, 0, s>>>(h->args, io);
+  g_launches += 1;
   if (h->args.C.mass_randomizer) k_step<true><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io); else k_step<false><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
   if (h->cfg.auto_reset) {
     // conveyor, early slice: on the second stream, next to k_step_contact (about half a wave of blocks)

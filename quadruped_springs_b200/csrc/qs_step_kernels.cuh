@@ -138,7 +138,8 @@ struct StepIO {
   uint8_t* truncated;
   float* term_obs;   // optional [N][O]: last observation of the episodes that finished in this step (qs_set_terminal_obs)
   int* slow_list;    // envs parked for the general solver, slow_list[n] = count
-  int* contact_list; // envs handed from the flight kernel to the contact kernel, contact_list[n] = count
+  int* contact_list; // envs with a foot on the ground (k_pre) or reaching it (flight kernel), contact_list[n] = count
+  int* flight_list;  // the others: k_step's work, flight_list[n] = count
   Conveyor cv;
 };
 
@@ -682,23 +683,18 @@ __device__ __forceinline__ void park_env(const KernelArgs& A, const StepIO& io, 
   list[atomicAdd(list + n, 1)] = env;
 }
 
-// -------------------------------------------------------------------- K1: step
-template <bool kEM>
-__global__ void __launch_bounds__(256, 1)
-k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
+// -------------------------------------------------------------------- K0: action -> motor command, and who goes where
+// The step's prologue for every env (quadruped_gym_env.py:229-234: scripted-controller overrides, _last_action, action
+// filter, action -> motor command) and the classification the step kernels work from: an env with a foot on the ground
+// goes straight to k_step_contact's list, the others to the flight kernel's, so that both run dense warps.
+__global__ void __launch_bounds__(256)
+k_pre(const __grid_constant__ KernelArgs A, const StepIO io) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const DeviceView& D = A.D;
   const EnvCfg& C = A.C;
   const int n = D.n;
-  // threads past the end shadow the last env (block-wide barriers inside run_ticks need every
-  // thread); they compute the same thing and write nothing
   const bool live = tid < n;
   const int env = live ? tid : n - 1;
-  const float dt = A.SC.dt;
-  EnvState<float> st;
-  ContactState<float> cs;
-  load_state(D, env, st, cs, dt);
-
   // ---- action (quadruped_gym_env.py:229-234)
   float act[12];
 #pragma unroll
@@ -780,19 +776,63 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
     torque_mode = C.control_mode == QS_CTRL_TORQUE;
   }
 
-  // ---- action_repeat substeps (:236-237), flight variant of the tick: no foot-contact code.  An env
-  // with a foot on (or reaching) the ground goes to k_step_contact, which runs dense warps of such envs.
+  bool grounded = false;
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) D.cmd[i * n + env] = cmd[i];
+    D.resume_tick[env] = 0;
+    grounded = (D.contact[env] & 15) != 0;  // standing / pushing
+  }
+  // one atomic per warp and list
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned mg = __ballot_sync(0xffffffffu, live && grounded), mf = __ballot_sync(0xffffffffu, live && !grounded);
+  int bg = 0, bf = 0;
+  if (lane == 0) {
+    if (mg) bg = atomicAdd(io.contact_list + n, __popc(mg));
+    if (mf) bf = atomicAdd(io.flight_list + n, __popc(mf));
+  }
+  bg = __shfl_sync(0xffffffffu, bg, 0);
+  bf = __shfl_sync(0xffffffffu, bf, 0);
+  const unsigned below = (1u << lane) - 1u;
+  if (live && grounded) io.contact_list[bg + __popc(mg & below)] = env;
+  if (live && !grounded) io.flight_list[bf + __popc(mf & below)] = env;
+  (void)torque_mode;
+}
+
+// -------------------------------------------------------------------- K1: step, flight part
+// The envs with no foot on the ground (dense warps: thread i takes flight_list[i]): flight variant of the tick, no
+// foot-contact code.  An env that reaches the ground goes on to k_step_contact as of the start of that tick.
+template <bool kEM>
+__global__ void __launch_bounds__(256, 1)
+k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const DeviceView& D = A.D;
+  const EnvCfg& C = A.C;
+  const int n = D.n;
+  const int count = io.flight_list[n];
+  if (blockIdx.x * blockDim.x >= count) return;  // uniform over the block
+  // threads past the end shadow the last entry (block-wide barriers inside run_ticks need every
+  // thread); they compute the same thing and write nothing
+  const bool live = tid < count;
+  const int env = io.flight_list[live ? tid : count - 1];
+  EnvState<float> st;
+  ContactState<float> cs;
+  load_state(D, env, st, cs, A.SC.dt);
+  float cmd[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) cmd[i] = D.cmd[i * n + env];
+  const bool torque_mode = !C.is_rl && C.control_mode == QS_CTRL_TORQUE;
+
+  // ---- action_repeat substeps (:236-237)
   float tau_m[12], tau_s[12];
   extern __shared__ float qs_smem[];
   const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
   int why;
-  const bool grounded = (cs.mask & 15) != 0;  // standing / pushing: straight to the contact kernel
   const int t_done = run_ticks<false, kEM>(st, cs, cmd, torque_mode, 0, C.action_repeat, env, D, C, A.RC, A.M, A.SC, tau_m, tau_s,
-                                      true, scr, &why, grounded);
+                                      true, scr, &why);
   if (!live) return;
   if (t_done < C.action_repeat) {
-    // (a grounded env is handed over as loaded: nothing to store)
-    park_env(A, io, env, st, cs, cmd, t_done, why == TICK_NEEDS_GENERAL ? io.slow_list : io.contact_list, !grounded);
+    park_env(A, io, env, st, cs, cmd, t_done, why == TICK_NEEDS_GENERAL ? io.slow_list : io.contact_list);
     return;
   }
   finish_step<kEM>(A, io, env, st, cs, tau_m, tau_s);

@@ -325,11 +325,7 @@ struct qs_env {
   void* pool;       // one allocation backing every SoA array
   size_t pool_bytes;
   int* lists;          // slow (n + 1) | reset (n + 1) | contact (n + 1) | flight (n + 1) | urgent (2 n) | conveyor fifo, tick, wip, control words
-  int *slow_list, *reset_list, *contact_list, *flight_list, *contact_list2, *slow_list2;
-  int dual_chain;      // the grounded envs' chain (contact -> general) runs next to the flight envs' (flight -> contact -> general)
-  cudaStream_t aux;    // ... on this stream
-  cudaEvent_t ev_pre, ev_aux;
-  cudaEvent_t ev1b[512];  // end of the second chain's contact kernel (kernel-time query)
+  int *slow_list, *reset_list, *contact_list, *flight_list;
   Conveyor cv;
   int wave_blocks;     // settle blocks resident at once (SMs x 2)
   int slice_min, slice_max, slice_early;
@@ -546,8 +542,6 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     h->slice_min = 4;
     h->slice_max = 1 << 20;  // no cap: the slice follows the demand
     h->slice_early = 10;  // ticks of the early slice (measured optimum 6-12: longer and it slows k_step_contact down)
-    h->dual_chain = 0;
-    if (const char* v = std::getenv("QS_DUAL_CHAIN")) h->dual_chain = std::atoi(v) != 0;
     h->slow_spread = 32;
     if (const char* v = std::getenv("QS_SLOW_SPREAD")) {
       const int k = std::atoi(v);
@@ -557,7 +551,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MIN")) h->slice_min = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MAX")) h->slice_max = std::max(h->slice_min, std::atoi(v));
     const size_t w = size_t(cv.width);
-    const size_t nints = 6 * (n + 1) + 2 * n + 2 * cap + cap + (WIP_ROWS + 1 + EM_ROWS) * w + CV_CTL_WORDS + 8;
+    const size_t nints = 4 * (n + 1) + 2 * n + 2 * cap + cap + (WIP_ROWS + 1 + EM_ROWS) * w + CV_CTL_WORDS + 8;
     e = cudaMalloc(&h->lists, nints * sizeof(int));
     if (e != cudaSuccess) { cudaFree(h->pool); delete h; return fail(QS_ERR_CUDA, "cudaMalloc lists"); }
     cudaMemset(h->lists, 0, nints * sizeof(int));
@@ -565,9 +559,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     h->reset_list = h->slow_list + n + 1;
     h->contact_list = h->reset_list + n + 1;
     h->flight_list = h->contact_list + n + 1;
-    h->contact_list2 = h->flight_list + n + 1;
-    h->slow_list2 = h->contact_list2 + n + 1;
-    cv.urgent_list = h->slow_list2 + n + 1;
+    cv.urgent_list = h->flight_list + n + 1;
     cv.fifo = cv.urgent_list + 2 * n;
     cv.tick = cv.fifo + 2 * cap;
     cv.wip = reinterpret_cast<float*>(cv.tick + cap);
@@ -578,9 +570,6 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     cudaMemset(cv.tick, 0xff, cap * sizeof(int));  // CV_DONE: nothing queued
     e = cudaStreamCreateWithFlags(&h->bg, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_results, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMallocHost(&h->host_urgent, sizeof(uint32_t));
@@ -620,9 +609,6 @@ int qs_destroy(qs_handle h) {
   if (h->dev_demo) cudaFree(h->dev_demo);
   cudaStreamDestroy(h->bg);
   cudaStreamDestroy(h->copy);
-  cudaStreamDestroy(h->aux);
-  cudaEventDestroy(h->ev_pre);
-  cudaEventDestroy(h->ev_aux);
   cudaEventDestroy(h->ev_results);
   cudaEventDestroy(h->ev_copied);
   cudaFreeHost(h->host_urgent);
@@ -636,7 +622,7 @@ int qs_destroy(qs_handle h) {
   if (h->ev_ready)
     for (int i = 0; i < qs_env::kRing; i++) {
       cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); cudaEventDestroy(h->ev2[i]); cudaEventDestroy(h->ev3[i]);
-      cudaEventDestroy(h->ev4[i]); cudaEventDestroy(h->ev5[i]); cudaEventDestroy(h->ev1b[i]);
+      cudaEventDestroy(h->ev4[i]); cudaEventDestroy(h->ev5[i]);
     }
   delete h;
   return QS_OK;
@@ -650,10 +636,8 @@ int qs_step_kernel_time(qs_handle h, int last_k, float* ms_sum) {
   float tot = 0.f;
   for (int64_t i = h->n_steps - last_k; i < h->n_steps; i++) {
     float ms = 0.f;
-    float ms2 = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0[i % qs_env::kRing], h->ev1[i % qs_env::kRing]));
-    CUDA_TRY(cudaEventElapsedTime(&ms2, h->ev0[i % qs_env::kRing], h->ev1b[i % qs_env::kRing]));  // second chain, if any
-    tot += std::max(ms, ms2);
+    tot += ms;
   }
   *ms_sum = tot;
   return QS_OK;
@@ -753,7 +737,7 @@ static int launch_conveyor(qs_handle h, cudaStream_t s, int phase, int flush) {
   // the latency-bound kernel the slice of this phase runs next to, and its block size
   const int* busy = phase == 0 ? h->contact_list + h->n : h->slow_list + h->n;
   k_conveyor_ctl<<<1, 1024, 0, s>>>(h->cv, phase, busy, phase == 0 ? B : 2 * h->slow_spread, h->wave_blocks, B, h->n, nsettle,
-                                    h->slice_min, h->slice_max, h->slice_early, flush, h->dual_chain);
+                                    h->slice_min, h->slice_max, h->slice_early, flush);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return QS_OK;
@@ -826,7 +810,6 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
       CUDA_TRY(cudaEventCreate(&h->ev0[i])); CUDA_TRY(cudaEventCreate(&h->ev1[i]));
       CUDA_TRY(cudaEventCreate(&h->ev2[i])); CUDA_TRY(cudaEventCreate(&h->ev3[i]));
       CUDA_TRY(cudaEventCreate(&h->ev4[i])); CUDA_TRY(cudaEventCreate(&h->ev5[i]));
-      CUDA_TRY(cudaEventCreate(&h->ev1b[i]));
     }
     h->ev_ready = true;
   }
@@ -836,77 +819,34 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   io.slow_list = h->slow_list;
   io.contact_list = h->contact_list;
   io.flight_list = h->flight_list;
-  const bool dual = h->dual_chain && h->cfg.auto_reset;
-  io.flight_contact_out = dual ? h->contact_list2 : h->contact_list;
-  io.flight_slow_out = dual ? h->slow_list2 : h->slow_list;
   io.cv = h->cv;
   const int slot = int(h->n_steps % qs_env::kRing);
-  const bool em = h->args.C.mass_randomizer != 0;
-  const unsigned G = grid_for(h->n, B);
-  const size_t SM = smem_of(B);
-#define QS_LAUNCH_FLIGHT(st) do { if (em) k_step<true><<<G, B, SM, st>>>(h->args, io); else k_step<false><<<G, B, SM, st>>>(h->args, io); } while (0)
-#define QS_LAUNCH_CONTACT(st, list, out) do { if (em) k_step_contact<true><<<G, B, SM, st>>>(h->args, io, list, out); \
-                                              else k_step_contact<false><<<G, B, SM, st>>>(h->args, io, list, out); } while (0)
-#define QS_LAUNCH_SLOW(st, list) do { if (em) k_step_slow<true><<<grid_for(h->n, 64), 64, 0, st>>>(h->args, io, list, h->slow_spread); \
-                                      else k_step_slow<false><<<grid_for(h->n, 64), 64, 0, st>>>(h->args, io, list, h->slow_spread); } while (0)
   cudaEventRecord(h->ev0[slot], s);
   k_pre<<<grid_for(h->n, 256), 256, 0, s>>>(h->args, io);
   g_launches += 1;
-  if (dual) {
-    // Two chains side by side.  The envs standing on the ground need nothing from the flight kernel: their contact
-    // kernel starts at once on the caller's stream and the general-solver pass for the crashes it finds follows it,
-    // while the flight envs run flight -> contact (touch-downs) -> general solver on a second stream.
-    CUDA_TRY(cudaMemsetAsync(h->contact_list2 + h->n, 0, sizeof(int), s));
-    CUDA_TRY(cudaMemsetAsync(h->slow_list2 + h->n, 0, sizeof(int), s));
-    if (int e = launch_conveyor(h, s, 0, 0)) return e;  // before the fork: nobody is pushing entries yet
-    CUDA_TRY(cudaEventRecord(h->ev_pre, s));
-    CUDA_TRY(cudaStreamWaitEvent(h->aux, h->ev_pre, 0));
-    QS_LAUNCH_FLIGHT(h->aux);
-    QS_LAUNCH_CONTACT(h->aux, h->contact_list2, h->slow_list2);
-    cudaEventRecord(h->ev1b[slot], h->aux);
-    QS_LAUNCH_SLOW(h->aux, h->slow_list2);
-    CUDA_TRY(cudaEventRecord(h->ev_aux, h->aux));
-    CUDA_TRY(cudaStreamWaitEvent(h->bg, h->ev_pre, 0));
+  if (h->args.C.mass_randomizer) k_step<true><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io); else k_step<false><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
+  if (h->cfg.auto_reset) {
+    // conveyor, early slice: on the second stream, next to k_step_contact (about half a wave of blocks)
+    if (int e = launch_conveyor(h, s, 0, 0)) return e;
+    CUDA_TRY(cudaEventRecord(h->ev_fork0, s));
+  }
+  if (h->args.C.mass_randomizer) k_step_contact<true><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io); else k_step_contact<false><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
+  g_launches += 1;
+  cudaEventRecord(h->ev1[slot], s);
+  h->n_steps++;
+  if (h->cfg.auto_reset) {
+    CUDA_TRY(cudaStreamWaitEvent(h->bg, h->ev_fork0, 0));
     cudaEventRecord(h->ev4[slot], h->bg);
     if (int e = launch_slice(h, h->bg, 1)) return e;
     cudaEventRecord(h->ev5[slot], h->bg);
-    QS_LAUNCH_CONTACT(s, h->contact_list, h->slow_list);
-    cudaEventRecord(h->ev1[slot], s);
-    h->n_steps++;
+    // late slice: bookkeeping in stream order, then the slice on the second stream next to k_step_slow
     if (int e = launch_conveyor(h, s, 1, 0)) return e;
     CUDA_TRY(cudaEventRecord(h->ev_fork, s));
-    QS_LAUNCH_SLOW(s, h->slow_list);
-    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_aux, 0));
-    g_launches += 5;
-  } else {
-    QS_LAUNCH_FLIGHT(s);
-    if (h->cfg.auto_reset) {
-      // conveyor, early slice: on the second stream, next to k_step_contact (about half a wave of blocks)
-      if (int e = launch_conveyor(h, s, 0, 0)) return e;
-      CUDA_TRY(cudaEventRecord(h->ev_fork0, s));
-    }
-    QS_LAUNCH_CONTACT(s, h->contact_list, h->slow_list);
-    g_launches += 1;
-    cudaEventRecord(h->ev1[slot], s);
-    cudaEventRecord(h->ev1b[slot], s);
-    h->n_steps++;
-    if (h->cfg.auto_reset) {
-      CUDA_TRY(cudaStreamWaitEvent(h->bg, h->ev_fork0, 0));
-      cudaEventRecord(h->ev4[slot], h->bg);
-      if (int e = launch_slice(h, h->bg, 1)) return e;
-      cudaEventRecord(h->ev5[slot], h->bg);
-      // late slice: bookkeeping in stream order, then the slice on the second stream next to k_step_slow
-      if (int e = launch_conveyor(h, s, 1, 0)) return e;
-      CUDA_TRY(cudaEventRecord(h->ev_fork, s));
-    }
-    // envs parked for the general solver (joint limits / body contacts); launched before the slice so
-    // that its few blocks are placed first
-    QS_LAUNCH_SLOW(s, h->slow_list);
-    g_launches += 2;
   }
-#undef QS_LAUNCH_FLIGHT
-#undef QS_LAUNCH_CONTACT
-#undef QS_LAUNCH_SLOW
+  // envs parked for the general solver (joint limits / body contacts); launched before the slice so
+  // that its few blocks are placed first
+  if (h->args.C.mass_randomizer) k_step_slow<true><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread); else k_step_slow<false><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread);
+  g_launches += 2;
   if (host) {
     // the step's outputs are final here (only an urgent settle, below, rewrites obs rows: the caller checks
     // host_urgent and repeats the obs copy in that case); the copies overlap the settle slice

@@ -140,8 +140,6 @@ struct StepIO {
   int* slow_list;    // envs parked for the general solver, slow_list[n] = count
   int* contact_list; // envs with a foot on the ground (k_pre) or reaching it (flight kernel), contact_list[n] = count
   int* flight_list;  // the others: k_step's work, flight_list[n] = count
-  int* flight_contact_out;  // where the flight kernel parks envs reaching the ground / needing the general solver:
-  int* flight_slow_out;     // the lists above, or a second pair when the two chains of a step run side by side
   Conveyor cv;
 };
 
@@ -834,7 +832,7 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
                                       true, scr, &why);
   if (!live) return;
   if (t_done < C.action_repeat) {
-    park_env(A, io, env, st, cs, cmd, t_done, why == TICK_NEEDS_GENERAL ? io.flight_slow_out : io.flight_contact_out);
+    park_env(A, io, env, st, cs, cmd, t_done, why == TICK_NEEDS_GENERAL ? io.slow_list : io.contact_list);
     return;
   }
   finish_step<kEM>(A, io, env, st, cs, tau_m, tau_s);
@@ -845,15 +843,15 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
 // the full fast tick; joint limits / body contacts still go on to k_step_slow.
 template <bool kEM>
 __global__ void __launch_bounds__(256, 1)
-k_step_contact(const __grid_constant__ KernelArgs A, const StepIO io, const int* __restrict__ list, int* slow_out) {
+k_step_contact(const __grid_constant__ KernelArgs A, const StepIO io) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const DeviceView& D = A.D;
   const EnvCfg& C = A.C;
   const int n = D.n;
-  const int count = list[n];
+  const int count = io.contact_list[n];
   if (blockIdx.x * blockDim.x >= count) return;  // uniform over the block
   const bool live = tid < count;
-  const int env = list[live ? tid : count - 1];
+  const int env = io.contact_list[live ? tid : count - 1];
   EnvState<float> st;
   ContactState<float> cs;
   load_state(D, env, st, cs, A.SC.dt);
@@ -868,7 +866,7 @@ k_step_contact(const __grid_constant__ KernelArgs A, const StepIO io, const int*
                                      A.SC, tau_m, tau_s, true, scr, &why);
   if (!live) return;
   if (t_done < C.action_repeat) {
-    park_env(A, io, env, st, cs, cmd, t_done, slow_out);
+    park_env(A, io, env, st, cs, cmd, t_done, io.slow_list);
     return;
   }
   finish_step<kEM>(A, io, env, st, cs, tau_m, tau_s);
@@ -877,14 +875,14 @@ k_step_contact(const __grid_constant__ KernelArgs A, const StepIO io, const int*
 // -------------------------------------------------------------------- K1b: general-solver continuation
 template <bool kEM>
 __global__ void __launch_bounds__(64)
-k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io, const int* __restrict__ list, int spread) {
+k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io, int spread) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const DeviceView& D = A.D;
   const int n = D.n;
   // `spread` envs per warp: these envs take different paths through the general solver (which shapes touch, which
   // limits are active), so a full warp runs the union of 32 paths; the kernel is a few hundred envs, latency-bound,
   // on an otherwise idle part of the GPU, so fewer envs per warp shorten the step's serial chain.
-  const int count = list[n];
+  const int count = io.slow_list[n];
   const int warps = int(gridDim.x * blockDim.x) >> 5;
   int K = spread;
   while (K < 32 && (count + K - 1) / K > warps) K <<= 1;  // a list too long for the grid packs denser
@@ -892,7 +890,7 @@ k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io, const int* __
   if (lane >= K) return;
   const int idx = (tid >> 5) * K + lane;
   if (idx >= count) return;
-  const int env = list[idx];
+  const int env = io.slow_list[idx];
   EnvState<float> st;
   ContactState<float> cs;
   load_state(D, env, st, cs, A.SC.dt);
@@ -1028,11 +1026,9 @@ __global__ void k_urgent_clear(Conveyor cv) {
 //                                   the oldest entries that fit next to k_step_contact's blocks `early` ticks;
 //   phase 1 (after k_step_contact): the entries that fit next to k_step_slow's blocks get the rest of the ticks.
 __global__ void k_conveyor_ctl(Conveyor cv, int phase, const int* __restrict__ busy_count, int busy_block, int wave_blocks,
-                               int block, int n_envs, int nsettle, int s_min, int s_max, int early, int flush, int snap) {
+                               int block, int n_envs, int nsettle, int s_min, int s_max, int early, int flush) {
   __shared__ uint32_t first_live;
-  // snap: step kernels of the other chain may be pushing right now (an index is reserved before its entry is written):
-  // phase 1 then stops at the head phase 0 saw, when nothing was running
-  const uint32_t head = (snap && phase == 1 && !flush) ? cv.ctl[CV_PREV_HEAD] : cv.ctl[CV_HEAD];
+  const uint32_t head = cv.ctl[CV_HEAD];
   uint32_t tail = cv.ctl[CV_TAIL];
   if (phase == 0 || flush) {
     const uint32_t span = min(head - tail, uint32_t(cv.width));

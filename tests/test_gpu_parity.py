@@ -755,3 +755,81 @@ def test_curriculum_randomizer_ranges(qs):
         np.testing.assert_allclose(total, 12.01301 * 9.8, rtol=1e-2)       # every robot settled standing on its feet
         mu = env._views["mu"].cpu().numpy()
         assert mu.min() >= 0.5 and mu.max() < 1.0 and mu.std() > 0.1      # the ground randomizer comes first (:17-20)
+
+
+# ------------------------------------------------------------------ contact-rich episodes: matched task statistics
+def _open_loop(kind, T, rng):
+    acts = np.zeros((T, 6))
+    for t in range(T):
+        ph = t % 70
+        if kind == "jump":            # crouch, extend, hold (PD, SYMMETRIC)
+            th, ca = (0.9, -0.9) if ph < 25 else ((-0.6, 1.0) if ph < 37 else (0.0, 0.0))
+            a = np.array([0, th, ca, 0, th, ca])
+        elif kind == "hop_forward":   # CARTESIAN_PD: feet up and forward, push down and back, hold
+            z, x = (1.0, 0.3) if ph < 25 else ((-1.0, -0.5) if ph < 37 else (-0.1, 0.0))
+            a = np.array([x, 0, z, x, 0, z])
+        else:                         # backflip attempt: front legs push first, rear legs six steps later
+            f = (0.9, -0.9) if t < 25 else ((-0.6, 1.0) if t < 33 else (0.0, 0.0))
+            r = (0.9, -0.9) if t < 31 else ((-0.6, 1.0) if t < 39 else (0.0, 0.0))
+            a = np.array([0, f[0], f[1], 0, r[0], r[1]])
+        acts[t] = a + rng.normal(size=6) * 0.02
+    return acts
+
+
+@pytest.mark.parametrize("task,control,obs,kind", [
+    ("JUMPING_IN_PLACE", "PD", "ARS_BASIC", "jump"),
+    ("JUMPING_FORWARD", "CARTESIAN_PD", "ARS_BASIC", "hop_forward"),
+    ("BACKFLIP", "PD", "ARS_BACKFLIP", "backflip"),
+])
+def test_contact_rich_episodes_match_in_task_statistics(qs, task, control, obs, kind):
+    """north_star: a different arithmetic (fp32, another formulation of the same solver) cannot replay a contact-rich
+    trajectory of the fp64 oracle tick for tick, so whole episodes -- settle, push-off, flight, touch-down, crash or time
+    limit -- are compared by the task's own statistics under the same open-loop actions: jump height, forward distance,
+    flight time, flip completion, return, length.  32 robots on 32 different grounds (mu ~ U[0.5, 1))."""
+    from oracle import oracle as O
+    n, T = 32, 140
+    cfg = dict(enable_springs=True, task_env=task, motor_control_mode=control, observation_space_mode=obs)
+    env = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=21, enable_noise=False, auto_reset=False, **cfg)
+    env.reset()
+    mu = env._views["mu"].cpu().numpy().astype(np.float64)
+    acts = _open_loop(kind, T, np.random.default_rng(7))
+    keys = {"max_height": 13, "rel_max_height": 11, "max_fwd": 9, "max_flight_time": 8, "flip": 14}
+
+    def fold(stat, ts, alive):
+        for k, i in keys.items():
+            stat[k] = np.where(alive, np.maximum(stat[k], ts[i]), stat[k])
+
+    g = {k: np.zeros(n) for k in keys}
+    g_ret, g_len, alive = np.zeros(n), np.zeros(n, int), np.ones(n, bool)
+    for t in range(T):
+        o, r, d, _ = env.step(cuda(acts[t]).expand(n, -1))
+        fold(g, env._views["task"].cpu().numpy(), alive)
+        g_ret += np.where(alive, r.cpu().numpy(), 0)
+        g_len += alive
+        alive &= ~d.cpu().numpy()
+    ref = {k: np.zeros(n) for k in keys}
+    r_ret, r_len = np.zeros(n), np.zeros(n, int)
+    for i in range(n):
+        e = O.Env(**cfg)
+        e.reset(mu=float(mu[i]))
+        for t in range(T):
+            _, r, d, _ = e.step(acts[t])
+            ts = e.task_state()
+            for k, j in keys.items():
+                ref[k][i] = max(ref[k][i], ts[j])
+            r_ret[i] += r
+            r_len[i] += 1
+            if d:
+                break
+    g["flip"] /= 2 * np.pi
+    ref["flip"] /= 2 * np.pi
+    # the episodes did something: the robots left the ground
+    assert ref["max_flight_time"].mean() > 0.15 and ref["rel_max_height"].mean() > 0.05
+    tol_mean = {"max_height": 0.01, "rel_max_height": 0.01, "max_fwd": 0.02, "max_flight_time": 0.02, "flip": 0.02}
+    for k in keys:
+        assert abs(g[k].mean() - ref[k].mean()) < tol_mean[k], (k, g[k].mean(), ref[k].mean())
+        # and robot by robot for most of them (an episode whose landing tips the other way is allowed to differ)
+        close = np.abs(g[k] - ref[k]) < 3 * tol_mean[k]
+        assert close.mean() >= 0.8, (k, close.mean())
+    assert abs(g_ret.mean() - r_ret.mean()) < 0.03, (g_ret.mean(), r_ret.mean())
+    assert (np.abs(g_len - r_len) <= 2).mean() >= 0.8, (g_len, r_len)

@@ -340,6 +340,11 @@ struct qs_env {
   float* dev_reward;
   uint8_t* dev_done;
   uint8_t* dev_trunc;
+  // qs_step_host: the results of the envs the general solver finishes last travel in a compact side buffer
+  float* dev_late;     // [4 + late_cap * (O + 4)]: count | rows of (env, reward, done, truncated, obs[O])
+  float* host_late;    // pinned twin
+  int late_cap;
+  cudaEvent_t ev_late;
   float* term_obs;     // caller-owned, optional (qs_set_terminal_obs)
   float* dev_demo;     // demonstration actions of the *_DEMO tasks (qs_set_demo)
   bool was_reset;
@@ -619,6 +624,7 @@ int qs_destroy(qs_handle h) {
   if (h->dev_obs) cudaFree(h->dev_obs);
   if (h->dev_reward) cudaFree(h->dev_reward);
   if (h->dev_done) cudaFree(h->dev_done);
+  if (h->dev_late) { cudaFree(h->dev_late); cudaFreeHost(h->host_late); cudaEventDestroy(h->ev_late); }
   if (h->ev_ready)
     for (int i = 0; i < qs_env::kRing; i++) {
       cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); cudaEventDestroy(h->ev2[i]); cudaEventDestroy(h->ev3[i]);
@@ -785,6 +791,24 @@ int qs_reset(qs_handle h, const uint8_t* mask, float* obs, void* stream) {
   return QS_OK;
 }
 
+// qs_step_host: rows of the envs k_step_slow finished, packed for one small copy (they are the only rows that change after
+// k_step_contact; everything else is already on its way to the host while the general solver and the settle slice run)
+__global__ void k_gather_late(const int* __restrict__ list, int n, int O, const float* __restrict__ obs,
+                              const float* __restrict__ reward, const uint8_t* __restrict__ done,
+                              const uint8_t* __restrict__ truncated, float* __restrict__ out, int cap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int count = list[n];
+  if (i == 0) out[0] = __int_as_float(count);
+  if (i >= min(count, cap)) return;
+  const int env = list[i];
+  float* row = out + 4 + size_t(i) * size_t(O + 4);
+  row[0] = __int_as_float(env);
+  row[1] = reward[env];
+  row[2] = float(done[env]);
+  row[3] = float(truncated[env]);
+  for (int k = 0; k < O; k++) row[4 + k] = obs[size_t(env) * O + k];
+}
+
 // host destinations of qs_step_host: copied as soon as the last step kernel has written them
 struct HostOut {
   float* obs;
@@ -834,6 +858,18 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   g_launches += 1;
   cudaEventRecord(h->ev1[slot], s);
   h->n_steps++;
+  if (host) {
+    // All rows but those of the envs now in the general solver's list are final: send everything to the host while
+    // k_step_slow and the late settle slice run; the stragglers follow in a compact buffer (below), and rows an
+    // urgent settle rewrites are fetched again by the caller (host_urgent).
+    const size_t n = size_t(h->n), O = size_t(h->args.C.obs_dim);
+    CUDA_TRY(cudaEventRecord(h->ev_results, s));
+    CUDA_TRY(cudaStreamWaitEvent(h->copy, h->ev_results, 0));
+    CUDA_TRY(cudaMemcpyAsync(host->obs, obs, n * O * sizeof(float), cudaMemcpyDeviceToHost, h->copy));
+    CUDA_TRY(cudaMemcpyAsync(host->reward, reward, n * sizeof(float), cudaMemcpyDeviceToHost, h->copy));
+    CUDA_TRY(cudaMemcpyAsync(host->done, done, n, cudaMemcpyDeviceToHost, h->copy));
+    CUDA_TRY(cudaMemcpyAsync(host->truncated, truncated, n, cudaMemcpyDeviceToHost, h->copy));
+  }
   if (h->cfg.auto_reset) {
     CUDA_TRY(cudaStreamWaitEvent(h->bg, h->ev_fork0, 0));
     cudaEventRecord(h->ev4[slot], h->bg);
@@ -848,15 +884,14 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   if (h->args.C.mass_randomizer) k_step_slow<true><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread); else k_step_slow<false><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread);
   g_launches += 2;
   if (host) {
-    // the step's outputs are final here (only an urgent settle, below, rewrites obs rows: the caller checks
-    // host_urgent and repeats the obs copy in that case); the copies overlap the settle slice
-    const size_t n = size_t(h->n), O = size_t(h->args.C.obs_dim);
-    CUDA_TRY(cudaEventRecord(h->ev_results, s));
-    CUDA_TRY(cudaStreamWaitEvent(h->copy, h->ev_results, 0));
-    CUDA_TRY(cudaMemcpyAsync(host->obs, obs, n * O * sizeof(float), cudaMemcpyDeviceToHost, h->copy));
-    CUDA_TRY(cudaMemcpyAsync(host->reward, reward, n * sizeof(float), cudaMemcpyDeviceToHost, h->copy));
-    CUDA_TRY(cudaMemcpyAsync(host->done, done, n, cudaMemcpyDeviceToHost, h->copy));
-    CUDA_TRY(cudaMemcpyAsync(host->truncated, truncated, n, cudaMemcpyDeviceToHost, h->copy));
+    const int O = h->args.C.obs_dim;
+    k_gather_late<<<grid_for(h->late_cap, 128), 128, 0, s>>>(h->slow_list, h->n, O, obs, reward, done, truncated, h->dev_late,
+                                                             h->late_cap);
+    g_launches += 1;
+    CUDA_TRY(cudaEventRecord(h->ev_late, s));
+    CUDA_TRY(cudaStreamWaitEvent(h->copy, h->ev_late, 0));
+    CUDA_TRY(cudaMemcpyAsync(h->host_late, h->dev_late, (4 + size_t(h->late_cap) * size_t(O + 4)) * sizeof(float),
+                             cudaMemcpyDeviceToHost, h->copy));
     CUDA_TRY(cudaEventRecord(h->ev_copied, h->copy));
   }
   if (h->cfg.auto_reset) {
@@ -941,6 +976,12 @@ static int ensure_staging(qs_handle h) {
     CUDA_TRY(cudaMalloc(&h->dev_reward, n * sizeof(float)));
     CUDA_TRY(cudaMalloc(&h->dev_done, 2 * n));
     h->dev_trunc = h->dev_done + n;
+    h->late_cap = int(std::max<size_t>(1024, n / 16));
+    if (const char* v = std::getenv("QS_LATE_CAP")) h->late_cap = std::max(1, std::atoi(v));  // (tests: force the overflow path)
+    const size_t late_bytes = (4 + size_t(h->late_cap) * size_t(QS_MAX_OBS + 4)) * sizeof(float);
+    CUDA_TRY(cudaMalloc(&h->dev_late, late_bytes));
+    CUDA_TRY(cudaMallocHost(&h->host_late, late_bytes));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_late, cudaEventDisableTiming));
   }
   return QS_OK;
 }
@@ -975,7 +1016,26 @@ int qs_step_host(qs_handle h, const float* actions, float* obs, float* reward, u
     CUDA_TRY(cudaMemcpyAsync(h->host_urgent, h->cv.ctl + CV_URGENT_LAST, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamWaitEvent(s, h->ev_copied, 0));
   CUDA_TRY(cudaStreamSynchronize(s));
-  if (*h->host_urgent > 0) {  // some episodes were settled and started after the early copy: fetch their first obs
+  int late = 0;
+  std::memcpy(&late, h->host_late, sizeof(int));
+  if (late > h->late_cap) {  // more stragglers than the side buffer holds (never seen; a robot pile-up): take everything again
+    CUDA_TRY(cudaMemcpyAsync(obs, h->dev_obs, n * O * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(reward, h->dev_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(done, h->dev_done, n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(truncated, h->dev_trunc, n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+  } else {
+    for (int i = 0; i < late; i++) {  // the rows the general solver finished after the bulk copy had left
+      const float* row = h->host_late + 4 + size_t(i) * (O + 4);
+      int env;
+      std::memcpy(&env, row, sizeof(int));
+      reward[env] = row[1];
+      done[env] = uint8_t(row[2]);
+      truncated[env] = uint8_t(row[3]);
+      std::memcpy(obs + size_t(env) * O, row + 4, O * sizeof(float));
+    }
+  }
+  if (*h->host_urgent > 0 && late <= h->late_cap) {  // episodes settled and started after the copies: fetch their first obs
     CUDA_TRY(cudaMemcpyAsync(obs, h->dev_obs, n * O * sizeof(float), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
   }

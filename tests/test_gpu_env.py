@@ -116,18 +116,28 @@ def test_sensor_noise_statistics(qs):
     assert torch.equal(o, quiet.get_observation(with_noise=False))
 
 
-def test_step_host_matches_device_step(qs):
+@pytest.mark.parametrize("late_cap", [None, 2])
+def test_step_host_matches_device_step(qs, monkeypatch, late_cap):
+    """qs_step_host sends the bulk of the results to the host as soon as k_step_contact is done and the rows of the envs
+    the general solver finishes afterwards in a compact side buffer (scattered on the host); with a side buffer of two
+    rows the overflow path (everything copied again) runs instead.  Either way: the device-buffer step, bit for bit."""
+    if late_cap is not None:
+        monkeypatch.setenv("QS_LATE_CAP", str(late_cap))
     n = 2048
     e1 = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=5, **JIP)
     e2 = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=5, **JIP)
     e1.reset(); e2.reset()
     rng = np.random.default_rng(0)
-    for _ in range(5):
+    late = 0
+    for _ in range(60):
         a = rng.uniform(-1, 1, size=(n, 6)).astype(np.float32)
         o, r, d, t = e1.step_host(a)
         od, rd, dd, info = e2.step(torch.from_numpy(a).cuda())
         assert np.array_equal(o, od.cpu().numpy()) and np.array_equal(r, rd.cpu().numpy())
         assert np.array_equal(d.astype(bool), dd.cpu().numpy())
+        assert np.array_equal(t.astype(bool), info["TimeLimit.truncated"].cpu().numpy())
+        late += int(d.sum())
+    assert late > 50    # crashes went through the general solver, i.e. through the side buffer
 
 
 def test_reset_host_matches_device_reset(qs):

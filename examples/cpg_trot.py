@@ -4,8 +4,11 @@
 
 Per 1 ms tick: cpg.update -> desired foot xz -> IK + joint PD + Cartesian impedance (kernel K4) ->
 torques -> env.step (TORQUE mode, action_repeat = 1), exactly the reference's __main__ loop."""
+import os
 import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 import torch

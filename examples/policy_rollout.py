@@ -2,8 +2,11 @@
 evaluated on the device every step -- observations never leave the GPU (load_model.py:109-134 on tensors).
 
     python examples/policy_rollout.py [N] [steps] [best_model.zip]"""
+import os
 import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 

@@ -143,7 +143,8 @@ class RunningMeanStdTorch:
         x = x.to(torch.float64)
         if x.dim() == self.mean.dim():
             x = x[None]
-        bm, bv, bc = x.mean(0), x.var(0, unbiased=False), x.shape[0]
+        bv, bm = torch.var_mean(x, dim=0, unbiased=False)
+        bc = x.shape[0]
         delta = bm - self.mean
         tot = self.count + bc
         m_a, m_b = self.var * self.count, bv * bc

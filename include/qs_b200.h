@@ -293,6 +293,10 @@ int qs_work_counters(qs_handle h, uint64_t* out3, void* stream);
  * {settle ticks, foot-contact ticks, contact x PGS-sweep count} done so far */
 int qs_settle_kernel_time(qs_handle h, int last_k, float* ms_sum);
 int qs_settle_work_counters(qs_handle h, uint64_t* out3, void* stream);
+/* device time of the general-solver launches (k_step_slow: joint limits, body contacts) of the last `last_k` steps,
+ * and the number of qs_step / qs_step_host calls made on this handle so far */
+int qs_slow_kernel_time(qs_handle h, int last_k, float* ms_sum);
+int64_t qs_step_count(qs_handle h);
 /* diagnostics of the last qs_step: out4 = {envs handed to the general solver, envs whose next episode was
  * settled on the spot because no settled slot was ready, entries on the settle conveyor, ticks of its last
  * slice}; synchronises the stream */

@@ -68,13 +68,27 @@ def build(force=False, verbose=False):
     """nvcc cross-compiles for sm_100a (works without a GPU)."""
     if not force and not needs_build():
         return SO_PATH
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-o", SO_PATH, os.path.join(CSRC, "qs_kernels.cu")]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout)
-    if verbose:
-        print(res.stdout)
+    # several processes may get here at once (torchrun ranks on a fresh checkout): one builds under a file lock into a
+    # temporary file that is renamed into place, the others wait and then find the library up to date
+    import fcntl
+    with open(SO_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return SO_PATH
+            tmp = f"{SO_PATH}.{os.getpid()}.tmp"
+            cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+                "-o", tmp, os.path.join(CSRC, "qs_kernels.cu")]
+            res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout)
+            os.replace(tmp, SO_PATH)
+            if verbose:
+                print(res.stdout)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO_PATH
 
 
@@ -117,6 +131,8 @@ EXPORTS = {
     "qs_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "qs_settle_kernel_time": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "qs_settle_work_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
+    "qs_slow_kernel_time": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "qs_step_count": (C.c_int64, [C.c_void_p]),
     "qs_launch_count": (C.c_int64, []),
 }
 

@@ -291,7 +291,7 @@ __global__ void k_stats(DeviceView D, float* __restrict__ out) {
   for (int i = 0; i < QS_STATS_DIM; i++) v[i] = 0.f;
   if (env < D.n) {
 #pragma unroll
-    for (int i = 0; i < 11; i++) v[1 + i] = D.stats[i * D.n + env];
+    for (int i = 0; i < 12; i++) v[1 + i] = D.stats[i * D.n + env];
     v[0] = 1.f;
   }
   // rows 3 and 6 of v (stats rows 2, 5) are maxima, everything else sums
@@ -353,6 +353,7 @@ struct qs_env {
   cudaEvent_t ev0[kRing], ev1[kRing];   // around k_step + k_step_contact, on the caller's stream
   cudaEvent_t ev2[kRing], ev3[kRing];   // around the late k_settle_slice, on the second stream
   cudaEvent_t ev4[kRing], ev5[kRing];   // around the early one
+  cudaEvent_t ev6[kRing], ev7[kRing];   // around k_step_slow, on the caller's stream
   cudaEvent_t ev_fork0;
   bool ev_ready;
   int64_t n_steps;
@@ -542,9 +543,11 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     Conveyor& cv = h->cv;
     cv.width = h->wave_blocks * B;
     size_t cap = 1024;
-    while (cap < 4 * size_t(QS_SLOTS) * n) cap <<= 1;
+    // at least twice the slice window: two queue indices that share a position (a push dropped on a full queue keeps its
+    // index) can then never be active in the same slice, whatever n
+    while (cap < 4 * size_t(QS_SLOTS) * n || cap < 2 * size_t(cv.width)) cap <<= 1;
     cv.cap_mask = uint32_t(cap - 1);
-    h->slice_min = 4;
+    h->slice_min = 24;  // a settle never takes more than ~100 steps even when few episodes end (24 ticks hide behind the step's chain)
     h->slice_max = 1 << 20;  // no cap: the slice follows the demand
     h->slice_early = 10;  // ticks of the early slice (measured optimum 6-12: longer and it slows k_step_contact down)
     h->slow_spread = 32;
@@ -629,6 +632,7 @@ int qs_destroy(qs_handle h) {
     for (int i = 0; i < qs_env::kRing; i++) {
       cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); cudaEventDestroy(h->ev2[i]); cudaEventDestroy(h->ev3[i]);
       cudaEventDestroy(h->ev4[i]); cudaEventDestroy(h->ev5[i]);
+      cudaEventDestroy(h->ev6[i]); cudaEventDestroy(h->ev7[i]);
     }
   delete h;
   return QS_OK;
@@ -665,6 +669,22 @@ int qs_settle_kernel_time(qs_handle h, int last_k, float* ms_sum) {
   *ms_sum = tot;
   return QS_OK;
 }
+
+int qs_slow_kernel_time(qs_handle h, int last_k, float* ms_sum) {
+  // same for the k_step_slow launches (events on the caller's stream)
+  if (!h || !ms_sum) return fail(QS_ERR_ARG, "NULL argument");
+  if (last_k <= 0 || last_k > qs_env::kRing || last_k > h->n_steps) return fail(QS_ERR_ARG, "last_k out of range");
+  float tot = 0.f;
+  for (int64_t i = h->n_steps - last_k; i < h->n_steps; i++) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev6[i % qs_env::kRing], h->ev7[i % qs_env::kRing]));
+    tot += ms;
+  }
+  *ms_sum = tot;
+  return QS_OK;
+}
+
+int64_t qs_step_count(qs_handle h) { return h ? h->n_steps : 0; }
 
 int qs_settle_work_counters(qs_handle h, uint64_t* out3, void* stream) {
   // totals of (settle ticks, foot-contact ticks, contact x PGS-sweep count) executed by k_settle_slice so far; synchronises
@@ -834,6 +854,7 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
       CUDA_TRY(cudaEventCreate(&h->ev0[i])); CUDA_TRY(cudaEventCreate(&h->ev1[i]));
       CUDA_TRY(cudaEventCreate(&h->ev2[i])); CUDA_TRY(cudaEventCreate(&h->ev3[i]));
       CUDA_TRY(cudaEventCreate(&h->ev4[i])); CUDA_TRY(cudaEventCreate(&h->ev5[i]));
+      CUDA_TRY(cudaEventCreate(&h->ev6[i])); CUDA_TRY(cudaEventCreate(&h->ev7[i]));
     }
     h->ev_ready = true;
   }
@@ -880,8 +901,12 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
     CUDA_TRY(cudaEventRecord(h->ev_fork, s));
   }
   // envs parked for the general solver (joint limits / body contacts); launched before the slice so
-  // that its few blocks are placed first
+  // that its few blocks are placed first.  (Tried: a stream of the greatest priority for this launch -- the
+  // hardware then placed the slice first most of the time and the general-solver blocks waited for the
+  // whole slice, 2.5 ms per step instead of 1.7.)
+  cudaEventRecord(h->ev6[slot], s);
   if (h->args.C.mass_randomizer) k_step_slow<true><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread); else k_step_slow<false><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread);
+  cudaEventRecord(h->ev7[slot], s);
   g_launches += 2;
   if (host) {
     const int O = h->args.C.obs_dim;

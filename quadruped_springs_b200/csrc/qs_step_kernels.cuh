@@ -82,9 +82,15 @@ __device__ __forceinline__ void settle_command(const EnvCfg& C, const RobotConst
 }
 
 __device__ __forceinline__ void finish_episode_stats(const DeviceView& D, int env, const float* ts, float ep_return,
-                                                     int ep_len, bool terminated, int task) {
+                                                     int ep_len, bool terminated, int task, bool nonfinite = false) {
   const int n = D.n;
   float* s = D.stats + env;
+  if (nonfinite) {  // an episode cut short by the NaN / Inf guard: counted, its (meaningless) maxima are not
+    s[0 * n] += 1.f;
+    s[9 * n] += float(ep_len);
+    s[11 * n] += 1.f;
+    return;
+  }
   s[0 * n] += 1.f;
   s[1 * n] += ts[TS_MAX_H];
   s[2 * n] = fmaxf(s[2 * n], ts[TS_MAX_H]);
@@ -547,6 +553,27 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   quat_to_R(st.quat, Rb);
   rpy_from_quat(st.quat, rpy);
   const float sim_time = float(double(sim_steps) * A.time_step_d);
+  // NaN / Inf guard: a state that stopped being finite (a poisoned set_state, a solver
+  // blow-up) must not spread into rewards, statistics and the policy's batch.  The env is cut off: done = 1,
+  // truncated = 0, reward 0, a zero observation, and -- with auto_reset -- a fresh episode like any other done.
+  bool finite = true;
+  {
+    // exponent all ones <=> NaN or +-Inf; min over the 37 words of (0x7f800000 - exponent bits) hits 0 for those
+    uint32_t room = 0x7f800000u;
+    auto look = [&](float x) { room = min(room, 0x7f800000u - (__float_as_uint(x) & 0x7f800000u)); };
+#pragma unroll
+    for (int i = 0; i < 3; i++) { look(st.pos[i]); look(st.vlin[i]); look(st.vang[i]); }
+#pragma unroll
+    for (int i = 0; i < 4; i++) look(st.quat[i]);
+#pragma unroll
+    for (int i = 0; i < 12; i++) { look(st.q[i]); look(st.qd[i]); }
+    finite = room != 0u;
+  }
+  if (!finite) {
+    fresh_state(A, st, cs);  // something finite to read back (without auto_reset the caller has to reset the env)
+    quat_to_R(st.quat, Rb);
+    rpy_from_quat(st.quat, rpy);
+  }
   float ts[QS_TASK_DIM];
 #pragma unroll
   for (int i = 0; i < TS_END; i++) ts[i] = i < task_slots(C.task) ? D.task[i * n + env] : 0.f;
@@ -568,10 +595,12 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
     ts[TS_DEMO_COUNTER] += 1.f;
     term = term || int(ts[TS_DEMO_COUNTER]) == C.demo_len;
   }
+  if (!finite) term = true;
   const bool dn = term || (double(sim_steps) * A.time_step_d > A.max_time_d);
   if (dn) r += task_reward_end(ts, term, C.task, sim_time, C.max_episode_time);
+  if (!finite) r = 0.f;
 #pragma unroll
-  for (int i = 0; i < 12; i++) ts[TS_OLD_TAU0 + i] = tau_m[i];
+  for (int i = 0; i < 12; i++) ts[TS_OLD_TAU0 + i] = finite ? tau_m[i] : 0.f;
   const float ep_ret = D.ep_return[env] + r;
   io.reward[env] = r;
   io.done[env] = dn;
@@ -623,7 +652,7 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
       D.custom_gains[env] = 1;
     }
   }
-  if (dn) finish_episode_stats(D, env, ts, ep_ret, env_steps, term, C.task);
+  if (dn) finish_episode_stats(D, env, ts, ep_ret, env_steps, term, C.task, !finite);
   // ---- sensors (:253-254)
   float o[QS_MAX_OBS];
 #pragma unroll
@@ -658,7 +687,7 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   store_obs(io.obs + size_t(env) * C.obs_dim, o, C, A.RC, gid, D.reset_count[env], uint32_t(env_steps), C.enable_noise);
   store_state(D, env, st, cs, dt);
 #pragma unroll
-  for (int i = 0; i < 12; i++) { D.tau_motor[i * n + env] = tau_m[i]; D.tau_spring[i * n + env] = tau_s[i]; }
+  for (int i = 0; i < 12; i++) { D.tau_motor[i * n + env] = finite ? tau_m[i] : 0.f; D.tau_spring[i * n + env] = finite ? tau_s[i] : 0.f; }
 #pragma unroll
   for (int i = 0; i < TS_END; i++) if (i < task_slots(C.task)) D.task[i * n + env] = ts[i];
   D.sim_steps[env] = sim_steps;

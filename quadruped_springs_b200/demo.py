@@ -37,21 +37,33 @@ class DemonstrationRecorder:
     like `save_demo`, :29-31).  `landing_started` latches when the task has switched and the base moves down (:45-47)."""
 
     def __init__(self, env, path=None, name="demo_list"):
+        if getattr(env, "_auto_reset", False):
+            # an auto-reset env starts the next episode inside step(): rows would run over episode boundaries and the
+            # terminal state would be lost.  The reference wrapper records ONE episode between two reset() calls.
+            raise ValueError("DemonstrationRecorder records per episode: build the env with auto_reset=False")
         self.env = env
         self.name = f"{name}.npy"
         self.save_path = path
         if path is not None:
             os.makedirs(path, exist_ok=True)
         self.rows = []
+        self.start = [0] * env.num_envs       # first row of each env's current episode
         self.landing_started = torch.zeros(env.num_envs, dtype=torch.bool, device=env.device)
 
     def __getattr__(self, k):      # gym.Wrapper forwarding
         return getattr(self.env, k)
 
-    def reset(self, *a, **k):
-        self.rows = []
-        self.landing_started.zero_()
-        return self.env.reset(*a, **k)
+    def reset(self, mask=None, **k):
+        if mask is None:
+            self.rows = []
+            self.start = [0] * self.env.num_envs
+            self.landing_started.zero_()
+        else:   # partial reset: only the selected envs start a new episode (and a new demonstration)
+            m = torch.as_tensor(mask, device=self.env.device).bool()
+            for i in m.nonzero().flatten().tolist():
+                self.start[i] = len(self.rows)
+            self.landing_started &= ~m
+        return self.env.reset(mask=mask, **k)
 
     def step(self, action):
         out = self.env.step(action)
@@ -68,9 +80,10 @@ class DemonstrationRecorder:
                           self.landing_started[:, None].to(torch.float32)], dim=1).clone()
 
     def demo(self, env_index=0):
-        if len(self.rows) < 2:
+        rows = self.rows[self.start[env_index]:]
+        if len(rows) < 2:
             return np.zeros((0, self.env.action_dim + 38), np.float32)
-        return torch.stack([r[env_index] for r in self.rows[:-1]]).cpu().numpy()
+        return torch.stack([r[env_index] for r in rows[:-1]]).cpu().numpy()
 
     def save_demo(self, env_index=0):
         d = self.demo(env_index)

@@ -553,6 +553,7 @@ class BatchedQuadrupedGymEnv:
         self._reward = torch.zeros(n, device=dev)
         self._done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._trunc = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._last_host_obs = None      # where the latest observation lives when it came through the host path
         self.sub_step_callback = None
         self.robot_desired_state = None
         if self.verbose > 0:
@@ -576,6 +577,9 @@ class BatchedQuadrupedGymEnv:
         m = None
         if mask is not None:
             m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        if self._last_host_obs is not None:   # a partial reset leaves the other rows as the last (host-path) step left them
+            self._obs.copy_(torch.as_tensor(self._last_host_obs, device=self.device))
+            self._last_host_obs = None
         _lib.check(self._L.qs_reset(self._h, _p(m), _p(self._obs), _stream_ptr(self.device)))
         return self._obs
 
@@ -591,6 +595,7 @@ class BatchedQuadrupedGymEnv:
         a = a.contiguous()
         _lib.check(self._L.qs_step(self._h, _p(a), _p(self._obs), _p(self._reward), _p(self._done), _p(self._trunc),
                                    _stream_ptr(self.device)))
+        self._last_host_obs = None
         infos = {"TimeLimit.truncated": self._trunc.bool()}
         if self._cfg.landing_mode:
             infos["landing_mode"] = self._views["land_mode"]
@@ -642,10 +647,13 @@ class BatchedQuadrupedGymEnv:
         out = np.zeros((self.num_envs, self.obs_dim), np.float32)
         m = None
         if mask_np is not None:
+            # rows of the envs that are NOT reset keep the observation of the last step, wherever that step left it:
+            # the host array step_host / reset_host returned, or the device tensor of step() / reset()
             m = np.ascontiguousarray(mask_np, dtype=np.uint8)
-            out[:] = self._obs.cpu().numpy()
+            out[:] = self._last_host_obs if self._last_host_obs is not None else self._obs.cpu().numpy()
         _lib.check(self._L.qs_reset_host(self._h, m.ctypes.data_as(C.c_void_p) if m is not None else None,
                                          out.ctypes.data_as(C.c_void_p), _stream_ptr(self.device)))
+        self._last_host_obs = out
         return out
 
     def step_host(self, action_np, out=None):
@@ -659,6 +667,7 @@ class BatchedQuadrupedGymEnv:
         _lib.check(self._L.qs_step_host(self._h, a.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
                                         r.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
                                         t.ctypes.data_as(C.c_void_p), _stream_ptr(self.device)))
+        self._last_host_obs = o
         return out
 
     def close(self):

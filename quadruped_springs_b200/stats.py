@@ -5,7 +5,7 @@ import torch
 import torch.distributed as dist
 
 NAMES = ["num_envs", "episodes", "sum_max_height", "max_max_height", "sum_rel_max_height", "sum_max_fwd",
-         "max_max_fwd", "sum_max_flight_time", "sum_flip_completion", "sum_return", "sum_length", "terminated"]
+         "max_max_fwd", "sum_max_flight_time", "sum_flip_completion", "sum_return", "sum_length", "terminated", "nonfinite"]
 _MAX_ROWS = (3, 6)
 
 

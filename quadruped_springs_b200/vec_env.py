@@ -109,12 +109,21 @@ class BatchedVecEnv:
         v = getattr(self.env, attr_name)
         return [v for _ in self._indices(indices)]
 
+    def _all_or_raise(self, indices, what):
+        # one handle holds every env: an attribute or a method call cannot apply to a strict subset of them
+        idx = self._indices(indices)
+        if sorted(set(idx)) != list(range(self.num_envs)):
+            raise ValueError(f"{what} applies to all {self.num_envs} envs of the batch; a subset of indices is not supported")
+        return idx
+
     def set_attr(self, attr_name, value, indices=None):
+        self._all_or_raise(indices, "set_attr")
         setattr(self.env, attr_name, value)
 
     def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        idx = self._all_or_raise(indices, "env_method")
         r = getattr(self.env, method_name)(*method_args, **method_kwargs)
-        return [r for _ in self._indices(indices)]
+        return [r for _ in idx]
 
     def env_is_wrapped(self, wrapper_class, indices=None):
         return [False for _ in self._indices(indices)]
@@ -297,7 +306,8 @@ class MlpPolicyTorch(torch.nn.Module):
                         arch = tuple(int(x) for x in na)
                     if "ReLU" in str(pk.get("activation_fn", "")):
                         activation = "relu"
-        pi = sorted(k for k in sd if k.startswith("mlp_extractor.policy_net.") and k.endswith(".weight"))
+        pi = sorted((k for k in sd if k.startswith("mlp_extractor.policy_net.") and k.endswith(".weight")),
+                    key=lambda k: int(k.split(".")[2]))   # numeric layer order ("10" after "2")
         if arch is None:
             arch = tuple(sd[k].shape[0] for k in pi)
         obs_dim = sd[pi[0]].shape[1] if pi else sd["action_net.weight"].shape[1]
@@ -316,6 +326,10 @@ class EvaluationWrapper:
     the state the step kernel leaves (a fused kernel cannot call back into Python between substeps)."""
 
     def __init__(self, env):
+        if getattr(env, "_auto_reset", False):
+            # with auto_reset the state read after step() already belongs to the next episode: the terminal height and
+            # distance would be lost and max_height would run over episode boundaries
+            raise ValueError("EvaluationWrapper evaluates episode by episode: build the env with auto_reset=False")
         self.env = env
         n, dev = env.num_envs, env.device
         self.max_h = torch.zeros(n, device=dev)
@@ -324,9 +338,12 @@ class EvaluationWrapper:
     def __getattr__(self, k):
         return getattr(self.env, k)
 
-    def reset(self, *a, **k):
-        self.max_h.zero_()
-        return self.env.reset(*a, **k)
+    def reset(self, mask=None, **k):
+        if mask is None:
+            self.max_h.zero_()
+        else:
+            self.max_h[torch.as_tensor(mask, device=self.env.device).bool()] = 0.0
+        return self.env.reset(mask=mask, **k)
 
     def step(self, action):
         obs, reward, done, infos = self.env.step(action)

@@ -358,3 +358,60 @@ def test_everything_on_is_shard_invariant_and_consistent(qs):
     half = run(n // 2, n // 2, slice(n // 2, n), False)
     for x, y in zip(full, half):
         assert torch.equal(x[n // 2:], y)
+
+
+def test_nan_guard_cuts_the_env_off_and_spares_the_others(qs):
+    """a state that stopped being finite ends the episode (done, not truncated, reward 0, finite
+    observation); with auto_reset the env starts a fresh episode like after any other done.  Nothing leaks into the other
+    envs, the rewards or the rollout statistics."""
+    n = 256
+    for auto in (False, True):
+        env = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=5, auto_reset=auto, **JIP)
+        twin = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=5, auto_reset=auto, **JIP)
+        env.reset(); twin.reset()
+        a = torch.zeros(n, 6, device="cuda")
+        env.step(a); twin.step(a)
+        S = env.get_state()
+        bad = [3, 77, 200]
+        S[3, 2] = float("nan")            # base height
+        S[77, 15] = float("inf")          # a joint angle (an Inf / NaN joint RATE is healed by the +-30.1 velocity clamp)
+        S[200, 4] = float("nan")          # a quaternion component
+        contact = env._views["contact"].clone(); ff = env._views["foot_force"].clone()
+        env.set_state(S)                  # (set_state clears the contact history: put it back for the healthy envs)
+        env._views["contact"].copy_(contact); env._views["foot_force"].copy_(ff)
+        obs, r, d, info = env.step(a)
+        o2, r2, d2, _ = twin.step(a)
+        assert d[bad].all() and not info["TimeLimit.truncated"][bad].any()
+        assert (r[bad] == 0).all()
+        assert torch.isfinite(obs).all() and torch.isfinite(r).all() and torch.isfinite(env.get_state()).all()
+        good = torch.ones(n, dtype=torch.bool, device="cuda"); good[bad] = False
+        assert torch.equal(obs[good], o2[good]) and torch.equal(r[good], r2[good]) and torch.equal(d[good], d2[good])
+        out = qs.stats.gather_rollout_stats(env.rollout_stats())
+        assert out["nonfinite"] == 3 and np.isfinite(list(out.values())).all()
+        if auto:
+            assert (env._views["env_steps"][bad] == 0).all()       # a new episode has started
+            for _ in range(3):
+                obs, r, d, info = env.step(a)
+            assert torch.isfinite(obs).all()
+
+
+def test_partial_host_reset_keeps_the_other_rows(qs):
+    """reset_host(mask) after step_host must return the last observation for the envs that are not reset"""
+    n = 512
+    env = qs.BatchedQuadrupedGymEnv(num_envs=n, seed=2, auto_reset=False, **JIP)
+    env.reset_host()
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        obs, r, d, t = env.step_host(rng.uniform(-1, 1, (n, 6)).astype(np.float32))
+    last = obs.copy()
+    mask = np.zeros(n, np.uint8); mask[::7] = 1
+    out = env.reset_host(mask)
+    keep = mask == 0
+    assert np.array_equal(out[keep], last[keep])
+    assert not np.array_equal(out[~keep], last[~keep])
+    assert (env._views["env_steps"].cpu().numpy()[~keep] == 0).all() and (env._views["env_steps"].cpu().numpy()[keep] == 3).all()
+    # and the device path after a host step: the rows of the tensor it returns are the same
+    obs, r, d, t = env.step_host(rng.uniform(-1, 1, (n, 6)).astype(np.float32))
+    last = obs.copy()
+    dev = env.reset(mask=torch.as_tensor(mask, device="cuda"))
+    assert np.array_equal(dev.cpu().numpy()[keep], last[keep])

@@ -158,7 +158,9 @@ def test_vecenv_protocol_and_terminal_observation():
     assert isinstance(obs, np.ndarray) and obs.shape == (n, 27) and obs.dtype == np.float32
     np.testing.assert_array_equal(obs, tobs.cpu().numpy())
     assert venv.get_attr("task_env") == ["JUMPING_IN_PLACE"] * n and venv.env_is_wrapped(object) == [False] * n
-    assert venv.env_method("are_springs_enabled", indices=[0, 1]) == [True, True]
+    assert venv.env_method("are_springs_enabled") == [True] * n
+    with pytest.raises(ValueError):      # one handle = all envs: a call on a strict subset cannot be honoured
+        venv.env_method("are_springs_enabled", indices=[0, 1])
     rng = np.random.default_rng(0)
     alive = np.ones(n, bool)       # envs still in their first episode: the twin is comparable
     seen = 0
@@ -234,3 +236,50 @@ def test_evaluation_wrapper_infos():
     assert (info["feet_forces"][flying] == 0).all()
     env.reset()
     assert (env.max_h == 0).all()
+
+
+def test_policy_loader_orders_layers_numerically(tmp_path):
+    """six or more hidden layers put Linear modules at indices 0, 2, ..., 10: '10' must sort after '2'"""
+    arch = (24, 20, 16, 12, 10, 8)
+    ref = MlpPolicyTorch(9, 3, arch)
+    path = tmp_path / "deep.zip"
+    buf = io.BytesIO()
+    torch.save(ref.state_dict(), buf)
+    with zipfile.ZipFile(path, "w") as z:
+        z.writestr("policy.pth", buf.getvalue())        # no "data": the architecture is inferred from the weights
+    pol = MlpPolicyTorch.from_sb3_zip(str(path), device="cpu")
+    obs = torch.randn(5, 9)
+    assert torch.equal(pol.predict(obs), ref.predict(obs))
+
+
+def test_vec_env_rejects_index_subsets():
+    class _E:
+        num_envs, obs_dim, action_dim, device = 4, 3, 2, torch.device("cpu")
+        observation_space = action_space = None
+        _auto_reset = True
+        foo = 1
+
+        def set_terminal_obs_buffer(self, b):
+            pass
+
+        def bar(self):
+            return 7
+
+    v = BatchedVecEnv(env=_E())
+    assert v.get_attr("foo", [1, 2]) == [1, 1]
+    assert v.env_method("bar") == [7] * 4
+    v.set_attr("foo", 5)
+    with pytest.raises(ValueError):
+        v.set_attr("foo", 6, indices=[0])
+    with pytest.raises(ValueError):
+        v.env_method("bar", indices=[1, 2])
+
+
+def test_episode_wrappers_refuse_auto_reset_envs():
+    from quadruped_springs_b200.demo import DemonstrationRecorder
+    from quadruped_springs_b200.vec_env import EvaluationWrapper
+    fake = type("E", (), {"_auto_reset": True, "num_envs": 2, "device": torch.device("cpu")})()
+    with pytest.raises(ValueError):
+        DemonstrationRecorder(fake)
+    with pytest.raises(ValueError):
+        EvaluationWrapper(fake)

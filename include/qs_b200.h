@@ -136,6 +136,8 @@ typedef struct qs_config {
   float rand_payload_max;        /* 1 kg -> 4 kg */
   float rand_payload_pos[3];     /* (0.1, 0, 0.1) m -> (0.2, 0, 0.2) */
   float rand_spring_err;         /* relative range of the spring stiffness / damping draws: 0.1 -> 0.3 (:242-262) */
+  int32_t self_collision;        /* URDF_USE_SELF_COLLISION (quadruped.py:530-543): calf-involved self contacts count as
+                                  * invalid contacts (quadruped.py:236-241); detection only.  Default 1 */
 } qs_config;
 
 typedef struct qs_env* qs_handle;

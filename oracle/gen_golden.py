@@ -652,9 +652,54 @@ def gen_hopf():
     np.savez_compressed(os.path.join(OUT, "hopf.npz"), **out)
 
 
+# ----------------------------------------------------------------------------- self collision (quadruped.py:236-241)
+def gen_self_collision():
+    """The reference's own GetContactInfo over getContactPoints rows with bodyA == bodyB (URDF_USE_SELF_COLLISION,
+    quadruped.py:530-543): (a) 96 airborne states, half of them with crossed legs, one stepSimulation each;
+    (b) a rollout in which the front calves hit the rear feet and the episode ends on that invalid contact."""
+    env = make_env(action_space_mode="DEFAULT")
+    env.reset()
+    bc, w = env._pybullet_client, env._pybullet_client.world
+    rng = np.random.default_rng(77)
+    lo = np.array([-1.047, -0.663, -2.722] * 4)
+    hi = np.array([1.047, 2.967, -0.838] * 4)
+    states, out = [], []
+    probe = w.get_state()
+    while len(states) < 96:
+        s = np.zeros(37)
+        s[2] = 1.0
+        quat = rng.normal(size=4)
+        s[3:7] = quat / np.linalg.norm(quat)
+        s[13:25] = rng.uniform(lo, hi)
+        s[25:37] = rng.uniform(-2, 2, 12)
+        probe[:] = s
+        w.set_state(probe)
+        sc = w.self_contacts(detect=True)
+        # keep the sets balanced and away from the contact threshold (fp32 kernels see the same side of it)
+        if any(abs(d - 0.0025) < 2e-4 or abs(d - 0.0008) < 2e-4 for _, _, d in sc):
+            continue
+        want_hit = len(states) % 2 == 0
+        if bool(sc) != want_hit:
+            continue
+        states.append(s)
+    for s in states:
+        w.set_state(s)
+        bc.stepSimulation()
+        nv, ninv, ff, fc = env.robot.GetContactInfo()
+        out.append([nv, ninv] + list(fc))
+    out = np.asarray(out, dtype=np.float64)
+    assert (out[:, 0] == 0).all() and (out[::2, 1] > 0).all() and (out[1::2, 1] == 0).all()
+    np.savez_compressed(os.path.join(OUT, "self_contact_info.npz"), state=np.asarray(states), info=out)
+    print("self_contact_info: invalid counts", np.bincount(out[:, 1].astype(int)))
+    base = dict(enable_springs=True, task_env="JUMPING_IN_PLACE", motor_control_mode="PD", action_space_mode="DEFAULT",
+                observation_space_mode="ARS_BASIC")
+    a = np.array([0, 1, 1, 0, 1, 1, 0, -1, -0.5, 0, -1, -0.5], dtype=np.float64)
+    rollout("self_collision", base, np.tile(a, (20, 1)), seed=21)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "continuous", "landing", "springs", "masses", "demo", "rollouts"]
+    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "continuous", "landing", "springs", "masses", "demo", "selfcollision", "rollouts"]
     if "urdf" in which:
         gen_urdf()
     # NB: gen_analytic and the last rollout build a BACKFLIP env, which mutates the module-level
@@ -675,6 +720,8 @@ if __name__ == "__main__":
         gen_mass_randomizer()
     if "demo" in which:
         gen_demo()
+    if "selfcollision" in which:
+        gen_self_collision()
     if "rollouts" in which:
         gen_rollouts()
     print("golden fixtures written to", OUT)

@@ -35,7 +35,7 @@ class WorldParams(C.Structure):
         ("limit_erp", C.c_double), ("linear_slop", C.c_double), ("warmstart", C.c_double),
         ("residual_threshold", C.c_double), ("max_coord_vel", C.c_double),
         ("breaking_threshold", C.c_double), ("enable_limits", C.c_int),
-        ("body_contact_response", C.c_int),
+        ("body_contact_response", C.c_int), ("self_collision", C.c_int),
     ]
 
 
@@ -78,6 +78,9 @@ def lib():
         "qso_world_step": (None, [vp]),
         "qso_world_num_contacts": (C.c_int, [vp]),
         "qso_world_get_contact": (None, [vp, C.c_int, ip, dp, dp, dp]),
+        "qso_world_num_self_contacts": (C.c_int, [vp]),
+        "qso_world_get_self_contact": (None, [vp, C.c_int, ip, ip, dp]),
+        "qso_world_detect_self_contacts": (C.c_int, [vp]),
         "qso_world_get_dynamics": (None, [vp, C.c_int, dp, dp, dp]),
         "qso_world_set_mass": (None, [vp, C.c_int, C.c_double]),
         "qso_world_set_payload": (None, [vp, C.c_double, dp]),
@@ -192,6 +195,18 @@ class World:
             pos, pp = _out(3)
             self.L.qso_world_get_contact(self.h, i, C.byref(link), C.byref(nf), C.byref(dist), pp)
             out.append((link.value, nf.value, dist.value, pos))
+        return out
+
+    def self_contacts(self, detect=False):
+        """[(pyb link a, pyb link b, distance)] of the calf-involved self contacts of the last step's collision phase
+        (detect=True: of the current state)"""
+        if detect:
+            self.L.qso_world_detect_self_contacts(self.h)
+        out = []
+        for i in range(self.L.qso_world_num_self_contacts(self.h)):
+            a, b, d = C.c_int(), C.c_int(), C.c_double()
+            self.L.qso_world_get_self_contact(self.h, i, C.byref(a), C.byref(b), C.byref(d))
+            out.append((a.value, b.value, d.value))
         return out
 
     def set_mass(self, pyb_link, mass):

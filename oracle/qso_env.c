@@ -374,6 +374,14 @@ static void contact_info(QsoEnv* e) {
     e->foot_force[k] += nf;
     e->foot_contact[k] = 1;
   }
+  /* self collisions count when a calf is involved (quadruped.py:236-241; calf link ids 4, 8, 12, 16) */
+  n = qso_world_num_self_contacts(e->w);
+  for (int i = 0; i < n; i++) {
+    int a, b; double dist;
+    qso_world_get_self_contact(e->w, i, &a, &b, &dist);
+    const int a_calf = a >= 4 && (a - 4) % 4 == 0, b_calf = b >= 4 && (b - 4) % 4 == 0;
+    if (a_calf || b_calf) e->n_invalid++;
+  }
 }
 static int is_flying(const QsoEnv* e) {
   return !(e->foot_contact[0] || e->foot_contact[1] || e->foot_contact[2] || e->foot_contact[3]);

@@ -35,6 +35,7 @@
 #define NL QSO_NLINKS
 #define ND QSO_NDOF
 #define MAXROWS (12 + 3 * QSO_MAX_CONTACTS)
+#define QSO_MAX_SELF 64
 #define MAXPTS 8
 
 enum { SH_NONE = 0, SH_BOX, SH_CYL_Y, SH_SPHERE };
@@ -85,6 +86,10 @@ struct QsoWorld {
   /* contacts */
   Contact C[QSO_MAX_CONTACTS];
   int nC;
+  /* self contacts of the last collision phase: link pairs (oracle indices) and their distance; detection only */
+  int selfA[QSO_MAX_SELF], selfB[QSO_MAX_SELF];
+  double selfD[QSO_MAX_SELF];
+  int nSelf;
   double prev_lambda[NL][MAXPTS];
   int prev_valid[NL][MAXPTS];
   Row rows[MAXROWS];
@@ -323,6 +328,7 @@ void qso_default_params(QsoWorldParams* p) {
   p->residual_threshold = 1e-7;
   p->max_coord_vel = 30.1;
   p->breaking_threshold = 0.02;
+  p->self_collision = 1;           /* URDF_USE_SELF_COLLISION, quadruped.py:530-543 */
   p->enable_limits = 1;
   p->body_contact_response = 1;
 }
@@ -670,6 +676,135 @@ static void collide(QsoWorld* w) {
   }
 }
 
+/* ------------------------------------------------------- self collision (detection only)
+ * The reference loads the robot with URDF_USE_SELF_COLLISION (quadruped.py:530-543) and counts a self contact as
+ * invalid only when a calf is involved (quadruped.py:237-241); every task ends the episode on an invalid contact
+ * (task_base.py:146-147), so the contact RESPONSE of such a pair never outlives the control step and is left out.
+ * Pairs tested per calf: trunk, imu_link, the four hips (its own hip is a grandparent: Bullet's default filter only
+ * drops parent-child pairs, i.e. calf-thigh and calf-foot of the same leg), the thighs, calves and feet of the other
+ * legs.  A pair is in contact while the distance between the two shapes is below the smaller of their contact
+ * breaking thresholds (btPersistentManifold).  Geometry (stated approximation of Bullet's GJK on the URDF
+ * primitives, the same in the CUDA kernels): the long boxes of calf and thigh are capsules -- the box's axis inset
+ * by the radius, radius = half the (mean) side: calf 0.008, thigh 0.0146 --, feet and imu_link are spheres, the hip
+ * is its exact cylinder and the trunk its exact box; segment-to-shape distances by a 20-step ternary search of the
+ * (convex) distance along the segment. */
+#define SELF_IT 20
+static const double CALF_R = 0.008, THIGH_R = 0.0146, LINK_LEN = 0.213;
+
+static double seg_seg_dist(const double* p0, const double* p1, const double* q0, const double* q1) {
+  double d1[3], d2[3], r[3];
+  for (int k = 0; k < 3; k++) { d1[k] = p1[k] - p0[k]; d2[k] = q1[k] - q0[k]; r[k] = p0[k] - q0[k]; }
+  const double a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r), c = dot3(d1, r), b = dot3(d1, d2);
+  const double den = a * e - b * b;
+  double sN = den > 1e-12 ? (b * f - c * e) / den : 0.0;
+  sN = sN < 0 ? 0 : (sN > 1 ? 1 : sN);
+  double tN = (b * sN + f) / e;
+  if (tN < 0) { tN = 0; sN = -c / a; sN = sN < 0 ? 0 : (sN > 1 ? 1 : sN); }
+  else if (tN > 1) { tN = 1; sN = (b - c) / a; sN = sN < 0 ? 0 : (sN > 1 ? 1 : sN); }
+  double d[3];
+  for (int k = 0; k < 3; k++) d[k] = r[k] + sN * d1[k] - tN * d2[k];
+  return sqrt(dot3(d, d));
+}
+static double pt_seg_dist(const double* c, const double* p0, const double* p1) {
+  double d[3], r[3];
+  for (int k = 0; k < 3; k++) { d[k] = p1[k] - p0[k]; r[k] = c[k] - p0[k]; }
+  double t = dot3(r, d) / dot3(d, d);
+  t = t < 0 ? 0 : (t > 1 ? 1 : t);
+  for (int k = 0; k < 3; k++) r[k] -= t * d[k];
+  return sqrt(dot3(r, r));
+}
+/* distance of a point (box frame) to the box of half extents h; 0 inside */
+static double pt_box_dist(const double* p, const double* h) {
+  double s = 0;
+  for (int k = 0; k < 3; k++) { double e = fabs(p[k]) - h[k]; if (e > 0) s += e * e; }
+  return sqrt(s);
+}
+/* distance of a point to the cylinder (centre c, unit axis a, radius r, half length hl); 0 inside */
+static double pt_cyl_dist(const double* p, const double* c, const double* a, double r, double hl) {
+  double v[3] = {p[0] - c[0], p[1] - c[1], p[2] - c[2]};
+  const double ax = dot3(v, a);
+  double rho2 = dot3(v, v) - ax * ax;
+  const double er = sqrt(rho2 > 0 ? rho2 : 0) - r, ea = fabs(ax) - hl;
+  return sqrt((er > 0 ? er * er : 0) + (ea > 0 ? ea * ea : 0));
+}
+static void self_add(QsoWorld* w, int a, int b, double d) {
+  if (w->nSelf >= QSO_MAX_SELF) return;
+  w->selfA[w->nSelf] = a; w->selfB[w->nSelf] = b; w->selfD[w->nSelf] = d; w->nSelf++;
+}
+static void link_point(const QsoWorld* w, int link, double z, double* out) {
+  const double loc[3] = {0, 0, z};
+  double t[3];
+  m3_v(w->Rw[link], loc, t);
+  for (int k = 0; k < 3; k++) out[k] = w->pw[link][k] + t[k];
+}
+static void collide_self(QsoWorld* w) {
+  w->nSelf = 0;
+  double c0[4][3], c1[4][3], t0[4][3], t1[4][3];
+  for (int k = 0; k < 4; k++) {
+    const int thigh = 4 + 4 * k, calf = 5 + 4 * k;
+    link_point(w, calf, -CALF_R, c0[k]); link_point(w, calf, -(LINK_LEN - CALF_R), c1[k]);
+    link_point(w, thigh, -THIGH_R, t0[k]); link_point(w, thigh, -(LINK_LEN - THIGH_R), t1[k]);
+  }
+  for (int i = 0; i < 4; i++) {
+    const int calf = 5 + 4 * i;
+    const double thc = w->L[calf].thresh;
+#define THR(other) (w->L[other].thresh < thc ? w->L[other].thresh : thc)
+    /* trunk box and hip cylinders: ternary search of the convex distance along the calf's axis */
+    for (int s = 0; s < 5; s++) {
+      const int other = s == 0 ? 1 : 3 + 4 * (s - 1);
+      double lo = 0, hi = 1, best = 1e30;
+      for (int it = 0; it <= SELF_IT; it++) {
+        const double ta = lo + (hi - lo) / 3, tb = hi - (hi - lo) / 3;
+        double da, db, pa[3], pb[3];
+        for (int k = 0; k < 3; k++) { pa[k] = c0[i][k] + ta * (c1[i][k] - c0[i][k]); pb[k] = c0[i][k] + tb * (c1[i][k] - c0[i][k]); }
+        if (s == 0) {
+          double la[3], lb[3], va[3], vb[3];
+          for (int k = 0; k < 3; k++) { va[k] = pa[k] - w->pw[1][k]; vb[k] = pb[k] - w->pw[1][k]; }
+          m3t_v(w->Rw[1], va, la); m3t_v(w->Rw[1], vb, lb);
+          da = pt_box_dist(la, w->L[1].sdim); db = pt_box_dist(lb, w->L[1].sdim);
+        } else {
+          const double ax[3] = {w->Rw[other][1], w->Rw[other][4], w->Rw[other][7]};
+          da = pt_cyl_dist(pa, w->pw[other], ax, w->L[other].sdim[0], w->L[other].sdim[1]);
+          db = pt_cyl_dist(pb, w->pw[other], ax, w->L[other].sdim[0], w->L[other].sdim[1]);
+        }
+        if (da < best) best = da;
+        if (db < best) best = db;
+        if (da <= db) hi = tb; else lo = ta;
+      }
+      const double d = best - CALF_R;
+      if (d < THR(other)) self_add(w, calf, other, d);
+    }
+    { /* imu_link: a 1 mm cube, taken as a sphere of its half side */
+      const double d = pt_seg_dist(w->pw[2], c0[i], c1[i]) - CALF_R - w->L[2].sdim[0];
+      if (d < THR(2)) self_add(w, calf, 2, d);
+    }
+    for (int j = 0; j < 4; j++) {
+      if (j == i) continue;
+      const int thigh = 4 + 4 * j, calf2 = 5 + 4 * j, foot = 6 + 4 * j;
+      double d = seg_seg_dist(c0[i], c1[i], t0[j], t1[j]) - CALF_R - THIGH_R;
+      if (d < THR(thigh)) self_add(w, calf, thigh, d);
+      if (j > i) {
+        d = seg_seg_dist(c0[i], c1[i], c0[j], c1[j]) - 2 * CALF_R;
+        if (d < THR(calf2)) self_add(w, calf, calf2, d);
+      }
+      d = pt_seg_dist(w->pw[foot], c0[i], c1[i]) - CALF_R - w->L[foot].sdim[0];
+      if (d < THR(foot)) self_add(w, calf, foot, d);
+    }
+#undef THR
+  }
+}
+
+int qso_world_num_self_contacts(const QsoWorld* w) { return w->nSelf; }
+void qso_world_get_self_contact(const QsoWorld* w, int i, int* pyb_link_a, int* pyb_link_b, double* dist) {
+  *pyb_link_a = w->selfA[i] - 1; *pyb_link_b = w->selfB[i] - 1; *dist = w->selfD[i];
+}
+/* the same detection on the current state without stepping (tests) */
+int qso_world_detect_self_contacts(QsoWorld* w) {
+  kinematics(w);
+  collide_self(w);
+  return w->nSelf;
+}
+
 int qso_world_num_contacts(const QsoWorld* w) { return w->nC; }
 void qso_world_get_contact(const QsoWorld* w, int i, int* pyb_link, double* nf, double* dist, double* pos) {
   const Contact* c = &w->C[i];
@@ -747,6 +882,7 @@ void qso_world_step(QsoWorld* w) {
   /* 1. collision detection on the current poses */
   kinematics(w);
   collide(w);
+  if (w->P.self_collision) collide_self(w); else w->nSelf = 0;
 
   /* 2. unconstrained forward dynamics; v += dt * a (clamped) */
   aba_factor(w);

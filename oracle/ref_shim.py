@@ -267,6 +267,10 @@ class FakeBulletClient:
         out = []
         for link, nf, dist, pos in self.world.contacts():
             out.append((0, self._robot, self._plane, link, -1, tuple(pos), tuple(pos), (0, 0, 1), dist, nf))
+        # URDF_USE_SELF_COLLISION (quadruped.py:530-543): rows with bodyA == bodyB, which GetContactInfo counts as
+        # invalid when a calf is involved (quadruped.py:236-241)
+        for la, lb, dist in self.world.self_contacts():
+            out.append((0, self._robot, self._robot, la, lb, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0), (0, 0, 1), dist, 0.0))
         return out
 
     # transforms

@@ -40,6 +40,7 @@ class QsConfig(C.Structure):
         ("breaking_threshold", C.c_float), ("landing_mode", C.c_int32),
         ("spring_randomizer", C.c_int32), ("rest_mode", C.c_int32), ("mass_randomizer", C.c_int32), ("rand_leg_mass_err", C.c_float),
         ("rand_payload_max", C.c_float), ("rand_payload_pos", C.c_float * 3), ("rand_spring_err", C.c_float),
+        ("self_collision", C.c_int32),
     ]
 
 

@@ -146,6 +146,159 @@ __device__ __noinline__ void run_ticks_general(EnvState<float>& st, ContactState
   }
 }
 
+// ---------------------------------------------------------------- self collision (detection only)
+// quadruped.py:530-543 loads the robot with URDF_USE_SELF_COLLISION and GetContactInfo counts a self contact as
+// invalid when a calf is involved (:236-241); every task ends the episode on an invalid contact (task_base.py:146-147),
+// so no contact RESPONSE is modelled for these pairs.  A pure function of the twelve joint angles (everything in the
+// base frame).  Pairs per calf: trunk, imu_link, the four hips (Bullet's default filter drops parent-child pairs only:
+// calf-thigh and calf-foot of the same leg), thighs, calves and feet of the other legs; in contact while the distance is
+// below the smaller of the two shapes' breaking thresholds.  Same geometry as the oracle (oracle/qso_physics.c
+// collide_self): calf / thigh boxes as capsules (axis inset by the radius; radii 0.008 / 0.0146), feet and imu_link
+// spheres, exact hip cylinder and trunk box, segment-to-shape distance by a 21-step ternary search.  Bounding spheres
+// cull the pairs first (conservative: the result is that of the full enumeration).
+QS_DEVONLY float sc_seg_seg(const float* p0, const float* p1, const float* q0, const float* q1) {
+  float d1[3], d2[3], r[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { d1[k] = p1[k] - p0[k]; d2[k] = q1[k] - q0[k]; r[k] = p0[k] - q0[k]; }
+  const float a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r), c = dot3(d1, r), b = dot3(d1, d2);
+  const float den = a * e - b * b;
+  float sN = den > 1e-12f ? (b * f - c * e) / den : 0.f;
+  sN = clampt(sN, 0.f, 1.f);
+  float tN = (b * sN + f) / e;
+  if (tN < 0.f) { tN = 0.f; sN = clampt(-c / a, 0.f, 1.f); }
+  else if (tN > 1.f) { tN = 1.f; sN = clampt((b - c) / a, 0.f, 1.f); }
+  float d[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) d[k] = r[k] + sN * d1[k] - tN * d2[k];
+  return sqrtf(dot3(d, d));
+}
+QS_DEVONLY float sc_pt_seg(const float* c, const float* p0, const float* p1) {
+  float d[3], r[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { d[k] = p1[k] - p0[k]; r[k] = c[k] - p0[k]; }
+  const float t = clampt(dot3(r, d) / dot3(d, d), 0.f, 1.f);
+#pragma unroll
+  for (int k = 0; k < 3; k++) r[k] -= t * d[k];
+  return sqrtf(dot3(r, r));
+}
+QS_DEVONLY float sc_pt_box(const float* p, const float* h) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { const float e = fabsf(p[k]) - h[k]; if (e > 0.f) s += e * e; }
+  return sqrtf(s);
+}
+QS_DEVONLY float sc_pt_cyl(const float* p, const float* c, const float* a, float r, float hl) {
+  const float v[3] = {p[0] - c[0], p[1] - c[1], p[2] - c[2]};
+  const float ax = dot3(v, a);
+  const float rho2 = dot3(v, v) - ax * ax;
+  const float er = sqrtf(fmaxf(rho2, 0.f)) - r, ea = fabsf(ax) - hl;
+  return sqrtf((er > 0.f ? er * er : 0.f) + (ea > 0.f ? ea * ea : 0.f));
+}
+// Per-leg points live in `sm` (this thread's column of a [QS_SELF_SCRATCH][stride] shared-memory area, dead tick scratch in
+// the step kernels): they are indexed by leg at run time, and as a local-memory array they cost more than the whole test
+// (the step kernels leave ~20 KB of L1 per SM next to their shared memory: measured +0.18 ms per step).
+constexpr int QS_SELF_SCRATCH = 7 * 12;
+static_assert(QS_SELF_SCRATCH <= QS_TICK_SCRATCH, "the self-collision points reuse the tick scratch");
+struct ScPts {
+  float* p; int stride;
+  QS_DEVONLY float& operator()(int arr, int leg, int a) const { return p[(arr * 12 + leg * 3 + a) * stride]; }
+  QS_DEVONLY void get(int arr, int leg, float* o) const { o[0] = (*this)(arr, leg, 0); o[1] = (*this)(arr, leg, 1); o[2] = (*this)(arr, leg, 2); }
+};
+enum { SC_C0 = 0, SC_C1, SC_T0, SC_T1, SC_R1, SC_R4, SC_AX };
+__device__ __forceinline__ int self_collision_count(const float* q12, const ModelConstT<float>& M, float* __restrict__ sm, int stride) {
+  constexpr float RC = 0.008f, RT = 0.0146f;
+  const ScPts P{sm, stride};
+#pragma unroll 1
+  for (int k = 0; k < 4; k++) {
+    LegKin<float> K;
+    leg_kin(k, q12 + 3 * k, M, K);
+    const float fc = RC / M.link_len, ft = RT / M.link_len;
+    for (int a = 0; a < 3; a++) {
+      P(SC_C0, k, a) = K.r3[a] + fc * (K.r4[a] - K.r3[a]);
+      P(SC_C1, k, a) = K.r3[a] + (1.f - fc) * (K.r4[a] - K.r3[a]);
+      P(SC_T0, k, a) = K.r2[a] + ft * (K.r3[a] - K.r2[a]);
+      P(SC_T1, k, a) = K.r2[a] + (1.f - ft) * (K.r3[a] - K.r2[a]);
+      P(SC_R1, k, a) = K.r1[a]; P(SC_R4, k, a) = K.r4[a]; P(SC_AX, k, a) = K.a2[a];
+    }
+  }
+  // Culling (conservative, so the count is that of the full enumeration): a calf capsule lies within half_c of the middle
+  // of its axis.  The calf of a leg never reaches that leg's own hip: its axis stays in the plane at 0.08 m from the hip
+  // centre along the hip axis, i.e. at least 0.08 - 0.02 - 0.008 = 0.052 m from the cylinder.
+  const float half_c = 0.5f * M.link_len, thc = M.calf_thresh;
+  const float reach = half_c + thc + 1e-4f;
+  int count = 0;
+#pragma unroll 1
+  for (int i = 0; i < 4; i++) {
+    float mid[3], ci0[3], ci1[3];
+    P.get(SC_C0, i, ci0); P.get(SC_C1, i, ci1);
+    for (int a = 0; a < 3; a++) mid[a] = 0.5f * (ci0[a] + ci1[a]);
+    // trunk box (s = 0) and the hip cylinders of the other legs (s = 1..4)
+#pragma unroll 1
+    for (int s = 0; s < 5; s++) {
+      const int j = s - 1;
+      if (j == i) continue;
+      float hj[3], aj[3];
+      if (s > 0) { P.get(SC_R1, j, hj); P.get(SC_AX, j, aj); }
+      // three samples of the (1-Lipschitz) distance along the axis: every point of the axis is within a quarter of its
+      // length of one of them
+      const float slack = 0.25f * M.link_len + RC + thc + 1e-4f;
+      if (s == 0) {
+        if (fminf(sc_pt_box(mid, M.trunk_half), fminf(sc_pt_box(ci0, M.trunk_half), sc_pt_box(ci1, M.trunk_half))) > slack) continue;
+      } else {
+        float d2 = 1e30f;
+        for (int e = 0; e < 3; e++) {
+          const float* p = e == 0 ? ci0 : (e == 1 ? mid : ci1);
+          const float v[3] = {p[0] - hj[0], p[1] - hj[1], p[2] - hj[2]};
+          d2 = fminf(d2, dot3(v, v));
+        }
+        const float ro = slack + 0.0502f;  // the hip cylinder lies within sqrt(0.046^2 + 0.02^2) of its centre
+        if (d2 > ro * ro) continue;
+      }
+      const float thr = fminf(thc, s == 0 ? M.trunk_thresh : M.hip_thresh);
+      float lo = 0.f, hi = 1.f, best = 1e30f;
+      for (int it = 0; it <= 20; it++) {
+        const float ta = lo + (hi - lo) / 3.f, tb = hi - (hi - lo) / 3.f;
+        float pa[3], pb[3];
+        for (int a = 0; a < 3; a++) { pa[a] = ci0[a] + ta * (ci1[a] - ci0[a]); pb[a] = ci0[a] + tb * (ci1[a] - ci0[a]); }
+        const float da = s == 0 ? sc_pt_box(pa, M.trunk_half) : sc_pt_cyl(pa, hj, aj, M.hip_r, M.hip_hl);
+        const float db = s == 0 ? sc_pt_box(pb, M.trunk_half) : sc_pt_cyl(pb, hj, aj, M.hip_r, M.hip_hl);
+        best = fminf(best, fminf(da, db));
+        if (da <= db) hi = tb; else lo = ta;
+      }
+      count += (best - RC) < thr;
+    }
+    {
+      const float v[3] = {mid[0] - M.imu_pos[0], mid[1] - M.imu_pos[1], mid[2] - M.imu_pos[2]};
+      if (dot3(v, v) <= (reach + 0.001f) * (reach + 0.001f))
+        count += (sc_pt_seg(M.imu_pos, ci0, ci1) - RC - M.imu_half) < fminf(thc, M.imu_thresh);
+    }
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) {
+      if (j == i) continue;
+      float v[3], a0[3], a1[3];
+      // capsule pairs: culled by the separation along the line between the two axis middles (each axis reaches
+      // |half axis . n| along a unit direction n)
+      const float hi_[3] = {0.5f * (ci1[0] - ci0[0]), 0.5f * (ci1[1] - ci0[1]), 0.5f * (ci1[2] - ci0[2])};
+#pragma unroll 1
+      for (int kind = 0; kind < 2; kind++) {   // 0: thigh of leg j, 1: calf of leg j (each pair of calves once)
+        if (kind == 1 && j < i) continue;
+        P.get(kind ? SC_C0 : SC_T0, j, a0); P.get(kind ? SC_C1 : SC_T1, j, a1);
+        float hj_[3];
+        for (int a = 0; a < 3; a++) { v[a] = mid[a] - 0.5f * (a0[a] + a1[a]); hj_[a] = 0.5f * (a1[a] - a0[a]); }
+        const float rr = RC + (kind ? RC : RT), thr = kind ? thc : fminf(thc, M.thigh_thresh);
+        const float dm = sqrtf(dot3(v, v));
+        if (dm * dm - fabsf(dot3(hi_, v)) - fabsf(dot3(hj_, v)) > (rr + thr + 1e-4f) * dm) continue;
+        count += (sc_seg_seg(ci0, ci1, a0, a1) - rr) < thr;
+      }
+      P.get(SC_R4, j, a0);
+      for (int a = 0; a < 3; a++) v[a] = mid[a] - a0[a];
+      if (dot3(v, v) <= (reach + M.foot_radius) * (reach + M.foot_radius))
+        count += (sc_pt_seg(a0, ci0, ci1) - RC - M.foot_radius) < fminf(thc, M.foot_thresh);
+    }
+  }
+  return count;
+}
+
 // ---------------------------------------------------------------- task logic
 QS_DEV bool is_jump_task(int task) { return task != QS_TASK_NO_TASK; }
 // 0 = TaskJumping, 1 = TaskContinuousJumping, 2 = TaskContinuousJumping2 (task_base.py:222,280)

@@ -354,7 +354,8 @@ struct qs_env {
   cudaEvent_t ev2[kRing], ev3[kRing];   // around the late k_settle_slice, on the second stream
   cudaEvent_t ev4[kRing], ev5[kRing];   // around the early one
   cudaEvent_t ev6[kRing], ev7[kRing];   // around k_step_slow, on the caller's stream
-  cudaEvent_t ev_fork0;
+  cudaEvent_t ev_fork0, ev_early_done;
+  unsigned long long* stamps;   // [kRing][4] device: per step {late slice start, end, general solver start, end} (globaltimer ns)
   bool ev_ready;
   int64_t n_steps;
 };
@@ -412,6 +413,7 @@ void qs_default_config(qs_config* c) {
   c->rand_payload_max = 1.0f;
   c->rand_payload_pos[0] = 0.1f; c->rand_payload_pos[1] = 0.0f; c->rand_payload_pos[2] = 0.1f;
   c->rand_spring_err = 0.1f;
+  c->self_collision = 1;                       // quadruped.py:530-543
 }
 
 static int check_config(const qs_config* c) {
@@ -483,6 +485,8 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   A.SC.num_iterations = cfg->num_iterations > 0 ? cfg->num_iterations : 300 / cfg->action_repeat;  // quadruped_gym_env.py:113
   A.SC.enable_limits = cfg->enable_limits;
   A.SC.body_response = cfg->body_contact_response;
+  A.SC.self_collision = cfg->self_collision;
+  if (const char* v = std::getenv("QS_SELF_COLLISION")) A.SC.self_collision = std::atoi(v);  // (experiments)
   A.time_step_d = cfg->time_step;
   A.max_time_d = cfg->max_episode_time;
   EnvCfg& C = A.C;
@@ -584,6 +588,9 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork0, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_early_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(&h->stamps, sizeof(unsigned long long) * 4 * qs_env::kRing);
+    if (e == cudaSuccess) e = cudaMemset(h->stamps, 0, sizeof(unsigned long long) * 4 * qs_env::kRing);
     if (e != cudaSuccess) { cudaFree(h->pool); cudaFree(h->lists); delete h; return fail(QS_ERR_CUDA, "stream / event creation"); }
   }
   {
@@ -623,6 +630,8 @@ int qs_destroy(qs_handle h) {
   cudaEventDestroy(h->ev_fork);
   cudaEventDestroy(h->ev_fork0);
   cudaEventDestroy(h->ev_join);
+  cudaEventDestroy(h->ev_early_done);
+  cudaFree(h->stamps);
   if (h->dev_actions) cudaFree(h->dev_actions);
   if (h->dev_obs) cudaFree(h->dev_obs);
   if (h->dev_reward) cudaFree(h->dev_reward);
@@ -658,11 +667,13 @@ int qs_settle_kernel_time(qs_handle h, int last_k, float* ms_sum) {
   if (!h || !ms_sum) return fail(QS_ERR_ARG, "NULL argument");
   if (!h->cfg.auto_reset) return fail(QS_ERR_STATE, "no settle slices without auto_reset");
   if (last_k <= 0 || last_k > qs_env::kRing || last_k > h->n_steps) return fail(QS_ERR_ARG, "last_k out of range");
+  static unsigned long long host_st[4 * qs_env::kRing];
+  CUDA_TRY(cudaMemcpy(host_st, h->stamps, sizeof(host_st), cudaMemcpyDeviceToHost));
   float tot = 0.f;
   for (int64_t i = h->n_steps - last_k; i < h->n_steps; i++) {
     float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev2[i % qs_env::kRing], h->ev3[i % qs_env::kRing]));
-    tot += ms;
+    const unsigned long long* st = host_st + 4 * (i % qs_env::kRing);
+    if (st[1] > st[0]) tot += float(double(st[1] - st[0]) * 1e-6);   // late slice: device-side stamps (it shares its stream)
     CUDA_TRY(cudaEventElapsedTime(&ms, h->ev4[i % qs_env::kRing], h->ev5[i % qs_env::kRing]));
     tot += ms;
   }
@@ -674,11 +685,12 @@ int qs_slow_kernel_time(qs_handle h, int last_k, float* ms_sum) {
   // same for the k_step_slow launches (events on the caller's stream)
   if (!h || !ms_sum) return fail(QS_ERR_ARG, "NULL argument");
   if (last_k <= 0 || last_k > qs_env::kRing || last_k > h->n_steps) return fail(QS_ERR_ARG, "last_k out of range");
+  static unsigned long long host_st[4 * qs_env::kRing];
+  CUDA_TRY(cudaMemcpy(host_st, h->stamps, sizeof(host_st), cudaMemcpyDeviceToHost));
   float tot = 0.f;
   for (int64_t i = h->n_steps - last_k; i < h->n_steps; i++) {
-    float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev6[i % qs_env::kRing], h->ev7[i % qs_env::kRing]));
-    tot += ms;
+    const unsigned long long* st = host_st + 4 * (i % qs_env::kRing);
+    if (st[3] > st[2]) tot += float(double(st[3] - st[2]) * 1e-6);
   }
   *ms_sum = tot;
   return QS_OK;
@@ -768,9 +780,22 @@ static int launch_conveyor(qs_handle h, cudaStream_t s, int phase, int flush) {
   CUDA_TRY(cudaGetLastError());
   return QS_OK;
 }
-static int launch_slice(qs_handle h, cudaStream_t s, int early) {
+// pdl: programmatic dependent launch behind the kernel just launched in `s` (k_step_slow, which issues
+// griddepcontrol.launch_dependents on entry): the slice starts once every block of that kernel has been placed
+static int launch_slice(qs_handle h, cudaStream_t s, int early, bool pdl = false, unsigned long long* stamps = nullptr) {
   const int B = block_of(h);
-  if (h->args.C.mass_randomizer) k_settle_slice<true><<<h->wave_blocks, B, smem_of(B), s>>>(h->args, h->cv, early); else k_settle_slice<false><<<h->wave_blocks, B, smem_of(B), s>>>(h->args, h->cv, early);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(h->wave_blocks));
+  cfg.blockDim = dim3(unsigned(B));
+  cfg.dynamicSmemBytes = smem_of(B);
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  if (h->args.C.mass_randomizer) CUDA_TRY(cudaLaunchKernelEx(&cfg, k_settle_slice<true>, h->args, h->cv, early, stamps));
+  else CUDA_TRY(cudaLaunchKernelEx(&cfg, k_settle_slice<false>, h->args, h->cv, early, stamps));
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return QS_OK;
@@ -866,6 +891,7 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   io.flight_list = h->flight_list;
   io.cv = h->cv;
   const int slot = int(h->n_steps % qs_env::kRing);
+  io.stamps = h->stamps + 4 * slot;
   cudaEventRecord(h->ev0[slot], s);
   k_pre<<<grid_for(h->n, 256), 256, 0, s>>>(h->args, io);
   g_launches += 1;
@@ -876,7 +902,9 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
     CUDA_TRY(cudaEventRecord(h->ev_fork0, s));
   }
   if (h->args.C.mass_randomizer) k_step_contact<true><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io); else k_step_contact<false><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
-  g_launches += 1;
+  // the epilogue of every env whose ticks are done (all but the general solver's)
+  if (h->args.C.mass_randomizer) k_finish<true><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, nullptr); else k_finish<false><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, nullptr);
+  g_launches += 2;
   cudaEventRecord(h->ev1[slot], s);
   h->n_steps++;
   if (host) {
@@ -896,18 +924,25 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
     cudaEventRecord(h->ev4[slot], h->bg);
     if (int e = launch_slice(h, h->bg, 1)) return e;
     cudaEventRecord(h->ev5[slot], h->bg);
-    // late slice: bookkeeping in stream order, then the slice on the second stream next to k_step_slow
+    CUDA_TRY(cudaEventRecord(h->ev_early_done, h->bg));
+    // the late slice works on the same entries: after the early one (over long before k_step_contact is)
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_early_done, 0));
     if (int e = launch_conveyor(h, s, 1, 0)) return e;
-    CUDA_TRY(cudaEventRecord(h->ev_fork, s));
   }
-  // envs parked for the general solver (joint limits / body contacts); launched before the slice so
-  // that its few blocks are placed first.  (Tried: a stream of the greatest priority for this launch -- the
-  // hardware then placed the slice first most of the time and the general-solver blocks waited for the
-  // whole slice, 2.5 ms per step instead of 1.7.)
+  // envs parked for the general solver (joint limits / body contacts), then -- programmatic dependent launch -- the late
+  // settle slice, which starts once every block of k_step_slow has been placed and runs next to it.  (Round 1 launched
+  // the slice on a second stream: when the hardware placed it first, which it did on the three steps that follow a host
+  // synchronisation, the general-solver blocks waited for the whole slice, +1 ms; a high-priority stream made it worse.)
   cudaEventRecord(h->ev6[slot], s);
   if (h->args.C.mass_randomizer) k_step_slow<true><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread); else k_step_slow<false><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread);
+  g_launches += 1;
+  if (h->cfg.auto_reset) {
+    if (int e = launch_slice(h, s, 0, true, io.stamps)) return e;
+  }
+  cudaEventRecord(h->ev3[slot], s);   // ev6 -> ev3: the longer of the general solver and the late slice
+  if (h->args.C.mass_randomizer) k_finish<true><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, h->slow_list); else k_finish<false><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, h->slow_list);
   cudaEventRecord(h->ev7[slot], s);
-  g_launches += 2;
+  g_launches += 1;
   if (host) {
     const int O = h->args.C.obs_dim;
     k_gather_late<<<grid_for(h->late_cap, 128), 128, 0, s>>>(h->slow_list, h->n, O, obs, reward, done, truncated, h->dev_late,
@@ -920,12 +955,6 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
     CUDA_TRY(cudaEventRecord(h->ev_copied, h->copy));
   }
   if (h->cfg.auto_reset) {
-    CUDA_TRY(cudaStreamWaitEvent(h->bg, h->ev_fork, 0));
-    cudaEventRecord(h->ev2[slot], h->bg);
-    if (int e = launch_slice(h, h->bg, 0)) return e;
-    cudaEventRecord(h->ev3[slot], h->bg);
-    CUDA_TRY(cudaEventRecord(h->ev_join, h->bg));
-    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
     // envs that finished without a settled slot (rare): settled and started now
     if (h->args.C.mass_randomizer) k_settle_urgent<true><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, h->cv, obs); else k_settle_urgent<false><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, h->cv, obs);
     k_urgent_clear<<<1, 1, 0, s>>>(h->cv);

@@ -147,7 +147,18 @@ struct StepIO {
   int* contact_list; // envs with a foot on the ground (k_pre) or reaching it (flight kernel), contact_list[n] = count
   int* flight_list;  // the others: k_step's work, flight_list[n] = count
   Conveyor cv;
+  unsigned long long* stamps;  // this step's {late slice start, end, general solver start, end} in globaltimer ns
 };
+
+// device-side duration of a kernel that runs concurrently with another one in the same stream (programmatic dependent
+// launch: no event can be recorded between the two without serialising them)
+__device__ __forceinline__ unsigned long long qs_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void stamp_begin(unsigned long long* st) { if (st) atomicMin(st, qs_globaltimer()); }
+__device__ __forceinline__ void stamp_end(unsigned long long* st) { if (st) atomicMax(st + 1, qs_globaltimer()); }
 
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
   uint32_t v;
@@ -542,7 +553,8 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
 // Epilogue of a control step (quadruped_gym_env.py:239-256) + write-back + auto-reset.
 template <bool kEM>
 __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& io, int env, EnvState<float>& st,
-                                            ContactState<float>& cs, const float* tau_m, const float* tau_s) {
+                                            ContactState<float>& cs, const float* tau_m, const float* tau_s,
+                                            float* sm /* this thread's column of >= QS_SELF_SCRATCH shared floats */, int sm_stride) {
   const DeviceView& D = A.D;
   const EnvCfg& C = A.C;
   const int n = D.n;
@@ -573,6 +585,14 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
     fresh_state(A, st, cs);  // something finite to read back (without auto_reset the caller has to reset the env)
     quat_to_R(st.quat, Rb);
     rpy_from_quat(st.quat, rpy);
+  }
+  if (A.SC.self_collision) {
+    // Self contacts of the last tick's collision phase, i.e. on the poses at the START of that tick:
+    // q_before = q - dt * qd (integrate_positions).  Calf-involved pairs are invalid contacts (quadruped.py:236-241).
+    float qb[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) qb[i] = st.q[i] - dt * st.qd[i];
+    cs.invalid += self_collision_count(qb, A.M, sm, sm_stride);
   }
   float ts[QS_TASK_DIM];
 #pragma unroll
@@ -606,8 +626,6 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   io.done[env] = dn;
   io.truncated[env] = dn && !term;
   D.work[0 * n + env] += uint32_t(C.action_repeat);
-  D.work[1 * n + env] += uint32_t(cs.work_contacts);
-  D.work[2 * n + env] += uint32_t(cs.work_row_iters);
   const uint64_t gid = uint64_t(C.gid0 + env);
   int land_now = C.landing_mode ? D.land_mode[env] : LAND_POLICY;
   if (C.landing_mode && !dn) {
@@ -695,6 +713,23 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   D.ep_return[env] = ep_ret;
 }
 
+// All ticks of the control step are done: the state and the last tick's torques go back to the env's rows, and k_finish
+// (one thread per env, a small kernel at full occupancy) runs the step's epilogue from there.  The tick kernels are
+// pinned at 255 registers and 8 warps per SM: the epilogue's dependent chains (task logic, self collision, Philox noise)
+// cost several times more inside them than in a kernel of their own (round 2: +0.07 ms per step for the self-collision
+// test alone when it ran in the tick kernels' tails).
+__device__ __forceinline__ void tick_done_store(const KernelArgs& A, int env, const EnvState<float>& st,
+                                                const ContactState<float>& cs, const float* tau_m, const float* tau_s) {
+  const DeviceView& D = A.D;
+  const int n = D.n;
+  store_state(D, env, st, cs, A.SC.dt);
+#pragma unroll
+  for (int i = 0; i < 12; i++) { D.tau_motor[i * n + env] = tau_m[i]; D.tau_spring[i * n + env] = tau_s[i]; }
+  D.work[1 * n + env] += uint32_t(cs.work_contacts);
+  D.work[2 * n + env] += uint32_t(cs.work_row_iters);
+  D.resume_tick[env] = A.C.action_repeat;   // "ticks done, epilogue pending"
+}
+
 // hand an env over to another kernel of the step: state as of the start of tick `t`
 __device__ __forceinline__ void park_env(const KernelArgs& A, const StepIO& io, int env, const EnvState<float>& st,
                                          const ContactState<float>& cs, const float* cmd, int t, int* list,
@@ -724,6 +759,7 @@ k_pre(const __grid_constant__ KernelArgs A, const StepIO io) {
   const int n = D.n;
   const bool live = tid < n;
   const int env = live ? tid : n - 1;
+  if (tid == 0 && io.stamps) { io.stamps[0] = ~0ull; io.stamps[1] = 0ull; io.stamps[2] = ~0ull; io.stamps[3] = 0ull; }
   // ---- action (quadruped_gym_env.py:229-234)
   float act[12];
 #pragma unroll
@@ -864,7 +900,7 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
     park_env(A, io, env, st, cs, cmd, t_done, why == TICK_NEEDS_GENERAL ? io.slow_list : io.contact_list);
     return;
   }
-  finish_step<kEM>(A, io, env, st, cs, tau_m, tau_s);
+  tick_done_store(A, env, st, cs, tau_m, tau_s);
 }
 
 // -------------------------------------------------------------------- K1a: envs with foot contacts
@@ -898,13 +934,18 @@ k_step_contact(const __grid_constant__ KernelArgs A, const StepIO io) {
     park_env(A, io, env, st, cs, cmd, t_done, io.slow_list);
     return;
   }
-  finish_step<kEM>(A, io, env, st, cs, tau_m, tau_s);
+  tick_done_store(A, env, st, cs, tau_m, tau_s);
 }
 
 // -------------------------------------------------------------------- K1b: general-solver continuation
 template <bool kEM>
 __global__ void __launch_bounds__(64)
 k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io, int spread) {
+  // Programmatic dependent launch: the late settle slice follows in the same stream and may start as soon as every block
+  // of this grid has been placed (has got here or exited), not when the grid is complete.  That ordering is the point: the
+  // slice fills every SM, and when the hardware happened to place it first (two streams racing), the few latency-bound
+  // blocks of this kernel waited for the whole slice: +1 ms on that step.
+  asm volatile("griddepcontrol.launch_dependents;");
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const DeviceView& D = A.D;
   const int n = D.n;
@@ -920,6 +961,7 @@ k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io, int spread) {
   const int idx = (tid >> 5) * K + lane;
   if (idx >= count) return;
   const int env = io.slow_list[idx];
+  if (lane == 0) stamp_begin(io.stamps ? io.stamps + 2 : nullptr);
   EnvState<float> st;
   ContactState<float> cs;
   load_state(D, env, st, cs, A.SC.dt);
@@ -929,7 +971,34 @@ k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io, int spread) {
   const bool torque_mode = !A.C.is_rl && A.C.control_mode == QS_CTRL_TORQUE;
   run_ticks_general<kEM>(st, cs, cmd, torque_mode, D.resume_tick[env], A.C.action_repeat, env, D, A.C, A.RC, A.M, A.SC,
                     tau_m, tau_s);
-  finish_step<kEM>(A, io, env, st, cs, tau_m, tau_s);
+  tick_done_store(A, env, st, cs, tau_m, tau_s);
+  stamp_end(io.stamps ? io.stamps + 2 : nullptr);
+}
+
+// -------------------------------------------------------------------- K1c: the step's epilogue
+// One thread per env (list == nullptr) or per entry of `list` (list[n] = count): the envs whose ticks are done run
+// finish_step -- task bookkeeping, reward, done, self-collision test, observation + noise, auto-reset.  Launched after
+// k_step_contact for everybody and after k_step_slow for the general solver's envs.
+constexpr int QS_FINISH_BLOCK = 128;
+template <bool kEM>
+__global__ void __launch_bounds__(QS_FINISH_BLOCK, 4)
+k_finish(const __grid_constant__ KernelArgs A, const StepIO io, const int* __restrict__ list) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const DeviceView& D = A.D;
+  const int n = D.n;
+  const int count = list ? list[n] : n;
+  if (tid >= count) return;
+  const int env = list ? list[tid] : tid;
+  if (D.resume_tick[env] != A.C.action_repeat) return;   // parked for the general solver, or already finished
+  D.resume_tick[env] = -1;
+  EnvState<float> st;
+  ContactState<float> cs;
+  load_state(D, env, st, cs, A.SC.dt);
+  float tau_m[12], tau_s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) { tau_m[i] = D.tau_motor[i * n + env]; tau_s[i] = D.tau_spring[i * n + env]; }
+  __shared__ float sc_pts[QS_SELF_SCRATCH * QS_FINISH_BLOCK];
+  finish_step<kEM>(A, io, env, st, cs, tau_m, tau_s, sc_pts + threadIdx.x, QS_FINISH_BLOCK);
 }
 
 // -------------------------------------------------------------------- K2: reset + settle
@@ -1123,11 +1192,12 @@ __global__ void k_conveyor_ctl(Conveyor cv, int phase, const int* __restrict__ b
 // reaches the end of its settle stores the episode's slot and retires.
 template <bool kEM>
 __global__ void __launch_bounds__(256, 1)
-k_settle_slice(const __grid_constant__ KernelArgs A, const Conveyor cv, int early) {
+k_settle_slice(const __grid_constant__ KernelArgs A, const Conveyor cv, int early, unsigned long long* stamps) {
   const DeviceView& D = A.D;
   const int n = D.n;
   const int active = int(cv.ctl[early ? CV_ACTIVE_EARLY : CV_ACTIVE]);
   if (blockIdx.x * blockDim.x >= active) return;  // uniform over the block
+  if (threadIdx.x == 0) stamp_begin(stamps);
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = j < active;
   const uint32_t idx = cv.ctl[CV_TAIL] + uint32_t(live ? j : active - 1);
@@ -1156,6 +1226,7 @@ k_settle_slice(const __grid_constant__ KernelArgs A, const Conveyor cv, int earl
   extern __shared__ float qs_smem[];
   const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
   settle_ticks<kEM>(A, uint64_t(A.C.gid0 + env), epoch, st, cs, mu, t0, t1, span, tau_m, tau_s, scr, cv.model, cv.width, col);
+  if (threadIdx.x == 0) stamp_end(stamps);   // (the block's ticks are over: settle_ticks ends on a barrier-matched loop)
   if (!need) return;
   {  // work counters of the bench's flop model, one atomic per warp
     const unsigned m = __activemask();

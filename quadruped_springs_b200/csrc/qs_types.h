@@ -45,7 +45,7 @@ template <typename T> struct ModelConstT {
 struct SolverConst {
   float dt, gravity_z, contact_erp, limit_erp, linear_slop, warmstart, residual_threshold;
   float max_coord_vel, mu_link;
-  int32_t num_iterations, enable_limits, body_response;
+  int32_t num_iterations, enable_limits, body_response, self_collision;
 };
 
 // Device view of the handle-owned SoA state (all arrays [dim][N]).

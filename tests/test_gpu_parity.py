@@ -833,3 +833,28 @@ def test_contact_rich_episodes_match_in_task_statistics(qs, task, control, obs, 
         assert close.mean() >= 0.8, (k, close.mean())
     assert abs(g_ret.mean() - r_ret.mean()) < 0.03, (g_ret.mean(), r_ret.mean())
     assert (np.abs(g_len - r_len) <= 2).mean() >= 0.8, (g_len, r_len)
+
+
+# ------------------------------------------------------------------ a15: self collision (quadruped.py:236-241)
+def test_self_collision_counts_match_reference_contact_info(qs):
+    """tests/golden/self_contact_info.npz: 96 airborne states, half with crossed legs; one physics tick each.  The number
+    of invalid contacts the kernels report must be the reference GetContactInfo's (bodyA == bodyB rows with a calf),
+    zero for the clean states, and zero everywhere with the detection switched off."""
+    g = load_golden("self_contact_info.npz")
+    n = len(g["state"])
+    kw = dict(num_envs=n, enable_springs=True, task_env="JUMPING_IN_PLACE", motor_control_mode="PD",
+              action_space_mode="DEFAULT", observation_space_mode="ARS_BASIC", action_repeat=1, auto_reset=False,
+              enable_noise=False)
+    for flag in (1, 0):
+        env = qs.BatchedQuadrupedGymEnv(solver=dict(self_collision=flag), **kw)
+        env.reset()
+        env.set_state(cuda(g["state"]))
+        obs, r, d, info = env.step(torch.zeros(n, 12, device="cuda"))
+        nvalid, ninv, _, _ = env.robot.GetContactInfo()
+        assert (nvalid == 0).all()
+        if flag:
+            np.testing.assert_array_equal(ninv.cpu().numpy(), g["info"][:, 1].astype(np.int64))
+            # an invalid contact ends the episode (task_base.py:146-147)
+            np.testing.assert_array_equal(d.cpu().numpy(), g["info"][:, 1] > 0)
+        else:
+            assert (ninv == 0).all() and not d.any()

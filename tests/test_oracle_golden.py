@@ -205,3 +205,22 @@ def test_landing_controller_matches_reference_wrapper(name):
         assert 3 in modes                                    # LandingWrapper2 hands control back to the policy
     if lm == 3:                                              # the continuous variant re-arms after every jump
         assert any(a == 2 and b == 0 for a, b in zip(modes, modes[1:]))
+
+
+def test_self_collision_contact_info_matches_reference():
+    """tests/golden/self_contact_info.npz: the reference's own GetContactInfo (quadruped.py:224-258) over getContactPoints
+    rows with bodyA == bodyB, 96 airborne states (half with crossed legs), one stepSimulation each.  The oracle env's
+    contact bookkeeping must count the same invalid contacts; the states without a hit must have none."""
+    from oracle import oracle as O
+    g = load_golden("self_contact_info.npz")
+    w = O.World()
+    for s, info in zip(g["state"], g["info"]):
+        w.set_state(s)
+        w.step()
+        calf_pairs = [(a, b) for a, b, d in w.self_contacts() if a in (4, 8, 12, 16) or b in (4, 8, 12, 16)]
+        assert len(calf_pairs) == int(info[1]) and len(w.contacts()) == 0
+    # parent-child pairs are never reported, and the flag turns the detection off
+    assert all((b - a) not in (1, -1) or a // 4 != b // 4 for s in g["state"][:8] for a, b, _ in (w.set_state(s), w.self_contacts(detect=True))[1])
+    w2 = O.World(self_collision=0)
+    w2.set_state(g["state"][0]); w2.step()
+    assert w2.self_contacts() == []

@@ -407,7 +407,7 @@ def run_ours(args):
     resets_timed = job.take_done_count()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     kms = C.c_float()
-    kk = min(env_calls, 512)
+    kk = min(env_calls, int(L.qs_timing_window(env._h)))
     _lib.check(L.qs_step_kernel_time(env._h, kk, C.byref(kms)))
     k_step_ms = kms.value / kk * (env_calls / args.steps)
     _lib.check(L.qs_settle_kernel_time(env._h, kk, C.byref(kms)))

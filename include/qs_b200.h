@@ -299,6 +299,9 @@ int qs_settle_work_counters(qs_handle h, uint64_t* out3, void* stream);
  * and the number of qs_step / qs_step_host calls made on this handle so far */
 int qs_slow_kernel_time(qs_handle h, int last_k, float* ms_sum);
 int64_t qs_step_count(qs_handle h);
+/* how many of the last steps the three timing hooks can look back on: 512 with direct launches, 16 when qs_step replays
+ * the step's CUDA graph (one captured graph per timing slot; QS_GRAPH=0 in the environment turns the graph off) */
+int qs_timing_window(qs_handle h);
 /* diagnostics of the last qs_step: out4 = {envs handed to the general solver, envs whose next episode was
  * settled on the spot because no settled slot was ready, entries on the settle conveyor, ticks of its last
  * slice}; synchronises the stream */

@@ -134,6 +134,7 @@ EXPORTS = {
     "qs_settle_work_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "qs_slow_kernel_time": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "qs_step_count": (C.c_int64, [C.c_void_p]),
+    "qs_timing_window": (C.c_int, [C.c_void_p]),
     "qs_launch_count": (C.c_int64, []),
 }
 

@@ -351,9 +351,20 @@ struct qs_env {
   // CUDA-event ring around k_step launches (roofline timing of the dominant kernel)
   static constexpr int kRing = 512;
   cudaEvent_t ev0[kRing], ev1[kRing];   // around k_step + k_step_contact, on the caller's stream
-  cudaEvent_t ev2[kRing], ev3[kRing];   // around the late k_settle_slice, on the second stream
-  cudaEvent_t ev4[kRing], ev5[kRing];   // around the early one
-  cudaEvent_t ev6[kRing], ev7[kRing];   // around k_step_slow, on the caller's stream
+  cudaEvent_t ev4[kRing], ev5[kRing];   // around the early settle slice, on the second stream
+  // CUDA graph of one step (qs_step): captured once per set of output buffers and timing-ring slot on the library's own
+  // stream `main`, relaunched per step; the caller's stream is joined with two events.  Every data-dependent count of
+  // the step lives on the device, so the graph never changes.
+  static constexpr int kGraphSlots = 16, kGraphKeys = 4;
+  struct GraphKey { float* obs; float* reward; uint8_t* done; uint8_t* trunc; float* term_obs; cudaGraphExec_t exec[kGraphSlots]; };
+  GraphKey gkeys[kGraphKeys];
+  int n_gkeys;
+  int ring;            // timing ring in use: kRing (direct launches) or kGraphSlots (graph launches)
+  bool use_graph;
+  cudaStream_t main;   // the graph is launched here
+  cudaEvent_t ev_in, ev_out;
+  float* act_buf;      // the graph's action input [N, A]: the caller's actions are copied here first
+  int launches_per_step;
   cudaEvent_t ev_fork0, ev_early_done;
   unsigned long long* stamps;   // [kRing][4] device: per step {late slice start, end, general solver start, end} (globaltimer ns)
   bool ev_ready;
@@ -589,6 +600,12 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork0, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_early_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->main, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming);
+    h->use_graph = true;
+    if (const char* v = std::getenv("QS_GRAPH")) h->use_graph = std::atoi(v) != 0;
+    h->ring = h->use_graph ? int(qs_env::kGraphSlots) : int(qs_env::kRing);
     if (e == cudaSuccess) e = cudaMalloc(&h->stamps, sizeof(unsigned long long) * 4 * qs_env::kRing);
     if (e == cudaSuccess) e = cudaMemset(h->stamps, 0, sizeof(unsigned long long) * 4 * qs_env::kRing);
     if (e != cudaSuccess) { cudaFree(h->pool); cudaFree(h->lists); delete h; return fail(QS_ERR_CUDA, "stream / event creation"); }
@@ -615,6 +632,8 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   return QS_OK;
 }
 
+static void drop_graphs(qs_handle h);
+
 int qs_destroy(qs_handle h) {
   if (!h) return fail(QS_ERR_ARG, "handle is NULL");
   cudaSetDevice(h->device);
@@ -631,6 +650,11 @@ int qs_destroy(qs_handle h) {
   cudaEventDestroy(h->ev_fork0);
   cudaEventDestroy(h->ev_join);
   cudaEventDestroy(h->ev_early_done);
+  drop_graphs(h);
+  cudaStreamDestroy(h->main);
+  cudaEventDestroy(h->ev_in);
+  cudaEventDestroy(h->ev_out);
+  if (h->act_buf) cudaFree(h->act_buf);
   cudaFree(h->stamps);
   if (h->dev_actions) cudaFree(h->dev_actions);
   if (h->dev_obs) cudaFree(h->dev_obs);
@@ -639,9 +663,8 @@ int qs_destroy(qs_handle h) {
   if (h->dev_late) { cudaFree(h->dev_late); cudaFreeHost(h->host_late); cudaEventDestroy(h->ev_late); }
   if (h->ev_ready)
     for (int i = 0; i < qs_env::kRing; i++) {
-      cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]); cudaEventDestroy(h->ev2[i]); cudaEventDestroy(h->ev3[i]);
+      cudaEventDestroy(h->ev0[i]); cudaEventDestroy(h->ev1[i]);
       cudaEventDestroy(h->ev4[i]); cudaEventDestroy(h->ev5[i]);
-      cudaEventDestroy(h->ev6[i]); cudaEventDestroy(h->ev7[i]);
     }
   delete h;
   return QS_OK;
@@ -651,11 +674,11 @@ int qs_step_kernel_time(qs_handle h, int last_k, float* ms_sum) {
   // sum of the device durations of the last `last_k` k_step launches (CUDA events on the
   // launching stream; k_step + k_step_contact); the stream must have been synchronised by the caller
   if (!h || !ms_sum) return fail(QS_ERR_ARG, "NULL argument");
-  if (last_k <= 0 || last_k > qs_env::kRing || last_k > h->n_steps) return fail(QS_ERR_ARG, "last_k out of range");
+  if (last_k <= 0 || last_k > h->ring || last_k > h->n_steps) return fail(QS_ERR_ARG, "last_k out of range (qs_timing_window)");
   float tot = 0.f;
   for (int64_t i = h->n_steps - last_k; i < h->n_steps; i++) {
     float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0[i % qs_env::kRing], h->ev1[i % qs_env::kRing]));
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0[i % h->ring], h->ev1[i % h->ring]));
     tot += ms;
   }
   *ms_sum = tot;
@@ -666,15 +689,15 @@ int qs_settle_kernel_time(qs_handle h, int last_k, float* ms_sum) {
   // same for the k_settle_slice launches of the last `last_k` steps (events on the library's second stream)
   if (!h || !ms_sum) return fail(QS_ERR_ARG, "NULL argument");
   if (!h->cfg.auto_reset) return fail(QS_ERR_STATE, "no settle slices without auto_reset");
-  if (last_k <= 0 || last_k > qs_env::kRing || last_k > h->n_steps) return fail(QS_ERR_ARG, "last_k out of range");
+  if (last_k <= 0 || last_k > h->ring || last_k > h->n_steps) return fail(QS_ERR_ARG, "last_k out of range (qs_timing_window)");
   static unsigned long long host_st[4 * qs_env::kRing];
   CUDA_TRY(cudaMemcpy(host_st, h->stamps, sizeof(host_st), cudaMemcpyDeviceToHost));
   float tot = 0.f;
   for (int64_t i = h->n_steps - last_k; i < h->n_steps; i++) {
     float ms = 0.f;
-    const unsigned long long* st = host_st + 4 * (i % qs_env::kRing);
+    const unsigned long long* st = host_st + 4 * (i % h->ring);
     if (st[1] > st[0]) tot += float(double(st[1] - st[0]) * 1e-6);   // late slice: device-side stamps (it shares its stream)
-    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev4[i % qs_env::kRing], h->ev5[i % qs_env::kRing]));
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev4[i % h->ring], h->ev5[i % h->ring]));
     tot += ms;
   }
   *ms_sum = tot;
@@ -684,12 +707,12 @@ int qs_settle_kernel_time(qs_handle h, int last_k, float* ms_sum) {
 int qs_slow_kernel_time(qs_handle h, int last_k, float* ms_sum) {
   // same for the k_step_slow launches (events on the caller's stream)
   if (!h || !ms_sum) return fail(QS_ERR_ARG, "NULL argument");
-  if (last_k <= 0 || last_k > qs_env::kRing || last_k > h->n_steps) return fail(QS_ERR_ARG, "last_k out of range");
+  if (last_k <= 0 || last_k > h->ring || last_k > h->n_steps) return fail(QS_ERR_ARG, "last_k out of range (qs_timing_window)");
   static unsigned long long host_st[4 * qs_env::kRing];
   CUDA_TRY(cudaMemcpy(host_st, h->stamps, sizeof(host_st), cudaMemcpyDeviceToHost));
   float tot = 0.f;
   for (int64_t i = h->n_steps - last_k; i < h->n_steps; i++) {
-    const unsigned long long* st = host_st + 4 * (i % qs_env::kRing);
+    const unsigned long long* st = host_st + 4 * (i % h->ring);
     if (st[3] > st[2]) tot += float(double(st[3] - st[2]) * 1e-6);
   }
   *ms_sum = tot;
@@ -697,6 +720,7 @@ int qs_slow_kernel_time(qs_handle h, int last_k, float* ms_sum) {
 }
 
 int64_t qs_step_count(qs_handle h) { return h ? h->n_steps : 0; }
+int qs_timing_window(qs_handle h) { return h ? h->ring : QS_ERR_ARG; }
 
 int qs_settle_work_counters(qs_handle h, uint64_t* out3, void* stream) {
   // totals of (settle ticks, foot-contact ticks, contact x PGS-sweep count) executed by k_settle_slice so far; synchronises
@@ -854,6 +878,10 @@ __global__ void k_gather_late(const int* __restrict__ list, int n, int O, const 
   for (int k = 0; k < O; k++) row[4 + k] = obs[size_t(env) * O + k];
 }
 
+__global__ void k_zero3(int* a, int* b, int* c) {
+  if (threadIdx.x == 0) { *a = 0; *b = 0; *c = 0; }
+}
+
 // host destinations of qs_step_host: copied as soon as the last step kernel has written them
 struct HostOut {
   float* obs;
@@ -862,27 +890,37 @@ struct HostOut {
   uint8_t* truncated;
 };
 
+static int ensure_events(qs_handle h) {
+  if (!h->ev_ready) {
+    for (int i = 0; i < qs_env::kRing; i++) {
+      CUDA_TRY(cudaEventCreate(&h->ev0[i])); CUDA_TRY(cudaEventCreate(&h->ev1[i]));
+      CUDA_TRY(cudaEventCreate(&h->ev4[i])); CUDA_TRY(cudaEventCreate(&h->ev5[i]));
+    }
+    h->ev_ready = true;
+  }
+  return QS_OK;
+}
+// a timing event: inside a stream capture it becomes an event-record node that can still be queried afterwards
+static cudaError_t rec_timing(cudaEvent_t ev, cudaStream_t s, bool capturing) {
+  return capturing ? cudaEventRecordWithFlags(ev, s, cudaEventRecordExternal) : cudaEventRecord(ev, s);
+}
+
+// The launches of one control step into stream s.  capture_slot >= 0: called under stream capture for the graph of
+// timing-ring slot `capture_slot` (no host-side bookkeeping; the launcher does it per graph launch).
 static int step_impl(qs_handle h, const float* actions, float* obs, float* reward, uint8_t* done, uint8_t* truncated,
-                     void* stream, const HostOut* host) {
+                     void* stream, const HostOut* host, int capture_slot = -1) {
   if (!h) return fail(QS_ERR_ARG, "handle is NULL");
   if (!actions || !obs || !reward || !done || !truncated) return fail(QS_ERR_ARG, "NULL buffer");
   if (!h->was_reset) return fail(QS_ERR_STATE, "qs_step before qs_reset");
   if (int e = need_demo(h)) return e;
+  const bool capturing = capture_slot >= 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  CUDA_TRY(cudaSetDevice(h->device));
+  if (!capturing) CUDA_TRY(cudaSetDevice(h->device));
   const int B = block_of(h);
-  CUDA_TRY(cudaMemsetAsync(h->slow_list + h->n, 0, sizeof(int), s));
-  CUDA_TRY(cudaMemsetAsync(h->contact_list + h->n, 0, sizeof(int), s));
-  CUDA_TRY(cudaMemsetAsync(h->flight_list + h->n, 0, sizeof(int), s));
-  if (!h->ev_ready) {
-    for (int i = 0; i < qs_env::kRing; i++) {
-      CUDA_TRY(cudaEventCreate(&h->ev0[i])); CUDA_TRY(cudaEventCreate(&h->ev1[i]));
-      CUDA_TRY(cudaEventCreate(&h->ev2[i])); CUDA_TRY(cudaEventCreate(&h->ev3[i]));
-      CUDA_TRY(cudaEventCreate(&h->ev4[i])); CUDA_TRY(cudaEventCreate(&h->ev5[i]));
-      CUDA_TRY(cudaEventCreate(&h->ev6[i])); CUDA_TRY(cudaEventCreate(&h->ev7[i]));
-    }
-    h->ev_ready = true;
-  }
+  const int64_t launches0 = g_launches.load();
+  k_zero3<<<1, 32, 0, s>>>(h->slow_list + h->n, h->contact_list + h->n, h->flight_list + h->n);
+  g_launches += 1;
+  if (int e = ensure_events(h)) return e;
   StepIO io;
   io.actions = actions; io.obs = obs; io.reward = reward; io.done = done; io.truncated = truncated;
   io.term_obs = h->term_obs;
@@ -890,9 +928,9 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   io.contact_list = h->contact_list;
   io.flight_list = h->flight_list;
   io.cv = h->cv;
-  const int slot = int(h->n_steps % qs_env::kRing);
+  const int slot = capturing ? capture_slot : int(h->n_steps % h->ring);
   io.stamps = h->stamps + 4 * slot;
-  cudaEventRecord(h->ev0[slot], s);
+  CUDA_TRY(rec_timing(h->ev0[slot], s, capturing));
   k_pre<<<grid_for(h->n, 256), 256, 0, s>>>(h->args, io);
   g_launches += 1;
   if (h->args.C.mass_randomizer) k_step<true><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io); else k_step<false><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
@@ -905,8 +943,8 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   // the epilogue of every env whose ticks are done (all but the general solver's)
   if (h->args.C.mass_randomizer) k_finish<true><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, nullptr); else k_finish<false><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, nullptr);
   g_launches += 2;
-  cudaEventRecord(h->ev1[slot], s);
-  h->n_steps++;
+  CUDA_TRY(rec_timing(h->ev1[slot], s, capturing));
+  if (!capturing) h->n_steps++;
   if (host) {
     // All rows but those of the envs now in the general solver's list are final: send everything to the host while
     // k_step_slow and the late settle slice run; the stragglers follow in a compact buffer (below), and rows an
@@ -921,9 +959,9 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   }
   if (h->cfg.auto_reset) {
     CUDA_TRY(cudaStreamWaitEvent(h->bg, h->ev_fork0, 0));
-    cudaEventRecord(h->ev4[slot], h->bg);
+    CUDA_TRY(rec_timing(h->ev4[slot], h->bg, capturing));
     if (int e = launch_slice(h, h->bg, 1)) return e;
-    cudaEventRecord(h->ev5[slot], h->bg);
+    CUDA_TRY(rec_timing(h->ev5[slot], h->bg, capturing));
     CUDA_TRY(cudaEventRecord(h->ev_early_done, h->bg));
     // the late slice works on the same entries: after the early one (over long before k_step_contact is)
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_early_done, 0));
@@ -933,15 +971,12 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   // settle slice, which starts once every block of k_step_slow has been placed and runs next to it.  (Round 1 launched
   // the slice on a second stream: when the hardware placed it first, which it did on the three steps that follow a host
   // synchronisation, the general-solver blocks waited for the whole slice, +1 ms; a high-priority stream made it worse.)
-  cudaEventRecord(h->ev6[slot], s);
   if (h->args.C.mass_randomizer) k_step_slow<true><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread); else k_step_slow<false><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread);
   g_launches += 1;
   if (h->cfg.auto_reset) {
     if (int e = launch_slice(h, s, 0, true, io.stamps)) return e;
   }
-  cudaEventRecord(h->ev3[slot], s);   // ev6 -> ev3: the longer of the general solver and the late slice
   if (h->args.C.mass_randomizer) k_finish<true><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, h->slow_list); else k_finish<false><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, h->slow_list);
-  cudaEventRecord(h->ev7[slot], s);
   g_launches += 1;
   if (host) {
     const int O = h->args.C.obs_dim;
@@ -961,7 +996,71 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
     g_launches += 2;
   }
   CUDA_TRY(cudaGetLastError());
+  h->launches_per_step = int(g_launches.load() - launches0);
+  if (capturing) g_launches -= h->launches_per_step;   // counted per graph launch instead
   return QS_OK;
+}
+
+// qs_step through the step's CUDA graph (see qs_env::GraphKey); falls back to direct launches when the capture is not
+// possible (more output-buffer sets than the cache holds, a driver that refuses the capture)
+static int step_graph(qs_handle h, const float* actions, float* obs, float* reward, uint8_t* done, uint8_t* truncated,
+                      void* stream) {
+  if (!h) return fail(QS_ERR_ARG, "handle is NULL");
+  if (!h->use_graph) return step_impl(h, actions, obs, reward, done, truncated, stream, nullptr);
+  if (!actions || !obs || !reward || !done || !truncated) return fail(QS_ERR_ARG, "NULL buffer");
+  if (!h->was_reset) return fail(QS_ERR_STATE, "qs_step before qs_reset");
+  if (int e = need_demo(h)) return e;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (int e = ensure_events(h)) return e;
+  const size_t abytes = size_t(h->n) * size_t(h->args.C.action_dim) * sizeof(float);
+  if (!h->act_buf) CUDA_TRY(cudaMalloc(&h->act_buf, size_t(h->n) * 12 * sizeof(float)));
+  qs_env::GraphKey* key = nullptr;
+  for (int i = 0; i < h->n_gkeys; i++) {
+    qs_env::GraphKey& k = h->gkeys[i];
+    if (k.obs == obs && k.reward == reward && k.done == done && k.trunc == truncated && k.term_obs == h->term_obs) { key = &k; break; }
+  }
+  if (!key) {
+    if (h->n_gkeys == qs_env::kGraphKeys) return step_impl(h, actions, obs, reward, done, truncated, stream, nullptr);
+    key = &h->gkeys[h->n_gkeys++];
+    std::memset(key, 0, sizeof(*key));
+    key->obs = obs; key->reward = reward; key->done = done; key->trunc = truncated; key->term_obs = h->term_obs;
+  }
+  const int v = int(h->n_steps % qs_env::kGraphSlots);
+  if (!key->exec[v]) {
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(h->main, cudaStreamCaptureModeThreadLocal);
+    int rc = QS_OK;
+    if (e == cudaSuccess) {
+      rc = step_impl(h, h->act_buf, obs, reward, done, truncated, h->main, nullptr, v);
+      e = cudaStreamEndCapture(h->main, &graph);
+    }
+    if (e == cudaSuccess && rc == QS_OK) e = cudaGraphInstantiate(&key->exec[v], graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess || rc != QS_OK) {   // no graph on this system: direct launches from now on
+      cudaGetLastError();
+      key->exec[v] = nullptr;
+      h->use_graph = false;
+      h->ring = qs_env::kRing;
+      return step_impl(h, actions, obs, reward, done, truncated, stream, nullptr);
+    }
+  }
+  if (actions != h->act_buf) CUDA_TRY(cudaMemcpyAsync(h->act_buf, actions, abytes, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaEventRecord(h->ev_in, s));
+  CUDA_TRY(cudaStreamWaitEvent(h->main, h->ev_in, 0));
+  CUDA_TRY(cudaGraphLaunch(key->exec[v], h->main));
+  CUDA_TRY(cudaEventRecord(h->ev_out, h->main));
+  CUDA_TRY(cudaStreamWaitEvent(s, h->ev_out, 0));
+  g_launches += h->launches_per_step;
+  h->n_steps++;
+  return QS_OK;
+}
+
+static void drop_graphs(qs_handle h) {
+  for (int i = 0; i < h->n_gkeys; i++)
+    for (int v = 0; v < qs_env::kGraphSlots; v++)
+      if (h->gkeys[i].exec[v]) cudaGraphExecDestroy(h->gkeys[i].exec[v]);
+  h->n_gkeys = 0;
 }
 
 int qs_reset_to_state(qs_handle h, const uint8_t* mask, const float* states, float* obs, void* stream) {
@@ -997,6 +1096,7 @@ int qs_set_demo(qs_handle h, const float* actions, int length) {
   CUDA_TRY(cudaMemcpy(h->dev_demo, actions, bytes, cudaMemcpyHostToDevice));
   h->args.C.demo = h->dev_demo;
   h->args.C.demo_len = length;
+  drop_graphs(h);   // the kernel arguments are baked into the captured nodes
   return QS_OK;
 }
 
@@ -1019,7 +1119,7 @@ int qs_set_terminal_obs(qs_handle h, float* term_obs) {
 
 int qs_step(qs_handle h, const float* actions, float* obs, float* reward, uint8_t* done, uint8_t* truncated,
             void* stream) {
-  return step_impl(h, actions, obs, reward, done, truncated, stream, nullptr);
+  return step_graph(h, actions, obs, reward, done, truncated, stream);
 }
 
 static int ensure_staging(qs_handle h) {

@@ -262,7 +262,7 @@ class Job:
                                              enable_noise=True, **cfg["env"])
         self.A, self.O = self.env.action_dim, self.env.obs_dim
         self.gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-        self.done_count = torch.zeros((), dtype=torch.int64, device=dev)
+        self.episodes_seen = 0
         self.obs = self.env.reset()
         if self.kind == "cpg":
             self.cpg = qs.HopfNetwork(num_envs=n, device=dev, time_step=0.001, seed=rank, **cfg["cpg"])
@@ -282,21 +282,19 @@ class Job:
         env = self.env
         if self.kind == "random":
             o, r, d, _ = env.step(inp)
-        elif self.kind == "cpg":    # hopf_network.py:241-289, ten 1 ms ticks
-            for _ in range(10):
-                _, _, tau = self.cpg.update(env.robot.GetMotorAngles(), env.robot.GetMotorVelocities())
-                o, r, d, _ = env.step(tau)
-                self.done_count += d.sum()
+        elif self.kind == "cpg":    # hopf_network.py:241-289, ten 1 ms ticks: qs_cpg_steps
+            self.cpg.drive(env, 10)
             return
         else:                       # load_model.py:127-134 with the policy on the device (stochastic, as in PPO rollouts)
             a = self.policy.predict(self.vn.normalize_obs(self.obs), deterministic=False, generator=self.gen)
             o, r, d, _ = env.step(a)
             self.obs = o
-        self.done_count += d.sum()
 
     def take_done_count(self):
-        v = int(self.done_count.item())
-        self.done_count.zero_()
+        """episodes finished since the last call (the env's own rollout statistics, kernel K5)"""
+        total = int(round(float(self.env.rollout_stats()[1].item())))
+        v = total - self.episodes_seen
+        self.episodes_seen = total
         return v
 
 

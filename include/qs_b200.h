@@ -277,6 +277,12 @@ int qs_ik(const float* xyz_dev, float* q_dev, int n, void* stream);
 int qs_cpg_update(double* X_dev, const double* params9, const double* phi16, const float* q_dev,
                   const float* qd_dev, const float* gains8, float foot_y, float* xs_dev,
                   float* zs_dev, float* tau_dev, int n, void* stream);
+/* n_ticks turns of the reference's CPG loop (hopf_network.py:241-289) inside the library: per tick qs_cpg_update's
+ * oscillator step and torque law on the env's own joint state, then qs_step on those torques.  The env must be a
+ * TORQUE-mode env with is_rl_interface = 0 (hopf_network.py:183-190).  Outputs as qs_step, of the last tick. */
+int qs_cpg_steps(qs_handle h, double* X_dev, const double* params9, const double* phi16, const float* gains8,
+                 float foot_y, int n_ticks, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                 uint8_t* truncated_dev, void* stream);
 /* rollout statistics of this shard (EvaluationWrapper infos,
  * evaluation_wrapper.py:43-53; task maxima, task_base.py:51-57): out[QS_STATS_DIM]
  * floats on the device: count, finished episodes, sum/max of max_height,

@@ -5,7 +5,7 @@ from .env import (  # noqa: F401
     MotorInterfaceCollection, SensorCollection, TaskCollection,
 )
 from .hopf_network import HopfNetwork  # noqa: F401
-from . import demo, ops, stats, vec_env  # noqa: F401
+from . import demo, load_model, ops, stats, vec_env  # noqa: F401
 from .vec_env import BatchedVecEnv, MlpPolicyTorch, VecNormalizeTorch  # noqa: F401
 
 __all__ = ["BatchedQuadrupedGymEnv", "BatchedQuadruped", "HopfNetwork", "ops", "BatchedVecEnv", "VecNormalizeTorch",

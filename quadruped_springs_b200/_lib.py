@@ -126,6 +126,8 @@ EXPORTS = {
     "qs_cpg_update": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p, C.c_void_p,
                                 C.POINTER(C.c_float), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_void_p]),
+    "qs_cpg_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_float),
+                               C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "qs_reduce_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "qs_step_kernel_time": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "qs_work_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),

@@ -220,9 +220,10 @@ struct CpgArgs {
   double p[9], phi[16];
   float gains[8], foot_y;
 };
+// q / qd element (env i, joint j) at q[i * q_si + j * q_sj]: [N,12] row-major (12, 1) or the env's own SoA rows (1, N)
 __global__ void k_cpg(const __grid_constant__ CpgArgs P, double* __restrict__ X, const float* __restrict__ q,
                       const float* __restrict__ qd, float* __restrict__ xs_o, float* __restrict__ zs_o,
-                      float* __restrict__ tau, int n) {
+                      float* __restrict__ tau, int n, int q_si, int q_sj) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double mu = P.p[0], om_sw = P.p[1], om_st = P.p[2], coup = P.p[3], dt = P.p[4], dstep = P.p[5],
@@ -263,7 +264,7 @@ __global__ void k_cpg(const __grid_constant__ CpgArgs P, double* __restrict__ X,
     float qdes[3], ql[3], qdl[3], J[9], p[3];
     leg_ik(xyz_d, k, qdes);
 #pragma unroll
-    for (int j = 0; j < 3; j++) { ql[j] = q[size_t(i) * 12 + 3 * k + j]; qdl[j] = qd[size_t(i) * 12 + 3 * k + j]; }
+    for (int j = 0; j < 3; j++) { ql[j] = q[size_t(i) * q_si + size_t(3 * k + j) * q_sj]; qdl[j] = qd[size_t(i) * q_si + size_t(3 * k + j) * q_sj]; }
     fk_jacobian(ql, k, p, J);
     float F[3];
 #pragma unroll
@@ -1295,8 +1296,36 @@ int qs_cpg_update(double* X, const double* params9, const double* phi16, const f
   std::memcpy(P.phi, phi16, sizeof P.phi);
   if (gains8) std::memcpy(P.gains, gains8, sizeof P.gains); else std::memset(P.gains, 0, sizeof P.gains);
   P.foot_y = foot_y;
-  k_cpg<<<grid_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(P, X, q, qd, xs, zs, tau, n);
+  k_cpg<<<grid_for(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(P, X, q, qd, xs, zs, tau, n, 12, 1);
   g_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return QS_OK;
+}
+
+int qs_cpg_steps(qs_handle h, double* X, const double* params9, const double* phi16, const float* gains8, float foot_y,
+                 int n_ticks, float* obs, float* reward, uint8_t* done, uint8_t* truncated, void* stream) {
+  // hopf_network.py:241-289 for n_ticks control ticks without leaving the library: per tick the oscillators advance and the
+  // torque law reads the joint state straight from the env's rows (k_cpg), then the env steps on those torques (the step's
+  // CUDA graph).  Same numbers as the caller's own loop over qs_cpg_update + qs_step.
+  if (!h || !X || !params9 || !phi16 || !gains8) return fail(QS_ERR_ARG, "NULL argument");
+  if (h->args.C.is_rl || h->args.C.control_mode != QS_CTRL_TORQUE)
+    return fail(QS_ERR_STATE, "the CPG drives a TORQUE-mode env built with isRLGymInterface=False (hopf_network.py:183-190)");
+  if (n_ticks < 1) return fail(QS_ERR_ARG, "n_ticks must be positive");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h->act_buf) CUDA_TRY(cudaMalloc(&h->act_buf, size_t(h->n) * 12 * sizeof(float)));
+  CpgArgs P;
+  std::memcpy(P.p, params9, sizeof P.p);
+  std::memcpy(P.phi, phi16, sizeof P.phi);
+  std::memcpy(P.gains, gains8, sizeof P.gains);
+  P.foot_y = foot_y;
+  const float* q = h->args.D.state + size_t(13) * h->n;
+  const float* qd = h->args.D.state + size_t(25) * h->n;
+  for (int t = 0; t < n_ticks; t++) {
+    k_cpg<<<grid_for(h->n, 128), 128, 0, s>>>(P, X, q, qd, nullptr, nullptr, h->act_buf, h->n, 1, h->n);
+    g_launches += 1;
+    if (int e = step_graph(h, h->act_buf, obs, reward, done, truncated, stream)) return e;
+  }
   CUDA_TRY(cudaGetLastError());
   return QS_OK;
 }

@@ -83,3 +83,17 @@ class HopfNetwork:
         if tau is None:
             return xs, zs
         return xs, zs, tau
+
+    def drive(self, env, n_ticks=1, kp=(150, 70, 70), kd=(2, 0.5, 0.5), kp_cartesian=2500.0, kd_cartesian=40.0, foot_y=0.0838):
+        """n_ticks turns of the reference's loop `tau = law(cpg.update(), q, qd); env.step(tau)` (hopf_network.py:241-289)
+        in one library call (qs_cpg_steps): the torque law reads the env's own joint state, nothing is staged through
+        torch.  Returns env.step's tuple of the last tick."""
+        p, phi = self._params()
+        gains = np.array(list(kp) + list(kd) + [kp_cartesian, kd_cartesian], dtype=np.float32)
+        _lib.check(self._L.qs_cpg_steps(
+            env._h, _p(self.X.view(self.num_envs, 8)), p.ctypes.data_as(C.POINTER(C.c_double)),
+            phi.ctypes.data_as(C.POINTER(C.c_double)), gains.ctypes.data_as(C.POINTER(C.c_float)), float(foot_y), int(n_ticks),
+            _p(env._obs), _p(env._reward), _p(env._done), _p(env._trunc),
+            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        env._last_host_obs = None
+        return env._obs, env._reward, env._done.bool(), {"TimeLimit.truncated": env._trunc.bool()}

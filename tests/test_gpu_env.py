@@ -415,3 +415,23 @@ def test_partial_host_reset_keeps_the_other_rows(qs):
     last = obs.copy()
     dev = env.reset(mask=torch.as_tensor(mask, device="cuda"))
     assert np.array_equal(dev.cpu().numpy()[keep], last[keep])
+
+
+def test_cpg_drive_equals_the_python_loop(qs):
+    """HopfNetwork.drive (qs_cpg_steps: the reference's CPG loop, hopf_network.py:241-289, inside the library) gives bit
+    for bit the states of the caller's own loop over cpg.update + env.step"""
+    n = 512
+    kw = dict(num_envs=n, isRLGymInterface=False, time_step=0.001, action_repeat=1, motor_control_mode="TORQUE",
+              enable_springs=True, auto_reset=False, seed=4)
+    a, b = qs.BatchedQuadrupedGymEnv(**kw), qs.BatchedQuadrupedGymEnv(**kw)
+    a.reset(); b.reset()
+    ca = qs.HopfNetwork(num_envs=n, gait="BOUND", omega_swing=16 * np.pi, omega_stance=4 * np.pi, time_step=0.001, seed=1)
+    cb = qs.HopfNetwork(num_envs=n, gait="BOUND", omega_swing=16 * np.pi, omega_stance=4 * np.pi, time_step=0.001, seed=1)
+    for _ in range(60):
+        _, _, tau = ca.update(a.robot.GetMotorAngles(), a.robot.GetMotorVelocities())
+        oa, ra, da, _ = a.step(tau)
+    ob, rb, db, _ = cb.drive(b, 60)
+    assert torch.equal(a.get_state(), b.get_state()) and torch.equal(ca.X, cb.X)
+    assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    with pytest.raises(ValueError if False else Exception):
+        cb.drive(qs.BatchedQuadrupedGymEnv(num_envs=4, **JIP), 1)      # not a TORQUE-mode env

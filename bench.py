@@ -51,7 +51,7 @@ CONFIGS = {
                      action_space_mode="SYMMETRIC", observation_space_mode="ARS_BASIC")),
     4: dict(name="go1_pea_hopf_cpg_torque_65536env_per_gpu", kind="cpg", envs_per_gpu=65536,
             env=dict(enable_springs=True, isRLGymInterface=False, action_repeat=1, motor_control_mode="TORQUE"),
-            cpg=dict(gait="BOUND", omega_swing=16 * 3.141592653589793, omega_stance=4 * 3.141592653589793)),
+            cpg=dict(gait="TROT", omega_swing=16 * 3.141592653589793, omega_stance=4 * 3.141592653589793)),
     5: dict(name="go1_pea_backflip_ppo_policy_32768env_per_gpu", kind="policy", envs_per_gpu=32768,
             env=dict(enable_springs=True, task_env="BACKFLIP_PPO", motor_control_mode="PD", action_space_mode="SYMMETRIC",
                      observation_space_mode="PPO_BACKFLIP", landing_wrapper="LandingWrapperBackflip")),

@@ -27,6 +27,80 @@ def qs():
     return m
 
 
+
+# ------------------------------------------------------------------ observation check, component by component
+L1, L2, L3 = 0.0847, 0.213, 0.213   # configs_go1_with_springs.py:56-58
+
+
+def _R_from_quat(q):
+    x, y, z, w = q / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _fk(q3, leg):                     # quadruped.py:364-392
+    s = -1.0 if leg in (0, 2) else 1.0
+    s1, c1, s2, c2 = np.sin(q3[0]), np.cos(q3[0]), np.sin(q3[1]), np.cos(q3[1])
+    s23, c23 = np.sin(q3[1] + q3[2]), np.cos(q3[1] + q3[2])
+    pos = np.array([-L3 * s23 - L2 * s2, L1 * s * c1 + L3 * s1 * c23 + L2 * c2 * s1, L1 * s * s1 - L3 * c1 * c23 - L2 * c1 * c2])
+    J = np.array([[0, -L3 * c23 - L2 * c2, -L3 * c23],
+                  [-s * L1 * s1 + L2 * c2 * c1 + L3 * c23 * c1, -L2 * s2 * s1 - L3 * s23 * s1, -L3 * s23 * s1],
+                  [s * L1 * c1 + L2 * c2 * s1 + L3 * c23 * s1, L2 * s2 * c1 + L3 * s23 * c1, L3 * s23 * c1]])
+    return pos, J
+
+
+def check_observation(env, obs, ref_obs, state, switched, t):
+    """the observation is checked sensor by sensor instead of under one loose bound.
+    (1) Every sensor is a READ of the state the kernel itself ended the step in (noise off): joint angles / rates, height
+        and base velocities bit for bit, the derived ones (pitch, pitch rate, back-flip pitch, foot positions and
+        velocities) to 1e-5 of a numpy restatement of the reference's formulas on that state -- whatever the physics did.
+    (2) Against the fixture, i.e. through ten fp32 ticks of physics: positions 5e-4, base velocities 5e-3, joint and foot
+        rates 5e-2; flags (landing, jumping, foot-contact booleans) must be equal."""
+    q, qd = state[13:25].astype(np.float64), state[25:37].astype(np.float64)
+    R = _R_from_quat(state[3:7].astype(np.float64))
+    for name, a, b in env._obs_layout:
+        o, r = obs[a:b], ref_obs[a:b]
+        if name in ("is landing", "is jumping", "BoolContatc"):
+            np.testing.assert_array_equal(o, r, err_msg=f"{name} {t}")
+            continue
+        read, tol = None, None
+        if name == "Encoder" or name == "JointPosition":
+            read, tol = state[13:25], 5e-4
+        elif name == "JointVelocity":
+            read, tol = state[25:37], 5e-2
+        elif name == "Height":
+            read, tol = state[2:3], 5e-4
+        elif name == "Base Linear Velocity z direction":
+            read, tol = state[9:10], 5e-3
+        elif name == "Base Height Velocity X":
+            read, tol = state[7:8], 5e-3
+        elif name == "Base Linear Velocity":
+            read, tol = state[7:10], 5e-3
+        elif name == "Base Angular Velocity":
+            read, tol = state[10:13], 5e-3
+        if read is not None:
+            np.testing.assert_array_equal(o, read, err_msg=f"{name} {t}: not a read of the kernel's own state")
+        else:
+            if name == "Pitch":            # Bullet getEulerFromQuaternion (SURVEY App. A.5)
+                sarg = -R[2, 0]                    # -2 (xz - wy); Bullet snaps to +-pi/2 in its gimbal branches
+                want = np.array([np.pi / 2 if sarg >= 0.99999 else (-np.pi / 2 if sarg <= -0.99999 else np.arcsin(sarg))])
+                tol = 1e-3 if abs(sarg) < 0.999 else 2e-2   # d asin / d sarg blows up towards the pole
+            elif name == "Pitch rate":     # quadruped.py:141-170: R^T omega
+                want, tol = np.array([(R.T @ state[10:13].astype(np.float64))[1]]), 5e-3
+            elif name == "Pitch-BackFlip":  # robot_sensors.py:333-340
+                p = np.arctan2(R[2, 0], R[2, 2])
+                want, tol = np.array([p + 2 * np.pi if (p < 0 and switched) else p]), 1e-3
+            elif name == "FeetPosition":
+                want, tol = np.concatenate([_fk(q[3 * k:3 * k + 3], k)[0] for k in range(4)]), 5e-4
+            elif name == "FeetVelocity":
+                want, tol = np.concatenate([_fk(q[3 * k:3 * k + 3], k)[1] @ qd[3 * k:3 * k + 3] for k in range(4)]), 5e-2
+            else:
+                raise AssertionError(f"unknown sensor {name}")
+            np.testing.assert_allclose(o, want, rtol=1e-5, atol=2e-5 if name != "FeetVelocity" else 2e-4, err_msg=f"{name} {t}: formula")
+        np.testing.assert_allclose(o, r, rtol=1e-4, atol=tol, err_msg=f"{name} {t}: vs the reference rollout")
+
+
 # ------------------------------------------------------------------ a11 / a12 torques
 @pytest.mark.parametrize("tag", ["s1", "s0"])
 def test_pd_pea_torque_matches_reference(qs, analytic, tag):
@@ -452,7 +526,7 @@ def test_rollout_teacher_forced_matches_reference_env(qs, name):
             assert err_q < 2e-3 and err_v < 1.0 and err_b < 5e-2, (t, err_q, err_v, err_b)
         if contact_now == ref_bits and not crashing:
             assert float(r[0]) == pytest.approx(float(g["reward"][t]), rel=1e-4, abs=3e-5), t
-            np.testing.assert_allclose(obs[0].cpu().numpy(), g["obs"][t], rtol=1e-4, atol=5e-2, err_msg=f"obs {t}")
+            check_observation(env, obs[0].cpu().numpy(), g["obs"][t], got, bool(env._views["task"][0][0] != 0), t)
         if crashing:
             assert float(r[0]) == pytest.approx(float(g["reward"][t]), abs=2e-3), t
         assert bool(d[0]) == bool(g["done"][t]), t

@@ -97,7 +97,8 @@ def check_observation(env, obs, ref_obs, state, switched, t):
                 want, tol = np.concatenate([_fk(q[3 * k:3 * k + 3], k)[1] @ qd[3 * k:3 * k + 3] for k in range(4)]), 5e-2
             else:
                 raise AssertionError(f"unknown sensor {name}")
-            np.testing.assert_allclose(o, want, rtol=1e-5, atol=2e-5 if name != "FeetVelocity" else 2e-4, err_msg=f"{name} {t}: formula")
+            fatol = 2e-4 if name == "FeetVelocity" else (5e-3 if name == "Pitch" and abs(R[2, 0]) > 0.999 else 2e-5)
+            np.testing.assert_allclose(o, want, rtol=1e-5, atol=fatol, err_msg=f"{name} {t}: formula")
         np.testing.assert_allclose(o, r, rtol=1e-4, atol=tol, err_msg=f"{name} {t}: vs the reference rollout")
 
 

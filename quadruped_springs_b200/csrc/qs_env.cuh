@@ -134,7 +134,7 @@ template <bool kEM>
 __device__ __noinline__ void run_ticks_general(EnvState<float>& st, ContactState<float>& cs, const float* cmd,
                                                bool torque_mode, int t0, int n_ticks, int env, const DeviceView& D,
                                                const EnvCfg& C, const RobotConst& RC, const ModelConstT<float>& M,
-                                               const SolverConst& SC, float* tau_m, float* tau_s) {
+                                               const SolverConst& SC, float* tau_m, float* tau_s, float* dl, int dl_stride) {
   const float mu = D.mu[env];
   const bool custom = D.custom_gains[env] != 0;
   float sk[3], sb[3], sr[3];
@@ -142,7 +142,7 @@ __device__ __noinline__ void run_ticks_general(EnvState<float>& st, ContactState
   for (int t = t0; t < n_ticks; t++) {
     float tau[12];
     tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s, custom);
-    physics_tick_general<float, kEM>(st, tau, mu, cs, M, SC, EnvModelRef{D.model, D.n, env});
+    physics_tick_general<float, kEM>(st, tau, mu, cs, M, SC, EnvModelRef{D.model, D.n, env}, dl, dl_stride);
   }
 }
 

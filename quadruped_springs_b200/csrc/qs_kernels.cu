@@ -127,7 +127,7 @@ k_debug_ticks(const __grid_constant__ DebugArgs<T> A, const float* __restrict__ 
   for (int t = 0; t < n_ticks; t++)
     {
     const EnvModelRef em{A.mass_randomizer ? D.model : nullptr, D.n, env};
-    if (physics_tick<T, true, 0, true>(st, t12, mu, cs, A.M, A.SC, true, scr, em)) physics_tick_general<T, true>(st, t12, mu, cs, A.M, A.SC, em);
+    if (physics_tick<T, true, 0, true>(st, t12, mu, cs, A.M, A.SC, true, scr, em)) { T dl[12]; physics_tick_general<T, true>(st, t12, mu, cs, A.M, A.SC, em, dl, 1); }
   }
 #pragma unroll
   for (int i = 0; i < 3; i++) { sf.pos[i] = float(st.pos[i]); sf.vlin[i] = float(st.vlin[i]); sf.vang[i] = float(st.vang[i]); }

@@ -794,12 +794,16 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
 constexpr int QS_MAX_CONTACTS = 17;
 constexpr int QS_MAX_LIMITS = 12;
 
-// A general row in dense form over u = [z(6), delta_leg0(3), ..., delta_leg3(3)]:
-//   w = a . u,  u += b dI   with a = [Y, Jk in the leg's slot], b = [Y, M_kk^-1 Jk^T in the leg's slot].
-// Dense rows cost twice the FMAs of the sparse form but keep u in registers with static indices, which
-// is what matters here: this path is bound by the latency of ONE thread's dependent chain.
+// A general row over u = [z(6), delta_leg0(3), ..., delta_leg3(3)]:  w = a . u,  u += b dI  with a = [Y, Jk in the
+// leg's slot], b = [Y, M_kk^-1 Jk^T in the leg's slot].  Rows are stored SPARSE (Y, Jk, W and the leg: 16 words instead
+// of the 36 of the dense form) and the twelve delta components live outside the registers, in an array the caller
+// provides (`dl`, element c at dl[c * dl_stride]: this thread's column of a shared-memory area in k_step_slow), where
+// indexing them by the row's leg costs nothing.  A row visit is 9 + 9 multiply-adds and 16 + 6 loads instead of 18 + 18
+// and 36: this kernel is bound by the latency of ONE thread's dependent chain (round 2: -30 % on k_step_slow, which
+// had become the step's critical path).
 template <typename T> struct alignas(16) GenRow {
-  T a[18], b[18], dinv, rhs, lam, pad;
+  T y[6], jk[3], w[3], dinv, rhs, lam;
+  int leg;   // 0..3; rows of the trunk carry zero jk / w on leg 0
 };
 
 template <typename T>
@@ -810,9 +814,10 @@ QS_DEV void gen_build_row(GenRow<T>& r, int leg, const T* Jb, const T* Jk, const
   T Y[6];
 #pragma unroll
   for (int c = 0; c < 6; c++) Y[c] = Jb ? Jb[c] : T(0);
-#pragma unroll
-  for (int c = 6; c < 18; c++) { r.a[c] = T(0); r.b[c] = T(0); }
   T hdiag = T(0);
+  r.leg = leg >= 0 ? leg : 0;
+#pragma unroll
+  for (int c = 0; c < 3; c++) { r.jk[c] = T(0); r.w[c] = T(0); }
   if (leg >= 0) {
     const T W0 = Mi[0] * Jk[0] + Mi[1] * Jk[1] + Mi[2] * Jk[2];
     const T W1 = Mi[1] * Jk[0] + Mi[3] * Jk[1] + Mi[4] * Jk[2];
@@ -821,27 +826,30 @@ QS_DEV void gen_build_row(GenRow<T>& r, int leg, const T* Jb, const T* Jk, const
     for (int c = 0; c < 6; c++) Y[c] -= Jk[0] * Bm[c] + Jk[1] * Bm[6 + c] + Jk[2] * Bm[12 + c];
     hdiag = Jk[0] * W0 + Jk[1] * W1 + Jk[2] * W2;
     rel += Jk[0] * qd_leg[0] + Jk[1] * qd_leg[1] + Jk[2] * qd_leg[2];
-    r.a[6 + 3 * leg] = Jk[0]; r.a[7 + 3 * leg] = Jk[1]; r.a[8 + 3 * leg] = Jk[2];
-    r.b[6 + 3 * leg] = W0; r.b[7 + 3 * leg] = W1; r.b[8 + 3 * leg] = W2;
+    r.jk[0] = Jk[0]; r.jk[1] = Jk[1]; r.jk[2] = Jk[2];
+    r.w[0] = W0; r.w[1] = W1; r.w[2] = W2;
   }
   chol_fwd(S6, Ld, Y);
   T nn = T(0);
 #pragma unroll
-  for (int c = 0; c < 6; c++) { nn += Y[c] * Y[c]; r.a[c] = Y[c]; r.b[c] = Y[c]; }
+  for (int c = 0; c < 6; c++) { nn += Y[c] * Y[c]; r.y[c] = Y[c]; }
   r.dinv = div_t(T(1), nn + hdiag);
   r.lam = T(0);
   *rel_out = rel;
 }
 
-template <typename T> QS_DEV T gen_row_w(const GenRow<T>& r, const T* u) {
-  T w0 = T(0), w1 = T(0), w2 = T(0);
-#pragma unroll
-  for (int c = 0; c < 18; c += 3) { w0 += r.a[c] * u[c]; w1 += r.a[c + 1] * u[c + 1]; w2 += r.a[c + 2] * u[c + 2]; }
+template <typename T> QS_DEV T gen_row_w(const GenRow<T>& r, const T* z, const T* dl, int ds) {
+  const T* d = dl + 3 * r.leg * ds;
+  const T w0 = r.y[0] * z[0] + r.y[3] * z[3] + r.jk[0] * d[0];
+  const T w1 = r.y[1] * z[1] + r.y[4] * z[4] + r.jk[1] * d[ds];
+  const T w2 = r.y[2] * z[2] + r.y[5] * z[5] + r.jk[2] * d[2 * ds];
   return (w0 + w1) + w2;
 }
-template <typename T> QS_DEV void gen_row_apply(const GenRow<T>& r, T dI, T* u) {
+template <typename T> QS_DEV void gen_row_apply(const GenRow<T>& r, T dI, T* z, T* dl, int ds) {
 #pragma unroll
-  for (int c = 0; c < 18; c++) u[c] += r.b[c] * dI;
+  for (int c = 0; c < 6; c++) z[c] += r.y[c] * dI;
+  T* d = dl + 3 * r.leg * ds;
+  d[0] += r.w[0] * dI; d[ds] += r.w[1] * dI; d[2 * ds] += r.w[2] * dI;
 }
 
 // Jacobian of a point pc on body `level` (0 hip, 1 thigh, 2 calf/foot) of a leg
@@ -855,7 +863,7 @@ QS_DEV void body_point_jac(const LegKin<T>& K, int level, const T* pc, const T* 
 template <typename T, bool kEM = false>
 __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
                                               const ModelConstT<T>& M, const SolverConst& SC,
-                                              const EnvModelRef em = EnvModelRef{nullptr, 0, 0}) {
+                                              const EnvModelRef em, T* dl /* 12 elements, stride dl_stride */, int dl_stride) {
   const T dt = T(SC.dt);
   const T mcv = T(SC.max_coord_vel);
   TickCtx<T> X;
@@ -1004,15 +1012,16 @@ __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T m
     }
     nn++;
   }
-  T u[18];
+  T u[6];   // z; the leg parts (delta) are in dl
 #pragma unroll
-  for (int c = 0; c < 18; c++) u[c] = T(0);
+  for (int c = 0; c < 6; c++) u[c] = T(0);
+  for (int c = 0; c < 12; c++) dl[c * dl_stride] = T(0);
   for (int r = 0; r < nn; r++) {  // warm start, feet only
     const int f = foot_of_row[r];
     if (f >= 0 && (cs.mask & (1 << f))) {
       const T imp = cs.lam_n[f] * T(SC.warmstart);
       nrm[r].lam = imp;
-      gen_row_apply(nrm[r], imp, u);
+      gen_row_apply(nrm[r], imp, u, dl, dl_stride);
     }
   }
   if (nlim + nn > 0) {
@@ -1021,29 +1030,29 @@ __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T m
       T res = T(0);
       for (int j = 0; j < nlim; j++) {
         GenRow<T>& r = lim[(it & 1) ? j : nlim - 1 - j];
-        T dI = (r.rhs - gen_row_w(r, u)) * r.dinv;
+        T dI = (r.rhs - gen_row_w(r, u, dl, dl_stride)) * r.dinv;
         const T sum = r.lam + dI;
         if (sum < T(0)) { dI = -r.lam; r.lam = T(0); }
         else if (sum > T(100)) { dI = T(100) - r.lam; r.lam = T(100); }
         else r.lam = sum;
-        gen_row_apply(r, dI, u);
+        gen_row_apply(r, dI, u, dl, dl_stride);
         const T dv = div_t(dI, r.dinv);
         res = tmax(res, dv * dv);
       }
       for (int j = 0; j < nn; j++) {
         GenRow<T>& r = nrm[j];
-        T dI = (r.rhs - gen_row_w(r, u)) * r.dinv;
+        T dI = (r.rhs - gen_row_w(r, u, dl, dl_stride)) * r.dinv;
         const T sum = r.lam + dI;
         if (sum < T(0)) { dI = -r.lam; r.lam = T(0); } else r.lam = sum;
-        gen_row_apply(r, dI, u);
+        gen_row_apply(r, dI, u, dl, dl_stride);
         const T dv = div_t(dI, r.dinv);
         res = tmax(res, dv * dv);
       }
       for (int j = 0; j < nn; j++) {
         GenRow<T>& ra = fr[2 * j];
         GenRow<T>& rb = fr[2 * j + 1];
-        T sa = ra.lam + (ra.rhs - gen_row_w(ra, u)) * ra.dinv;
-        T sb = rb.lam + (rb.rhs - gen_row_w(rb, u)) * rb.dinv;
+        T sa = ra.lam + (ra.rhs - gen_row_w(ra, u, dl, dl_stride)) * ra.dinv;
+        T sb = rb.lam + (rb.rhs - gen_row_w(rb, u, dl, dl_stride)) * rb.dinv;
         const T limf = mu * T(SC.mu_link) * nrm[j].lam;
         const T r2 = sa * sa + sb * sb;
         if (r2 >= limf * limf) {
@@ -1052,8 +1061,8 @@ __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T m
         }
         const T dIa = sa - ra.lam, dIb = sb - rb.lam;
         ra.lam = sa; rb.lam = sb;
-        gen_row_apply(ra, dIa, u);
-        gen_row_apply(rb, dIb, u);
+        gen_row_apply(ra, dIa, u, dl, dl_stride);
+        gen_row_apply(rb, dIb, u, dl, dl_stride);
         const T qa = div_t(dIa, ra.dinv), qb = div_t(dIb, rb.dinv);
         res = tmax(res, qa * qa + qb * qb);
       }
@@ -1072,7 +1081,7 @@ __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T m
     for (int k = 0; k < 4; k++)
 #pragma unroll
       for (int j = 0; j < 3; j++) {
-        T acc = u[6 + 3 * k + j];
+        T acc = dl[(3 * k + j) * dl_stride];
         for (int c = 0; c < 6; c++) acc -= Bm[k][6 * j + c] * dnu[c];
         st.qd[3 * k + j] = clamp_vel(st.qd[3 * k + j] + acc, mcv);
       }

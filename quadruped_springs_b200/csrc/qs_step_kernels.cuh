@@ -969,8 +969,9 @@ k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io, int spread) {
 #pragma unroll
   for (int i = 0; i < 12; i++) cmd[i] = D.cmd[i * n + env];
   const bool torque_mode = !A.C.is_rl && A.C.control_mode == QS_CTRL_TORQUE;
+  __shared__ float dl_sm[12 * 64];   // the solver's per-leg vector delta (qs_physics.cuh GenRow), one column per thread
   run_ticks_general<kEM>(st, cs, cmd, torque_mode, D.resume_tick[env], A.C.action_repeat, env, D, A.C, A.RC, A.M, A.SC,
-                    tau_m, tau_s);
+                    tau_m, tau_s, dl_sm + threadIdx.x, 64);
   tick_done_store(A, env, st, cs, tau_m, tau_s);
   stamp_end(io.stamps ? io.stamps + 2 : nullptr);
 }

@@ -977,8 +977,6 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   if (h->cfg.auto_reset) {
     if (int e = launch_slice(h, s, 0, true, io.stamps)) return e;
   }
-  if (h->args.C.mass_randomizer) k_finish<true><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, h->slow_list); else k_finish<false><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, h->slow_list);
-  g_launches += 1;
   if (host) {
     const int O = h->args.C.obs_dim;
     k_gather_late<<<grid_for(h->late_cap, 128), 128, 0, s>>>(h->slow_list, h->n, O, obs, reward, done, truncated, h->dev_late,

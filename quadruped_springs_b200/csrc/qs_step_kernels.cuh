@@ -551,7 +551,9 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
 }
 
 // Epilogue of a control step (quadruped_gym_env.py:239-256) + write-back + auto-reset.
-template <bool kEM>
+// kStored: the caller (k_finish) read state and torques from the env's rows, where the tick kernel left them: the plain
+// write-back at the end does not store them again
+template <bool kEM, bool kStored = false>
 __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& io, int env, EnvState<float>& st,
                                             ContactState<float>& cs, const float* tau_m, const float* tau_s,
                                             float* sm /* this thread's column of >= QS_SELF_SCRATCH shared floats */, int sm_stride) {
@@ -703,9 +705,13 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   }
   // ---- write-back
   store_obs(io.obs + size_t(env) * C.obs_dim, o, C, A.RC, gid, D.reset_count[env], uint32_t(env_steps), C.enable_noise);
-  store_state(D, env, st, cs, dt);
+  if (!kStored || !finite) {
+    store_state(D, env, st, cs, dt);
 #pragma unroll
-  for (int i = 0; i < 12; i++) { D.tau_motor[i * n + env] = finite ? tau_m[i] : 0.f; D.tau_spring[i * n + env] = finite ? tau_s[i] : 0.f; }
+    for (int i = 0; i < 12; i++) { D.tau_motor[i * n + env] = finite ? tau_m[i] : 0.f; D.tau_spring[i * n + env] = finite ? tau_s[i] : 0.f; }
+  } else if (A.SC.self_collision) {
+    D.contact[env] = (cs.mask & 15) | (cs.invalid << 8);   // the self-collision count joined cs.invalid after the store
+  }
 #pragma unroll
   for (int i = 0; i < TS_END; i++) if (i < task_slots(C.task)) D.task[i * n + env] = ts[i];
   D.sim_steps[env] = sim_steps;
@@ -972,7 +978,14 @@ k_step_slow(const __grid_constant__ KernelArgs A, const StepIO io, int spread) {
   __shared__ float dl_sm[12 * 64];   // the solver's per-leg vector delta (qs_physics.cuh GenRow), one column per thread
   run_ticks_general<kEM>(st, cs, cmd, torque_mode, D.resume_tick[env], A.C.action_repeat, env, D, A.C, A.RC, A.M, A.SC,
                     tau_m, tau_s, dl_sm + threadIdx.x, 64);
-  tick_done_store(A, env, st, cs, tau_m, tau_s);
+  // The epilogue of these envs runs here (not in k_finish): this kernel ends well before the late settle slice it runs
+  // next to, while a kernel launched after it would have to wait for that slice.
+  D.work[1 * n + env] += uint32_t(cs.work_contacts);
+  D.work[2 * n + env] += uint32_t(cs.work_row_iters);
+  D.resume_tick[env] = -1;
+  float sc_pts[QS_SELF_SCRATCH];   // (local memory like the solver rows: more shared memory would keep this kernel's blocks off
+                                   // the SMs the settle slice fills)
+  finish_step<kEM>(A, io, env, st, cs, tau_m, tau_s, sc_pts, 1);
   stamp_end(io.stamps ? io.stamps + 2 : nullptr);
 }
 
@@ -995,11 +1008,11 @@ k_finish(const __grid_constant__ KernelArgs A, const StepIO io, const int* __res
   EnvState<float> st;
   ContactState<float> cs;
   load_state(D, env, st, cs, A.SC.dt);
-  float tau_m[12], tau_s[12];
+  float tau_m[12];
 #pragma unroll
-  for (int i = 0; i < 12; i++) { tau_m[i] = D.tau_motor[i * n + env]; tau_s[i] = D.tau_spring[i * n + env]; }
+  for (int i = 0; i < 12; i++) tau_m[i] = D.tau_motor[i * n + env];
   __shared__ float sc_pts[QS_SELF_SCRATCH * QS_FINISH_BLOCK];
-  finish_step<kEM>(A, io, env, st, cs, tau_m, tau_s, sc_pts + threadIdx.x, QS_FINISH_BLOCK);
+  finish_step<kEM, true>(A, io, env, st, cs, tau_m, tau_m /* spring torques: only stored, and not by this caller */, sc_pts + threadIdx.x, QS_FINISH_BLOCK);
 }
 
 // -------------------------------------------------------------------- K2: reset + settle

@@ -330,6 +330,7 @@ struct qs_env {
   Conveyor cv;
   int wave_blocks;     // settle blocks resident at once (SMs x 2)
   int slice_min, slice_max, slice_early;
+  int flight_cap;      // envs per flight launch (k_pre sends the overflow to the contact kernel)
   int slow_spread;     // envs per warp in k_step_slow (power of two)
   cudaStream_t bg;     // the conveyor's slices run here, next to k_step_slow on the caller's stream
   cudaStream_t copy;   // qs_step_host: results go to the host while the slice is still running
@@ -565,6 +566,8 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     cv.cap_mask = uint32_t(cap - 1);
     h->slice_min = 24;  // a settle never takes more than ~100 steps even when few episodes end (24 ticks hide behind the step's chain)
     h->slice_max = 1 << 20;  // no cap: the slice follows the demand
+    h->flight_cap = h->wave_blocks * B;   // one wave of the flight kernel's blocks
+    if (const char* v = std::getenv("QS_FLIGHT_CAP")) h->flight_cap = std::max(0, std::atoi(v));
     h->slice_early = 10;  // ticks of the early slice (measured optimum 6-12: longer and it slows k_step_contact down)
     h->slow_spread = 32;
     if (const char* v = std::getenv("QS_SLOW_SPREAD")) {
@@ -931,6 +934,7 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   io.cv = h->cv;
   const int slot = capturing ? capture_slot : int(h->n_steps % h->ring);
   io.stamps = h->stamps + 4 * slot;
+  io.flight_cap = h->flight_cap;
   CUDA_TRY(rec_timing(h->ev0[slot], s, capturing));
   k_pre<<<grid_for(h->n, 256), 256, 0, s>>>(h->args, io);
   g_launches += 1;

@@ -63,7 +63,8 @@ enum qs_task {
    * left at reset), episode ends with the demonstration; the demonstration is given with qs_set_demo */
   QS_TASK_JUMPING_IN_PLACE_DEMO = 13,
   QS_TASK_JUMPING_FORWARD_DEMO = 14,
-  QS_TASK_BACKFLIP_DEMO = 15
+  QS_TASK_BACKFLIP_DEMO = 15,
+  QS_TASK_CONTINUOUS_JUMPING_FORWARD_DEMO = 16 /* TaskJumpingDemo2, tasks/task_base.py:402-452, robot_tasks.py:244-247 */
 };
 enum qs_obs_mode {
   QS_OBS_ENCODER = 0,
@@ -209,6 +210,8 @@ int qs_step(qs_handle h, const float* actions_dev, float* obs_dev, float* reward
  * The per-env position in it is task-state row QS_TS_DEMO_COUNTER (set_demo_counter, task_base.py:218-219). */
 int qs_set_demo(qs_handle h, const float* actions_host, int length);
 #define QS_TS_DEMO_COUNTER 29
+/* ... and for QS_TASK_CONTINUOUS_JUMPING_FORWARD_DEMO, whose continuous-jumping bookkeeping occupies those rows */
+#define QS_TS_DEMO2_COUNTER 42
 
 /* Quadruped.SetLegMasses / SetBaseMass / _add_base_mass_offset (quadruped.py:744-819) on the batch: after the caller
  * wrote qs_state_ptrs.mass_draw, recompute the per-env mass properties the physics reads.  Needs

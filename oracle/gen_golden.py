@@ -547,6 +547,36 @@ def gen_demo():
         np.load = np_load
 
 
+def gen_demo2():
+    """CONTINUOUS_JUMPING_FORWARD_DEMO = TaskJumpingDemo2 (task_base.py:402-452, robot_tasks.py:244-247): imitation reward on
+    top of TaskContinuousJumping2's bookkeeping.  The demonstration is recorded with the reference's own
+    GetDemonstrationWrapper from the hopping episode of rollout_cjf3 and handed to the task through its np.load."""
+    import tempfile
+    from quadruped_spring.env.wrappers.get_demonstration_wrapper import GetDemonstrationWrapper
+    base = dict(enable_springs=True, motor_control_mode="PD", action_space_mode="SYMMETRIC",
+                observation_space_mode="PPO_CONTINUOUS_JUMPING_FORWARD")
+    hops = np.load(os.path.join(OUT, "rollout_cjf3.npz"))["actions"]
+    tmp = tempfile.mkdtemp()
+    np.random.seed(61)
+    env = GetDemonstrationWrapper(make_env(**dict(base, task_env="CONTINUOUS_JUMPING_FORWARD3")), path=tmp)
+    env.reset()
+    for a in hops[:150]:
+        _, _, d, _ = env.step(a)
+        if d:
+            break
+    env.save_demo()
+    demo = np.load(os.path.join(tmp, "demo_list.npy"))
+    np_load = np.load
+    np.load = lambda p, *a, **k: np_load(os.path.join(tmp, "demo_list.npy") if "demonstrations" in str(p) else p, *a, **k)
+    try:
+        rng = np.random.default_rng(62)
+        acts = demo[:, :6] + rng.normal(size=(len(demo), 6)) * 0.04
+        rollout("demo_cjf", dict(base, task_env="CONTINUOUS_JUMPING_FORWARD_DEMO"), np.concatenate([acts, acts[-5:]]), seed=63,
+                extra=lambda e, w: dict(demo=demo, demo_counter_end=e.task.demo_counter, demo_start=0))
+    finally:
+        np.load = np_load
+
+
 def backflip_actions(n, rng, delay_rear):
     """crouch, then front and (delayed) rear push: pitches the trunk up at take-off"""
     acts = np.zeros((n, 6))
@@ -699,7 +729,7 @@ def gen_self_collision():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "continuous", "landing", "springs", "masses", "demo", "selfcollision", "rollouts"]
+    which = sys.argv[1:] or ["urdf", "analytic", "obs", "hopf", "continuous", "landing", "springs", "masses", "demo", "demo2", "selfcollision", "rollouts"]
     if "urdf" in which:
         gen_urdf()
     # NB: gen_analytic and the last rollout build a BACKFLIP env, which mutates the module-level
@@ -720,6 +750,8 @@ if __name__ == "__main__":
         gen_mass_randomizer()
     if "demo" in which:
         gen_demo()
+    if "demo2" in which:
+        gen_demo2()
     if "selfcollision" in which:
         gen_self_collision()
     if "rollouts" in which:

@@ -18,6 +18,7 @@ TASKS = {
     "JUMPING_IN_PLACE_PPO_HP": 7, "JUMPING_FORWARD_PPO_HP": 8, "CONTINUOUS_JUMPING_FORWARD": 9,
     "CONTINUOUS_JUMPING_FORWARD2": 10, "CONTINUOUS_JUMPING_FORWARD3": 11, "CONTINUOUS_JUMPING_FORWARD_PPO": 12,
     "JUMPING_IN_PLACE_DEMO": 13, "JUMPING_FORWARD_DEMO": 14, "BACKFLIP_DEMO": 15,
+    "CONTINUOUS_JUMPING_FORWARD_DEMO": 16,
 }
 CONTROL = {"PD": 0, "CARTESIAN_PD": 1, "TORQUE": 2}
 ACTION = {"DEFAULT": 0, "SYMMETRIC": 1, "SYMMETRIC_NO_HIP": 2}

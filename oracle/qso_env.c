@@ -418,7 +418,8 @@ static double jumping_distance(const QsoEnv* e) { /* task_base.py:109-116 */
 /* task families: 0 = TaskJumping, 1 = TaskContinuousJumping, 2 = TaskContinuousJumping2 */
 static int task_family(int t) {
   if (t == QSO_TASK_CONTINUOUS_JUMPING_FORWARD || t == QSO_TASK_CONTINUOUS_JUMPING_FORWARD2) return 1;
-  if (t == QSO_TASK_CONTINUOUS_JUMPING_FORWARD3 || t == QSO_TASK_CONTINUOUS_JUMPING_FORWARD_PPO) return 2;
+  if (t == QSO_TASK_CONTINUOUS_JUMPING_FORWARD3 || t == QSO_TASK_CONTINUOUS_JUMPING_FORWARD_PPO ||
+      t == QSO_TASK_CONTINUOUS_JUMPING_FORWARD_DEMO) return 2; /* TaskJumpingDemo2(TaskContinuousJumping2), task_base.py:402 */
   return 0;
 }
 static void cont2_params(int t, double* jump_limit, double* height_limit, double* bound) {
@@ -550,7 +551,7 @@ static void task_on_step(QsoEnv* e) { /* task_base.py:61-107 */
   }
 }
 
-static int is_demo_task(int t) { return t >= QSO_TASK_JUMPING_IN_PLACE_DEMO && t <= QSO_TASK_BACKFLIP_DEMO; }
+static int is_demo_task(int t) { return t >= QSO_TASK_JUMPING_IN_PLACE_DEMO && t <= QSO_TASK_CONTINUOUS_JUMPING_FORWARD_DEMO; }
 
 static void task_reset(QsoEnv* e) { /* task_base.py:40-59 */
   TaskState* t = &e->ts;

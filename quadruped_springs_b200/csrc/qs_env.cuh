@@ -304,12 +304,18 @@ QS_DEV bool is_jump_task(int task) { return task != QS_TASK_NO_TASK; }
 // 0 = TaskJumping, 1 = TaskContinuousJumping, 2 = TaskContinuousJumping2 (task_base.py:222,280)
 QS_DEV int task_family(int task) {
   if (task == QS_TASK_CONTINUOUS_JUMPING_FORWARD || task == QS_TASK_CONTINUOUS_JUMPING_FORWARD2) return 1;
-  if (task == QS_TASK_CONTINUOUS_JUMPING_FORWARD3 || task == QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO) return 2;
+  if (task == QS_TASK_CONTINUOUS_JUMPING_FORWARD3 || task == QS_TASK_CONTINUOUS_JUMPING_FORWARD_PPO ||
+      task == QS_TASK_CONTINUOUS_JUMPING_FORWARD_DEMO) return 2;   // TaskJumpingDemo2(TaskContinuousJumping2), task_base.py:402
   return 0;
 }
 // rows of DeviceView::task this task reads and writes
-QS_DEV bool is_demo_task(int task) { return task >= QS_TASK_JUMPING_IN_PLACE_DEMO && task <= QS_TASK_BACKFLIP_DEMO; }
-QS_DEV int task_slots(int task) { return task_family(task) ? int(TS_END) : (is_demo_task(task) ? int(TS_END_DEMO) : int(TS_END_BASIC)); }
+QS_DEV bool is_demo_task(int task) { return task >= QS_TASK_JUMPING_IN_PLACE_DEMO && task <= QS_TASK_CONTINUOUS_JUMPING_FORWARD_DEMO; }
+// row of the imitation tasks' position in the demonstration (the rows left at reset follow it)
+QS_DEV int demo_slot(int task) { return task == QS_TASK_CONTINUOUS_JUMPING_FORWARD_DEMO ? int(TS_DEMO2_COUNTER) : int(TS_DEMO_COUNTER); }
+QS_DEV int task_slots(int task) {
+  if (task == QS_TASK_CONTINUOUS_JUMPING_FORWARD_DEMO) return int(TS_END_ALL);
+  return task_family(task) ? int(TS_END) : (is_demo_task(task) ? int(TS_END_DEMO) : int(TS_END_BASIC));
+}
 
 QS_DEVONLY float jumping_distance(const float* ts, const float* pos) {  // task_base.py:109-116
   float s, c;

@@ -58,7 +58,7 @@ __global__ void k_observe(const __grid_constant__ KernelArgs A, float* __restric
   quat_to_R(st.quat, Rb);
   rpy_from_quat(st.quat, rpy);
 #pragma unroll
-  for (int i = 0; i < TS_END; i++) ts[i] = i < task_slots(A.C.task) ? D.task[i * D.n + env] : 0.f;
+  for (int i = 0; i < TS_END_ALL; i++) ts[i] = i < task_slots(A.C.task) ? D.task[i * D.n + env] : 0.f;
 #pragma unroll
   for (int i = 0; i < QS_MAX_OBS; i++) o[i] = 0.f;
   observe(st, cs, ts, rpy, Rb, A.C.obs_mode, A.C.task, o);
@@ -433,7 +433,7 @@ static int check_config(const qs_config* c) {
   if (!c) return fail(QS_ERR_ARG, "config is NULL");
   if (c->control_mode < 0 || c->control_mode > 2) return fail(QS_ERR_ARG, "unknown motor control mode");
   if (c->action_mode < 0 || c->action_mode > 2) return fail(QS_ERR_ARG, "unknown action space mode");
-  if (c->task < 0 || c->task > QS_TASK_BACKFLIP_DEMO) return fail(QS_ERR_ARG, "unknown task");
+  if (c->task < 0 || c->task > QS_TASK_CONTINUOUS_JUMPING_FORWARD_DEMO) return fail(QS_ERR_ARG, "unknown task");
   if (c->block_size != 0 && c->block_size != QS_BLOCK) return fail(QS_ERR_ARG, "block_size is fixed at 128 (0 = default)");
   if (c->landing_mode < 0 || c->landing_mode > 5) return fail(QS_ERR_ARG, "unknown landing_mode");
   if (c->landing_mode >= 4 && c->action_mode != QS_ACT_SYMMETRIC)

@@ -520,15 +520,16 @@ __device__ __forceinline__ void begin_episode(const KernelArgs& A, int env, uint
   rpy_from_quat(st.quat, rpy);
   float ts[QS_TASK_DIM];
 #pragma unroll
-  for (int i = 0; i < TS_END; i++) ts[i] = i < task_slots(C.task) ? D.task[i * n + env] : 0.f;
-  const float demo_at = ts[TS_DEMO_COUNTER];
+  for (int i = 0; i < TS_END_ALL; i++) ts[i] = i < task_slots(C.task) ? D.task[i * n + env] : 0.f;
+  const int ds = demo_slot(C.task);
+  const float demo_at = ts[ds];
   task_reset(ts, st, cs, tau_m, rpy, Rb, 0.f, C.task);
   if (is_demo_task(C.task)) {  // TaskJumpingDemo._reset (task_base.py:178-183): the counter survives a desired-state reset
-    ts[TS_DEMO_COUNTER] = settled ? 0.f : demo_at;
-    ts[TS_DELTA_DEMO] = float(C.demo_len) - ts[TS_DEMO_COUNTER];
+    ts[ds] = settled ? 0.f : demo_at;
+    ts[ds + 1] = float(C.demo_len) - ts[ds];
   }
 #pragma unroll
-  for (int i = 0; i < TS_END; i++) if (i < task_slots(C.task)) D.task[i * n + env] = ts[i];
+  for (int i = 0; i < TS_END_ALL; i++) if (i < task_slots(C.task)) D.task[i * n + env] = ts[i];
 #pragma unroll
   for (int i = 0; i < 12; i++) {
     D.last_action[i * n + env] = act12[i];
@@ -599,7 +600,7 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   }
   float ts[QS_TASK_DIM];
 #pragma unroll
-  for (int i = 0; i < TS_END; i++) ts[i] = i < task_slots(C.task) ? D.task[i * n + env] : 0.f;
+  for (int i = 0; i < TS_END_ALL; i++) ts[i] = i < task_slots(C.task) ? D.task[i * n + env] : 0.f;
   float foot_force[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) foot_force[k] = (cs.mask >> k) & 1 ? cs.lam_n[k] / dt : 0.f;
@@ -608,15 +609,16 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
   bool term = task_terminated(ts, st, cs, Rb, A.RC.fallen_height, C.task);
   if (is_demo_task(C.task)) {
     // TaskJumpingDemo._reward / _terminated (task_base.py:194-212): distance of this step's action to the demonstration's
-    const int row = min(int(ts[TS_DEMO_COUNTER]), C.demo_len - 1);
+    const int ds = demo_slot(C.task);
+    const int row = min(int(ts[ds]), C.demo_len - 1);
     float s = 0.f;
     for (int i = 0; i < C.action_dim; i++) {
       const float d = C.demo[row * C.action_dim + i] - D.last_action[i * n + env];
       s += d * d;
     }
-    r = expf(-0.35f * sqrtf(s)) / ts[TS_DELTA_DEMO];
-    ts[TS_DEMO_COUNTER] += 1.f;
-    term = term || int(ts[TS_DEMO_COUNTER]) == C.demo_len;
+    r = expf(-0.35f * sqrtf(s)) / ts[ds + 1];
+    ts[ds] += 1.f;
+    term = term || int(ts[ds]) == C.demo_len;
   }
   if (!finite) term = true;
   const bool dn = term || (double(sim_steps) * A.time_step_d > A.max_time_d);
@@ -686,7 +688,7 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
     // the finished env starts its next episode inside the same call; its obs row becomes the
     // first observation of that episode (SB3 VecEnv convention)
 #pragma unroll
-    for (int i = 0; i < TS_END; i++) if (i < task_slots(C.task)) D.task[i * n + env] = ts[i];  // BackFlip.max_pitch survives resets
+    for (int i = 0; i < TS_END_ALL; i++) if (i < task_slots(C.task)) D.task[i * n + env] = ts[i];  // BackFlip.max_pitch survives resets
     const uint32_t epoch = D.reset_count[env] + 1;
     if (slot_ready(D, env, epoch)) {
       float tm[12], tsp[12], mu;
@@ -714,7 +716,7 @@ __device__ __forceinline__ void finish_step(const KernelArgs& A, const StepIO& i
     D.contact[env] = (cs.mask & 15) | (cs.invalid << 8);   // the self-collision count joined cs.invalid after the store
   }
 #pragma unroll
-  for (int i = 0; i < TS_END; i++) if (i < task_slots(C.task)) D.task[i * n + env] = ts[i];
+  for (int i = 0; i < TS_END_ALL; i++) if (i < task_slots(C.task)) D.task[i * n + env] = ts[i];
   D.sim_steps[env] = sim_steps;
   D.env_steps[env] = env_steps;
   D.ep_return[env] = ep_ret;

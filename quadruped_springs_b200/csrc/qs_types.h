@@ -94,9 +94,13 @@ enum TaskSlot {
   TS_SUM_FWD, TS_SUM_FLOG, TS_SUM_PERF, TS_MAX_PERF, TS_LAST_PERF, TS_END_JUMP, TS_END,
   // imitation tasks only (task_base.py:169-220): position in the demonstration, rows left at reset (they share the
   // continuous-jumping rows: a task is one or the other)
-  TS_DEMO_COUNTER = TS_END_BASIC, TS_DELTA_DEMO, TS_END_DEMO
+  TS_DEMO_COUNTER = TS_END_BASIC, TS_DELTA_DEMO, TS_END_DEMO,
+  // TaskJumpingDemo2 (task_base.py:402-452) is an imitation task ON TOP of the continuous-jumping bookkeeping: its two rows
+  // come after those
+  TS_DEMO2_COUNTER = TS_END, TS_DEMO2_DELTA, TS_END_ALL
 };
 static_assert(TS_DEMO_COUNTER == QS_TS_DEMO_COUNTER, "header constant out of date");
-static_assert(TS_END <= QS_TASK_DIM, "task state too large");
+static_assert(TS_DEMO2_COUNTER == QS_TS_DEMO2_COUNTER, "header constant out of date");
+static_assert(TS_END_ALL <= QS_TASK_DIM, "task state too large");
 
 }  // namespace qs

@@ -46,7 +46,7 @@ TaskCollection = lambda: _Collection("task", [
     "NO_TASK", "JUMPING_IN_PLACE", "JUMPING_FORWARD", "BACKFLIP", "JUMPING_IN_PLACE_PPO", "JUMPING_FORWARD_PPO",
     "BACKFLIP_PPO", "JUMPING_IN_PLACE_PPO_HP", "JUMPING_FORWARD_PPO_HP", "CONTINUOUS_JUMPING_FORWARD",
     "CONTINUOUS_JUMPING_FORWARD2", "CONTINUOUS_JUMPING_FORWARD3", "CONTINUOUS_JUMPING_FORWARD_PPO",
-    "JUMPING_IN_PLACE_DEMO", "JUMPING_FORWARD_DEMO", "BACKFLIP_DEMO"])
+    "JUMPING_IN_PLACE_DEMO", "JUMPING_FORWARD_DEMO", "BACKFLIP_DEMO", "CONTINUOUS_JUMPING_FORWARD_DEMO"])
 # sensors/sensor_collection.py:92-105
 SensorCollection = lambda: _Collection("sensor package", list(SENSOR_SETS))
 # env_randomizers/env_randomizer_collection.py:15-21 (mass / curriculum randomizers: SURVEY.md 8f "next")
@@ -358,13 +358,18 @@ class _Task:
 
     def __getattr__(self, name):
         if name in _DEMO_TASK_FIELDS and self._env.task_env.endswith("_DEMO"):
-            return self._env._views["task"][_DEMO_TASK_FIELDS[name]]
+            return self._env._views["task"][self._demo_row(name)]
         if name in _TASK_FIELDS:
             return self._env._views["task"][_TASK_FIELDS[name]]
         raise AttributeError(name)
 
-    def set_demo_counter(self, value, mask=None):    # task_base.py:218-219
-        row = self._env._views["task"][_DEMO_TASK_FIELDS["demo_counter"]]
+    def _demo_row(self, name):
+        # TaskJumpingDemo2 keeps the continuous-jumping rows: its two imitation rows come after them (QS_TS_DEMO2_COUNTER)
+        off = 13 if self._env.task_env == "CONTINUOUS_JUMPING_FORWARD_DEMO" else 0
+        return _DEMO_TASK_FIELDS[name] + off
+
+    def set_demo_counter(self, value, mask=None):    # task_base.py:218-219, 451-452
+        row = self._env._views["task"][self._demo_row("demo_counter")]
         v = torch.as_tensor(value, dtype=torch.float32, device=self._env.device)
         if mask is None:
             row[:] = v

@@ -102,6 +102,8 @@ template <typename T> inline void build_model(ModelConstT<T>& M, double gthr) {
     add_body(ca, 0.131, cca, Ica);
     const double If3[3] = {Ifoot, Ifoot, Ifoot};
     add_body(ca, 0.06, cfo, If3);
+    // leg_dynamics relies on it (body_spi_hip / body_spi_diag): hip and thigh are single links, diagonal about their com
+    for (int i : {1, 2, 4}) if (hip.Ic[i] != 0.0 || th.Ic[i] != 0.0) std::abort();
     const RigidBody* B[3] = {&hip, &th, &ca};
     for (int b = 0; b < 3; b++) {
       M.body_m[k][b] = T(B[b]->m);

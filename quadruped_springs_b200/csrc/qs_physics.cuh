@@ -58,6 +58,19 @@ template <typename T> QS_DEV void spi_apply(const SpI<T>& A, const T* w, const T
   cross3(A.h, w, t);
   p[0] = A.m * v[0] - t[0]; p[1] = A.m * v[1] - t[1]; p[2] = A.m * v[2] - t[2];
 }
+// the same for the joint axes' motion vectors: w = (1,0,0) (hip) and w = (0, c, s) (thigh, calf)
+template <typename T> QS_DEV void spi_apply_x(const SpI<T>& A, const T* v, T* L, T* p) {
+  L[0] = A.I[0]; L[1] = A.I[1]; L[2] = A.I[2];
+  cross3_add(A.h, v, L);
+  p[0] = A.m * v[0]; p[1] = A.m * v[1] - A.h[2]; p[2] = A.m * v[2] + A.h[1];          // h x w = (0, h2, -h1)
+}
+template <typename T> QS_DEV void spi_apply_yz(const SpI<T>& A, T c, T s, const T* v, T* L, T* p) {
+  L[0] = A.I[1] * c + A.I[2] * s; L[1] = A.I[3] * c + A.I[4] * s; L[2] = A.I[4] * c + A.I[5] * s;
+  cross3_add(A.h, v, L);
+  p[0] = A.m * v[0] - (A.h[1] * s - A.h[2] * c);                                       // h x w = (h1 s - h2 c, -h0 s, h0 c)
+  p[1] = A.m * v[1] + A.h[0] * s;
+  p[2] = A.m * v[2] - A.h[0] * c;
+}
 template <typename T> QS_DEV void spi_add(SpI<T>& a, const SpI<T>& b) {
   a.m += b.m;
 #pragma unroll
@@ -86,6 +99,45 @@ QS_DEV void body_spi(T m, const T* com, const T* Ic, const T* R, const T* r, SpI
   o.I[3] = t[3] * R[3] + t[4] * R[4] + t[5] * R[5] + m * (cc - c[1] * c[1]);
   o.I[4] = t[3] * R[6] + t[4] * R[7] + t[5] * R[8] - m * c[1] * c[2];
   o.I[5] = t[6] * R[6] + t[7] * R[7] + t[8] * R[8] + m * (cc - c[2] * c[2]);
+  o.m = m;
+  o.h[0] = m * c[0]; o.h[1] = m * c[1]; o.h[2] = m * c[2];
+}
+
+// The same for a link whose inertia about its com is DIAGONAL in the link frame (hip and thigh: single URDF links with
+// bounding-box inertias, qs_model_host.h; the calf + foot body is not): I = sum_k d_k r_k r_k^T over the columns r_k of R,
+// 27 multiply-adds instead of 45 -- and none of them multiplies one of the three structural zeros of Ic, which IEEE
+// rules forbid the compiler to drop.
+template <typename T>
+QS_DEV void body_spi_diag(T m, const T* com, const T* Ic, const T* R, const T* r, SpI<T>& o) {
+  T c[3];
+  m3_v(R, com, c);
+  c[0] += r[0]; c[1] += r[1]; c[2] += r[2];
+  const T d0 = Ic[0], d1 = Ic[3], d2 = Ic[5];
+  const T t0 = R[0] * d0, t1 = R[1] * d1, t2 = R[2] * d2;   // row 0 of R D
+  const T t3 = R[3] * d0, t4 = R[4] * d1, t5 = R[5] * d2;   // row 1
+  const T t6 = R[6] * d0, t7 = R[7] * d1, t8 = R[8] * d2;   // row 2
+  const T cc = dot3(c, c);
+  o.I[0] = t0 * R[0] + t1 * R[1] + t2 * R[2] + m * (cc - c[0] * c[0]);
+  o.I[1] = t0 * R[3] + t1 * R[4] + t2 * R[5] - m * c[0] * c[1];
+  o.I[2] = t0 * R[6] + t1 * R[7] + t2 * R[8] - m * c[0] * c[2];
+  o.I[3] = t3 * R[3] + t4 * R[4] + t5 * R[5] + m * (cc - c[1] * c[1]);
+  o.I[4] = t3 * R[6] + t4 * R[7] + t5 * R[8] - m * c[1] * c[2];
+  o.I[5] = t6 * R[6] + t7 * R[7] + t8 * R[8] + m * (cc - c[2] * c[2]);
+  o.m = m;
+  o.h[0] = m * c[0]; o.h[1] = m * c[1]; o.h[2] = m * c[2];
+}
+// ... and for the hip link, whose rotation is about x by the hip angle (R = [1 0 0; 0 c -s; 0 s c])
+template <typename T>
+QS_DEV void body_spi_hip(T m, const T* com, const T* Ic, T c1, T s1, const T* r, SpI<T>& o) {
+  const T c[3] = {com[0] + r[0], c1 * com[1] - s1 * com[2] + r[1], s1 * com[1] + c1 * com[2] + r[2]};
+  const T d0 = Ic[0], d1 = Ic[3], d2 = Ic[5];
+  const T cc = dot3(c, c);
+  o.I[0] = d0 + m * (cc - c[0] * c[0]);
+  o.I[1] = -m * c[0] * c[1];
+  o.I[2] = -m * c[0] * c[2];
+  o.I[3] = c1 * c1 * d1 + s1 * s1 * d2 + m * (cc - c[1] * c[1]);
+  o.I[4] = c1 * s1 * (d1 - d2) - m * c[1] * c[2];
+  o.I[5] = s1 * s1 * d1 + c1 * c1 * d2 + m * (cc - c[2] * c[2]);
   o.m = m;
   o.h[0] = m * c[0]; o.h[1] = m * c[1]; o.h[2] = m * c[2];
 }
@@ -151,10 +203,10 @@ QS_DEV void foot_jac_dir(const LegKin<T>& K, const T* pc, const T* d, T* Jb /*6*
   Jk[0] = t[0];  // hip axis = x
   u[0] = pc[0] - K.r2[0]; u[1] = pc[1] - K.r2[1]; u[2] = pc[2] - K.r2[2];
   cross3(u, d, t);
-  Jk[1] = dot3(K.a2, t);
+  Jk[1] = K.c1 * t[1] + K.s1 * t[2];   // a2 = (0, c1, s1)
   u[0] = pc[0] - K.r3[0]; u[1] = pc[1] - K.r3[1]; u[2] = pc[2] - K.r3[2];
   cross3(u, d, t);
-  Jk[2] = dot3(K.a2, t);
+  Jk[2] = K.c1 * t[1] + K.s1 * t[2];
 }
 
 // f += I A + V x* (I V) for one body; V = (Vw, Vv), A = (Aw, Av)
@@ -240,58 +292,72 @@ QS_DEV void leg_dynamics(int k, const T* q, const T* qd, const T* tau3, const Ti
     for (int i = 0; i < 3; i++) cc[i] = em_get<T>(em, EM_CALF_COM + i);
 #pragma unroll
     for (int i = 0; i < 6; i++) ci[i] = em_get<T>(em, EM_CALF_IC + i);
-    body_spi(em_get<T>(em, EM_HIP_M), M.body_com[k][0], M.body_Ic[k][0], RH, K.r1, Ih);
-    body_spi(em_get<T>(em, EM_THIGH_M), M.body_com[k][1], M.body_Ic[k][1], RT, K.r2, It);
+    body_spi_hip(em_get<T>(em, EM_HIP_M), M.body_com[k][0], M.body_Ic[k][0], K.c1, K.s1, K.r1, Ih);
+    body_spi_diag(em_get<T>(em, EM_THIGH_M), M.body_com[k][1], M.body_Ic[k][1], RT, K.r2, It);
     body_spi(em_get<T>(em, EM_CALF_M), cc, ci, RC, K.r3, Ic);
   } else {
-    body_spi(M.body_m[k][0], M.body_com[k][0], M.body_Ic[k][0], RH, K.r1, Ih);
-    body_spi(M.body_m[k][1], M.body_com[k][1], M.body_Ic[k][1], RT, K.r2, It);
+    body_spi_hip(M.body_m[k][0], M.body_com[k][0], M.body_Ic[k][0], K.c1, K.s1, K.r1, Ih);
+    body_spi_diag(M.body_m[k][1], M.body_com[k][1], M.body_Ic[k][1], RT, K.r2, It);
     body_spi(M.body_m[k][2], M.body_com[k][2], M.body_Ic[k][2], RC, K.r3, Ic);
   }
+  (void)RH;
 
-  // motion subspaces S_j = (a_j, r_j x a_j)
+  // motion subspaces S_j = (a_j, r_j x a_j).  The axes have structural zeros -- hip a1 = (1,0,0), thigh / calf
+  // a2 = (0, c1, s1) -- and a product with a zero is an instruction the compiler has to keep (0 * x is not 0 for every x
+  // under IEEE rules): the products below are written out for those axes.
   const T a1[3] = {T(1), T(0), T(0)};
-  T S1v[3], S2v[3], S3v[3];
-  cross3(K.r1, a1, S1v);
-  cross3(K.r2, K.a2, S2v);
-  cross3(K.r3, K.a2, S3v);
+  const T c1 = K.c1, s1 = K.s1;
+  const T S1v[3] = {T(0), K.r1[2], -K.r1[1]};                                            // r1 x a1
+  const T S2v[3] = {K.r2[1] * s1 - K.r2[2] * c1, -K.r2[0] * s1, K.r2[0] * c1};           // r2 x a2
+  const T S3v[3] = {K.r3[1] * s1 - K.r3[2] * c1, -K.r3[0] * s1, K.r3[0] * c1};           // r3 x a2
 
   // ---- Newton-Euler bias (velocity products + gravity), individual bodies
-  T m1w[3], m1v[3], m2w[3], m2v[3], m3w[3], m3v[3];
+  const T m1w0 = qd[0];                                         // m1w = (qd0, 0, 0)
+  const T m1v[3] = {T(0), S1v[1] * qd[0], S1v[2] * qd[0]};
+  const T m2w[3] = {T(0), c1 * qd[1], s1 * qd[1]}, m3w[3] = {T(0), c1 * qd[2], s1 * qd[2]};
+  T m2v[3], m3v[3];
 #pragma unroll
-  for (int i = 0; i < 3; i++) {
-    m1w[i] = a1[i] * qd[0]; m1v[i] = S1v[i] * qd[0];
-    m2w[i] = K.a2[i] * qd[1]; m2v[i] = S2v[i] * qd[1];
-    m3w[i] = K.a2[i] * qd[2]; m3v[i] = S3v[i] * qd[2];
-  }
+  for (int i = 0; i < 3; i++) { m2v[i] = S2v[i] * qd[1]; m3v[i] = S3v[i] * qd[2]; }
+  // x-axis and (0, p, q) cross products: u x (w0,0,0) = (0, u2 w0, -u1 w0);  u x (0,p,q) = (u1 q - u2 p, -u0 q, u0 p)
   T V1w[3], V1v[3], A1w[3], A1v[3];
-  cross3(wb, m1w, A1w);
-  cross3(wb, m1v, A1v);
-  cross3_add(vb, m1w, A1v);
-#pragma unroll
-  for (int i = 0; i < 3; i++) { V1w[i] = wb[i] + m1w[i]; V1v[i] = vb[i] + m1v[i]; A1v[i] += X.A0[i]; }
+  A1w[0] = T(0); A1w[1] = wb[2] * m1w0; A1w[2] = -wb[1] * m1w0;                          // wb x m1w
+  A1v[0] = wb[1] * m1v[2] - wb[2] * m1v[1] + X.A0[0];                                    // wb x m1v + vb x m1w + A0
+  A1v[1] = -wb[0] * m1v[2] + vb[2] * m1w0 + X.A0[1];
+  A1v[2] = wb[0] * m1v[1] - vb[1] * m1w0 + X.A0[2];
+  V1w[0] = wb[0] + m1w0; V1w[1] = wb[1]; V1w[2] = wb[2];
+  V1v[0] = vb[0]; V1v[1] = vb[1] + m1v[1]; V1v[2] = vb[2] + m1v[2];
   T V2w[3], V2v[3], A2w[3], A2v[3];
+  A2w[0] = A1w[0] + V1w[1] * m2w[2] - V1w[2] * m2w[1];                                   // + V1w x m2w
+  A2w[1] = A1w[1] - V1w[0] * m2w[2];
+  A2w[2] = A1w[2] + V1w[0] * m2w[1];
 #pragma unroll
-  for (int i = 0; i < 3; i++) { A2w[i] = A1w[i]; A2v[i] = A1v[i]; }
-  cross3_add(V1w, m2w, A2w);
+  for (int i = 0; i < 3; i++) A2v[i] = A1v[i];
   cross3_add(V1w, m2v, A2v);
-  cross3_add(V1v, m2w, A2v);
+  A2v[0] += V1v[1] * m2w[2] - V1v[2] * m2w[1];                                           // + V1v x m2w
+  A2v[1] -= V1v[0] * m2w[2];
+  A2v[2] += V1v[0] * m2w[1];
+  V2w[0] = V1w[0]; V2w[1] = V1w[1] + m2w[1]; V2w[2] = V1w[2] + m2w[2];
 #pragma unroll
-  for (int i = 0; i < 3; i++) { V2w[i] = V1w[i] + m2w[i]; V2v[i] = V1v[i] + m2v[i]; }
+  for (int i = 0; i < 3; i++) V2v[i] = V1v[i] + m2v[i];
   T V3w[3], V3v[3], A3w[3], A3v[3];
+  A3w[0] = A2w[0] + V2w[1] * m3w[2] - V2w[2] * m3w[1];                                   // + V2w x m3w
+  A3w[1] = A2w[1] - V2w[0] * m3w[2];
+  A3w[2] = A2w[2] + V2w[0] * m3w[1];
 #pragma unroll
-  for (int i = 0; i < 3; i++) { A3w[i] = A2w[i]; A3v[i] = A2v[i]; }
-  cross3_add(V2w, m3w, A3w);
+  for (int i = 0; i < 3; i++) A3v[i] = A2v[i];
   cross3_add(V2w, m3v, A3v);
-  cross3_add(V2v, m3w, A3v);
+  A3v[0] += V2v[1] * m3w[2] - V2v[2] * m3w[1];                                           // + V2v x m3w
+  A3v[1] -= V2v[0] * m3w[2];
+  A3v[2] += V2v[0] * m3w[1];
+  V3w[0] = V2w[0]; V3w[1] = V2w[1] + m3w[1]; V3w[2] = V2w[2] + m3w[2];
 #pragma unroll
-  for (int i = 0; i < 3; i++) { V3w[i] = V2w[i] + m3w[i]; V3v[i] = V2v[i] + m3v[i]; }
+  for (int i = 0; i < 3; i++) V3v[i] = V2v[i] + m3v[i];
 
   T f3n[3] = {T(0), T(0), T(0)}, f3l[3] = {T(0), T(0), T(0)};
   body_force(Ic, V3w, V3v, A3w, A3v, f3n, f3l);
-  const T h3 = dot3(K.a2, f3n) + dot3(S3v, f3l);
+  const T h3 = c1 * f3n[1] + s1 * f3n[2] + dot3(S3v, f3l);
   body_force(It, V2w, V2v, A2w, A2v, f3n, f3l);  // now thigh + calf
-  const T h2 = dot3(K.a2, f3n) + dot3(S2v, f3l);
+  const T h2 = c1 * f3n[1] + s1 * f3n[2] + dot3(S2v, f3l);
   body_force(Ih, V1w, V1v, A1w, A1v, f3n, f3l);  // now the whole leg
   const T h1 = f3n[0] + dot3(S1v, f3l);
 
@@ -299,13 +365,15 @@ QS_DEV void leg_dynamics(int k, const T* q, const T* qd, const T* tau3, const Ti
   spi_add(It, Ic);  // thigh + calf
   spi_add(Ih, It);  // whole leg
   T F1[6], F2[6], F3[6];
-  spi_apply(Ic, K.a2, S3v, F3, F3 + 3);
-  spi_apply(It, K.a2, S2v, F2, F2 + 3);
-  spi_apply(Ih, a1, S1v, F1, F1 + 3);
-  const T M33 = dot3(K.a2, F3) + dot3(S3v, F3 + 3);
-  const T M23 = dot3(K.a2, F3) + dot3(S2v, F3 + 3);
+  spi_apply_yz(Ic, c1, s1, S3v, F3, F3 + 3);
+  spi_apply_yz(It, c1, s1, S2v, F2, F2 + 3);
+  spi_apply_x(Ih, S1v, F1, F1 + 3);
+  (void)a1;
+  const T a2F3 = c1 * F3[1] + s1 * F3[2];
+  const T M33 = a2F3 + dot3(S3v, F3 + 3);
+  const T M23 = a2F3 + dot3(S2v, F3 + 3);
   const T M13 = F3[0] + dot3(S1v, F3 + 3);
-  const T M22 = dot3(K.a2, F2) + dot3(S2v, F2 + 3);
+  const T M22 = c1 * F2[1] + s1 * F2[2] + dot3(S2v, F2 + 3);
   const T M12 = F2[0] + dot3(S1v, F2 + 3);
   const T M11 = F1[0] + dot3(S1v, F1 + 3);
   // inverse of the symmetric 3x3 (adjugate)

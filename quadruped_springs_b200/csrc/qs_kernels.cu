@@ -568,7 +568,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     h->slice_max = 1 << 20;  // no cap: the slice follows the demand
     h->flight_cap = h->wave_blocks * B;   // one wave of the flight kernel's blocks
     if (const char* v = std::getenv("QS_FLIGHT_CAP")) h->flight_cap = std::max(0, std::atoi(v));
-    h->slice_early = 10;  // ticks of the early slice (measured optimum 6-12: longer and it slows k_step_contact down)
+    h->slice_early = 18;  // ticks of the early slice (round-2 sweep: 8 -> 1.443 ms per step, 12 -> 1.437, 16 -> 1.429, 20 -> 1.417, 24 -> 1.448, 32 -> 1.471)
     h->slow_spread = 32;
     if (const char* v = std::getenv("QS_SLOW_SPREAD")) {
       const int k = std::atoi(v);

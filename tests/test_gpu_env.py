@@ -435,3 +435,29 @@ def test_cpg_drive_equals_the_python_loop(qs):
     assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
     with pytest.raises(ValueError if False else Exception):
         cb.drive(qs.BatchedQuadrupedGymEnv(num_envs=4, **JIP), 1)      # not a TORQUE-mode env
+
+
+def test_graph_replay_equals_direct_launches(qs, monkeypatch):
+    """qs_step replays a CUDA graph of the step (side stream, programmatic dependent launch and all); with QS_GRAPH=0 the
+    same kernels are launched one by one.  Same numbers, bit for bit, with auto-reset and sensor noise on -- also when the
+    caller hands over a new action tensor every step and when the output buffers change (a second graph key)."""
+    n = 2048
+    kw = dict(num_envs=n, seed=11, auto_reset=True, enable_springs=True, task_env="JUMPING_FORWARD",
+              motor_control_mode="CARTESIAN_PD", observation_space_mode="ARS_BASIC")
+    a = qs.BatchedQuadrupedGymEnv(**kw)
+    monkeypatch.setenv("QS_GRAPH", "0")
+    b = qs.BatchedQuadrupedGymEnv(**kw)
+    monkeypatch.delenv("QS_GRAPH")
+    assert a._L.qs_timing_window(a._h) == 16 and b._L.qs_timing_window(b._h) == 512
+    a.reset(); b.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(70):
+        act = torch.rand(n, 6, device="cuda", generator=g) * 2 - 1          # a fresh tensor every step
+        if t == 40:                                                          # new output buffers: a second graph key
+            a._obs = torch.zeros_like(a._obs); a._reward = torch.zeros_like(a._reward)
+        oa, ra, da, ia = a.step(act)
+        ob, rb, db, ib = b.step(act.clone())
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), t
+        assert torch.equal(ia["TimeLimit.truncated"], ib["TimeLimit.truncated"])
+    assert torch.equal(a.get_state(), b.get_state())
+    assert int(da.sum()) >= 0 and float(a.rollout_stats()[1]) > 0           # episodes did end and restart on the way

@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(CSRC, "libqs_b200.so")
-SOURCES = ["qs_kernels.cu", "qs_step_kernels.cuh", "qs_env.cuh", "qs_physics.cuh", "qs_robot.cuh", "qs_types.h", "qs_model_host.h"]
+SOURCES = ["qs_kernels.cu", "qs_step_kernels.cuh", "qs_env.cuh", "qs_physics.cuh", "qs_packed.cuh", "qs_robot.cuh", "qs_types.h", "qs_model_host.h"]
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "qs_b200.h")
 
 NVCC_FLAGS = [

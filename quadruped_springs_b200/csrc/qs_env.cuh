@@ -105,26 +105,55 @@ template <bool kContacts, bool kEM>
 __device__ __forceinline__ int run_ticks(EnvState<float>& st, ContactState<float>& cs, const float* cmd,
                                          bool torque_mode, int t0, int n_ticks, int env, const DeviceView& D,
                                          const EnvCfg& C, const RobotConst& RC, const ModelConstT<float>& M,
-                                         const SolverConst& SC, float* tau_m /*12 out*/, float* tau_s /*12 out*/,
-                                         bool detect_invalid_last, const StepScratch& scr, int* why, bool skip = false) {
+                                         const ModelLegPairsT<float>& M2, const SolverConst& SC, float* tau_m /*12 out*/,
+                                         float* tau_s /*12 out*/, bool detect_invalid_last, const StepScratch& scr, int* why,
+                                         bool skip = false) {
   const float mu = D.mu[env];
   const bool custom = D.custom_gains[env] != 0;
-  float sk[3], sb[3], sr[3];
-  load_springs(D, env, sk, sb, sr);
+  {  // the motor command and the springs are the same for every tick: parked in the scratch, read back by each tick
+     // (volatile, so that they do not sit in 21 registers across the loop)
+    float sk[3], sb[3], sr[3];
+    load_springs(D, env, sk, sb, sr);
+#pragma unroll
+    for (int i = 0; i < 12; i++) scr.park(i) = cmd[i];
+#pragma unroll
+    for (int j = 0; j < 3; j++) { scr.park(12 + j) = sk[j]; scr.park(15 + j) = sb[j]; scr.park(18 + j) = sr[j]; }
+  }
   // skip: this thread only keeps the block's barriers matched (its env is handed over at t0)
   int bail = skip ? t0 : n_ticks;
   *why = skip ? TICK_NEEDS_CONTACT : TICK_DONE;
+  // tau_m / tau_s = the torques of the LAST tick (what the step stores): parked in local memory when that tick comes
+  // (volatile: a store, not 24 registers that stay allocated over the whole loop)
+  volatile float keep[24];
+  bool kept = false;
   for (int t = t0; t < n_ticks; t++) {
     // keep the warps of the block in lockstep: the tick is several times larger than the
     // instruction cache, so warps that run it together share every fetched line
     if (!__syncthreads_or(bail == n_ticks)) break;  // every env of the block was handed over
     if (bail == n_ticks) {
-      float tau[12];
-      tick_torques(st, cmd, torque_mode, env, D, C, RC, sk, sb, sr, tau, tau_m, tau_s, custom);
+      float tau[12], tm[12], ts[12], c12[12], sk[3], sb[3], sr[3];
+#pragma unroll
+      for (int i = 0; i < 12; i++) c12[i] = *static_cast<const volatile float*>(&scr.park(i));
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        sk[j] = *static_cast<const volatile float*>(&scr.park(12 + j));
+        sb[j] = *static_cast<const volatile float*>(&scr.park(15 + j));
+        sr[j] = *static_cast<const volatile float*>(&scr.park(18 + j));
+      }
+      tick_torques(st, c12, torque_mode, env, D, C, RC, sk, sb, sr, tau, tm, ts, custom);
+      if (t == n_ticks - 1) {
+        kept = true;
+#pragma unroll
+        for (int i = 0; i < 12; i++) { keep[i] = tm[i]; keep[12 + i] = ts[i]; }
+      }
       const int r = physics_tick<float, kContacts, QS_BLOCK, kEM>(st, tau, mu, cs, M, SC, detect_invalid_last && (t == n_ticks - 1), scr,
-                                                             EnvModelRef{D.model, D.n, env});
+                                                             EnvModelRef{D.model, D.n, env}, &M2);
       if (r != TICK_DONE) { bail = t; *why = r; }
     }
+  }
+  if (kept) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) { tau_m[i] = keep[i]; tau_s[i] = keep[12 + i]; }
   }
   return bail;
 }

@@ -25,9 +25,11 @@ struct KernelArgs {
   EnvCfg C;
   RobotConst RC;
   ModelConstT<float> M;
+  ModelLegPairsT<float> M2;  // M's leg tables for the leg pairs (packed per-leg passes of the tick, qs_packed.cuh)
   SolverConst SC;
   double time_step_d, max_time_d;
 };
+static_assert(sizeof(KernelArgs) <= 3600, "kernel parameter space (4 KB) also holds StepIO / Conveyor");
 
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
@@ -97,6 +99,7 @@ __global__ void k_apply_masses(DeviceView D) {
 template <typename T> struct DebugArgs {
   DeviceView D;
   ModelConstT<T> M;
+  ModelLegPairsT<T> M2;
   SolverConst SC;
   int mass_randomizer;
 };
@@ -127,7 +130,7 @@ k_debug_ticks(const __grid_constant__ DebugArgs<T> A, const float* __restrict__ 
   for (int t = 0; t < n_ticks; t++)
     {
     const EnvModelRef em{A.mass_randomizer ? D.model : nullptr, D.n, env};
-    if (physics_tick<T, true, 0, true>(st, t12, mu, cs, A.M, A.SC, true, scr, em)) { T dl[12]; physics_tick_general<T, true>(st, t12, mu, cs, A.M, A.SC, em, dl, 1); }
+    if (physics_tick<T, true, 0, true>(st, t12, mu, cs, A.M, A.SC, true, scr, em, &A.M2)) { T dl[12]; physics_tick_general<T, true>(st, t12, mu, cs, A.M, A.SC, em, dl, 1); }
   }
 #pragma unroll
   for (int i = 0; i < 3; i++) { sf.pos[i] = float(st.pos[i]); sf.vlin[i] = float(st.vlin[i]); sf.vang[i] = float(st.vang[i]); }
@@ -330,6 +333,7 @@ struct qs_env {
   Conveyor cv;
   int wave_blocks;     // settle blocks resident at once (SMs x 2)
   int slice_min, slice_max, slice_early;
+  int fill_pct;  // target occupancy of the settle window, percent (k_conveyor_ctl)
   int flight_cap;      // envs per flight launch (k_pre sends the overflow to the contact kernel)
   int slow_spread;     // envs per warp in k_step_slow (power of two)
   cudaStream_t bg;     // the conveyor's slices run here, next to k_step_slow on the caller's stream
@@ -485,6 +489,7 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   KernelArgs& A = h->args;
   host::build_robot(*cfg, A.RC);
   host::build_model<float>(A.M, cfg->breaking_threshold);
+  make_leg_pairs(A.M, A.M2);
   host::build_model<double>(h->model_d, cfg->breaking_threshold);
   A.SC.dt = float(cfg->time_step);
   A.SC.gravity_z = cfg->gravity_z;
@@ -516,6 +521,16 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
   for (int i = 0; i < 3; i++) C.payload_pos[i] = cfg->rand_payload_pos[i];
   C.max_episode_time = float(cfg->max_episode_time); C.mu_ground = cfg->mu_ground;
   C.seed = cfg->seed; C.gid0 = cfg->env_id_offset;
+  {  // RobotConst::settle_cmd = settle_command() as the device evaluates it
+    float* d_cmd = nullptr;
+    cudaError_t ec = cudaMalloc(&d_cmd, 12 * sizeof(float));
+    if (ec == cudaSuccess) {
+      k_settle_cmd<<<1, 1>>>(A, d_cmd);
+      ec = cudaMemcpy(A.RC.settle_cmd, d_cmd, 12 * sizeof(float), cudaMemcpyDeviceToHost);
+      cudaFree(d_cmd);
+    }
+    if (ec != cudaSuccess) { delete h; return fail(QS_ERR_CUDA, std::string("settle command: ") + cudaGetErrorString(ec)); }
+  }
 
   // one pool for all SoA arrays (4-byte elements), 256 B aligned segments
   const size_t n = size_t(n_envs);
@@ -574,6 +589,8 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
       const int k = std::atoi(v);
       if (k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32) h->slow_spread = k;
     }
+    h->fill_pct = 90;
+    if (const char* v = std::getenv("QS_FILL")) h->fill_pct = std::min(120, std::max(50, std::atoi(v)));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_EARLY")) h->slice_early = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MIN")) h->slice_min = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MAX")) h->slice_max = std::max(h->slice_min, std::atoi(v));
@@ -803,7 +820,7 @@ static int launch_conveyor(qs_handle h, cudaStream_t s, int phase, int flush) {
   // the latency-bound kernel the slice of this phase runs next to, and its block size
   const int* busy = phase == 0 ? h->contact_list + h->n : h->slow_list + h->n;
   k_conveyor_ctl<<<1, 1024, 0, s>>>(h->cv, phase, busy, phase == 0 ? B : 2 * h->slow_spread, h->wave_blocks, B, h->n, nsettle,
-                                    h->slice_min, h->slice_max, h->slice_early, flush);
+                                    h->slice_min, h->slice_max, h->slice_early, flush, h->fill_pct);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return QS_OK;
@@ -1231,11 +1248,11 @@ int qs_debug_ticks(qs_handle h, const float* tau, int n_ticks, int use_f64, void
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (use_f64) {
     DebugArgs<double> a;
-    a.D = h->args.D; a.M = h->model_d; a.SC = h->args.SC; a.mass_randomizer = h->args.C.mass_randomizer;
+    a.D = h->args.D; a.M = h->model_d; make_leg_pairs(a.M, a.M2); a.SC = h->args.SC; a.mass_randomizer = h->args.C.mass_randomizer;
     k_debug_ticks<double><<<grid_for(h->n, 64), 64, 64 * QS_TICK_SCRATCH * sizeof(double), s>>>(a, tau, n_ticks);
   } else {
     DebugArgs<float> a;
-    a.D = h->args.D; a.M = h->args.M; a.SC = h->args.SC; a.mass_randomizer = h->args.C.mass_randomizer;
+    a.D = h->args.D; a.M = h->args.M; a.M2 = h->args.M2; a.SC = h->args.SC; a.mass_randomizer = h->args.C.mass_randomizer;
     k_debug_ticks<float><<<grid_for(h->n, 64), 64, 64 * QS_TICK_SCRATCH * sizeof(float), s>>>(a, tau, n_ticks);
   }
   g_launches += 1;

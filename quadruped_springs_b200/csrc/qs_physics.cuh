@@ -16,6 +16,7 @@
 //     start and early exit are Bullet's (see the oracle for the restatement).
 #pragma once
 #include "qs_robot.cuh"
+#include "qs_packed.cuh"
 
 namespace qs {
 
@@ -23,12 +24,12 @@ template <typename T> QS_DEV void cross3(const T* a, const T* b, T* o) {
   const T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
   o[0] = x; o[1] = y; o[2] = z;
 }
-template <typename T> QS_DEV void cross3_add(const T* a, const T* b, T* o) {
-  const T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
-  o[0] += x; o[1] += y; o[2] += z;
+template <typename T> QS_DEV void cross3_add(const T* a, const T* b, T* o) {   // accumulator first: two fused multiply-adds each
+  const T x = o[0] + a[1] * b[2] - a[2] * b[1], y = o[1] + a[2] * b[0] - a[0] * b[2], z = o[2] + a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
 }
 template <typename T> QS_DEV T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-template <typename T> QS_DEV void m3_v(const T* R, const T* v, T* o) {  // o = R v
+template <typename T, typename U> QS_DEV void m3_v(const T* R, const U* v, T* o) {  // o = R v
   const T x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
   const T y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
   const T z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
@@ -77,6 +78,14 @@ template <typename T> QS_DEV void spi_add(SpI<T>& a, const SpI<T>& b) {
   for (int i = 0; i < 3; i++) a.h[i] += b.h[i];
 #pragma unroll
   for (int i = 0; i < 6; i++) a.I[i] += b.I[i];
+}
+// the robot's composite inertia takes a leg's, or both legs' of a pair
+template <typename A, typename T> QS_DEV void spi_acc(SpI<A>& a, const SpI<T>& b) {
+  acc_add(a.m, b.m);
+#pragma unroll
+  for (int i = 0; i < 3; i++) acc_add(a.h[i], b.h[i]);
+#pragma unroll
+  for (int i = 0; i < 6; i++) acc_add(a.I[i], b.I[i]);
 }
 // inertia of a body given in its link frame (mass, com, Ic about com) placed at
 // rotation R (link->base) and origin r (base coords)
@@ -175,7 +184,7 @@ template <typename T> struct LegKin {
   T r1[3], r2[3], r3[3], r4[3];  // joint origins and foot centre (base coords)
 };
 
-template <typename T> QS_DEV void leg_kin(int k, const T* q, const ModelConstT<T>& M, LegKin<T>& K) {
+template <typename T, typename ML> QS_DEV void leg_kin(int k, const T* q, const ML& M, LegKin<T>& K) {
   T s3, c3;
   sincos_tick(q[0], &K.s1, &K.c1);
   sincos_tick(q[1], &K.s2, &K.c2);
@@ -279,107 +288,144 @@ template <typename T, bool kEM> QS_DEV void trunk_spi(const ModelConstT<T>& M, c
 // Bm = M_kk^-1 F_k (3x6), ev = M_kk^-1 (tau - h) + B_lin (w x v); accumulates the
 // Schur complement S6 -= F^T B, the base force fb += f_leg + F^T d and the
 // composite inertia tot += I_leg.
-template <typename T, bool kEM>
-QS_DEV void leg_dynamics(int k, const T* q, const T* qd, const T* tau3, const TickCtx<T>& X, const ModelConstT<T>& M,
-                         const LegKin<T>& K, const T* RH, const T* RT, const T* RC, T* Mi, T* Bm, T* ev, T* S6, T* fb,
-                         SpI<T>& tot, const EnvModelRef& em) {
+//
+// The three bodies are visited ROOT TO TIP and each is finished before the next starts: its inertia, velocity and bias
+// acceleration are built, its bias wrench is projected on the joints at or above it (h_j = S_j . sum_{i >= j} f_i) and
+// its momentum columns I_i S_j are added to F_j (= I^c_j S_j by linearity).  Against the textbook order (velocities
+// down, forces and composite inertias up) this costs three more projections and three more I S products, ~5 % of
+// the function, and keeps ONE body's inertia and ONE pair of velocity / acceleration vectors alive instead of three:
+// what lets the pair instantiation (two legs per thread, twice the registers per value) fit the register file.
+//
+// T = a scalar and k = a leg, or T = a pair of scalars and k = a pair of legs (M = ModelLegPairsT); the sums over the
+// legs (S6, fb, tot) are scalars of type A either way.
+template <typename T> QS_DEV void body_force_set(const SpI<T>& I, const T* Vw, const T* Vv, const T* Aw, const T* Av, T* fn, T* fl) {
+  T L[3], p[3];
+  spi_apply(I, Vw, Vv, L, p);
+  spi_apply(I, Aw, Av, fn, fl);
+  // crf(V)(L,p) = (w x L + v x p, w x p)
+  cross3_add(Vw, L, fn);
+  cross3_add(Vv, p, fn);
+  cross3_add(Vw, p, fl);
+}
+template <typename T, bool kEM, typename ML, typename A>
+QS_DEV void leg_dynamics(int k, const T* q, const T* qd, const T* tau3, const TickCtx<T>& X, const ML& M,
+                         const LegKin<T>& K, T* Mi, T* Bm, T* ev, A* S6, A* fb, SpI<A>& tot, const EnvModelRef& em) {
   const T* wb = X.wb;
   const T* vb = X.vb;
-  SpI<T> Ih, It, Ic;
-  if (kEM && em.base) {  // randomized masses: changeDynamics(mass=) keeps each link's inertia diagonal and inertial frame
-    T cc[3], ci[6];
-#pragma unroll
-    for (int i = 0; i < 3; i++) cc[i] = em_get<T>(em, EM_CALF_COM + i);
-#pragma unroll
-    for (int i = 0; i < 6; i++) ci[i] = em_get<T>(em, EM_CALF_IC + i);
-    body_spi_hip(em_get<T>(em, EM_HIP_M), M.body_com[k][0], M.body_Ic[k][0], K.c1, K.s1, K.r1, Ih);
-    body_spi_diag(em_get<T>(em, EM_THIGH_M), M.body_com[k][1], M.body_Ic[k][1], RT, K.r2, It);
-    body_spi(em_get<T>(em, EM_CALF_M), cc, ci, RC, K.r3, Ic);
-  } else {
-    body_spi_hip(M.body_m[k][0], M.body_com[k][0], M.body_Ic[k][0], K.c1, K.s1, K.r1, Ih);
-    body_spi_diag(M.body_m[k][1], M.body_com[k][1], M.body_Ic[k][1], RT, K.r2, It);
-    body_spi(M.body_m[k][2], M.body_com[k][2], M.body_Ic[k][2], RC, K.r3, Ic);
-  }
-  (void)RH;
-
+  const bool rand_m = kEM && em.base;  // randomized masses: changeDynamics(mass=) keeps each link's inertia diagonal and inertial frame
+  const T c1 = K.c1, s1 = K.s1;
+  (void)q;
   // motion subspaces S_j = (a_j, r_j x a_j).  The axes have structural zeros -- hip a1 = (1,0,0), thigh / calf
   // a2 = (0, c1, s1) -- and a product with a zero is an instruction the compiler has to keep (0 * x is not 0 for every x
   // under IEEE rules): the products below are written out for those axes.
-  const T a1[3] = {T(1), T(0), T(0)};
-  const T c1 = K.c1, s1 = K.s1;
-  const T S1v[3] = {T(0), K.r1[2], -K.r1[1]};                                            // r1 x a1
+  const T S1v1 = K.r1[2], S1v2 = -K.r1[1];                                               // r1 x a1 = (0, r1z, -r1y)
   const T S2v[3] = {K.r2[1] * s1 - K.r2[2] * c1, -K.r2[0] * s1, K.r2[0] * c1};           // r2 x a2
   const T S3v[3] = {K.r3[1] * s1 - K.r3[2] * c1, -K.r3[0] * s1, K.r3[0] * c1};           // r3 x a2
-
-  // ---- Newton-Euler bias (velocity products + gravity), individual bodies
-  const T m1w0 = qd[0];                                         // m1w = (qd0, 0, 0)
-  const T m1v[3] = {T(0), S1v[1] * qd[0], S1v[2] * qd[0]};
-  const T m2w[3] = {T(0), c1 * qd[1], s1 * qd[1]}, m3w[3] = {T(0), c1 * qd[2], s1 * qd[2]};
-  T m2v[3], m3v[3];
-#pragma unroll
-  for (int i = 0; i < 3; i++) { m2v[i] = S2v[i] * qd[1]; m3v[i] = S3v[i] * qd[2]; }
+  const T S1v[3] = {T(0), S1v1, S1v2};
   // x-axis and (0, p, q) cross products: u x (w0,0,0) = (0, u2 w0, -u1 w0);  u x (0,p,q) = (u1 q - u2 p, -u0 q, u0 p)
-  T V1w[3], V1v[3], A1w[3], A1v[3];
-  A1w[0] = T(0); A1w[1] = wb[2] * m1w0; A1w[2] = -wb[1] * m1w0;                          // wb x m1w
-  A1v[0] = wb[1] * m1v[2] - wb[2] * m1v[1] + X.A0[0];                                    // wb x m1v + vb x m1w + A0
-  A1v[1] = -wb[0] * m1v[2] + vb[2] * m1w0 + X.A0[1];
-  A1v[2] = wb[0] * m1v[1] - vb[1] * m1w0 + X.A0[2];
-  V1w[0] = wb[0] + m1w0; V1w[1] = wb[1]; V1w[2] = wb[2];
-  V1v[0] = vb[0]; V1v[1] = vb[1] + m1v[1]; V1v[2] = vb[2] + m1v[2];
-  T V2w[3], V2v[3], A2w[3], A2v[3];
-  A2w[0] = A1w[0] + V1w[1] * m2w[2] - V1w[2] * m2w[1];                                   // + V1w x m2w
-  A2w[1] = A1w[1] - V1w[0] * m2w[2];
-  A2w[2] = A1w[2] + V1w[0] * m2w[1];
-#pragma unroll
-  for (int i = 0; i < 3; i++) A2v[i] = A1v[i];
-  cross3_add(V1w, m2v, A2v);
-  A2v[0] += V1v[1] * m2w[2] - V1v[2] * m2w[1];                                           // + V1v x m2w
-  A2v[1] -= V1v[0] * m2w[2];
-  A2v[2] += V1v[0] * m2w[1];
-  V2w[0] = V1w[0]; V2w[1] = V1w[1] + m2w[1]; V2w[2] = V1w[2] + m2w[2];
-#pragma unroll
-  for (int i = 0; i < 3; i++) V2v[i] = V1v[i] + m2v[i];
-  T V3w[3], V3v[3], A3w[3], A3v[3];
-  A3w[0] = A2w[0] + V2w[1] * m3w[2] - V2w[2] * m3w[1];                                   // + V2w x m3w
-  A3w[1] = A2w[1] - V2w[0] * m3w[2];
-  A3w[2] = A2w[2] + V2w[0] * m3w[1];
-#pragma unroll
-  for (int i = 0; i < 3; i++) A3v[i] = A2v[i];
-  cross3_add(V2w, m3v, A3v);
-  A3v[0] += V2v[1] * m3w[2] - V2v[2] * m3w[1];                                           // + V2v x m3w
-  A3v[1] -= V2v[0] * m3w[2];
-  A3v[2] += V2v[0] * m3w[1];
-  V3w[0] = V2w[0]; V3w[1] = V2w[1] + m3w[1]; V3w[2] = V2w[2] + m3w[2];
-#pragma unroll
-  for (int i = 0; i < 3; i++) V3v[i] = V2v[i] + m3v[i];
+  T F1[6], F2[6], F3[6], fn[3], fl[3], bn[3], bl[3], g[6];
+  T Vw[3], Vv[3], Aw[3], Av[3];
+  SpI<T> I;
+  T h1, h2, h3;
 
-  T f3n[3] = {T(0), T(0), T(0)}, f3l[3] = {T(0), T(0), T(0)};
-  body_force(Ic, V3w, V3v, A3w, A3v, f3n, f3l);
-  const T h3 = c1 * f3n[1] + s1 * f3n[2] + dot3(S3v, f3l);
-  body_force(It, V2w, V2v, A2w, A2v, f3n, f3l);  // now thigh + calf
-  const T h2 = c1 * f3n[1] + s1 * f3n[2] + dot3(S2v, f3l);
-  body_force(Ih, V1w, V1v, A1w, A1v, f3n, f3l);  // now the whole leg
-  const T h1 = f3n[0] + dot3(S1v, f3l);
+  // ---- hip link
+  {
+    const T m1w0 = qd[0];                                         // m1w = (qd0, 0, 0)
+    const T m1v1 = S1v1 * m1w0, m1v2 = S1v2 * m1w0;               // m1v = (0, .., ..)
+    Aw[0] = T(0); Aw[1] = wb[2] * m1w0; Aw[2] = -wb[1] * m1w0;                           // wb x m1w
+    Av[0] = wb[1] * m1v2 - wb[2] * m1v1 + X.A0[0];                                       // wb x m1v + vb x m1w + A0
+    Av[1] = -wb[0] * m1v2 + vb[2] * m1w0 + X.A0[1];
+    Av[2] = wb[0] * m1v1 - vb[1] * m1w0 + X.A0[2];
+    Vw[0] = wb[0] + m1w0; Vw[1] = wb[1]; Vw[2] = wb[2];
+    Vv[0] = vb[0]; Vv[1] = vb[1] + m1v1; Vv[2] = vb[2] + m1v2;
+    body_spi_hip(rand_m ? em_get<T>(em, EM_HIP_M) : T(M.body_m[k][0]), M.body_com[k][0], M.body_Ic[k][0], c1, s1, K.r1, I);
+    body_force_set(I, Vw, Vv, Aw, Av, fn, fl);
+    h1 = fn[0] + S1v1 * fl[1] + S1v2 * fl[2];
+    spi_apply_x(I, S1v, F1, F1 + 3);
+    spi_acc(tot, I);
+  }
+  // ---- thigh
+  {
+    const T w1 = c1 * qd[1], w2 = s1 * qd[1];                     // m2w = (0, w1, w2)
+    const T m2v[3] = {S2v[0] * qd[1], S2v[1] * qd[1], S2v[2] * qd[1]};
+    Aw[0] = Aw[0] + Vw[1] * w2 - Vw[2] * w1;                                             // + V1w x m2w
+    Aw[1] = Aw[1] - Vw[0] * w2;
+    Aw[2] = Aw[2] + Vw[0] * w1;
+    cross3_add(Vw, m2v, Av);                                                             // + V1w x m2v
+    Av[0] = Av[0] + Vv[1] * w2 - Vv[2] * w1;                                             // + V1v x m2w
+    Av[1] = Av[1] - Vv[0] * w2;
+    Av[2] = Av[2] + Vv[0] * w1;
+    Vw[1] = Vw[1] + w1; Vw[2] = Vw[2] + w2;
+#pragma unroll
+    for (int i = 0; i < 3; i++) Vv[i] = Vv[i] + m2v[i];
+    // thigh link rotation: Rx(q1) Ry(q2)
+    const T RT[9] = {K.c2, T(0), K.s2, s1 * K.s2, c1, -s1 * K.c2, -c1 * K.s2, s1, c1 * K.c2};
+    body_spi_diag(rand_m ? em_get<T>(em, EM_THIGH_M) : T(M.body_m[k][1]), M.body_com[k][1], M.body_Ic[k][1], RT, K.r2, I);
+    body_force_set(I, Vw, Vv, Aw, Av, bn, bl);
+    h1 = h1 + bn[0] + S1v1 * bl[1] + S1v2 * bl[2];
+    h2 = c1 * bn[1] + s1 * bn[2] + dot3(S2v, bl);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { fn[i] = fn[i] + bn[i]; fl[i] = fl[i] + bl[i]; }
+    spi_apply_x(I, S1v, g, g + 3);
+#pragma unroll
+    for (int i = 0; i < 6; i++) F1[i] = F1[i] + g[i];
+    spi_apply_yz(I, c1, s1, S2v, F2, F2 + 3);
+    spi_acc(tot, I);
+  }
+  // ---- calf + foot
+  {
+    const T w1 = c1 * qd[2], w2 = s1 * qd[2];                     // m3w = (0, w1, w2)
+    const T m3v[3] = {S3v[0] * qd[2], S3v[1] * qd[2], S3v[2] * qd[2]};
+    Aw[0] = Aw[0] + Vw[1] * w2 - Vw[2] * w1;                                             // + V2w x m3w
+    Aw[1] = Aw[1] - Vw[0] * w2;
+    Aw[2] = Aw[2] + Vw[0] * w1;
+    cross3_add(Vw, m3v, Av);                                                             // + V2w x m3v
+    Av[0] = Av[0] + Vv[1] * w2 - Vv[2] * w1;                                             // + V2v x m3w
+    Av[1] = Av[1] - Vv[0] * w2;
+    Av[2] = Av[2] + Vv[0] * w1;
+    Vw[1] = Vw[1] + w1; Vw[2] = Vw[2] + w2;
+#pragma unroll
+    for (int i = 0; i < 3; i++) Vv[i] = Vv[i] + m3v[i];
+    const T RC[9] = {K.c23, T(0), K.s23, s1 * K.s23, c1, -s1 * K.c23, -c1 * K.s23, s1, c1 * K.c23};
+    if (rand_m) {
+      T cc[3], ci[6];
+#pragma unroll
+      for (int i = 0; i < 3; i++) cc[i] = em_get<T>(em, EM_CALF_COM + i);
+#pragma unroll
+      for (int i = 0; i < 6; i++) ci[i] = em_get<T>(em, EM_CALF_IC + i);
+      body_spi(em_get<T>(em, EM_CALF_M), cc, ci, RC, K.r3, I);
+    } else {
+      body_spi(T(M.body_m[k][2]), M.body_com[k][2], M.body_Ic[k][2], RC, K.r3, I);
+    }
+    body_force_set(I, Vw, Vv, Aw, Av, bn, bl);
+    h1 = h1 + bn[0] + S1v1 * bl[1] + S1v2 * bl[2];
+    const T a2bn = c1 * bn[1] + s1 * bn[2];
+    h2 = h2 + a2bn + dot3(S2v, bl);
+    h3 = a2bn + dot3(S3v, bl);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { fn[i] = fn[i] + bn[i]; fl[i] = fl[i] + bl[i]; }
+    spi_apply_x(I, S1v, g, g + 3);
+#pragma unroll
+    for (int i = 0; i < 6; i++) F1[i] = F1[i] + g[i];
+    spi_apply_yz(I, c1, s1, S2v, g, g + 3);
+#pragma unroll
+    for (int i = 0; i < 6; i++) F2[i] = F2[i] + g[i];
+    spi_apply_yz(I, c1, s1, S3v, F3, F3 + 3);
+    spi_acc(tot, I);
+  }
 
-  // ---- composite inertias and joint-space blocks
-  spi_add(It, Ic);  // thigh + calf
-  spi_add(Ih, It);  // whole leg
-  T F1[6], F2[6], F3[6];
-  spi_apply_yz(Ic, c1, s1, S3v, F3, F3 + 3);
-  spi_apply_yz(It, c1, s1, S2v, F2, F2 + 3);
-  spi_apply_x(Ih, S1v, F1, F1 + 3);
-  (void)a1;
+  // ---- joint-space inertia M_ij = S_i . F_j
   const T a2F3 = c1 * F3[1] + s1 * F3[2];
   const T M33 = a2F3 + dot3(S3v, F3 + 3);
   const T M23 = a2F3 + dot3(S2v, F3 + 3);
-  const T M13 = F3[0] + dot3(S1v, F3 + 3);
+  const T M13 = F3[0] + S1v1 * F3[4] + S1v2 * F3[5];
   const T M22 = c1 * F2[1] + s1 * F2[2] + dot3(S2v, F2 + 3);
-  const T M12 = F2[0] + dot3(S1v, F2 + 3);
-  const T M11 = F1[0] + dot3(S1v, F1 + 3);
+  const T M12 = F2[0] + S1v1 * F2[4] + S1v2 * F2[5];
+  const T M11 = F1[0] + S1v1 * F1[4] + S1v2 * F1[5];
   // inverse of the symmetric 3x3 (adjugate)
   const T c00 = M22 * M33 - M23 * M23, c01 = M13 * M23 - M12 * M33, c02 = M12 * M23 - M13 * M22;
   const T c11 = M11 * M33 - M13 * M13, c12 = M12 * M13 - M11 * M23, c22 = M11 * M22 - M12 * M12;
-  const T idet = div_t(T(1), M11 * c00 + M12 * c01 + M13 * c02);
+  const T idet = div_t(T(1), T(M11 * c00 + M12 * c01 + M13 * c02));
   Mi[0] = c00 * idet; Mi[1] = c01 * idet; Mi[2] = c02 * idet; Mi[3] = c11 * idet; Mi[4] = c12 * idet; Mi[5] = c22 * idet;
   const T t1 = tau3[0] - h1, t2 = tau3[1] - h2, t3 = tau3[2] - h3;
   const T d0 = Mi[0] * t1 + Mi[1] * t2 + Mi[2] * t3;
@@ -397,27 +443,27 @@ QS_DEV void leg_dynamics(int k, const T* q, const T* qd, const T* tau3, const Ti
 #pragma unroll
   for (int a = 0; a < 6; a++) {
 #pragma unroll
-    for (int b = a; b < 6; b++) S6[s6(a, b)] -= F1[a] * Bm[b] + F2[a] * Bm[6 + b] + F3[a] * Bm[12 + b];
-    fb[a] += (a < 3 ? f3n[a] : f3l[a - 3]) + F1[a] * d0 + F2[a] * d1 + F3[a] * d2;
+    for (int b = a; b < 6; b++) acc_add(S6[s6(a, b)], T(-(F1[a] * Bm[b] + F2[a] * Bm[6 + b] + F3[a] * Bm[12 + b])));
+    acc_add(fb[a], T((a < 3 ? fn[a] : fl[a - 3]) + F1[a] * d0 + F2[a] * d1 + F3[a] * d2));
   }
-  spi_add(tot, Ih);
 }
 
 // support-function gap of the leg's non-foot shapes (hip cylinder, thigh box, calf box)
-template <typename T>
-QS_DEV void leg_shape_gaps(const EnvState<T>& st, const TickCtx<T>& X, const ModelConstT<T>& M, const LegKin<T>& K,
+// (pz = height of the base origin; MC = the scalar model: for a pair of legs its constants are broadcast)
+template <typename T, typename S, typename MC>
+QS_DEV void leg_shape_gaps(S pz, const TickCtx<T>& X, const MC& M, const LegKin<T>& K,
                            const T* RT, const T* RC, T* zh, T* zt, T* zc) {
   const T* nb = X.nb;
   const T nz = dot3(nb, K.a2);
-  *zh = st.pos[2] + dot3(nb, K.r1) - (abs_t(nz) * M.hip_hl + M.hip_r * sqrt_t(tmax(T(1) - nz * nz, T(0))));
+  *zh = pz + dot3(nb, K.r1) - (abs_t(nz) * M.hip_hl + M.hip_r * sqrt_t(tmax(T(T(1) - nz * nz), T(0))));
   T c[3];
   m3_v(RT, M.thigh_c, c);
-  *zt = st.pos[2] + dot3(nb, K.r2) + dot3(nb, c) -
+  *zt = pz + dot3(nb, K.r2) + dot3(nb, c) -
         (abs_t(nb[0] * RT[0] + nb[1] * RT[3] + nb[2] * RT[6]) * M.thigh_half[0] +
          abs_t(nb[0] * RT[1] + nb[1] * RT[4] + nb[2] * RT[7]) * M.thigh_half[1] +
          abs_t(nb[0] * RT[2] + nb[1] * RT[5] + nb[2] * RT[8]) * M.thigh_half[2]);
   m3_v(RC, M.calf_c, c);
-  *zc = st.pos[2] + dot3(nb, K.r3) + dot3(nb, c) -
+  *zc = pz + dot3(nb, K.r3) + dot3(nb, c) -
         (abs_t(nb[0] * RC[0] + nb[1] * RC[3] + nb[2] * RC[6]) * M.calf_half[0] +
          abs_t(nb[0] * RC[1] + nb[1] * RC[4] + nb[2] * RC[7]) * M.calf_half[1] +
          abs_t(nb[0] * RC[2] + nb[1] * RC[5] + nb[2] * RC[8]) * M.calf_half[2]);
@@ -539,7 +585,8 @@ template <typename T> QS_DEV void integrate_positions(EnvState<T>& st, T dt) {
 // ground while SC.body_response is set); the caller then hands the env to physics_tick_general.
 // ------------------------------------------------------------------------------------------
 constexpr int QS_LEG_SCRATCH = 18 + 3 + 6 + 6 + 9 + 9;      // Bm, ev, Mi, sincos, W, (q, qd, tau)
-constexpr int QS_TICK_SCRATCH = 4 * QS_LEG_SCRATCH;          // floats per thread
+constexpr int QS_PARK = 21;                                  // the caller's: motor command (12), spring k / b / rest (9)
+constexpr int QS_TICK_SCRATCH = 4 * QS_LEG_SCRATCH + QS_PARK;  // floats per thread: 225 (2 blocks of 128 threads fill an SM's 228 KB)
 
 // kStride > 0: the stride is a compile-time constant (the block size of the step / settle kernels), so every
 // slot of a leg is an immediate offset from one per-leg base address; kStride = 0 reads it at run time.
@@ -549,13 +596,17 @@ template <typename T, int kStride = 0> struct Scratch {
   QS_DEV T& operator()(int leg, int slot) const {
     return p[(leg * QS_LEG_SCRATCH + slot) * (kStride > 0 ? kStride : stride)];
   }
+  // what the tick loop's caller keeps here instead of in registers across the ticks (the tick itself never touches it)
+  QS_DEV T& park(int i) const { return p[(4 * QS_LEG_SCRATCH + i) * (kStride > 0 ? kStride : stride)]; }
 };
 enum { SCR_BM = 0, SCR_EV = 18, SCR_MI = 21, SCR_SC = 27, SCR_W = 33, SCR_Q = 42, SCR_QD = 45, SCR_TAU = 48 };
-// Once a foot's contact rows are built, EV / MI / SC / Q of its leg are dead: the 18 floats of the rows'
-// base part Y = L^-1 G^T live there during the PGS sweeps instead of in (spilling) registers.
-QS_DEV constexpr int scr_y(int i) { return i < 15 ? SCR_EV + i : SCR_Q + (i - 15); }
+// Once a foot's contact rows are built, EV / MI / SC / TAU of its leg are dead: the 18 floats of the rows'
+// base part Y = L^-1 G^T live there during the PGS sweeps instead of in (spilling) registers.  (Not Q: the joint angles
+// stay parked in the scratch for the whole tick and come back for the integration, so that they hold no registers
+// in between.)
+QS_DEV constexpr int scr_y(int i) { return i < 15 ? SCR_EV + i : SCR_TAU + (i - 15); }
 
-template <typename T> QS_DEV void leg_kin_from_sc(int k, const T* sc, const ModelConstT<T>& M, LegKin<T>& K) {
+template <typename T, typename ML> QS_DEV void leg_kin_from_sc(int k, const T* sc, const ML& M, LegKin<T>& K) {
   K.s1 = sc[0]; K.c1 = sc[1]; K.s2 = sc[2]; K.c2 = sc[3]; K.s23 = sc[4]; K.c23 = sc[5];
   K.a2[0] = T(0); K.a2[1] = K.c1; K.a2[2] = K.s1;
   const T l = M.link_len, dy = M.thigh_off_y[k];
@@ -571,10 +622,16 @@ template <typename T> QS_DEV void leg_kin_from_sc(int k, const T* sc, const Mode
 // kernel), TICK_NEEDS_CONTACT when a foot is within its contact threshold.
 enum { TICK_DONE = 0, TICK_NEEDS_GENERAL = 1, TICK_NEEDS_CONTACT = 2 };
 // kEM: read the per-env mass properties `em` (compiled out of the default kernels)
+// M2 != nullptr (float / double only): the per-leg passes run on PAIRS of legs with packed arithmetic (qs_packed.cuh).
+#ifndef QS_PACK_LEGS
+#define QS_PACK_LEGS 1
+#endif
 template <typename T, bool kContacts = true, int kStride = 0, bool kEM = false>
 __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, ContactState<T>& cs,
                                      const ModelConstT<T>& M, const SolverConst& SC, bool detect_invalid,
-                                     const Scratch<T, kStride>& scr, const EnvModelRef em = EnvModelRef{nullptr, 0, 0}) {
+                                     const Scratch<T, kStride>& scr, const EnvModelRef em = EnvModelRef{nullptr, 0, 0},
+                                     const ModelLegPairsT<T>* M2 = nullptr) {
+  constexpr bool kPack = QS_PACK_LEGS && std::is_floating_point<T>::value;
   const T dt = T(SC.dt);
   const T idt = div_t(T(1), dt);
   const T mcv = T(SC.max_coord_vel);
@@ -607,7 +664,56 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
     }
   }
 
-  // ---- pass A: one rolled loop over the legs
+  // ---- pass A: one rolled loop over the legs, two at a time when packed
+  if constexpr (kPack) {
+    using P = PkT<T>;
+    TickCtx<P> X2;   // the base's quantities are the same for both legs of a pair: broadcast operands
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      X2.wb[i] = P(X.wb[i]); X2.vb[i] = P(X.vb[i]); X2.nb[i] = P(X.nb[i]); X2.A0[i] = P(X.A0[i]); X2.wxv[i] = P(X.wxv[i]);
+    }
+#pragma unroll 1
+    for (int kp = 0; kp < 2; kp++) {
+      const int k0 = 2 * kp, k1 = k0 + 1;
+      P q[3], qd[3], tk[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        q[j] = P(scr(k0, SCR_Q + j), scr(k1, SCR_Q + j));
+        qd[j] = P(scr(k0, SCR_QD + j), scr(k1, SCR_QD + j));
+        tk[j] = P(scr(k0, SCR_TAU + j), scr(k1, SCR_TAU + j));
+      }
+      LegKin<P> K;
+      leg_kin(kp, q, *M2, K);
+      // everything that only needs the kinematics comes first, so that it is dead while the dynamics run
+      const P sc6[6] = {K.s1, K.c1, K.s2, K.c2, K.s23, K.c23};
+#pragma unroll
+      for (int i = 0; i < 6; i++) { scr(k0, SCR_SC + i) = sc6[i].x; scr(k1, SCR_SC + i) = sc6[i].y; }
+      if (SC.enable_limits) {
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          need_general |= (q[j].x <= M.joint_lo[j]) | (q[j].x >= M.joint_hi[j]) | (q[j].y <= M.joint_lo[j]) | (q[j].y >= M.joint_hi[j]);
+      }
+      // collision detection on the poses at the start of the tick
+      const P gap = st.pos[2] + dot3(X2.nb, K.r4) - M.foot_radius;
+      if (gap.x < M.foot_thresh) active |= 1 << k0;
+      if (gap.y < M.foot_thresh) active |= 1 << k1;
+      if (watch_shapes) {
+        P RH[9], RT[9], RC[9], zh, zt, zc;
+        link_rotations(K, RH, RT, RC);
+        leg_shape_gaps(st.pos[2], X2, M, K, RT, RC, &zh, &zt, &zc);
+        invalid += (zh.x < M.hip_thresh) + (zt.x < M.thigh_thresh) + (zc.x < M.calf_thresh) +
+                   (zh.y < M.hip_thresh) + (zt.y < M.thigh_thresh) + (zc.y < M.calf_thresh);
+      }
+      P Mi[6], Bm[18], ev[3];
+      leg_dynamics<P, kEM>(kp, q, qd, tk, X2, *M2, K, Mi, Bm, ev, S6, fb, tot, em);
+#pragma unroll
+      for (int i = 0; i < 18; i++) { scr(k0, SCR_BM + i) = Bm[i].x; scr(k1, SCR_BM + i) = Bm[i].y; }
+#pragma unroll
+      for (int i = 0; i < 3; i++) { scr(k0, SCR_EV + i) = ev[i].x; scr(k1, SCR_EV + i) = ev[i].y; }
+#pragma unroll
+      for (int i = 0; i < 6; i++) { scr(k0, SCR_MI + i) = Mi[i].x; scr(k1, SCR_MI + i) = Mi[i].y; }
+    }
+  } else {
 #pragma unroll 1
   for (int k = 0; k < 4; k++) {
     const T q[3] = {scr(k, SCR_Q), scr(k, SCR_Q + 1), scr(k, SCR_Q + 2)};
@@ -615,9 +721,8 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
     const T tk[3] = {scr(k, SCR_TAU), scr(k, SCR_TAU + 1), scr(k, SCR_TAU + 2)};
     LegKin<T> K;
     leg_kin(k, q, M, K);
-    T RH[9], RT[9], RC[9], Mi[6], Bm[18], ev[3];
-    link_rotations(K, RH, RT, RC);
-    leg_dynamics<T, kEM>(k, q, qd, tk, X, M, K, RH, RT, RC, Mi, Bm, ev, S6, fb, tot, em);
+    T Mi[6], Bm[18], ev[3];
+    leg_dynamics<T, kEM>(k, q, qd, tk, X, M, K, Mi, Bm, ev, S6, fb, tot, em);
 #pragma unroll
     for (int i = 0; i < 18; i++) scr(k, SCR_BM + i) = Bm[i];
 #pragma unroll
@@ -636,10 +741,12 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
     if (watch_shapes) {
       // non-foot shapes vs the plane: support-function distance below the link's
       // contact breaking threshold (quadruped.py:243-249 -> invalid contact)
-      T zh, zt, zc;
-      leg_shape_gaps(st, X, M, K, RT, RC, &zh, &zt, &zc);
+      T RH[9], RT[9], RC[9], zh, zt, zc;
+      link_rotations(K, RH, RT, RC);
+      leg_shape_gaps(st.pos[2], X, M, K, RT, RC, &zh, &zt, &zc);
       invalid += (zh < M.hip_thresh) + (zt < M.thigh_thresh) + (zc < M.calf_thresh);
     }
+  }
   }
   if (watch_shapes) {
     T zt, zi;
@@ -682,13 +789,24 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
   if constexpr (kContacts) in_contact = active != 0;
   if constexpr (kContacts) if (in_contact) {
     // ---- contact rows of the active feet (rolled loop), results routed into registers
-    T H[4][6], rhs[4][3], dinv[4][3], lam[4][3];
+    T H[4][6], rhs[4][3], dinv[4][3], diag[4][3], lam[4][3];
     T z[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+    // a foot without contact is an all-zero set of rows: the sweeps below then need no branch per foot (their
+    // instructions are free to overlap across the feet), and zeros stay zeros through them
 #pragma unroll
-    for (int k = 0; k < 4; k++) lam[k][0] = lam[k][1] = lam[k][2] = T(0);
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) lam[k][i] = rhs[k][i] = dinv[k][i] = diag[k][i] = T(0);
+#pragma unroll
+      for (int i = 0; i < 6; i++) H[k][i] = T(0);
+    }
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
-      if (!(active & (1 << k))) continue;
+      if (!(active & (1 << k))) {
+#pragma unroll
+        for (int i = 0; i < 18; i++) scr(k, scr_y(i)) = T(0);   // (EV / MI / SC / TAU of an idle leg are dead by now)
+        continue;
+      }
       T sc[6], Mi[6], Bm[18];
 #pragma unroll
       for (int i = 0; i < 6; i++) { sc[i] = scr(k, SCR_SC + i); Mi[i] = scr(k, SCR_MI + i); }
@@ -700,7 +818,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
       const T pc[3] = {K.r4[0] - M.foot_radius * nb[0], K.r4[1] - M.foot_radius * nb[1],
                        K.r4[2] - M.foot_radius * nb[2]};
       const T qk[3] = {scr(k, SCR_QD), scr(k, SCR_QD + 1), scr(k, SCR_QD + 2)};
-      T y[18], h[6], r3[3], di[3], Jk[3][3], Wl[9];
+      T y[18], h[6], r3[3], di[3], dg[3], Jk[3][3], Wl[9];
 #pragma unroll
       for (int dd = 0; dd < 3; dd++) {
         T Jb[6];
@@ -734,7 +852,8 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
         T nn = T(0);
 #pragma unroll
         for (int i = 0; i < 6; i++) nn += y[6 * dd + i] * y[6 * dd + i];
-        di[dd] = div_t(T(1), nn + hd[dd]);
+        dg[dd] = nn + hd[dd];           // the row's diagonal of the Delassus matrix, and its inverse
+        di[dd] = div_t(T(1), dg[dd]);
       }
       // warm start of the normal impulse (Bullet m_warmstartingFactor)
       T l0 = T(0);
@@ -750,7 +869,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
 #define QS_ROUTE(KK)                                                                    \
   case KK: {                                                                            \
     _Pragma("unroll") for (int i = 0; i < 6; i++) H[KK][i] = h[i];                       \
-    _Pragma("unroll") for (int i = 0; i < 3; i++) { rhs[KK][i] = r3[i]; dinv[KK][i] = di[i]; } \
+    _Pragma("unroll") for (int i = 0; i < 3; i++) { rhs[KK][i] = r3[i]; dinv[KK][i] = di[i]; diag[KK][i] = dg[i]; } \
     lam[KK][0] = l0;                                                                    \
   } break;
       switch (k) { QS_ROUTE(0) QS_ROUTE(1) QS_ROUTE(2) default: QS_ROUTE(3) }
@@ -758,40 +877,75 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
     }
 
     // ---- projected Gauss-Seidel (rows: normals of all feet, then friction cones)
+    //
+    // The sweep is a chain: every row needs the z the row before it left.  Written naively that is, per row, a
+    // nine-term dot product, the clamp and the update in sequence -- fourteen dependent instructions, and with two
+    // warps per scheduler the chain, not the instruction count, is what a sweep costs (ncu: the dot product's FFMAs
+    // carry the PGS's stall samples).  Same arithmetic, shorter chain:
+    //  * normal rows: w_k = H_k lam_k + Yn_k . (z + sum_{l<k} Yn_l dI_l) = [H_k lam_k + Yn_k . z] + sum_{l<k} N_kl dI_l with
+    //    the six couplings N_kl = Yn_k . Yn_l computed once per tick.  The brackets of the four feet are independent
+    //    (computed side by side), and a row then hangs on its predecessor by ONE multiply-add;
+    //  * friction rows: the dot product as two chains of three;
+    //  * the residual uses the stored diagonal instead of a division.
+    // Still Gauss-Seidel in Bullet's row order: each row sees every impulse change before it.
     const T thr = T(SC.residual_threshold);
     const int iters = SC.num_iterations;
     const int nact = (active & 1) + ((active >> 1) & 1) + ((active >> 2) & 1) + ((active >> 3) & 1);
     cs.work_contacts += nact;
+    T N10, N20, N21, N30, N31, N32;
+    {
+      T Yn[4][6];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) Yn[k][i] = scr(k, scr_y(i));
+      }
+#define QS_N(a, b) ((Yn[a][0] * Yn[b][0] + Yn[a][1] * Yn[b][1] + Yn[a][2] * Yn[b][2]) + (Yn[a][3] * Yn[b][3] + Yn[a][4] * Yn[b][4] + Yn[a][5] * Yn[b][5]))
+      N10 = QS_N(1, 0); N20 = QS_N(2, 0); N21 = QS_N(2, 1); N30 = QS_N(3, 0); N31 = QS_N(3, 1); N32 = QS_N(3, 2);
+#undef QS_N
+    }
     for (int it = 0; it < iters; it++) {
       T res = T(0);
       cs.work_row_iters += nact;
+      {  // normal rows
+        T Yn[4][6], bs[4], dIn[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (!(active & (1 << k))) continue;
-        T Yn[6];
+        for (int k = 0; k < 4; k++) {
 #pragma unroll
-        for (int i = 0; i < 6; i++) Yn[i] = scr(k, scr_y(i));
-        T w = H[k][0] * lam[k][0] + H[k][1] * lam[k][1] + H[k][2] * lam[k][2];
+          for (int i = 0; i < 6; i++) Yn[k][i] = scr(k, scr_y(i));
+          bs[k] = rhs[k][0] - ((H[k][0] * lam[k][0] + H[k][1] * lam[k][1] + H[k][2] * lam[k][2] + Yn[k][0] * z[0] + Yn[k][1] * z[1] + Yn[k][2] * z[2]) +
+                               (Yn[k][3] * z[3] + Yn[k][4] * z[4] + Yn[k][5] * z[5]));
+        }
 #pragma unroll
-        for (int i = 0; i < 6; i++) w += Yn[i] * z[i];
-        T dI = (rhs[k][0] - w) * dinv[k][0];
-        const T sum = lam[k][0] + dI;
-        if (sum < T(0)) { dI = -lam[k][0]; lam[k][0] = T(0); } else lam[k][0] = sum;
+        for (int k = 0; k < 4; k++) {
+          T r = bs[k];
+          if (k == 1) r = r - N10 * dIn[0];
+          if (k == 2) r = r - N20 * dIn[0] - N21 * dIn[1];
+          if (k == 3) r = r - N30 * dIn[0] - N31 * dIn[1] - N32 * dIn[2];
+          T dI = r * dinv[k][0];
+          const T sum = lam[k][0] + dI;
+          const bool neg = sum < T(0);
+          dI = neg ? -lam[k][0] : dI;
+          lam[k][0] = neg ? T(0) : sum;
+          dIn[k] = dI;
+          const T dv = dI * diag[k][0];
+          res = tmax(res, dv * dv);
+        }
 #pragma unroll
-        for (int i = 0; i < 6; i++) z[i] += Yn[i] * dI;
-        const T dv = div_t(dI, dinv[k][0]);
-        res = tmax(res, dv * dv);
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+          for (int i = 0; i < 6; i++) z[i] += Yn[k][i] * dIn[k];
+        }
       }
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        if (!(active & (1 << k))) continue;
         T Ya[6], Yb[6];
 #pragma unroll
         for (int i = 0; i < 6; i++) { Ya[i] = scr(k, scr_y(6 + i)); Yb[i] = scr(k, scr_y(12 + i)); }
-        T wa = H[k][1] * lam[k][0] + H[k][3] * lam[k][1] + H[k][4] * lam[k][2];
-        T wbb = H[k][2] * lam[k][0] + H[k][4] * lam[k][1] + H[k][5] * lam[k][2];
-#pragma unroll
-        for (int i = 0; i < 6; i++) { wa += Ya[i] * z[i]; wbb += Yb[i] * z[i]; }
+        const T wa = (H[k][1] * lam[k][0] + H[k][3] * lam[k][1] + H[k][4] * lam[k][2] + Ya[0] * z[0] + Ya[1] * z[1] + Ya[2] * z[2]) +
+                     (Ya[3] * z[3] + Ya[4] * z[4] + Ya[5] * z[5]);
+        const T wbb = (H[k][2] * lam[k][0] + H[k][4] * lam[k][1] + H[k][5] * lam[k][2] + Yb[0] * z[0] + Yb[1] * z[1] + Yb[2] * z[2]) +
+                      (Yb[3] * z[3] + Yb[4] * z[4] + Yb[5] * z[5]);
         T sa = lam[k][1] + (rhs[k][1] - wa) * dinv[k][1];
         T sb = lam[k][2] + (rhs[k][2] - wbb) * dinv[k][2];
         const T lim = mu * T(SC.mu_link) * lam[k][0];
@@ -804,7 +958,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
         lam[k][1] = sa; lam[k][2] = sb;
 #pragma unroll
         for (int i = 0; i < 6; i++) z[i] += Ya[i] * dIa + Yb[i] * dIb;
-        const T ra = div_t(dIa, dinv[k][1]), rb = div_t(dIb, dinv[k][2]);
+        const T ra = dIa * diag[k][1], rb = dIb * diag[k][2];
         res = tmax(res, ra * ra + rb * rb);
       }
       if (res <= thr) break;
@@ -846,6 +1000,13 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
   }
   cs.mask = active;
   cs.invalid = invalid;
+  // the joint angles come back from the scratch (a volatile read: the compiler must not keep the twelve registers
+  // alive across the tick instead)
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) st.q[3 * k + j] = *static_cast<const volatile T*>(&scr(k, SCR_Q + j));
+  }
   integrate_positions(st, dt);
   return TICK_DONE;
 }
@@ -971,9 +1132,9 @@ __host__ __device__ void physics_tick_general(EnvState<T>& st, const T* tau, T m
     leg_kin(k, st.q + 3 * k, M, K[k]);
     T RH[9], RT[9], RC[9];
     link_rotations(K[k], RH, RT, RC);
-    leg_dynamics<T, kEM>(k, st.q + 3 * k, st.qd + 3 * k, tau + 3 * k, X, M, K[k], RH, RT, RC, Mi[k], Bm[k], ev[k], S6, fb, tot, em);
+    leg_dynamics<T, kEM>(k, st.q + 3 * k, st.qd + 3 * k, tau + 3 * k, X, M, K[k], Mi[k], Bm[k], ev[k], S6, fb, tot, em);
     T zh, zt, zc;
-    leg_shape_gaps(st, X, M, K[k], RT, RC, &zh, &zt, &zc);
+    leg_shape_gaps(st.pos[2], X, M, K[k], RT, RC, &zh, &zt, &zc);
     if (zh < M.hip_thresh) {  // lowest point of the lower rim of the hip cylinder (axis a2)
       Cand& c = cand[ncand++];
       c.leg = k; c.level = 0; c.foot = 0; c.gap = zh;

@@ -81,6 +81,14 @@ __device__ __forceinline__ void settle_command(const EnvCfg& C, const RobotConst
   }
 }
 
+// settle_command() once, on the device (its inverse kinematics must be the device's own arithmetic), for
+// RobotConst::settle_cmd: run by qs_create with one thread
+__global__ void k_settle_cmd(const __grid_constant__ KernelArgs A, float* __restrict__ out) {
+  float cmd[12], act12[12];
+  settle_command(A.C, A.RC, cmd, act12);
+  for (int i = 0; i < 12; i++) out[i] = cmd[i];
+}
+
 __device__ __forceinline__ void finish_episode_stats(const DeviceView& D, int env, const float* ts, float ep_return,
                                                      int ep_len, bool terminated, int task, bool nonfinite = false) {
   const int n = D.n;
@@ -408,35 +416,58 @@ __device__ __forceinline__ void settle_ticks(const KernelArgs& A, uint64_t gid, 
   // (em_base, em_stride, em_idx) -- the env's own rows, or the conveyor's for an episode settled ahead
   if (kEM && t1 > t0) episode_model_store(C, gid, epoch, em_base, em_stride, em_idx, nullptr);
   const EnvModelRef em{em_base, em_stride, em_idx};
-  float cmd[12], act12[12];
-  settle_command(C, A.RC, cmd, act12);
+  const float* cmd = A.RC.settle_cmd;   // = settle_command(), from the constant bank
   // a fresh Quadruped has the default gains / springs (quadruped_gym_env.py:299-319); the settle
   // runs on the fast tick only: the standing pose is far from every joint limit and body contact
   SolverConst SCs = A.SC;
   SCs.enable_limits = 0;
   SCs.body_response = 0;
   const int nsettle = settle_length(C);
-  float sk[3], sb[3], sr[3];
-  episode_springs(C, A.RC, gid, epoch, sk, sb, sr);
+  {  // the episode's springs: parked in the scratch, read back by each tick (not 9 registers across the loop)
+    float sk[3], sb[3], sr[3];
+    episode_springs(C, A.RC, gid, epoch, sk, sb, sr);
+#pragma unroll
+    for (int j = 0; j < 3; j++) { scr.park(12 + j) = sk[j]; scr.park(15 + j) = sb[j]; scr.park(18 + j) = sr[j]; }
+  }
+  // The callers want the motor / spring torques of the LAST settle tick only.  They are parked in local memory when that
+  // tick comes (volatile: a store, not 24 registers that stay allocated over the whole loop).
+  volatile float keep[24];
+  bool kept = false;
   for (int i = 0; i < span; i++) {
     __syncthreads();  // lockstep across the block (see run_ticks)
     const int t = t0 + i;
     if (t >= t1) continue;
-    float tau[12];
+    float tau[12], tm[12], ts[12], sk[3], sb[3], sr[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      sk[j] = *static_cast<const volatile float*>(&scr.park(12 + j));
+      sb[j] = *static_cast<const volatile float*>(&scr.park(15 + j));
+      sr[j] = *static_cast<const volatile float*>(&scr.park(18 + j));
+    }
 #pragma unroll
     for (int i2 = 0; i2 < 12; i2++) {
-      tau_m[i2] = pd_torque1(A.RC.kp[i2], A.RC.kd[i2], A.RC.tau_max[i2], cmd[i2], st.q[i2], st.qd[i2], false);
-      tau[i2] = tau_m[i2];
+      tm[i2] = pd_torque1(A.RC.kp[i2], A.RC.kd[i2], A.RC.tau_max[i2], cmd[i2], st.q[i2], st.qd[i2], false);
+      tau[i2] = tm[i2];
+      ts[i2] = 0.f;
     }
     if (C.enable_springs) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        spring_torque_leg(k, sk, sb, sr, st.q + 3 * k, st.qd + 3 * k, tau_s + 3 * k);
+        spring_torque_leg(k, sk, sb, sr, st.q + 3 * k, st.qd + 3 * k, ts + 3 * k);
 #pragma unroll
-        for (int j = 0; j < 3; j++) tau[3 * k + j] += tau_s[3 * k + j];
+        for (int j = 0; j < 3; j++) tau[3 * k + j] += ts[3 * k + j];
       }
     }
-    physics_tick<float, true, QS_BLOCK, kEM>(st, tau, mu, cs, A.M, SCs, t == nsettle - 1, scr, em);
+    if (t == nsettle - 1) {
+      kept = true;
+#pragma unroll
+      for (int i2 = 0; i2 < 12; i2++) { keep[i2] = tm[i2]; keep[12 + i2] = ts[i2]; }
+    }
+    physics_tick<float, true, QS_BLOCK, kEM>(st, tau, mu, cs, A.M, SCs, t == nsettle - 1, scr, em, &A.M2);
+  }
+  if (kept) {
+#pragma unroll
+    for (int i2 = 0; i2 < 12; i2++) { tau_m[i2] = keep[i2]; tau_s[i2] = keep[12 + i2]; }
   }
 }
 
@@ -910,7 +941,7 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
   extern __shared__ float qs_smem[];
   const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
   int why;
-  const int t_done = run_ticks<false, kEM>(st, cs, cmd, torque_mode, 0, C.action_repeat, env, D, C, A.RC, A.M, A.SC, tau_m, tau_s,
+  const int t_done = run_ticks<false, kEM>(st, cs, cmd, torque_mode, 0, C.action_repeat, env, D, C, A.RC, A.M, A.M2, A.SC, tau_m, tau_s,
                                       true, scr, &why);
   if (!live) return;
   if (t_done < C.action_repeat) {
@@ -944,7 +975,7 @@ k_step_contact(const __grid_constant__ KernelArgs A, const StepIO io) {
   extern __shared__ float qs_smem[];
   const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
   int why;
-  const int t_done = run_ticks<true, kEM>(st, cs, cmd, torque_mode, D.resume_tick[env], C.action_repeat, env, D, C, A.RC, A.M,
+  const int t_done = run_ticks<true, kEM>(st, cs, cmd, torque_mode, D.resume_tick[env], C.action_repeat, env, D, C, A.RC, A.M, A.M2,
                                      A.SC, tau_m, tau_s, true, scr, &why);
   if (!live) return;
   if (t_done < C.action_repeat) {
@@ -1149,7 +1180,7 @@ __global__ void k_urgent_clear(Conveyor cv) {
 //                                   the oldest entries that fit next to k_step_contact's blocks `early` ticks;
 //   phase 1 (after k_step_contact): the entries that fit next to k_step_slow's blocks get the rest of the ticks.
 __global__ void k_conveyor_ctl(Conveyor cv, int phase, const int* __restrict__ busy_count, int busy_block, int wave_blocks,
-                               int block, int n_envs, int nsettle, int s_min, int s_max, int early, int flush) {
+                               int block, int n_envs, int nsettle, int s_min, int s_max, int early, int flush, int fill_pct) {
   __shared__ uint32_t first_live;
   const uint32_t head = cv.ctl[CV_HEAD];
   uint32_t tail = cv.ctl[CV_TAIL];
@@ -1173,7 +1204,9 @@ __global__ void k_conveyor_ctl(Conveyor cv, int phase, const int* __restrict__ b
   }
   // room next to the other kernel of this phase: one settle block displaced per block of it
   const int lanes = max(0, min(cv.width, (wave_blocks - (*busy_count + busy_block - 1) / busy_block) * block));
-  const bool backlog = pending > uint32_t(cv.width);
+  // more entries than the window holds: they wait their turn in the queue (they are needed ~QS_SLOTS episodes from now);
+  // only a pile-up (start-up: every env queues its whole ring at once) is worked off as whole settles
+  const bool backlog = fill_pct > 90 ? pending > 2u * uint32_t(cv.width) : pending > uint32_t(cv.width);
   if (phase == 0) {
     float demand = __uint_as_float(cv.ctl[CV_DEMAND]);
     demand += (float(head - cv.ctl[CV_PREV_HEAD]) - demand) * 0.125f;
@@ -1181,9 +1214,9 @@ __global__ void k_conveyor_ctl(Conveyor cv, int phase, const int* __restrict__ b
     cv.ctl[CV_PREV_HEAD] = head;
     // dense wave: nsettle * demand / slice entries in flight = target; ring safety: the settle must not take
     // longer than half a mean episode (n_envs / demand steps, Little's law)
-    const float target = 0.9f * float(cv.width);
+    const float target = 0.01f * float(fill_pct) * float(cv.width);
     float want = float(nsettle) * demand * fmaxf(1.f / target, 2.f / float(n_envs));
-    if (float(pending) > 0.97f * float(cv.width)) want *= 1.5f;  // nearly full: catch up before a backlog forms
+    if (float(pending) > fmaxf(0.97f, 0.01f * float(fill_pct) + 0.07f) * float(cv.width)) want *= 1.5f;  // catch up before a backlog forms
     // ring pressure (smoothed): more than 2 % of the finishing envs one episode from running dry
     float taken = __uint_as_float(cv.ctl[CV_EMA_TAKEN]), low2 = __uint_as_float(cv.ctl[CV_EMA_LOW2]);
     float press = fmaxf(__uint_as_float(cv.ctl[CV_PRESS]), 1.f);

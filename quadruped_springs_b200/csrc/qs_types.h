@@ -20,6 +20,8 @@ struct RobotConst {
   float filt_b[3], filt_a[3];      // Butterworth(2, 3 Hz) coefficients, action_filter.py:191-213
   float landing_action[12];        // env.get_landing_action() in the configured action space, quadruped_gym_env.py:375-379
   float env_dt;                    // action_repeat * time_step
+  float settle_cmd[12];            // the settling command (settle_command(), qs_step_kernels.cuh), evaluated once on the device at qs_create:
+                                   // an operand from the constant bank in the settle kernels instead of twelve registers
 };
 
 // Merged 13-body dynamics model of go1.urdf: fixed links folded into their

@@ -333,7 +333,6 @@ struct qs_env {
   Conveyor cv;
   int wave_blocks;     // settle blocks resident at once (SMs x 2)
   int slice_min, slice_max, slice_early;
-  int fill_pct;  // target occupancy of the settle window, percent (k_conveyor_ctl)
   int flight_cap;      // envs per flight launch (k_pre sends the overflow to the contact kernel)
   int slow_spread;     // envs per warp in k_step_slow (power of two)
   cudaStream_t bg;     // the conveyor's slices run here, next to k_step_slow on the caller's stream
@@ -589,8 +588,6 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
       const int k = std::atoi(v);
       if (k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32) h->slow_spread = k;
     }
-    h->fill_pct = 90;
-    if (const char* v = std::getenv("QS_FILL")) h->fill_pct = std::min(120, std::max(50, std::atoi(v)));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_EARLY")) h->slice_early = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MIN")) h->slice_min = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MAX")) h->slice_max = std::max(h->slice_min, std::atoi(v));
@@ -817,10 +814,15 @@ int qs_get_state_ptrs(qs_handle h, qs_state_ptrs* o) {
 static int launch_conveyor(qs_handle h, cudaStream_t s, int phase, int flush) {
   const int B = block_of(h);
   const int nsettle = h->cfg.is_rl_interface ? h->cfg.settling_steps : 1500;
-  // the latency-bound kernel the slice of this phase runs next to, and its block size
+  // the latency-bound kernel the slice of this phase runs next to, and how many of its envs cost the slice one block slot.
+  // A block of the general solver (2 warps of slow_spread envs) costs TWO: an SM keeps one shared-memory / L1 split while
+  // blocks are resident, that kernel lives on a large L1 (its solver rows are local memory; with the slice's split it
+  // runs 2.4 x longer, measured), so an SM that holds one of its blocks takes no slice block at all.  Counting one slot
+  // per block put the slice one wave + a few blocks past the free slots whenever more than ~1200 envs were in the
+  // general solver, and those few blocks then ran as a second wave (+0.4 ms on the step).
   const int* busy = phase == 0 ? h->contact_list + h->n : h->slow_list + h->n;
-  k_conveyor_ctl<<<1, 1024, 0, s>>>(h->cv, phase, busy, phase == 0 ? B : 2 * h->slow_spread, h->wave_blocks, B, h->n, nsettle,
-                                    h->slice_min, h->slice_max, h->slice_early, flush, h->fill_pct);
+  k_conveyor_ctl<<<1, 1024, 0, s>>>(h->cv, phase, busy, phase == 0 ? B : h->slow_spread, h->wave_blocks, B, h->n, nsettle,
+                                    h->slice_min, h->slice_max, h->slice_early, flush);
   g_launches += 1;
   CUDA_TRY(cudaGetLastError());
   return QS_OK;

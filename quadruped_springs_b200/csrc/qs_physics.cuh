@@ -154,6 +154,13 @@ QS_DEV void body_spi_hip(T m, const T* com, const T* Ic, T c1, T s1, const T* r,
 // upper-triangular index of a symmetric 6x6 stored in 21 entries
 __host__ __device__ constexpr int s6(int i, int j) { return i <= j ? i * (11 - i) / 2 + j : j * (11 - j) / 2 + i; }
 
+// a value parked in memory comes back: a volatile read for the machine types (the compiler must not keep the register
+// alive instead), a plain one for the instrumented scalar of tools/count_flops.cu
+template <typename T> QS_DEV T reload(const T& x) {
+  if constexpr (std::is_arithmetic<T>::value) return *static_cast<const volatile T*>(&x);
+  else return x;
+}
+
 template <typename T> struct EnvState {
   T pos[3], quat[4], vlin[3], vang[3], q[12], qd[12];
 };
@@ -490,7 +497,7 @@ template <typename T> QS_DEV void base_factor(const SpI<T>& tot, T* S6, T* Ld) {
     T dj = S6[s6(j, j)];
 #pragma unroll
     for (int k2 = 0; k2 < j; k2++) dj -= S6[s6(k2, j)] * S6[s6(k2, j)];
-    const T inv = rsqrt_t(dj);
+    const T inv = rsqrt_pos(dj);
     Ld[j] = inv;
     S6[s6(j, j)] = dj * inv;
 #pragma unroll
@@ -548,23 +555,18 @@ template <typename T> QS_DEV void integrate_positions(EnvState<T>& st, T dt) {
   const T* om = st.vang;
   T ang = sqrt_t(dot3(om, om));
   if (ang * dt > T(0.25 * QS_PI)) ang = div_t(T(0.25 * QS_PI), dt);
-  T sc, cw;
-  if (ang < T(0.001)) {
-    sc = T(0.5) * dt - dt * dt * dt * T(0.020833333333) * ang * ang;
-    T sdummy;
-    sincos_t(T(0.5) * ang * dt, &sdummy, &cw);
-  } else {
-    T sn;
-    sincos_t(T(0.5) * ang * dt, &sn, &cw);
-    sc = div_t(sn, ang);
-  }
+  // axis * sin(ang dt / 2) = om * (sin(x) / x) * dt / 2 with x = ang dt / 2 <= pi / 8: one branch-free form for every rate
+  // (Bullet switches to a Taylor series below ang = 1e-3; the series used here is exact to rounding on the whole range)
+  T sinc, cw;
+  sinc_cos_small(T(T(0.5) * ang * dt), &sinc, &cw);
+  const T sc = T(0.5) * dt * sinc;
   const T ax = om[0] * sc, ay = om[1] * sc, az = om[2] * sc;
   const T* q = st.quat;
   const T nw = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
   const T nx = cw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
   const T ny = cw * q[1] - ax * q[2] + ay * q[3] + az * q[0];
   const T nz = cw * q[2] + ax * q[1] - ay * q[0] + az * q[3];
-  const T inv = rsqrt_t(nx * nx + ny * ny + nz * nz + nw * nw);
+  const T inv = rsqrt_pos(nx * nx + ny * ny + nz * nz + nw * nw);
   st.quat[0] = nx * inv; st.quat[1] = ny * inv; st.quat[2] = nz * inv; st.quat[3] = nw * inv;
 #pragma unroll
   for (int i = 0; i < 12; i++) st.q[i] += dt * st.qd[i];
@@ -1005,7 +1007,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
 #pragma unroll
   for (int k = 0; k < 4; k++) {
 #pragma unroll
-    for (int j = 0; j < 3; j++) st.q[3 * k + j] = *static_cast<const volatile T*>(&scr(k, SCR_Q + j));
+    for (int j = 0; j < 3; j++) st.q[3 * k + j] = reload(scr(k, SCR_Q + j));
   }
   integrate_positions(st, dt);
   return TICK_DONE;

@@ -31,15 +31,40 @@ QS_DEV double asin_t(double x) { return asin(x); }
 QS_DEV float exp_t(float x) { return expf(x); }
 QS_DEV double exp_t(double x) { return exp(x); }
 QS_DEV float abs_t(float x) { return fabsf(x); }
-// division on the hot path: fp32 device code uses the 2-instruction approximate divide (<= 2 ulp,
-// no IEEE slow-path subroutine: the slow paths alone were ~10% of the tick's code size); the
-// fp64 check instantiation and host code divide exactly
+// division on the hot path: fp32 device code multiplies by the hardware reciprocal (one MUFU.RCP and one FMUL, <= 2 ulp).
+// The divisors of the tick are masses, inertias, Delassus diagonals and dt, all far inside the normal range, so neither
+// the IEEE slow-path subroutine (~10% of the tick's code size once) nor the range scaling of div.approx (four more
+// instructions per division, ~40 divisions per tick) buys anything.  The fp64 check instantiation and host code divide exactly.
 QS_DEV float div_t(float a, float b) {
 #ifdef __CUDA_ARCH__
-  return __fdividef(a, b);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+  return a * r;
 #else
   return a / b;
 #endif
+}
+// 1/sqrt of a quantity that is O(1) and positive by construction (Cholesky pivots, quaternion norm): the bare MUFU.RSQ
+QS_DEV float rsqrt_pos(float x) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+QS_DEV double rsqrt_pos(double x) { return 1.0 / sqrt(x); }
+// sin x / x and cos x for |x| <= pi/8 (half the rotation of one tick, clamped there by the integrator): Taylor series to
+// x^10 / x^12, exact to fp32 rounding on that range -- a dozen multiply-adds instead of sincosf's range reduction
+QS_DEV void sinc_cos_small(float x, float* sinc, float* c) {
+  const float x2 = x * x;
+  *sinc = 1.f + x2 * (-1.f / 6.f + x2 * (1.f / 120.f + x2 * (-1.f / 5040.f + x2 * (1.f / 362880.f + x2 * (-1.f / 39916800.f)))));
+  *c = 1.f + x2 * (-0.5f + x2 * (1.f / 24.f + x2 * (-1.f / 720.f + x2 * (1.f / 40320.f + x2 * (-1.f / 3628800.f + x2 * (1.f / 479001600.f))))));
+}
+QS_DEV void sinc_cos_small(double x, double* sinc, double* c) {
+  *c = cos(x);
+  *sinc = fabs(x) < 1e-8 ? 1.0 - x * x / 6.0 : sin(x) / x;
 }
 QS_DEV double div_t(double a, double b) { return a / b; }
 // sin/cos of a joint angle inside the physics tick: |x| <= pi, so the 2-MUFU approximation (abs error

@@ -1180,7 +1180,7 @@ __global__ void k_urgent_clear(Conveyor cv) {
 //                                   the oldest entries that fit next to k_step_contact's blocks `early` ticks;
 //   phase 1 (after k_step_contact): the entries that fit next to k_step_slow's blocks get the rest of the ticks.
 __global__ void k_conveyor_ctl(Conveyor cv, int phase, const int* __restrict__ busy_count, int busy_block, int wave_blocks,
-                               int block, int n_envs, int nsettle, int s_min, int s_max, int early, int flush, int fill_pct) {
+                               int block, int n_envs, int nsettle, int s_min, int s_max, int early, int flush) {
   __shared__ uint32_t first_live;
   const uint32_t head = cv.ctl[CV_HEAD];
   uint32_t tail = cv.ctl[CV_TAIL];
@@ -1202,11 +1202,9 @@ __global__ void k_conveyor_ctl(Conveyor cv, int phase, const int* __restrict__ b
     cv.ctl[CV_PREV_HEAD] = head;
     return;
   }
-  // room next to the other kernel of this phase: one settle block displaced per block of it
+  // room next to the other kernel of this phase (busy_block = envs of it per block slot it takes from the slice)
   const int lanes = max(0, min(cv.width, (wave_blocks - (*busy_count + busy_block - 1) / busy_block) * block));
-  // more entries than the window holds: they wait their turn in the queue (they are needed ~QS_SLOTS episodes from now);
-  // only a pile-up (start-up: every env queues its whole ring at once) is worked off as whole settles
-  const bool backlog = fill_pct > 90 ? pending > 2u * uint32_t(cv.width) : pending > uint32_t(cv.width);
+  const bool backlog = pending > uint32_t(cv.width);
   if (phase == 0) {
     float demand = __uint_as_float(cv.ctl[CV_DEMAND]);
     demand += (float(head - cv.ctl[CV_PREV_HEAD]) - demand) * 0.125f;
@@ -1214,9 +1212,9 @@ __global__ void k_conveyor_ctl(Conveyor cv, int phase, const int* __restrict__ b
     cv.ctl[CV_PREV_HEAD] = head;
     // dense wave: nsettle * demand / slice entries in flight = target; ring safety: the settle must not take
     // longer than half a mean episode (n_envs / demand steps, Little's law)
-    const float target = 0.01f * float(fill_pct) * float(cv.width);
+    const float target = 0.9f * float(cv.width);
     float want = float(nsettle) * demand * fmaxf(1.f / target, 2.f / float(n_envs));
-    if (float(pending) > fmaxf(0.97f, 0.01f * float(fill_pct) + 0.07f) * float(cv.width)) want *= 1.5f;  // catch up before a backlog forms
+    if (float(pending) > 0.97f * float(cv.width)) want *= 1.5f;  // nearly full: catch up before a backlog forms
     // ring pressure (smoothed): more than 2 % of the finishing envs one episode from running dry
     float taken = __uint_as_float(cv.ctl[CV_EMA_TAKEN]), low2 = __uint_as_float(cv.ctl[CV_EMA_LOW2]);
     float press = fmaxf(__uint_as_float(cv.ctl[CV_PRESS]), 1.f);

@@ -509,7 +509,7 @@ template <typename T> QS_DEV void base_factor(const SpI<T>& tot, T* S6, T* Ld) {
     }
   }
 }
-template <typename T> QS_DEV void chol_fwd(const T* S6, const T* Ld, T* g) {  // g <- L^-1 g
+template <typename S, typename T> QS_DEV void chol_fwd(const S* S6, const S* Ld, T* g) {  // g <- L^-1 g (g: scalars or pairs)
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     T v = g[i];
@@ -776,6 +776,21 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
   // ---- v += dt a, clamped like btMultiBody::applyDeltaVeeMultiDof
   T wb1[3], vb1[3];
   base_velocity_update(st, X, ab, dt, mcv, wb1, vb1);
+  if constexpr (kPack) {
+    using P = PkT<T>;
+#pragma unroll 1
+    for (int kp = 0; kp < 2; kp++) {
+      const int k0 = 2 * kp, k1 = k0 + 1;
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        P acc(scr(k0, SCR_EV + j), scr(k1, SCR_EV + j));
+#pragma unroll
+        for (int c = 0; c < 6; c++) acc -= P(scr(k0, SCR_BM + 6 * j + c), scr(k1, SCR_BM + 6 * j + c)) * P(ab[c]);
+        const P v = clamp_vel(P(P(scr(k0, SCR_QD + j), scr(k1, SCR_QD + j)) + P(dt) * acc), P(mcv));
+        scr(k0, SCR_QD + j) = v.x; scr(k1, SCR_QD + j) = v.y;
+      }
+    }
+  } else {
 #pragma unroll 1
   for (int k = 0; k < 4; k++) {
 #pragma unroll
@@ -785,6 +800,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
       for (int c = 0; c < 6; c++) acc -= scr(k, SCR_BM + 6 * j + c) * ab[c];
       scr(k, SCR_QD + j) = clamp_vel(scr(k, SCR_QD + j) + dt * acc, mcv);
     }
+  }
   }
 
   bool in_contact = false;
@@ -802,6 +818,106 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
 #pragma unroll
       for (int i = 0; i < 6; i++) H[k][i] = T(0);
     }
+    if constexpr (kPack) {
+      // two feet at a time (qs_packed.cuh).  A pair with one foot down runs the arithmetic on both and keeps the rows of
+      // that foot only (the idle leg's inputs are valid numbers: pass A fills them for every leg).
+      using P = PkT<T>;
+      P nbp[3], tdp[3][3], wb1p[3], vb1p[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        nbp[i] = P(nb[i]); wb1p[i] = P(wb1[i]); vb1p[i] = P(vb1[i]);
+        tdp[0][i] = P(X.tdir[0][i]); tdp[1][i] = P(X.tdir[1][i]); tdp[2][i] = P(X.tdir[2][i]);
+      }
+#pragma unroll 1
+      for (int kp = 0; kp < 2; kp++) {
+        const int k0 = 2 * kp, k1 = k0 + 1;
+        const bool a0 = active & (1 << k0), a1 = active & (1 << k1);
+        if (!a0 && !a1) {
+#pragma unroll
+          for (int i = 0; i < 18; i++) { scr(k0, scr_y(i)) = T(0); scr(k1, scr_y(i)) = T(0); }
+          continue;
+        }
+        P sc[6], Mi[6], Bm[18];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          sc[i] = P(scr(k0, SCR_SC + i), scr(k1, SCR_SC + i));
+          Mi[i] = P(scr(k0, SCR_MI + i), scr(k1, SCR_MI + i));
+        }
+#pragma unroll
+        for (int i = 0; i < 18; i++) Bm[i] = P(scr(k0, SCR_BM + i), scr(k1, SCR_BM + i));
+        LegKin<P> K;
+        leg_kin_from_sc(kp, sc, *M2, K);
+        const P gap = st.pos[2] + dot3(nbp, K.r4) - M.foot_radius;
+        const P pc[3] = {K.r4[0] - M.foot_radius * nbp[0], K.r4[1] - M.foot_radius * nbp[1], K.r4[2] - M.foot_radius * nbp[2]};
+        const P qk[3] = {P(scr(k0, SCR_QD), scr(k1, SCR_QD)), P(scr(k0, SCR_QD + 1), scr(k1, SCR_QD + 1)),
+                         P(scr(k0, SCR_QD + 2), scr(k1, SCR_QD + 2))};
+        P y[18], h[6], r3[3], di[3], dg[3], Jk[3][3], Wl[9];
+#pragma unroll
+        for (int dd = 0; dd < 3; dd++) {
+          P Jb[6];
+          foot_jac_dir(K, pc, tdp[dd], Jb, Jk[dd]);
+          r3[dd] = Jb[0] * wb1p[0] + Jb[1] * wb1p[1] + Jb[2] * wb1p[2] + Jb[3] * vb1p[0] + Jb[4] * vb1p[1] + Jb[5] * vb1p[2] +
+                   Jk[dd][0] * qk[0] + Jk[dd][1] * qk[1] + Jk[dd][2] * qk[2];
+#pragma unroll
+          for (int c = 0; c < 6; c++)
+            y[6 * dd + c] = Jb[c] - (Jk[dd][0] * Bm[c] + Jk[dd][1] * Bm[6 + c] + Jk[dd][2] * Bm[12 + c]);
+          Wl[0 * 3 + dd] = Mi[0] * Jk[dd][0] + Mi[1] * Jk[dd][1] + Mi[2] * Jk[dd][2];
+          Wl[1 * 3 + dd] = Mi[1] * Jk[dd][0] + Mi[3] * Jk[dd][1] + Mi[4] * Jk[dd][2];
+          Wl[2 * 3 + dd] = Mi[2] * Jk[dd][0] + Mi[4] * Jk[dd][1] + Mi[5] * Jk[dd][2];
+        }
+#define QS_H(a, b) (Jk[a][0] * Wl[0 * 3 + b] + Jk[a][1] * Wl[1 * 3 + b] + Jk[a][2] * Wl[2 * 3 + b])
+        h[0] = QS_H(0, 0); h[1] = QS_H(0, 1); h[2] = QS_H(0, 2);
+        h[3] = QS_H(1, 1); h[4] = QS_H(1, 2); h[5] = QS_H(2, 2);
+#undef QS_H
+#pragma unroll
+        for (int i = 0; i < 9; i++) { scr(k0, SCR_W + i) = Wl[i].x; scr(k1, SCR_W + i) = Wl[i].y; }
+        {
+          const T slop = T(SC.linear_slop), erp = T(SC.contact_erp);
+          const T d0 = gap.x + slop, d1 = gap.y + slop;
+          T pe0 = T(0), ve0 = -r3[0].x, pe1 = T(0), ve1 = -r3[0].y;
+          if (d0 > T(0)) ve0 -= d0 * idt; else pe0 = -d0 * erp * idt;
+          if (d1 > T(0)) ve1 -= d1 * idt; else pe1 = -d1 * erp * idt;
+          r3[0] = P(pe0 + ve0, pe1 + ve1);
+          r3[1] = -r3[1];
+          r3[2] = -r3[2];
+        }
+        const P hd[3] = {h[0], h[3], h[5]};
+#pragma unroll
+        for (int dd = 0; dd < 3; dd++) {
+          chol_fwd(S6, Ld, y + 6 * dd);
+          P nn = y[6 * dd] * y[6 * dd];
+#pragma unroll
+          for (int i = 1; i < 6; i++) nn += y[6 * dd + i] * y[6 * dd + i];
+          dg[dd] = nn + hd[dd];
+          di[dd] = div_t(P(T(1)), dg[dd]);
+        }
+        // warm start of the normal impulses (Bullet m_warmstartingFactor), foot k0 then foot k1 as in the scalar order
+        T l00 = T(0), l01 = T(0);
+        if (a0 && (cs.mask & (1 << k0))) {
+          l00 = cs.lam_n[k0] * T(SC.warmstart);
+#pragma unroll
+          for (int i = 0; i < 6; i++) z[i] += y[i].x * l00;
+        }
+        if (a1 && (cs.mask & (1 << k1))) {
+          l01 = cs.lam_n[k1] * T(SC.warmstart);
+#pragma unroll
+          for (int i = 0; i < 6; i++) z[i] += y[i].y * l01;
+        }
+#pragma unroll
+        for (int i = 0; i < 18; i++) { scr(k0, scr_y(i)) = a0 ? y[i].x : T(0); scr(k1, scr_y(i)) = a1 ? y[i].y : T(0); }
+#define QS_ROUTE2(KA, KB)                                                                                                \
+  {                                                                                                                     \
+    _Pragma("unroll") for (int i = 0; i < 6; i++) { H[KA][i] = a0 ? h[i].x : T(0); H[KB][i] = a1 ? h[i].y : T(0); }       \
+    _Pragma("unroll") for (int i = 0; i < 3; i++) {                                                                       \
+      rhs[KA][i] = a0 ? r3[i].x : T(0); dinv[KA][i] = a0 ? di[i].x : T(0); diag[KA][i] = a0 ? dg[i].x : T(0);             \
+      rhs[KB][i] = a1 ? r3[i].y : T(0); dinv[KB][i] = a1 ? di[i].y : T(0); diag[KB][i] = a1 ? dg[i].y : T(0);             \
+    }                                                                                                                   \
+    lam[KA][0] = l00; lam[KB][0] = l01;                                                                                 \
+  }
+        if (kp == 0) QS_ROUTE2(0, 1) else QS_ROUTE2(2, 3)
+#undef QS_ROUTE2
+      }
+    } else {
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
       if (!(active & (1 << k))) {
@@ -876,6 +992,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
   } break;
       switch (k) { QS_ROUTE(0) QS_ROUTE(1) QS_ROUTE(2) default: QS_ROUTE(3) }
 #undef QS_ROUTE
+    }
     }
 
     // ---- projected Gauss-Seidel (rows: normals of all feet, then friction cones)
@@ -976,6 +1093,26 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
       st.vang[i] = clamp_vel(st.vang[i] + dw[i], mcv);
       st.vlin[i] = clamp_vel(st.vlin[i] + dv[i], mcv);
     }
+    if constexpr (kPack) {
+      using P = PkT<T>;
+#pragma unroll
+      for (int kp = 0; kp < 2; kp++) {
+        const int k0 = 2 * kp, k1 = k0 + 1;
+        const bool on0 = active & (1 << k0), on1 = active & (1 << k1);
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          P acc = -(P(scr(k0, SCR_BM + 6 * j), scr(k1, SCR_BM + 6 * j)) * P(dnu[0]));
+#pragma unroll
+          for (int c = 1; c < 6; c++) acc -= P(scr(k0, SCR_BM + 6 * j + c), scr(k1, SCR_BM + 6 * j + c)) * P(dnu[c]);
+          // (the W slots of an idle leg hold nothing meaningful: its impulses are zero, its W is read as zero)
+#pragma unroll
+          for (int c = 0; c < 3; c++)
+            acc += P(on0 ? scr(k0, SCR_W + 3 * j + c) : T(0), on1 ? scr(k1, SCR_W + 3 * j + c) : T(0)) * P(lam[k0][c], lam[k1][c]);
+          const P v = clamp_vel(P(P(scr(k0, SCR_QD + j), scr(k1, SCR_QD + j)) + acc), P(mcv));
+          st.qd[3 * k0 + j] = v.x; st.qd[3 * k1 + j] = v.y;
+        }
+      }
+    } else {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const bool on = active & (1 << k);
@@ -988,6 +1125,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
                        scr(k, SCR_W + 3 * j + 2) * lam[k][2];
         st.qd[3 * k + j] = clamp_vel(scr(k, SCR_QD + j) + acc, mcv);
       }
+    }
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) cs.lam_n[k] = lam[k][0];

@@ -583,7 +583,11 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
     h->flight_cap = h->wave_blocks * B;   // one wave of the flight kernel's blocks
     if (const char* v = std::getenv("QS_FLIGHT_CAP")) h->flight_cap = std::max(0, std::atoi(v));
     h->slice_early = 18;  // ticks of the early slice (round-2 sweep: 8 -> 1.443 ms per step, 12 -> 1.437, 16 -> 1.429, 20 -> 1.417, 24 -> 1.448, 32 -> 1.471)
-    h->slow_spread = 32;
+    // envs per warp of the general solver.  Its duration is the longest env's chain, and lanes of a warp that take
+    // different paths through it run one after the other: fewer envs per warp shorten it -- when there are idle SMs to put
+    // the extra warps on (each of its blocks wants an SM of its own, see launch_conveyor).  With the GPU full (65536 envs)
+    // 32 per warp is best (16: +11 % step time); at 4096 envs one env per warp takes the step from 0.89 to 0.70 ms.
+    h->slow_spread = n_envs <= 8192 ? 1 : (n_envs <= 16384 ? 8 : 32);
     if (const char* v = std::getenv("QS_SLOW_SPREAD")) {
       const int k = std::atoi(v);
       if (k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32) h->slow_spread = k;

@@ -92,6 +92,8 @@ template <typename S> QS_DEV PkT<S>& PkT<S>::operator-=(const PkProd<S>& p) { *t
 // the scalar helpers of qs_robot.cuh, half by half (no packed forms of these exist)
 template <typename S> QS_DEV PkT<S> tmin(PkT<S> a, PkT<S> b) { return PkT<S>(tmin(a.x, b.x), tmin(a.y, b.y)); }
 template <typename S> QS_DEV PkT<S> tmax(PkT<S> a, PkT<S> b) { return PkT<S>(tmax(a.x, b.x), tmax(a.y, b.y)); }
+template <typename S> QS_DEV PkT<S> fmin_t(PkT<S> a, PkT<S> b) { return PkT<S>(fmin_t(a.x, b.x), fmin_t(a.y, b.y)); }
+template <typename S> QS_DEV PkT<S> fmax_t(PkT<S> a, PkT<S> b) { return PkT<S>(fmax_t(a.x, b.x), fmax_t(a.y, b.y)); }
 template <typename S> QS_DEV PkT<S> abs_t(PkT<S> a) { return PkT<S>(abs_t(a.x), abs_t(a.y)); }
 template <typename S> QS_DEV PkT<S> sqrt_t(PkT<S> a) { return PkT<S>(sqrt_t(a.x), sqrt_t(a.y)); }
 template <typename S> QS_DEV PkT<S> rsqrt_t(PkT<S> a) { return PkT<S>(rsqrt_t(a.x), rsqrt_t(a.y)); }

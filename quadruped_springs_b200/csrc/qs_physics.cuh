@@ -239,7 +239,7 @@ QS_DEV void body_force(const SpI<T>& I, const T* Vw, const T* Vv, const T* Aw, c
   for (int i = 0; i < 3; i++) { fn[i] += La[i]; fl[i] += pa[i]; }
 }
 
-template <typename T> QS_DEV T clamp_vel(T v, T mx) { return tmin(tmax(v, -mx), mx); }
+template <typename T> QS_DEV T clamp_vel(T v, T mx) { return fmin_t(fmax_t(v, T(-mx)), mx); }
 
 
 // ------------------------------------------------------------------------------------------
@@ -251,7 +251,13 @@ template <typename T> struct TickCtx {
 };
 
 template <typename T> QS_DEV void tick_ctx(const EnvState<T>& st, const SolverConst& SC, TickCtx<T>& X) {
-  quat_to_R(st.quat, X.Rb);
+  {  // quat_to_R (qs_robot.cuh) with the tick's reciprocal-multiply division
+    const T x = st.quat[0], y = st.quat[1], z = st.quat[2], w = st.quat[3];
+    const T s = div_t(T(2), T(x * x + y * y + z * z + w * w));
+    X.Rb[0] = T(1) - s * (y * y + z * z); X.Rb[1] = s * (x * y - w * z); X.Rb[2] = s * (x * z + w * y);
+    X.Rb[3] = s * (x * y + w * z); X.Rb[4] = T(1) - s * (x * x + z * z); X.Rb[5] = s * (y * z - w * x);
+    X.Rb[6] = s * (x * z - w * y); X.Rb[7] = s * (y * z + w * x); X.Rb[8] = T(1) - s * (x * x + y * y);
+  }
   m3t_v(X.Rb, st.vang, X.wb);
   m3t_v(X.Rb, st.vlin, X.vb);
   const T gacc = T(-SC.gravity_z);
@@ -553,7 +559,7 @@ template <typename T> QS_DEV void integrate_positions(EnvState<T>& st, T dt) {
 #pragma unroll
   for (int i = 0; i < 3; i++) st.pos[i] += dt * st.vlin[i];
   const T* om = st.vang;
-  T ang = sqrt_t(dot3(om, om));
+  T ang = sqrt_pos(dot3(om, om));
   if (ang * dt > T(0.25 * QS_PI)) ang = div_t(T(0.25 * QS_PI), dt);
   // axis * sin(ang dt / 2) = om * (sin(x) / x) * dt / 2 with x = ang dt / 2 <= pi / 8: one branch-free form for every rate
   // (Bullet switches to a Taylor series below ang = 1e-3; the series used here is exact to rounding on the whole range)
@@ -1048,7 +1054,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
           lam[k][0] = neg ? T(0) : sum;
           dIn[k] = dI;
           const T dv = dI * diag[k][0];
-          res = tmax(res, dv * dv);
+          res = fmax_t(res, T(dv * dv));
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -1078,7 +1084,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
 #pragma unroll
         for (int i = 0; i < 6; i++) z[i] += Ya[i] * dIa + Yb[i] * dIb;
         const T ra = dIa * diag[k][1], rb = dIb * diag[k][2];
-        res = tmax(res, ra * ra + rb * rb);
+        res = fmax_t(res, T(ra * ra + rb * rb));
       }
       if (res <= thr) break;
     }

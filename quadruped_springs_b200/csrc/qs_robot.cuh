@@ -16,7 +16,14 @@ namespace qs {
 
 template <typename T> QS_DEV T tmin(T a, T b) { return a < b ? a : b; }
 template <typename T> QS_DEV T tmax(T a, T b) { return a > b ? a : b; }
-template <typename T> QS_DEV T clampt(T x, T lo, T hi) { return tmin(tmax(x, lo), hi); }
+// min / max as ONE instruction (FMNMX) where the select's NaN behaviour is not needed: `a > b ? a : b` has to be a compare
+// and a select (it returns b when either is NaN, FMNMX returns the other operand), and a tick has ~130 of them.  In a
+// clamp tmin(tmax(x, lo), hi) the two agree even for a NaN x (both give lo); a max-reduction differs only in dropping a NaN.
+template <typename T> QS_DEV T fmin_t(T a, T b) { return tmin(a, b); }
+template <typename T> QS_DEV T fmax_t(T a, T b) { return tmax(a, b); }
+QS_DEV float fmin_t(float a, float b) { return fminf(a, b); }
+QS_DEV float fmax_t(float a, float b) { return fmaxf(a, b); }
+template <typename T> QS_DEV T clampt(T x, T lo, T hi) { return fmin_t(fmax_t(x, lo), hi); }
 
 QS_DEV void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
 QS_DEV void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
@@ -55,6 +62,17 @@ QS_DEV float rsqrt_pos(float x) {
 #endif
 }
 QS_DEV double rsqrt_pos(double x) { return 1.0 / sqrt(x); }
+// sqrt of a non-negative quantity inside the tick (|omega|): the bare MUFU.SQRT (0 -> 0, ~1 ulp)
+QS_DEV float sqrt_pos(float x) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
+#endif
+}
+QS_DEV double sqrt_pos(double x) { return sqrt(x); }
 // sin x / x and cos x for |x| <= pi/8 (half the rotation of one tick, clamped there by the integrator): Taylor series to
 // x^10 / x^12, exact to fp32 rounding on that range -- a dozen multiply-adds instead of sincosf's range reduction
 QS_DEV void sinc_cos_small(float x, float* sinc, float* c) {

@@ -48,6 +48,7 @@ namespace qs {  // overloads of the hot-path helpers for the counting type (decl
 inline void sincos_tick(Cnt x, Cnt* s, Cnt* c) { sincos_t(x, s, c); }
 inline Cnt div_t(Cnt a, Cnt b) { return a / b; }
 inline Cnt rsqrt_pos(Cnt x) { return rsqrt_t(x); }
+inline Cnt sqrt_pos(Cnt x) { return sqrt_t(x); }
 inline void sinc_cos_small(Cnt x, Cnt* sinc, Cnt* c) { g_trig += 2; c->v = std::cos(x.v); sinc->v = std::fabs(x.v) < 1e-8 ? 1.0 : std::sin(x.v) / x.v; }
 }  // namespace qs
 

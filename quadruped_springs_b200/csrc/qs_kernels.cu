@@ -125,8 +125,8 @@ k_debug_ticks(const __grid_constant__ DebugArgs<T> A, const float* __restrict__ 
 #pragma unroll
   for (int i = 0; i < 12; i++) t12[i] = T(tau[size_t(env) * 12 + i]);
   const T mu = T(D.mu[env]);
-  extern __shared__ unsigned char qs_smem_raw[];
-  const Scratch<T> scr{reinterpret_cast<T*>(qs_smem_raw) + threadIdx.x, int(blockDim.x)};
+  extern __shared__ __align__(16) unsigned char qs_smem_raw[];
+  const Scratch<T> scr{reinterpret_cast<T*>(qs_smem_raw), int(blockDim.x), int(threadIdx.x)};
   for (int t = 0; t < n_ticks; t++)
     {
     const EnvModelRef em{A.mass_randomizer ? D.model : nullptr, D.n, env};

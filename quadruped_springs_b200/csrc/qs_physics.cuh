@@ -598,14 +598,22 @@ constexpr int QS_TICK_SCRATCH = 4 * QS_LEG_SCRATCH + QS_PARK;  // floats per thr
 
 // kStride > 0: the stride is a compile-time constant (the block size of the step / settle kernels), so every
 // slot of a leg is an immediate offset from one per-leg base address; kStride = 0 reads it at run time.
+// Layout: slot s of legs (2 kp, 2 kp + 1) of thread t are the two halves of ONE 64-bit word at
+// [(kp * QS_LEG_SCRATCH + s) * 2 * stride + 2 t]: the pair passes read and write both legs with one LDS.64 / STS.64
+// (consecutive threads -> consecutive words, conflict-free), a single leg's value is a 32-bit access at stride 2.
 template <typename T, int kStride = 0> struct Scratch {
-  T* p;        // this thread's first element
-  int stride;  // elements between consecutive slots of one thread (ignored when kStride > 0)
+  T* p;        // the block's area
+  int stride;  // threads of the block (ignored when kStride > 0)
+  int tid = 0; // this thread
+  QS_DEV int st() const { return kStride > 0 ? kStride : stride; }
   QS_DEV T& operator()(int leg, int slot) const {
-    return p[(leg * QS_LEG_SCRATCH + slot) * (kStride > 0 ? kStride : stride)];
+    return p[((leg >> 1) * QS_LEG_SCRATCH + slot) * 2 * st() + 2 * tid + (leg & 1)];
+  }
+  QS_DEV PkT<T>& pair(int kp, int slot) const {
+    return *reinterpret_cast<PkT<T>*>(p + (kp * QS_LEG_SCRATCH + slot) * 2 * st() + 2 * tid);
   }
   // what the tick loop's caller keeps here instead of in registers across the ticks (the tick itself never touches it)
-  QS_DEV T& park(int i) const { return p[(4 * QS_LEG_SCRATCH + i) * (kStride > 0 ? kStride : stride)]; }
+  QS_DEV T& park(int i) const { return p[(4 * QS_LEG_SCRATCH + i) * st() + tid]; }
 };
 enum { SCR_BM = 0, SCR_EV = 18, SCR_MI = 21, SCR_SC = 27, SCR_W = 33, SCR_Q = 42, SCR_QD = 45, SCR_TAU = 48 };
 // Once a foot's contact rows are built, EV / MI / SC / TAU of its leg are dead: the 18 floats of the rows'
@@ -662,6 +670,17 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
   const bool watch_shapes = detect_invalid || SC.body_response;
 
   // joint state and torques go through the scratch so that the rolled loops can index them by leg
+  if constexpr (kPack) {
+#pragma unroll
+    for (int kp = 0; kp < 2; kp++) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        scr.pair(kp, SCR_Q + j) = PkT<T>(st.q[6 * kp + j], st.q[6 * kp + 3 + j]);
+        scr.pair(kp, SCR_QD + j) = PkT<T>(st.qd[6 * kp + j], st.qd[6 * kp + 3 + j]);
+        scr.pair(kp, SCR_TAU + j) = PkT<T>(tau[6 * kp + j], tau[6 * kp + 3 + j]);
+      }
+    }
+  } else {
 #pragma unroll
   for (int k = 0; k < 4; k++) {
 #pragma unroll
@@ -670,6 +689,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
       scr(k, SCR_QD + j) = st.qd[3 * k + j];
       scr(k, SCR_TAU + j) = tau[3 * k + j];
     }
+  }
   }
 
   // ---- pass A: one rolled loop over the legs, two at a time when packed
@@ -686,16 +706,16 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
       P q[3], qd[3], tk[3];
 #pragma unroll
       for (int j = 0; j < 3; j++) {
-        q[j] = P(scr(k0, SCR_Q + j), scr(k1, SCR_Q + j));
-        qd[j] = P(scr(k0, SCR_QD + j), scr(k1, SCR_QD + j));
-        tk[j] = P(scr(k0, SCR_TAU + j), scr(k1, SCR_TAU + j));
+        q[j] = scr.pair(kp, SCR_Q + j);
+        qd[j] = scr.pair(kp, SCR_QD + j);
+        tk[j] = scr.pair(kp, SCR_TAU + j);
       }
       LegKin<P> K;
       leg_kin(kp, q, *M2, K);
       // everything that only needs the kinematics comes first, so that it is dead while the dynamics run
       const P sc6[6] = {K.s1, K.c1, K.s2, K.c2, K.s23, K.c23};
 #pragma unroll
-      for (int i = 0; i < 6; i++) { scr(k0, SCR_SC + i) = sc6[i].x; scr(k1, SCR_SC + i) = sc6[i].y; }
+      for (int i = 0; i < 6; i++) scr.pair(kp, SCR_SC + i) = sc6[i];
       if (SC.enable_limits) {
 #pragma unroll
         for (int j = 0; j < 3; j++)
@@ -715,11 +735,11 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
       P Mi[6], Bm[18], ev[3];
       leg_dynamics<P, kEM>(kp, q, qd, tk, X2, *M2, K, Mi, Bm, ev, S6, fb, tot, em);
 #pragma unroll
-      for (int i = 0; i < 18; i++) { scr(k0, SCR_BM + i) = Bm[i].x; scr(k1, SCR_BM + i) = Bm[i].y; }
+      for (int i = 0; i < 18; i++) scr.pair(kp, SCR_BM + i) = Bm[i];
 #pragma unroll
-      for (int i = 0; i < 3; i++) { scr(k0, SCR_EV + i) = ev[i].x; scr(k1, SCR_EV + i) = ev[i].y; }
+      for (int i = 0; i < 3; i++) scr.pair(kp, SCR_EV + i) = ev[i];
 #pragma unroll
-      for (int i = 0; i < 6; i++) { scr(k0, SCR_MI + i) = Mi[i].x; scr(k1, SCR_MI + i) = Mi[i].y; }
+      for (int i = 0; i < 6; i++) scr.pair(kp, SCR_MI + i) = Mi[i];
     }
   } else {
 #pragma unroll 1
@@ -789,11 +809,10 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
       const int k0 = 2 * kp, k1 = k0 + 1;
 #pragma unroll
       for (int j = 0; j < 3; j++) {
-        P acc(scr(k0, SCR_EV + j), scr(k1, SCR_EV + j));
+        P acc = scr.pair(kp, SCR_EV + j);
 #pragma unroll
-        for (int c = 0; c < 6; c++) acc -= P(scr(k0, SCR_BM + 6 * j + c), scr(k1, SCR_BM + 6 * j + c)) * P(ab[c]);
-        const P v = clamp_vel(P(P(scr(k0, SCR_QD + j), scr(k1, SCR_QD + j)) + P(dt) * acc), P(mcv));
-        scr(k0, SCR_QD + j) = v.x; scr(k1, SCR_QD + j) = v.y;
+        for (int c = 0; c < 6; c++) acc -= scr.pair(kp, SCR_BM + 6 * j + c) * P(ab[c]);
+        scr.pair(kp, SCR_QD + j) = clamp_vel(P(scr.pair(kp, SCR_QD + j) + P(dt) * acc), P(mcv));
       }
     }
   } else {
@@ -840,23 +859,19 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
         const bool a0 = active & (1 << k0), a1 = active & (1 << k1);
         if (!a0 && !a1) {
 #pragma unroll
-          for (int i = 0; i < 18; i++) { scr(k0, scr_y(i)) = T(0); scr(k1, scr_y(i)) = T(0); }
+          for (int i = 0; i < 18; i++) scr.pair(kp, scr_y(i)) = P(T(0));
           continue;
         }
         P sc[6], Mi[6], Bm[18];
 #pragma unroll
-        for (int i = 0; i < 6; i++) {
-          sc[i] = P(scr(k0, SCR_SC + i), scr(k1, SCR_SC + i));
-          Mi[i] = P(scr(k0, SCR_MI + i), scr(k1, SCR_MI + i));
-        }
+        for (int i = 0; i < 6; i++) { sc[i] = scr.pair(kp, SCR_SC + i); Mi[i] = scr.pair(kp, SCR_MI + i); }
 #pragma unroll
-        for (int i = 0; i < 18; i++) Bm[i] = P(scr(k0, SCR_BM + i), scr(k1, SCR_BM + i));
+        for (int i = 0; i < 18; i++) Bm[i] = scr.pair(kp, SCR_BM + i);
         LegKin<P> K;
         leg_kin_from_sc(kp, sc, *M2, K);
         const P gap = st.pos[2] + dot3(nbp, K.r4) - M.foot_radius;
         const P pc[3] = {K.r4[0] - M.foot_radius * nbp[0], K.r4[1] - M.foot_radius * nbp[1], K.r4[2] - M.foot_radius * nbp[2]};
-        const P qk[3] = {P(scr(k0, SCR_QD), scr(k1, SCR_QD)), P(scr(k0, SCR_QD + 1), scr(k1, SCR_QD + 1)),
-                         P(scr(k0, SCR_QD + 2), scr(k1, SCR_QD + 2))};
+        const P qk[3] = {scr.pair(kp, SCR_QD), scr.pair(kp, SCR_QD + 1), scr.pair(kp, SCR_QD + 2)};
         P y[18], h[6], r3[3], di[3], dg[3], Jk[3][3], Wl[9];
 #pragma unroll
         for (int dd = 0; dd < 3; dd++) {
@@ -876,7 +891,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
         h[3] = QS_H(1, 1); h[4] = QS_H(1, 2); h[5] = QS_H(2, 2);
 #undef QS_H
 #pragma unroll
-        for (int i = 0; i < 9; i++) { scr(k0, SCR_W + i) = Wl[i].x; scr(k1, SCR_W + i) = Wl[i].y; }
+        for (int i = 0; i < 9; i++) scr.pair(kp, SCR_W + i) = Wl[i];
         {
           const T slop = T(SC.linear_slop), erp = T(SC.contact_erp);
           const T d0 = gap.x + slop, d1 = gap.y + slop;
@@ -910,7 +925,7 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
           for (int i = 0; i < 6; i++) z[i] += y[i].y * l01;
         }
 #pragma unroll
-        for (int i = 0; i < 18; i++) { scr(k0, scr_y(i)) = a0 ? y[i].x : T(0); scr(k1, scr_y(i)) = a1 ? y[i].y : T(0); }
+        for (int i = 0; i < 18; i++) scr.pair(kp, scr_y(i)) = P(a0 ? y[i].x : T(0), a1 ? y[i].y : T(0));
 #define QS_ROUTE2(KA, KB)                                                                                                \
   {                                                                                                                     \
     _Pragma("unroll") for (int i = 0; i < 6; i++) { H[KA][i] = a0 ? h[i].x : T(0); H[KB][i] = a1 ? h[i].y : T(0); }       \
@@ -1020,10 +1035,18 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
     T N10, N20, N21, N30, N31, N32;
     {
       T Yn[4][6];
+      if constexpr (kPack) {
+#pragma unroll
+        for (int kp = 0; kp < 2; kp++) {
+#pragma unroll
+          for (int i = 0; i < 6; i++) { const PkT<T> v = scr.pair(kp, scr_y(i)); Yn[2 * kp][i] = v.x; Yn[2 * kp + 1][i] = v.y; }
+        }
+      } else {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
 #pragma unroll
         for (int i = 0; i < 6; i++) Yn[k][i] = scr(k, scr_y(i));
+      }
       }
 #define QS_N(a, b) ((Yn[a][0] * Yn[b][0] + Yn[a][1] * Yn[b][1] + Yn[a][2] * Yn[b][2]) + (Yn[a][3] * Yn[b][3] + Yn[a][4] * Yn[b][4] + Yn[a][5] * Yn[b][5]))
       N10 = QS_N(1, 0); N20 = QS_N(2, 0); N21 = QS_N(2, 1); N30 = QS_N(3, 0); N31 = QS_N(3, 1); N32 = QS_N(3, 2);
@@ -1032,12 +1055,24 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
     for (int it = 0; it < iters; it++) {
       T res = T(0);
       cs.work_row_iters += nact;
+      PkT<T> yab[12];   // (pair builds) friction rows of the two feet of a pair
       {  // normal rows
         T Yn[4][6], bs[4], dIn[4];
+        if constexpr (kPack) {
+#pragma unroll
+          for (int kp = 0; kp < 2; kp++) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) { const PkT<T> v = scr.pair(kp, scr_y(i)); Yn[2 * kp][i] = v.x; Yn[2 * kp + 1][i] = v.y; }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) Yn[k][i] = scr(k, scr_y(i));
+          }
+        }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-#pragma unroll
-          for (int i = 0; i < 6; i++) Yn[k][i] = scr(k, scr_y(i));
           bs[k] = rhs[k][0] - ((H[k][0] * lam[k][0] + H[k][1] * lam[k][1] + H[k][2] * lam[k][2] + Yn[k][0] * z[0] + Yn[k][1] * z[1] + Yn[k][2] * z[2]) +
                                (Yn[k][3] * z[3] + Yn[k][4] * z[4] + Yn[k][5] * z[5]));
         }
@@ -1065,8 +1100,17 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         T Ya[6], Yb[6];
+        if constexpr (kPack) {   // one 64-bit read serves the two feet of a pair: the odd foot's values come from the even foot's reads
+          if ((k & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) { yab[i] = scr.pair(k >> 1, scr_y(6 + i)); yab[6 + i] = scr.pair(k >> 1, scr_y(12 + i)); }
+          }
+#pragma unroll
+          for (int i = 0; i < 6; i++) { Ya[i] = (k & 1) ? yab[i].y : yab[i].x; Yb[i] = (k & 1) ? yab[6 + i].y : yab[6 + i].x; }
+        } else {
 #pragma unroll
         for (int i = 0; i < 6; i++) { Ya[i] = scr(k, scr_y(6 + i)); Yb[i] = scr(k, scr_y(12 + i)); }
+        }
         const T wa = (H[k][1] * lam[k][0] + H[k][3] * lam[k][1] + H[k][4] * lam[k][2] + Ya[0] * z[0] + Ya[1] * z[1] + Ya[2] * z[2]) +
                      (Ya[3] * z[3] + Ya[4] * z[4] + Ya[5] * z[5]);
         const T wbb = (H[k][2] * lam[k][0] + H[k][4] * lam[k][1] + H[k][5] * lam[k][2] + Yb[0] * z[0] + Yb[1] * z[1] + Yb[2] * z[2]) +
@@ -1107,14 +1151,16 @@ __host__ __device__ int physics_tick(EnvState<T>& st, const T* tau, T mu, Contac
         const bool on0 = active & (1 << k0), on1 = active & (1 << k1);
 #pragma unroll
         for (int j = 0; j < 3; j++) {
-          P acc = -(P(scr(k0, SCR_BM + 6 * j), scr(k1, SCR_BM + 6 * j)) * P(dnu[0]));
+          P acc = -(scr.pair(kp, SCR_BM + 6 * j) * P(dnu[0]));
 #pragma unroll
-          for (int c = 1; c < 6; c++) acc -= P(scr(k0, SCR_BM + 6 * j + c), scr(k1, SCR_BM + 6 * j + c)) * P(dnu[c]);
+          for (int c = 1; c < 6; c++) acc -= scr.pair(kp, SCR_BM + 6 * j + c) * P(dnu[c]);
           // (the W slots of an idle leg hold nothing meaningful: its impulses are zero, its W is read as zero)
 #pragma unroll
-          for (int c = 0; c < 3; c++)
-            acc += P(on0 ? scr(k0, SCR_W + 3 * j + c) : T(0), on1 ? scr(k1, SCR_W + 3 * j + c) : T(0)) * P(lam[k0][c], lam[k1][c]);
-          const P v = clamp_vel(P(P(scr(k0, SCR_QD + j), scr(k1, SCR_QD + j)) + acc), P(mcv));
+          for (int c = 0; c < 3; c++) {
+            const P w = scr.pair(kp, SCR_W + 3 * j + c);
+            acc += P(on0 ? w.x : T(0), on1 ? w.y : T(0)) * P(lam[k0][c], lam[k1][c]);
+          }
+          const P v = clamp_vel(P(scr.pair(kp, SCR_QD + j) + acc), P(mcv));
           st.qd[3 * k0 + j] = v.x; st.qd[3 * k1 + j] = v.y;
         }
       }

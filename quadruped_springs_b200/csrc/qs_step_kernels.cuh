@@ -938,8 +938,8 @@ k_step(const __grid_constant__ KernelArgs A, const StepIO io) {
 
   // ---- action_repeat substeps (:236-237)
   float tau_m[12], tau_s[12];
-  extern __shared__ float qs_smem[];
-  const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
+  extern __shared__ __align__(16) float qs_smem[];
+  const StepScratch scr{qs_smem, QS_BLOCK, int(threadIdx.x)};
   int why;
   const int t_done = run_ticks<false, kEM>(st, cs, cmd, torque_mode, 0, C.action_repeat, env, D, C, A.RC, A.M, A.M2, A.SC, tau_m, tau_s,
                                       true, scr, &why);
@@ -972,8 +972,8 @@ k_step_contact(const __grid_constant__ KernelArgs A, const StepIO io) {
 #pragma unroll
   for (int i = 0; i < 12; i++) cmd[i] = D.cmd[i * n + env];
   const bool torque_mode = !C.is_rl && C.control_mode == QS_CTRL_TORQUE;
-  extern __shared__ float qs_smem[];
-  const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
+  extern __shared__ __align__(16) float qs_smem[];
+  const StepScratch scr{qs_smem, QS_BLOCK, int(threadIdx.x)};
   int why;
   const int t_done = run_ticks<true, kEM>(st, cs, cmd, torque_mode, D.resume_tick[env], C.action_repeat, env, D, C, A.RC, A.M, A.M2,
                                      A.SC, tau_m, tau_s, true, scr, &why);
@@ -1079,8 +1079,8 @@ k_reset(const __grid_constant__ KernelArgs A, const int* __restrict__ list, cons
   ContactState<float> cs;
   float tau_m[12], tau_s[12], mu;
   const bool have = slot_ready(D, env, epoch);
-  extern __shared__ float qs_smem[];
-  const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
+  extern __shared__ __align__(16) float qs_smem[];
+  const StepScratch scr{qs_smem, QS_BLOCK, int(threadIdx.x)};
   float tm2[12], ts2[12];
   settle_fresh<kEM>(A, env, gid, epoch, st, cs, tm2, ts2, &mu, scr, !have);
   if (have) {
@@ -1153,8 +1153,8 @@ k_settle_urgent(const __grid_constant__ KernelArgs A, const Conveyor cv, float* 
   EnvState<float> st;
   ContactState<float> cs;
   float tau_m[12], tau_s[12], mu = 0.f;
-  extern __shared__ float qs_smem[];
-  const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
+  extern __shared__ __align__(16) float qs_smem[];
+  const StepScratch scr{qs_smem, QS_BLOCK, int(threadIdx.x)};
   settle_fresh<kEM>(A, env, uint64_t(A.C.gid0 + env), epoch, st, cs, tau_m, tau_s, &mu, scr, live);
   if (!live) return;
   // its ring: the slot of this episode never became ready, the others may be missing too
@@ -1279,8 +1279,8 @@ k_settle_slice(const __grid_constant__ KernelArgs A, const Conveyor cv, int earl
   if (need && t0 > 0) wip_load(cv, col, st, cs);
   const float mu = episode_mu(A.C, uint64_t(A.C.gid0 + env), epoch);
   const int t1 = need ? min(t0 + span, nsettle) : 0;
-  extern __shared__ float qs_smem[];
-  const StepScratch scr{qs_smem + threadIdx.x, QS_BLOCK};
+  extern __shared__ __align__(16) float qs_smem[];
+  const StepScratch scr{qs_smem, QS_BLOCK, int(threadIdx.x)};
   settle_ticks<kEM>(A, uint64_t(A.C.gid0 + env), epoch, st, cs, mu, t0, t1, span, tau_m, tau_s, scr, cv.model, cv.width, col);
   if (threadIdx.x == 0) stamp_end(stamps);   // (the block's ticks are over: settle_ticks ends on a barrier-matched loop)
   if (!need) return;

@@ -523,7 +523,8 @@ def run_ours(args):
         "mean_foot_contacts_per_tick": scticks / max(sticks, 1), "mean_pgs_sweeps_per_contact_tick": scsweeps / max(scticks, 1)})
     step_line = fp32_line("k_step + k_step_contact", step_flops, k_step_ms, {
         "what": "the physics ticks of step(): k_pre, the flight variant, then the envs with foot contacts (the general-solver "
-                "launch k_step_slow is timed apart: k_step_slow_ms)",
+                "launch k_step_slow is timed apart: k_step_slow_ms; the epilogue kernel k_finish runs next to k_step_slow as a "
+                "programmatic dependent launch and is not in this interval)",
         "algorithmic_flops_per_env_step": step_flops / args.steps / n,
         "mean_foot_contacts_per_tick": cticks / max(ticks, 1), "mean_pgs_sweeps_per_contact_tick": csweeps / max(cticks, 1),
         "hbm": {"algorithmic_bytes_per_step": state_bytes, "achieved_GBps": state_bytes / (max(k_step_ms, 1e-9) * 1e-3) / 1e9,

@@ -333,6 +333,7 @@ struct qs_env {
   Conveyor cv;
   int wave_blocks;     // settle blocks resident at once (SMs x 2)
   int slice_min, slice_max, slice_early;
+  int finish_pdl;  // device-buffer steps: k_finish next to k_step_slow (programmatic dependent launches)
   int flight_cap;      // envs per flight launch (k_pre sends the overflow to the contact kernel)
   int slow_spread;     // envs per warp in k_step_slow (power of two)
   cudaStream_t bg;     // the conveyor's slices run here, next to k_step_slow on the caller's stream
@@ -592,6 +593,8 @@ int qs_create(const qs_config* cfg, int n_envs, int device, qs_handle* out) {
       const int k = std::atoi(v);
       if (k == 1 || k == 2 || k == 4 || k == 8 || k == 16 || k == 32) h->slow_spread = k;
     }
+    h->finish_pdl = 1;
+    if (const char* v = std::getenv("QS_FINISH_PDL")) h->finish_pdl = std::atoi(v) != 0;
     if (const char* v = std::getenv("QS_SETTLE_SLICE_EARLY")) h->slice_early = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MIN")) h->slice_min = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("QS_SETTLE_SLICE_MAX")) h->slice_max = std::max(h->slice_min, std::atoi(v));
@@ -968,9 +971,16 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
     CUDA_TRY(cudaEventRecord(h->ev_fork0, s));
   }
   if (h->args.C.mass_randomizer) k_step_contact<true><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io); else k_step_contact<false><<<grid_for(h->n, B), B, smem_of(B), s>>>(h->args, io);
-  // the epilogue of every env whose ticks are done (all but the general solver's)
-  if (h->args.C.mass_randomizer) k_finish<true><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, nullptr); else k_finish<false><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, nullptr);
-  g_launches += 2;
+  g_launches += 1;
+  // The epilogue of every env whose ticks are done (all but the general solver's).  With host buffers it runs here, so
+  // that the bulk of the results can leave for the host while k_step_slow and the late slice run.  With device buffers
+  // it runs NEXT TO k_step_slow (a chain of programmatic dependent launches, below): the general solver's few blocks and
+  // the late slice had come to end together, and this kernel's 0.08 ms in front of both was serial time.
+  const bool finish_late = !host && h->cfg.auto_reset && h->finish_pdl;
+  if (!finish_late) {
+    if (h->args.C.mass_randomizer) k_finish<true><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, nullptr); else k_finish<false><<<grid_for(h->n, QS_FINISH_BLOCK), QS_FINISH_BLOCK, 0, s>>>(h->args, io, nullptr);
+    g_launches += 1;
+  }
   CUDA_TRY(rec_timing(h->ev1[slot], s, capturing));
   if (!capturing) h->n_steps++;
   if (host) {
@@ -1001,6 +1011,22 @@ static int step_impl(qs_handle h, const float* actions, float* obs, float* rewar
   // synchronisation, the general-solver blocks waited for the whole slice, +1 ms; a high-priority stream made it worse.)
   if (h->args.C.mass_randomizer) k_step_slow<true><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread); else k_step_slow<false><<<grid_for(h->n, 64), 64, 0, s>>>(h->args, io, h->slow_spread);
   g_launches += 1;
+  if (finish_late) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(grid_for(h->n, QS_FINISH_BLOCK)));
+    cfg.blockDim = dim3(unsigned(QS_FINISH_BLOCK));
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const int* no_list = nullptr;
+    if (h->args.C.mass_randomizer) CUDA_TRY(cudaLaunchKernelEx(&cfg, k_finish<true>, h->args, io, no_list));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, k_finish<false>, h->args, io, no_list));
+    g_launches += 1;
+  }
   if (h->cfg.auto_reset) {
     if (int e = launch_slice(h, s, 0, true, io.stamps)) return e;
   }

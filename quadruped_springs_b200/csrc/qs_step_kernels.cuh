@@ -1039,6 +1039,10 @@ constexpr int QS_FINISH_BLOCK = 128;
 template <bool kEM>
 __global__ void __launch_bounds__(QS_FINISH_BLOCK, 4)
 k_finish(const __grid_constant__ KernelArgs A, const StepIO io, const int* __restrict__ list) {
+  // (device-buffer steps launch this kernel behind k_step_slow and the late settle slice behind it, both as programmatic
+  // dependents: the slice may be scheduled once every block of this grid has been placed -- none of them then waits
+  // behind a slice block -- and fills the SMs as they drain.  A no-op under an ordinary launch.)
+  asm volatile("griddepcontrol.launch_dependents;");
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const DeviceView& D = A.D;
   const int n = D.n;
